@@ -1,0 +1,132 @@
+"""The CPU oracle (oracle/*.py) against fixtures produced by the unmodified
+reference (tests/golden/*.npz, made by oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import golden_cases as gc
+from oracle import lift_oracle as lo
+from oracle import mlp_oracle as mo
+from oracle import render_oracle as ro
+
+LIFT_CASES = [k for k, v in gc.CASES.items() if v['kind'] == 'lift']
+
+
+def _close(a, b, rtol=1e-5, atol_scale=1e-6, name=''):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    atol = atol_scale * max(1.0, float(np.abs(b).max()))
+    bad = np.abs(a - b) > rtol * np.abs(b) + atol
+    assert not bad.any(), f'{name}: {bad.sum()} / {bad.size} differ, max abs {np.abs(a - b).max():.3e}'
+
+
+@pytest.mark.parametrize('name', LIFT_CASES)
+def test_lift_oracle_matches_reference(name):
+    case = gc.CASES[name]
+    g = gc.load_golden(name)
+    inp = gc.lift_inputs(case)
+    proj = lo.compute_projection(inp['img_meta'], inp['stride'])
+    pts = lo.get_points(inp['n_voxels'], inp['voxel_size'], inp['img_meta']['lidar2img']['origin'])
+    assert np.array_equal(proj.numpy(), g['projection'])
+    assert np.array_equal(pts.numpy(), g['points'])
+    f = inp['features_sliced']
+    x, y, valid, _ = lo.project_voxels(pts, proj, f.shape[2], f.shape[3])
+    assert np.array_equal(valid.numpy(), g['valid'])
+    pix = (y * f.shape[3] + x)
+    pix[~valid] = -1
+    assert np.array_equal(pix.numpy(), g['pix'].astype(np.int64))
+    assert 0.02 < valid.float().mean() < 0.98          # the case is not degenerate
+    mean, cov, cnt = lo.lift_mean_var(f, pts, proj)
+    assert np.array_equal(cnt.numpy(), g['count'])
+    _close(mean, g['volume_mean'], name='mean')
+    _close(cov, g['volume_cov'], name='cov')
+    if case.get('with_depth'):
+        vol, vd = lo.backproject(f, pts, proj, inp['depth'], inp['voxel_size'])
+        assert np.array_equal(vd.view(vd.shape[0], -1).numpy(), g['valid_depth'])
+        _close(vol.sum(dim=0), g['volume_depth_sum'], name='depth volume')
+        assert vd.sum() < valid.sum()
+
+
+def test_mlp_oracle_matches_reference():
+    g = gc.load_golden('mlp_small')
+    inp = gc.mlp_inputs(gc.CASES['mlp_small'])
+    field = mo.FieldOracle(inp['state'])
+    assert np.array_equal(mo.sinusoidal_encode(inp['pts'], 10).numpy(), g['posenc'])
+    rgb, sigma = field(inp['pts'], inp['ray_d'], inp['feats'])
+    _close(rgb, g['rgb'], name='rgb')
+    _close(sigma, g['sigma'], name='sigma')
+    dens = field.query_density(inp['pts'].reshape(-1, 3), inp['feats'].reshape(-1, 70))
+    _close(dens, g['density'], name='density')
+    assert (g['sigma'] > 0).mean() > 0.1
+
+
+def test_render_oracle_matches_reference():
+    case = gc.CASES['render_det']
+    g = gc.load_golden('render_det')
+    inp = gc.render_inputs(case)
+    cams = ro.pack_cameras(inp['img_meta'])
+    assert np.array_equal(cams.numpy(), g['cameras'])
+    pts, z = ro.sample_along_rays(inp['ray_o'], inp['ray_d'], *inp['near_far_range'],
+                                  inp['N_samples'], det=True)
+    assert np.array_equal(z.numpy(), g['z_vals'])
+    assert np.array_equal(pts.numpy(), g['pts'])
+    pix, front = ro.project_samples(pts, cams[0])
+    assert np.array_equal(front.numpy(), g['in_front'])
+    assert np.array_equal(pix.numpy(), g['pixel_locations'])
+    feat, mask = ro.gather_views(pts, inp['images'], cams[0], inp['featmaps'])
+    assert np.array_equal(mask[..., 0].numpy().astype(np.uint8), g['view_mask'])
+    mean, var = ro.view_statistics(feat, mask)
+    _close(mean.squeeze(2), g['mean'], name='mean35')
+    _close(var.squeeze(2), g['expvar'], name='expvar35')
+    out = ro.render_image_mode(inp['ray_o'], inp['ray_d'], inp['featmaps'], inp['images'],
+                               inp['near_far_range'], inp['N_samples'],
+                               mo.FieldOracle(inp['state']), inp['img_meta'], det=True)
+    oc = out['outputs_coarse']
+    assert np.array_equal(oc['mask'].numpy(), g['mask'])
+    for k in ('rgb', 'depth', 'weights', 'alpha', 'transparency'):
+        _close(oc[k], g[k], rtol=2e-5, name=k)
+    _close(out['sigma'], g['sigma'], name='sigma')
+    assert 0.05 < g['view_mask'].mean() < 0.95
+
+
+def test_volume_lookup_oracle_matches_reference():
+    g = gc.load_golden('volume_lookup')
+    inp = gc.volume_lookup_inputs(gc.CASES['volume_lookup'])
+    feats, inside = ro.volume_lookup(inp['pts'], inp['volume'], inp['aabb'])
+    assert np.array_equal(inside.numpy(), g['inside'])
+    _close(feats, g['features'], name='trilinear')
+    assert 0.1 < g['inside'].mean() < 0.9
+
+
+def test_extract_feat_oracle_matches_reference():
+    """Whole voxel side + render branch of nerfdet.extract_feat, train mode."""
+    case = gc.CASES['extract_small']
+    g = gc.load_golden('extract_small')
+    inp = gc.extract_inputs(case)
+    sd = inp['state']
+    field = mo.FieldOracle(sd)
+    meta = inp['img_meta']
+    h, w = meta['img_shape'][0] // 4, meta['img_shape'][1] // 4
+    fs = inp['features'][:, :, :h, :w]
+    res = lo.extract_lift(fs, meta, inp['n_voxels'], inp['voxel_size'],
+                          inp['ray_batch']['denorm_images'], sd['mapping.0.weight'],
+                          sd['mapping.0.bias'], field)
+    assert np.array_equal(res['count'].numpy(), g['valids'])
+    _close(res['x_scene'], g['x'], rtol=1e-4, atol_scale=1e-5, name='x_scene')
+    assert (g['valids'] == 0).any() and (g['valids'] > 0).any()
+    # render branch with the reference's host draws
+    ray_o, ray_d, gt_rgb, gt_depth, sel = ro.select_training_rays(
+        inp['ray_batch'], inp['N_rand'], np.random.RandomState(234))
+    assert np.array_equal(sel, g['select_inds'])
+    imgs = inp['ray_batch']['denorm_images'][0]
+    out = ro.render_image_mode(ray_o, ray_d, res['feature_2d'], imgs, inp['near_far_range'],
+                               inp['N_samples'], field, meta, det=False,
+                               t_rand=torch.from_numpy(g['t_rand']))
+    oc = out['outputs_coarse']
+    assert np.array_equal(oc['z_vals'].numpy(), g['z_vals'])
+    assert np.array_equal(oc['mask'].numpy(), g['mask'])
+    for k in ('rgb', 'depth', 'weights', 'alpha', 'transparency'):
+        _close(oc[k], g[k], rtol=1e-4, atol_scale=1e-5, name=k)
+    _close(gt_rgb, g['gt_rgb'], name='gt_rgb')
+    _close(gt_depth, g['gt_depth'], name='gt_depth')
