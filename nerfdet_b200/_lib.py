@@ -1,0 +1,76 @@
+"""ctypes binding of ``libnerfdet_lift.so`` (C ABI declared in include/nerfdet_lift.h).
+
+There is NO fallback: if the library is missing the import of any op raises, and on a
+machine with a GPU every op runs the CUDA kernels or fails loudly."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
+
+from . import build as _build
+
+ND_F32, ND_BF16 = 0, 1
+
+
+class NdMaps(ctypes.Structure):
+    _fields_ = [('data', c_void_p), ('dtype', c_int32), ('n_views', c_int32), ('channels', c_int32),
+                ('height', c_int32), ('width', c_int32), ('stride_v', c_int64), ('stride_c', c_int64),
+                ('stride_y', c_int64), ('stride_x', c_int64)]
+
+
+class NdLiftOptions(ctypes.Structure):
+    _fields_ = [('scratch_budget_bytes', c_size_t), ('voxels_per_cta', c_int32), ('reserved', c_int32)]
+
+
+# name -> (restype, argtypes); must list every symbol of include/nerfdet_lift.h
+SIGNATURES = {
+    'nd_version': (c_int, []),
+    'nd_last_error_string': (ctypes.c_char_p, []),
+    'nd_project_voxels': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
+    'nd_backproject': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int64, c_void_p, c_float, c_void_p,
+                               c_void_p, c_void_p]),
+    'nd_lift_workspace_bytes': (c_size_t, [POINTER(NdMaps), c_int64, POINTER(NdLiftOptions)]),
+    'nd_lift_mean_var': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_size_t, POINTER(NdLiftOptions), c_void_p]),
+    'nd_lift_accumulate': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_size_t, POINTER(NdLiftOptions), c_void_p]),
+    'nd_lift_finalize': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Loads (building first if the sources changed and nvcc is present) the C-ABI library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not _build.is_current():
+        try:
+            _build.build_library()
+        except Exception as e:  # no nvcc on this machine: use the shipped .so if there is one
+            if not os.path.isfile(path):
+                raise RuntimeError(
+                    f'libnerfdet_lift.so is missing and could not be built ({e}); '
+                    'the nerfdet_b200 ops have no CPU or eager fallback') from e
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = load().nd_last_error_string()
+        raise RuntimeError(f'{what} failed with nd_status {status}: {msg.decode() if msg else ""}')

@@ -1,0 +1,76 @@
+"""Voxel lifting with the reference's call signatures (drop-in for that stage of
+``nerfdet.extract_feat``, reference ``mmdet3d/models/detectors/nerfdet.py:152-181``).
+
+* ``compute_projection`` / ``get_points`` stay host-side torch code exactly like the
+  reference (they are built on the CPU and moved to the device there too,
+  nerfdet.py:155-160): bit-exact pixel indices need the very same fp32 inputs.
+* ``backproject`` keeps the reference signature and return value (materialised
+  per-view volume) -- the compatibility path.
+* ``lift_mean_var`` is the fused replacement of nerfdet.py:164-181 that never
+  materialises the per-view volume.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+def compute_projection(img_meta, stride: int, angles=None) -> torch.Tensor:
+    """``nerfdet._compute_projection`` (nerfdet.py:364-378): [nv, 3, 4] on the CPU.
+    ``angles`` (SUN RGB-D total-3D branch) is out of scope and must be None."""
+    if angles is not None:
+        raise NotImplementedError('predicted-angle extrinsics (SUN RGB-D head_2d) are out of scope')
+    intrinsic = torch.tensor(img_meta['lidar2img']['intrinsic'][:3, :3])
+    ratio = img_meta['ori_shape'][0] / (img_meta['img_shape'][0] / stride)
+    intrinsic[:2] /= ratio
+    return torch.stack([intrinsic @ torch.tensor(e)[:3] for e in img_meta['lidar2img']['extrinsic']])
+
+
+@torch.no_grad()
+def get_points(n_voxels, voxel_size, origin) -> torch.Tensor:
+    """``get_points`` (nerfdet.py:380-390): [3, X, Y, Z], min-corner lattice."""
+    n_voxels = torch.as_tensor(n_voxels)
+    voxel_size = torch.as_tensor(voxel_size, dtype=torch.float32)
+    origin = torch.as_tensor(origin, dtype=torch.float32)
+    lattice = torch.stack(torch.meshgrid([torch.arange(int(k)) for k in n_voxels], indexing='ij'))
+    new_origin = origin - n_voxels / 2. * voxel_size
+    return lattice * voxel_size.view(3, 1, 1, 1) + new_origin.view(3, 1, 1, 1)
+
+
+def project_voxels(points: torch.Tensor, projection: torch.Tensor, height: int, width: int):
+    """x, y (int64) and valid (bool), each [nv, N]: the index arithmetic of
+    nerfdet.py:396-403, bit-exact."""
+    return ops.project_voxels(points.reshape(3, -1), projection, int(height), int(width))
+
+
+def backproject(features, points, projection, depth, voxel_size):
+    """Same contract as the reference ``backproject`` (nerfdet.py:393-420):
+    returns volume [nv, C, X, Y, Z] f32 and valid [nv, 1, X, Y, Z] bool."""
+    nv, c, h, w = features.shape
+    gx, gy, gz = points.shape[-3:]
+    depth_resized = None
+    voxel_z = 0.0
+    if depth is not None:
+        depth_resized = F.interpolate(depth.unsqueeze(1), size=(h, w), mode='bilinear').squeeze(1)
+        voxel_z = float(voxel_size[-1])
+    volume, valid = ops.backproject(features, points.reshape(3, -1), projection, depth_resized, voxel_z)
+    return volume.view(nv, c, gx, gy, gz), valid.view(nv, 1, gx, gy, gz)
+
+
+def lift_mean_var(features, points, projection, alpha: Optional[torch.Tensor] = None,
+                  want_cov: bool = True, scratch_budget_bytes: int = 0):
+    """Fused nerfdet.py:164-181.  Returns
+    ``volume_mean [C,X,Y,Z]`` (times ``alpha`` per voxel when given, nerfdet.py:259-261),
+    ``volume_cov [C,X,Y,Z]`` = exp(-var) (None when ``want_cov`` is False) and
+    ``valid [1,X,Y,Z]`` int64 view counts."""
+    c = features.shape[1]
+    gx, gy, gz = points.shape[-3:]
+    mean, cov, count = ops.lift_mean_var(features, points.reshape(3, -1), projection,
+                                         alpha.reshape(-1) if alpha is not None else None,
+                                         want_cov, scratch_budget_bytes)
+    return (mean.view(c, gx, gy, gz), cov.view(c, gx, gy, gz) if want_cov else None,
+            count.view(1, gx, gy, gz))
