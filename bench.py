@@ -301,7 +301,7 @@ def main():
         bytes_per_step = algorithmic_bytes(NV_PER_GPU, CHANNELS, FEAT_HW[0], FEAT_HW[1], n_vox)
         achieved = bytes_per_step / (ms_per_step * 1e-3) / 1e9
         # launches per step: 1 pixel-index pre-pass + (stage, gather) per channel chunk (+ finalize when sharded)
-        launches = 1 + 2 * lift_chunks(dev_sets[0]) + (1 if n_gpus > 1 else 0)
+        launches = ops.lift_launch_count(dev_sets[0][:, :, :FEAT_HW[0], :FEAT_HW[1]], n_vox) + (1 if n_gpus > 1 else 0)
         line = {
             'metric': 'voxel_view_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': n_gpus,
             'steps': steps, 'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -310,23 +310,13 @@ def main():
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': ncu_traffic(), 'peak_source': peak_src,
                          'algorithmic_bytes_per_step': bytes_per_step,
-                         'note': 'per-GPU; the fused lift (pixel-index, per-chunk stage+gather launches) timed '
-                                 'as one unit with CUDA events on the launching stream'},
+                         'note': 'per-GPU; the fused lift (its phase launches) timed as one unit with CUDA events on '
+                                 'the launching stream'},
             'cpu_baseline': cpu_baseline, 'e2e': e2e, 'gpu_launches': launches * steps, 'clocks': clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def lift_chunks(feats) -> int:
-    """Number of channel chunks the library plans for this input (64 MiB L2-resident staging)."""
-    nv, c = feats.shape[:2]
-    p = FEAT_HW[0] * FEAT_HW[1]
-    chunk = 256
-    while chunk > 32 and (chunk // 2 >= c or nv * p * chunk * 4 > (64 << 20)):
-        chunk //= 2
-    return -(-c // chunk)
 
 
 def ncu_traffic():

@@ -100,6 +100,10 @@ int nd_backproject(const nd_maps *features, const float *points, const float *pr
  * ------------------------------------------------------------------------------------- */
 size_t nd_lift_workspace_bytes(const nd_maps *features, int64_t n_voxels, const nd_lift_options *opt);
 
+/* Number of kernel launches nd_lift_mean_var / nd_lift_accumulate will issue for this input
+ * (bench.py reports it as gpu_launches). */
+int nd_lift_launch_count(const nd_maps *features, int64_t n_voxels, const nd_lift_options *opt);
+
 int nd_lift_mean_var(const nd_maps *features, const float *points, const float *projection,
                      int64_t n_voxels, const float *alpha, float *mean, float *cov, int64_t *count,
                      void *workspace, size_t workspace_bytes, const nd_lift_options *opt, void *stream);

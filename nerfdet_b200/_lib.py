@@ -32,6 +32,7 @@ SIGNATURES = {
     'nd_backproject': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int64, c_void_p, c_float, c_void_p,
                                c_void_p, c_void_p]),
     'nd_lift_workspace_bytes': (c_size_t, [POINTER(NdMaps), c_int64, POINTER(NdLiftOptions)]),
+    'nd_lift_launch_count': (c_int, [POINTER(NdMaps), c_int64, POINTER(NdLiftOptions)]),
     'nd_lift_mean_var': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_size_t, POINTER(NdLiftOptions), c_void_p]),
     'nd_lift_accumulate': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,

@@ -405,7 +405,20 @@ __global__ void k_backproject(const T *__restrict__ in, int64_t sv, int64_t sc, 
 // ======================================================================================
 // Host side
 // ======================================================================================
+// fast path (lift_fast.cu)
+bool lift_fast_eligible(const nd_maps *f, size_t budget_bytes);
+size_t lift_fast_workspace_bytes(const nd_maps *f, int64_t n_vox);
+template <bool kRaw>
+nd_status run_lift_fast(const nd_maps *f, const float *points, const float *proj, int64_t n_vox, const float *alpha,
+                        float *out_a, float *out_b, int64_t *count_i64, float *count_f32, void *ws, size_t ws_bytes,
+                        cudaStream_t st);
+
+static size_t scratch_budget(const nd_lift_options *opt) {
+    return (opt && opt->scratch_budget_bytes) ? opt->scratch_budget_bytes : ((size_t)64 << 20);
+}
+
 struct LiftPlan {
+    bool fast;              // phase-overlapped fp32 NCHW path (lift_fast.cu)
     int nv, nvp, c, h, w, n_pix;
     int elt;                // bytes per feature element
     bool direct;            // features already pixel-major (channels-last): no staging
@@ -443,6 +456,11 @@ static LiftPlan make_plan(const nd_maps *f, int64_t n_vox, const nd_lift_options
                (reinterpret_cast<uintptr_t>(f->data) % 16) == 0 &&
                (f->stride_y / f->stride_x) * (int64_t)p.h < (1ll << 30) && p.c % 32 == 0 && p.c <= 256 &&
                (p.c == 32 || p.c == 64 || p.c == 128 || p.c == 256);
+    p.fast = !p.direct && lift_fast_eligible(f, scratch_budget(opt));
+    if (p.fast) {
+        p.total_bytes = lift_fast_workspace_bytes(f, n_vox);
+        return p;
+    }
     if (p.direct) {
         p.chunk = p.c;
         p.n_chunks = 1;
@@ -452,7 +470,7 @@ static LiftPlan make_plan(const nd_maps *f, int64_t n_vox, const nd_lift_options
         p.pix_sy = (int)(f->stride_y / f->stride_x);
         p.pix_sx = 1;
     } else {
-        size_t budget = (opt && opt->scratch_budget_bytes) ? opt->scratch_budget_bytes : ((size_t)64 << 20);
+        const size_t budget = scratch_budget(opt);
         int chunk = 256;
         while (chunk > 32 && (chunk / 2 >= p.c || (size_t)p.nv * p.n_pix * chunk * p.elt > budget)) chunk /= 2;
         p.chunk = chunk;
@@ -516,6 +534,10 @@ static nd_status run_lift(const nd_maps *f, const float *points, const float *pr
                           const float *alpha, float *out_a, float *out_b, int64_t *count_i64, float *count_f32,
                           void *ws, size_t ws_bytes, const nd_lift_options *opt, cudaStream_t st) {
     const LiftPlan p = make_plan(f, n_vox, opt);
+    if (p.fast) {
+        if constexpr (sizeof(T) == 4)
+            return run_lift_fast<kRaw>(f, points, proj, n_vox, alpha, out_a, out_b, count_i64, count_f32, ws, ws_bytes, st);
+    }
     ND_REQUIRE(ws != nullptr && ws_bytes >= p.total_bytes, ND_ERR_WORKSPACE,
                "lift: workspace too small (%zu < %zu bytes)", ws_bytes, p.total_bytes);
     ND_REQUIRE((reinterpret_cast<uintptr_t>(ws) % 256) == 0, ND_ERR_BAD_ALIGNMENT, "lift: workspace not 256-byte aligned");
@@ -605,6 +627,14 @@ int nd_backproject(const nd_maps *f, const float *points, const float *projectio
 size_t nd_lift_workspace_bytes(const nd_maps *f, int64_t n_voxels, const nd_lift_options *opt) {
     if (validate_maps(f, "nd_lift_workspace_bytes") != ND_OK || n_voxels < 0) return 0;
     return make_plan(f, n_voxels, opt).total_bytes;
+}
+
+int nd_lift_launch_count(const nd_maps *f, int64_t n_voxels, const nd_lift_options *opt) {
+    if (validate_maps(f, "nd_lift_launch_count") != ND_OK || n_voxels < 0) return -1;
+    const LiftPlan p = make_plan(f, n_voxels, opt);
+    if (p.fast) return f->channels / 32 + 1;
+    if (p.direct) return 2;
+    return 1 + 2 * p.n_chunks;
 }
 
 int nd_lift_mean_var(const nd_maps *f, const float *points, const float *projection, int64_t n_voxels,

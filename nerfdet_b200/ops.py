@@ -217,3 +217,11 @@ def _(acc, n_views_total, channels, n_voxels, alpha, want_cov):
     mean = acc.new_empty((channels, n_voxels))
     cov = acc.new_empty((channels, n_voxels) if want_cov else (0,))
     return mean, cov, acc.new_empty((n_voxels,), dtype=torch.int64)
+
+
+def lift_launch_count(features: Tensor, n_voxels: int, scratch_budget_bytes: int = 0) -> int:
+    """Kernel launches one fused lift of ``features`` issues (for bench.py's ``gpu_launches``)."""
+    m = _maps(features)
+    opt = _options(scratch_budget_bytes)
+    return int(_lib.load().nd_lift_launch_count(ctypes.byref(m), n_voxels,
+                                                ctypes.byref(opt) if opt is not None else None))
