@@ -59,10 +59,15 @@ typedef struct nd_maps {
 } nd_maps;
 
 /* Tuning knobs; pass NULL for defaults. */
+typedef enum nd_lift_path {
+    ND_LIFT_PATH_AUTO = 0,     /* plane-resident kernel when the maps are contiguous NCHW planes, else staged */
+    ND_LIFT_PATH_STAGED = 1    /* force the generic pixel-major staging path (any strides / channels-last) */
+} nd_lift_path;
+
 typedef struct nd_lift_options {
-    size_t scratch_budget_bytes;   /* pixel-major staging kept L2-resident; 0 = default (64 MiB) */
+    size_t scratch_budget_bytes;   /* staged path: pixel-major staging kept L2-resident; 0 = default (64 MiB) */
     int32_t voxels_per_cta;        /* 0 = default */
-    int32_t reserved;
+    int32_t path;                  /* nd_lift_path */
 } nd_lift_options;
 
 int nd_version(void);

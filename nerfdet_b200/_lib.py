@@ -11,6 +11,7 @@ from ctypes import POINTER, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8,
 from . import build as _build
 
 ND_F32, ND_BF16 = 0, 1
+ND_LIFT_PATH_AUTO, ND_LIFT_PATH_STAGED = 0, 1
 
 
 class NdMaps(ctypes.Structure):
@@ -20,7 +21,7 @@ class NdMaps(ctypes.Structure):
 
 
 class NdLiftOptions(ctypes.Structure):
-    _fields_ = [('scratch_budget_bytes', c_size_t), ('voxels_per_cta', c_int32), ('reserved', c_int32)]
+    _fields_ = [('scratch_budget_bytes', c_size_t), ('voxels_per_cta', c_int32), ('path', c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/nerfdet_lift.h

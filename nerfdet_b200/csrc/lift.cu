@@ -405,20 +405,20 @@ __global__ void k_backproject(const T *__restrict__ in, int64_t sv, int64_t sc, 
 // ======================================================================================
 // Host side
 // ======================================================================================
-// fast path (lift_fast.cu)
-bool lift_fast_eligible(const nd_maps *f, size_t budget_bytes);
-size_t lift_fast_workspace_bytes(const nd_maps *f, int64_t n_vox);
-template <bool kRaw>
-nd_status run_lift_fast(const nd_maps *f, const float *points, const float *proj, int64_t n_vox, const float *alpha,
-                        float *out_a, float *out_b, int64_t *count_i64, float *count_f32, void *ws, size_t ws_bytes,
-                        cudaStream_t st);
+// plane-resident path (lift_planes.cu)
+bool lift_planes_eligible(const nd_maps *f, int64_t n_vox);
+size_t lift_planes_workspace_bytes(const nd_maps *f, int64_t n_vox);
+template <typename T, bool kRaw>
+nd_status run_lift_planes(const nd_maps *f, const float *points, const float *proj, int64_t n_vox, const float *alpha,
+                          float *out_a, float *out_b, int64_t *count_i64, float *count_f32, void *ws, size_t ws_bytes,
+                          cudaStream_t st);
 
 static size_t scratch_budget(const nd_lift_options *opt) {
     return (opt && opt->scratch_budget_bytes) ? opt->scratch_budget_bytes : ((size_t)64 << 20);
 }
 
 struct LiftPlan {
-    bool fast;              // phase-overlapped fp32 NCHW path (lift_fast.cu)
+    bool planes;            // plane-resident path (lift_planes.cu): contiguous NCHW planes in shared memory
     int nv, nvp, c, h, w, n_pix;
     int elt;                // bytes per feature element
     bool direct;            // features already pixel-major (channels-last): no staging
@@ -456,9 +456,10 @@ static LiftPlan make_plan(const nd_maps *f, int64_t n_vox, const nd_lift_options
                (reinterpret_cast<uintptr_t>(f->data) % 16) == 0 &&
                (f->stride_y / f->stride_x) * (int64_t)p.h < (1ll << 30) && p.c % 32 == 0 && p.c <= 256 &&
                (p.c == 32 || p.c == 64 || p.c == 128 || p.c == 256);
-    p.fast = !p.direct && lift_fast_eligible(f, scratch_budget(opt));
-    if (p.fast) {
-        p.total_bytes = lift_fast_workspace_bytes(f, n_vox);
+    const bool force_staged = opt != nullptr && opt->path == ND_LIFT_PATH_STAGED;
+    p.planes = !p.direct && !force_staged && lift_planes_eligible(f, n_vox);
+    if (p.planes) {
+        p.total_bytes = lift_planes_workspace_bytes(f, n_vox);
         return p;
     }
     if (p.direct) {
@@ -534,10 +535,8 @@ static nd_status run_lift(const nd_maps *f, const float *points, const float *pr
                           const float *alpha, float *out_a, float *out_b, int64_t *count_i64, float *count_f32,
                           void *ws, size_t ws_bytes, const nd_lift_options *opt, cudaStream_t st) {
     const LiftPlan p = make_plan(f, n_vox, opt);
-    if (p.fast) {
-        if constexpr (sizeof(T) == 4)
-            return run_lift_fast<kRaw>(f, points, proj, n_vox, alpha, out_a, out_b, count_i64, count_f32, ws, ws_bytes, st);
-    }
+    if (p.planes)
+        return run_lift_planes<T, kRaw>(f, points, proj, n_vox, alpha, out_a, out_b, count_i64, count_f32, ws, ws_bytes, st);
     ND_REQUIRE(ws != nullptr && ws_bytes >= p.total_bytes, ND_ERR_WORKSPACE,
                "lift: workspace too small (%zu < %zu bytes)", ws_bytes, p.total_bytes);
     ND_REQUIRE((reinterpret_cast<uintptr_t>(ws) % 256) == 0, ND_ERR_BAD_ALIGNMENT, "lift: workspace not 256-byte aligned");
@@ -632,7 +631,7 @@ size_t nd_lift_workspace_bytes(const nd_maps *f, int64_t n_voxels, const nd_lift
 int nd_lift_launch_count(const nd_maps *f, int64_t n_voxels, const nd_lift_options *opt) {
     if (validate_maps(f, "nd_lift_launch_count") != ND_OK || n_voxels < 0) return -1;
     const LiftPlan p = make_plan(f, n_voxels, opt);
-    if (p.fast) return f->channels / 32 + 1;
+    if (p.planes) return 2;
     if (p.direct) return 2;
     return 1 + 2 * p.n_chunks;
 }

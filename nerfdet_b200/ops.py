@@ -55,9 +55,11 @@ def _check_geometry(points: Tensor, projection: Tensor, n_views: int):
 
 
 def _options(scratch_budget_bytes: int) -> Optional[NdLiftOptions]:
+    """``scratch_budget_bytes`` > 0 selects the generic staged path (any strides) with that much
+    L2-resident staging; 0 = automatic (plane-resident kernel for contiguous NCHW planes)."""
     if scratch_budget_bytes <= 0:
         return None
-    return NdLiftOptions(scratch_budget_bytes, 0, 0)
+    return NdLiftOptions(scratch_budget_bytes, 0, _lib.ND_LIFT_PATH_STAGED)
 
 
 # ------------------------------------------------------------------------------------------
