@@ -68,6 +68,10 @@ typedef struct nd_lift_options {
     size_t scratch_budget_bytes;   /* staged path: pixel-major staging kept L2-resident; 0 = default (64 MiB) */
     int32_t voxels_per_cta;        /* 0 = default */
     int32_t path;                  /* nd_lift_path */
+    int32_t grid_x, grid_y, grid_z; /* optional: the voxel lattice behind `points` (Z fastest, X*Y*Z == n_voxels),
+                                      as in get_points (nerfdet.py:381-390); lets the plane-resident kernel
+                                      use spatially compact warp tiles.  0 = unknown (results are identical) */
+    int32_t reserved;
 } nd_lift_options;
 
 int nd_version(void);

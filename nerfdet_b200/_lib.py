@@ -21,7 +21,8 @@ class NdMaps(ctypes.Structure):
 
 
 class NdLiftOptions(ctypes.Structure):
-    _fields_ = [('scratch_budget_bytes', c_size_t), ('voxels_per_cta', c_int32), ('path', c_int32)]
+    _fields_ = [('scratch_budget_bytes', c_size_t), ('voxels_per_cta', c_int32), ('path', c_int32),
+                ('grid_x', c_int32), ('grid_y', c_int32), ('grid_z', c_int32), ('reserved', c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/nerfdet_lift.h

@@ -406,12 +406,12 @@ __global__ void k_backproject(const T *__restrict__ in, int64_t sv, int64_t sc, 
 // Host side
 // ======================================================================================
 // plane-resident path (lift_planes.cu)
-bool lift_planes_eligible(const nd_maps *f, int64_t n_vox);
-size_t lift_planes_workspace_bytes(const nd_maps *f, int64_t n_vox);
+bool lift_planes_eligible(const nd_maps *f, int64_t n_vox, const nd_lift_options *opt);
+size_t lift_planes_workspace_bytes(const nd_maps *f, int64_t n_vox, const nd_lift_options *opt);
 template <typename T, bool kRaw>
 nd_status run_lift_planes(const nd_maps *f, const float *points, const float *proj, int64_t n_vox, const float *alpha,
                           float *out_a, float *out_b, int64_t *count_i64, float *count_f32, void *ws, size_t ws_bytes,
-                          cudaStream_t st);
+                          const nd_lift_options *opt, cudaStream_t st);
 
 static size_t scratch_budget(const nd_lift_options *opt) {
     return (opt && opt->scratch_budget_bytes) ? opt->scratch_budget_bytes : ((size_t)64 << 20);
@@ -457,9 +457,9 @@ static LiftPlan make_plan(const nd_maps *f, int64_t n_vox, const nd_lift_options
                (f->stride_y / f->stride_x) * (int64_t)p.h < (1ll << 30) && p.c % 32 == 0 && p.c <= 256 &&
                (p.c == 32 || p.c == 64 || p.c == 128 || p.c == 256);
     const bool force_staged = opt != nullptr && opt->path == ND_LIFT_PATH_STAGED;
-    p.planes = !p.direct && !force_staged && lift_planes_eligible(f, n_vox);
+    p.planes = !p.direct && !force_staged && lift_planes_eligible(f, n_vox, opt);
     if (p.planes) {
-        p.total_bytes = lift_planes_workspace_bytes(f, n_vox);
+        p.total_bytes = lift_planes_workspace_bytes(f, n_vox, opt);
         return p;
     }
     if (p.direct) {
@@ -536,7 +536,8 @@ static nd_status run_lift(const nd_maps *f, const float *points, const float *pr
                           void *ws, size_t ws_bytes, const nd_lift_options *opt, cudaStream_t st) {
     const LiftPlan p = make_plan(f, n_vox, opt);
     if (p.planes)
-        return run_lift_planes<T, kRaw>(f, points, proj, n_vox, alpha, out_a, out_b, count_i64, count_f32, ws, ws_bytes, st);
+        return run_lift_planes<T, kRaw>(f, points, proj, n_vox, alpha, out_a, out_b, count_i64, count_f32, ws, ws_bytes, opt,
+                                        st);
     ND_REQUIRE(ws != nullptr && ws_bytes >= p.total_bytes, ND_ERR_WORKSPACE,
                "lift: workspace too small (%zu < %zu bytes)", ws_bytes, p.total_bytes);
     ND_REQUIRE((reinterpret_cast<uintptr_t>(ws) % 256) == 0, ND_ERR_BAD_ALIGNMENT, "lift: workspace not 256-byte aligned");

@@ -31,7 +31,7 @@ def view_shard(n_views: int, rank: int, world_size: int) -> Tuple[int, int]:
 
 def _cuda_accumulate(features, points, projection):
     from . import ops
-    return ops.lift_accumulate(features, points.reshape(3, -1), projection, 0)
+    return ops.lift_accumulate(features, points, projection, 0)
 
 
 def _cuda_finalize(acc, n_views_total, channels, n_voxels, alpha, want_cov):

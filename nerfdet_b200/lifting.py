@@ -69,7 +69,7 @@ def lift_mean_var(features, points, projection, alpha: Optional[torch.Tensor] = 
     ``valid [1,X,Y,Z]`` int64 view counts."""
     c = features.shape[1]
     gx, gy, gz = points.shape[-3:]
-    mean, cov, count = ops.lift_mean_var(features, points.reshape(3, -1), projection,
+    mean, cov, count = ops.lift_mean_var(features, points, projection,
                                          alpha.reshape(-1) if alpha is not None else None,
                                          want_cov, scratch_budget_bytes)
     return (mean.view(c, gx, gy, gz), cov.view(c, gx, gy, gz) if want_cov else None,

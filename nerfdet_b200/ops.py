@@ -48,18 +48,23 @@ def _maps(features: Tensor) -> NdMaps:
 def _check_geometry(points: Tensor, projection: Tensor, n_views: int):
     if points.dtype != torch.float32 or projection.dtype != torch.float32:
         raise TypeError('points and projection must be float32')
-    if points.dim() != 2 or points.shape[0] != 3:
-        raise ValueError(f'points must be [3, N], got {tuple(points.shape)}')
+    if points.dim() not in (2, 4) or points.shape[0] != 3:
+        raise ValueError(f'points must be [3, N] or [3, X, Y, Z], got {tuple(points.shape)}')
     if tuple(projection.shape) != (n_views, 3, 4):
         raise ValueError(f'projection must be [{n_views}, 3, 4], got {tuple(projection.shape)}')
 
 
-def _options(scratch_budget_bytes: int) -> Optional[NdLiftOptions]:
+def _flat_points(points: Tensor) -> Tuple[Tensor, Tuple[int, int, int]]:
+    """[3, N] points plus the lattice shape when ``points`` came as [3, X, Y, Z] (get_points)."""
+    grid = tuple(points.shape[1:]) if points.dim() == 4 else (0, 0, 0)
+    return points.reshape(3, -1).contiguous(), grid
+
+
+def _options(scratch_budget_bytes: int, grid=(0, 0, 0)) -> NdLiftOptions:
     """``scratch_budget_bytes`` > 0 selects the generic staged path (any strides) with that much
     L2-resident staging; 0 = automatic (plane-resident kernel for contiguous NCHW planes)."""
-    if scratch_budget_bytes <= 0:
-        return None
-    return NdLiftOptions(scratch_budget_bytes, 0, _lib.ND_LIFT_PATH_STAGED)
+    path = _lib.ND_LIFT_PATH_STAGED if scratch_budget_bytes > 0 else _lib.ND_LIFT_PATH_AUTO
+    return NdLiftOptions(max(scratch_budget_bytes, 0), 0, path, int(grid[0]), int(grid[1]), int(grid[2]), 0)
 
 
 # ------------------------------------------------------------------------------------------
@@ -128,7 +133,7 @@ def lift_mean_var(features: Tensor, points: Tensor, projection: Tensor, alpha: O
     _need_cuda(features, points, projection, alpha)
     m = _maps(features)
     _check_geometry(points, projection, m.n_views)
-    points = points.contiguous()
+    points, grid = _flat_points(points)
     projection = projection.contiguous()
     n = points.shape[1]
     if alpha is not None:
@@ -140,8 +145,8 @@ def lift_mean_var(features: Tensor, points: Tensor, projection: Tensor, alpha: O
     cov = torch.empty((m.channels, n) if want_cov else (0,), dtype=torch.float32, device=dev)
     count = torch.empty((n,), dtype=torch.int64, device=dev)
     lib = _lib.load()
-    opt = _options(scratch_budget_bytes)
-    optp = ctypes.byref(opt) if opt is not None else None
+    opt = _options(scratch_budget_bytes, grid)
+    optp = ctypes.byref(opt)
     ws_bytes = lib.nd_lift_workspace_bytes(ctypes.byref(m), n, optp)
     ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=dev)
     _lib.check(lib.nd_lift_mean_var(ctypes.byref(m), _ptr(points), _ptr(projection), n, _ptr(alpha), _ptr(mean),
@@ -152,7 +157,7 @@ def lift_mean_var(features: Tensor, points: Tensor, projection: Tensor, alpha: O
 
 @lift_mean_var.register_fake
 def _(features, points, projection, alpha, want_cov, scratch_budget_bytes):
-    c, n = features.shape[1], points.shape[1]
+    c, n = features.shape[1], points[0].numel()
     mean = features.new_empty((c, n), dtype=torch.float32)
     cov = features.new_empty((c, n) if want_cov else (0,), dtype=torch.float32)
     return mean, cov, features.new_empty((n,), dtype=torch.int64)
@@ -166,15 +171,15 @@ def lift_accumulate(features: Tensor, points: Tensor, projection: Tensor, scratc
     _need_cuda(features, points, projection)
     m = _maps(features)
     _check_geometry(points, projection, m.n_views)
-    points = points.contiguous()
+    points, grid = _flat_points(points)
     projection = projection.contiguous()
     n = points.shape[1]
     c = m.channels
     dev = features.device
     acc = torch.empty(((2 * c + 1) * n,), dtype=torch.float32, device=dev)
     lib = _lib.load()
-    opt = _options(scratch_budget_bytes)
-    optp = ctypes.byref(opt) if opt is not None else None
+    opt = _options(scratch_budget_bytes, grid)
+    optp = ctypes.byref(opt)
     ws_bytes = lib.nd_lift_workspace_bytes(ctypes.byref(m), n, optp)
     ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=dev)
     base = acc.data_ptr()
@@ -187,7 +192,7 @@ def lift_accumulate(features: Tensor, points: Tensor, projection: Tensor, scratc
 
 @lift_accumulate.register_fake
 def _(features, points, projection, scratch_budget_bytes):
-    c, n = features.shape[1], points.shape[1]
+    c, n = features.shape[1], points[0].numel()
     return features.new_empty(((2 * c + 1) * n,), dtype=torch.float32)
 
 
@@ -225,5 +230,4 @@ def lift_launch_count(features: Tensor, n_voxels: int, scratch_budget_bytes: int
     """Kernel launches one fused lift of ``features`` issues (for bench.py's ``gpu_launches``)."""
     m = _maps(features)
     opt = _options(scratch_budget_bytes)
-    return int(_lib.load().nd_lift_launch_count(ctypes.byref(m), n_voxels,
-                                                ctypes.byref(opt) if opt is not None else None))
+    return int(_lib.load().nd_lift_launch_count(ctypes.byref(m), n_voxels, ctypes.byref(opt)))
