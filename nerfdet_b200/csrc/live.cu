@@ -1,0 +1,127 @@
+// Live 35-channel voxel statistics (B8 + B9 of SURVEY.md section 8a; reference nerfdet.py:200-210, 232-253).
+//
+// For every voxel n and view v the reference gathers
+//   * 3 RGB channels from the stride-1 projection onto denorm_images[:, :, :h, :w]  (0 where that projection is invalid),
+//   * Cm = 32 mapped channels: mapping(volume) where `volume` is 0 for invalid views, i.e. the Linear bias
+//     (SURVEY.md section 0.6); gather-of-mapped-2D == map-of-gathered-3D bit-identically (section 8a B9),
+//     so the mapped 2-D maps (B7) are gathered directly,
+// and reduces them over views with the FEATURE-level count:
+//   mean = sum / (count + 1e-8)            (NOT zeroed where count == 0)
+//   var  = sum over ALL views (h - mean)^2 / (count + 1e-8), 1e6 where count == 0;  cov = exp(-var)
+// The MLP input row of voxel n is channel-INTERLEAVED [m0, c0, m1, c1, ...].
+//
+// One thread per voxel, 2 * 35 accumulators in registers; the sources (76 MB at nv = 50) are L2-resident
+// and adjacent voxels (Z fastest) hit neighbouring pixels.
+#include "nd_common.cuh"
+
+namespace nd {
+
+constexpr int kLiveMaxCm = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_live_stats(const T *__restrict__ mapped, int64_t m_sv, int64_t m_sc, int64_t m_sy, int64_t m_sx, int cm, int hf, int wf,
+             const float *__restrict__ rgb, int64_t r_sv, int64_t r_sc, int64_t r_sy, int64_t r_sx, int hr, int wr,
+             const float *__restrict__ points, const float *__restrict__ proj_f, const float *__restrict__ proj_r, int nv,
+             int64_t n_vox, const float *__restrict__ bias, float *__restrict__ glob, float *__restrict__ mean_out,
+             float *__restrict__ cov_out, int64_t *__restrict__ count_out) {
+    extern __shared__ float sp[];                       // [nv][12] feature-level, [nv][12] rgb-level, [cm] bias
+    float *spr = sp + nv * 12;
+    float *sb = spr + nv * 12;
+    for (int i = threadIdx.x; i < nv * 12; i += blockDim.x) {
+        sp[i] = proj_f[i];
+        spr[i] = proj_r[i];
+    }
+    for (int i = threadIdx.x; i < cm; i += blockDim.x) sb[i] = bias[i];
+    __syncthreads();
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_vox) return;
+    const float X = points[n], Y = points[n_vox + n], Z = points[2 * n_vox + n];
+
+    float s1[3 + kLiveMaxCm], s2[3 + kLiveMaxCm];
+#pragma unroll
+    for (int k = 0; k < 3 + kLiveMaxCm; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    int cnt = 0;
+    for (int v = 0; v < nv; ++v) {
+        float xr, yr, q2;
+        const bool ok_f = project_nearest(sp + v * 12, X, Y, Z, hf, wf, xr, yr, q2);
+        const int64_t off_f = (int64_t)v * m_sv + (int64_t)(int)yr * m_sy + (int64_t)(int)xr * m_sx;
+        float xr2, yr2, q22;
+        const bool ok_r = project_nearest(spr + v * 12, X, Y, Z, hr, wr, xr2, yr2, q22);
+        const int64_t off_r = (int64_t)v * r_sv + (int64_t)(int)yr2 * r_sy + (int64_t)(int)xr2 * r_sx;
+        cnt += ok_f ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float h = ok_r ? __ldg(rgb + off_r + k * r_sc) : 0.0f;
+            s1[k] += h;
+            s2[k] = fmaf(h, h, s2[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kLiveMaxCm; ++k) {
+            if (k < cm) {
+                const float h = ok_f ? to_f32<T>(mapped[off_f + k * m_sc]) : sb[k];
+                s1[3 + k] += h;
+                s2[3 + k] = fmaf(h, h, s2[3 + k]);
+            }
+        }
+    }
+    const int ct = 3 + cm;
+    const float denom = __fadd_rn((float)cnt, 1e-8f);   // count + 1e-8 in fp32 (== count for count >= 1)
+    float *row = glob + n * (int64_t)(2 * ct);
+#pragma unroll
+    for (int k = 0; k < 3 + kLiveMaxCm; ++k) {
+        if (k < ct) {
+            const float m = s1[k] / denom;
+            float cv = 0.0f;                             // exp(-1e6) == 0 where count == 0 (nerfdet.py:249-250)
+            if (cnt > 0) {
+                // sum over all views of (h - m)^2 = S2 - 2 m S1 + nv m^2
+                float ssd = fmaf(-2.0f * m, s1[k], s2[k]);
+                ssd = fmaxf(fmaf((float)nv * m, m, ssd), 0.0f);
+                cv = expf(-(ssd / denom));
+            }
+            row[2 * k] = m;
+            row[2 * k + 1] = cv;
+            if (mean_out != nullptr) mean_out[(int64_t)k * n_vox + n] = m;
+            if (cov_out != nullptr) cov_out[(int64_t)k * n_vox + n] = cv;
+        }
+    }
+    if (count_out != nullptr) count_out[n] = cnt;
+}
+
+}  // namespace nd
+
+using namespace nd;
+
+extern "C" int nd_live_stats(const nd_maps *mapped, const nd_maps *rgb, const float *points, const float *projection,
+                             const float *rgb_projection, int64_t n_voxels, const float *map_bias, float *global_volume,
+                             float *mean35, float *cov35, int64_t *count, void *stream) {
+    ND_REQUIRE(mapped && rgb && mapped->data && rgb->data && points && projection && rgb_projection && map_bias &&
+                   global_volume,
+               ND_ERR_BAD_ARG, "nd_live_stats: null pointer");
+    ND_REQUIRE(mapped->n_views == rgb->n_views && mapped->n_views > 0, ND_ERR_BAD_SHAPE,
+               "nd_live_stats: %d mapped views vs %d rgb views", mapped->n_views, rgb->n_views);
+    ND_REQUIRE(rgb->channels == 3 && rgb->dtype == ND_F32, ND_ERR_BAD_SHAPE, "nd_live_stats: rgb must be f32 with 3 channels");
+    ND_REQUIRE(mapped->channels >= 1 && mapped->channels <= kLiveMaxCm, ND_ERR_BAD_SHAPE,
+               "nd_live_stats: %d mapped channels (max %d)", mapped->channels, kLiveMaxCm);
+    ND_REQUIRE(n_voxels >= 0, ND_ERR_BAD_SHAPE, "nd_live_stats: negative voxel count");
+    if (n_voxels == 0) return ND_OK;
+    const int nv = mapped->n_views;
+    const size_t smem = ((size_t)nv * 24 + mapped->channels) * sizeof(float);
+    ND_REQUIRE(smem <= 48 * 1024, ND_ERR_BAD_SHAPE, "nd_live_stats: too many views (%d)", nv);
+    const unsigned grid = (unsigned)ceil_div(n_voxels, 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mapped->dtype == ND_F32)
+        k_live_stats<float><<<grid, 128, smem, st>>>(
+            (const float *)mapped->data, mapped->stride_v, mapped->stride_c, mapped->stride_y, mapped->stride_x,
+            mapped->channels, mapped->height, mapped->width, (const float *)rgb->data, rgb->stride_v, rgb->stride_c,
+            rgb->stride_y, rgb->stride_x, rgb->height, rgb->width, points, projection, rgb_projection, nv, n_voxels,
+            map_bias, global_volume, mean35, cov35, count);
+    else
+        k_live_stats<__nv_bfloat16><<<grid, 128, smem, st>>>(
+            (const __nv_bfloat16 *)mapped->data, mapped->stride_v, mapped->stride_c, mapped->stride_y, mapped->stride_x,
+            mapped->channels, mapped->height, mapped->width, (const float *)rgb->data, rgb->stride_v, rgb->stride_c,
+            rgb->stride_y, rgb->stride_x, rgb->height, rgb->width, points, projection, rgb_projection, nv, n_voxels,
+            map_bias, global_volume, mean35, cov35, count);
+    ND_CUDA_LAUNCH_CHECK("k_live_stats");
+    return ND_OK;
+}

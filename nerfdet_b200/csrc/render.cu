@@ -1,0 +1,368 @@
+// NeRF-branch kernels around the shared MLP (R2, R4-R8 of SURVEY.md section 8a).
+//
+//   k_sample_rays          render_ray.py:145-189   z_vals and sample points (jitter numbers supplied by the caller)
+//   k_render_gather_stats  projection.py:24-151 + render_ray.py:71-93, 301-303
+//                          per ray sample: projection into every source view, bilinear gather of the 3 image
+//                          channels and the D mapped-feature channels, masked mean / all-view variance,
+//                          globalfeat [P][2*(3+D)] -- the reference's [rays, samples, views, 35] tensor
+//                          (917 MB at nv = 50) is never materialised
+//   k_composite            render_ray.py:196-247   alpha compositing per ray
+//   k_volume_sample        render_ray.py:26-46     trilinear lookup (dead branch in nerfdet, standalone-callable)
+#include "nd_common.cuh"
+
+namespace nd {
+
+// -------------------------------------------------------------------------------------------------
+// R2
+// -------------------------------------------------------------------------------------------------
+__global__ void k_sample_rays(const float *__restrict__ ray_o, const float *__restrict__ ray_d, int64_t n_rays, int ns,
+                              float near, float far, const float *__restrict__ t_rand, float *__restrict__ pts,
+                              float *__restrict__ z_vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays * ns) return;
+    const int64_t r = i / ns;
+    const int s = (int)(i - r * ns);
+    // near_depth * ones, (far - near) / (N - 1), near + i * step: every op rounded like the torch expression
+    const float step = __fdiv_rn(__fsub_rn(far, near), (float)(ns - 1));
+    auto zi = [&](int k) { return __fadd_rn(near, __fmul_rn((float)k, step)); };
+    float z = zi(s);
+    if (t_rand != nullptr) {
+        const float lower = s == 0 ? z : __fmul_rn(0.5f, __fadd_rn(z, zi(s - 1)));
+        const float upper = s == ns - 1 ? z : __fmul_rn(0.5f, __fadd_rn(zi(s + 1), z));
+        z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand[i]));
+    }
+    z_vals[i] = z;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pts[i * 3 + k] = __fadd_rn(__fmul_rn(z, ray_d[r * 3 + k]), ray_o[r * 3 + k]);
+}
+
+// -------------------------------------------------------------------------------------------------
+// R4 + R5 + R6
+// -------------------------------------------------------------------------------------------------
+struct ViewSample {          // what one (point, view) needs for the bilinear gathers of one source
+    int32_t base;            // element offset of the north-west corner inside a plane (may be out of range)
+    float fx, fy;            // ix - floor(ix), iy - floor(iy)
+    uint32_t inb;            // bit0 nw, bit1 ne, bit2 sw, bit3 se in bounds; bit 8: view mask (in-bound & in-front)
+};
+
+// ATen grid_sampler_2d, bilinear, zeros padding, align_corners = True
+__device__ __forceinline__ ViewSample make_sample(float gx, float gy, int hs, int ws) {
+    const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), (float)(ws - 1));
+    const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), (float)(hs - 1));
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    ViewSample s;
+    s.fx = ix - x0f;
+    s.fy = iy - y0f;
+    // clamp before the int conversion: coordinates are clamped to +-1e6 pixels upstream, far outside any plane
+    const int x0 = (int)fminf(fmaxf(x0f, -4.0f), (float)(ws + 2));
+    const int y0 = (int)fminf(fmaxf(y0f, -4.0f), (float)(hs + 2));
+    const bool xin0 = x0 >= 0 && x0 < ws, xin1 = x0 + 1 >= 0 && x0 + 1 < ws;
+    const bool yin0 = y0 >= 0 && y0 < hs, yin1 = y0 + 1 >= 0 && y0 + 1 < hs;
+    s.inb = (xin0 && yin0 ? 1u : 0u) | (xin1 && yin0 ? 2u : 0u) | (xin0 && yin1 ? 4u : 0u) | (xin1 && yin1 ? 8u : 0u);
+    if (!(ix == ix) || !(iy == iy)) s.inb = 0;          // NaN coordinates sample nothing
+    s.base = y0 * ws + x0;
+    return s;
+}
+
+template <typename T>
+__device__ __forceinline__ float bilinear(const T *__restrict__ plane, const ViewSample &s, int ws) {
+    const float nw = (1.0f - s.fx) * (1.0f - s.fy), ne = s.fx * (1.0f - s.fy);
+    const float sw = (1.0f - s.fx) * s.fy, se = s.fx * s.fy;
+    float acc = 0.0f;
+    if (s.inb & 1u) acc = fmaf(to_f32<T>(plane[s.base]), nw, acc);
+    if (s.inb & 2u) acc = fmaf(to_f32<T>(plane[s.base + 1]), ne, acc);
+    if (s.inb & 4u) acc = fmaf(to_f32<T>(plane[s.base + ws]), sw, acc);
+    if (s.inb & 8u) acc = fmaf(to_f32<T>(plane[s.base + ws + 1]), se, acc);
+    return acc;
+}
+
+constexpr int kRgThreads = 128;
+constexpr int kRgChunk = 8;          // feature channels per pass (3 accumulators each)
+
+// One thread per ray sample.  Pass 0 projects the sample into every view and parks the two
+// ViewSamples (image, feature map) in shared memory; the channel passes then walk the views.
+template <typename T>
+__global__ void __launch_bounds__(kRgThreads)
+k_render_gather_stats(const float *__restrict__ pts, int64_t n_pts, const float *__restrict__ cams, int nv,
+                      const float *__restrict__ img, int64_t i_sv, int64_t i_sc, int hi, int wi,
+                      const T *__restrict__ feat, int64_t f_sv, int64_t f_sc, int d, int hf, int wf,
+                      float *__restrict__ glob, uint8_t *__restrict__ view_mask, uint8_t *__restrict__ pixel_mask,
+                      float *__restrict__ pix_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sP = reinterpret_cast<float *>(smem_raw);                       // [nv][12] rows 0-2 of K @ E
+    ViewSample *sI = reinterpret_cast<ViewSample *>(sP + nv * 12);        // [nv][threads] image samples
+    ViewSample *sF = sI + (size_t)nv * kRgThreads;                        // [nv][threads] feature-map samples
+    // P = K4 @ E (projection.py:57, a 4x4 bmm): the K = 4 FMA chain in k order, rows 0-2
+    for (int i = threadIdx.x; i < nv * 12; i += blockDim.x) {
+        const int v = i / 12, rc = i - v * 12, r = rc >> 2, c = rc & 3;
+        const float *K = cams + v * 34 + 2, *E = cams + v * 34 + 18;
+        float t = __fmul_rn(K[r * 4 + 0], E[0 * 4 + c]);
+        t = __fmaf_rn(K[r * 4 + 1], E[1 * 4 + c], t);
+        t = __fmaf_rn(K[r * 4 + 2], E[2 * 4 + c], t);
+        t = __fmaf_rn(K[r * 4 + 3], E[3 * 4 + c], t);
+        sP[i] = t;
+    }
+    __syncthreads();
+    const int64_t p = (int64_t)blockIdx.x * kRgThreads + threadIdx.x;
+    const bool live = p < n_pts;
+    const float h = cams[0], w = cams[1];                                  // img_shape of the source views
+    float X = 0.f, Y = 0.f, Z = 0.f;
+    if (live) { X = pts[p * 3]; Y = pts[p * 3 + 1]; Z = pts[p * 3 + 2]; }
+    const float wm1 = __fsub_rn(w, 1.0f), hm1 = __fsub_rn(h, 1.0f);
+    int cnt = 0;
+    for (int v = 0; v < nv; ++v) {
+        const float *P = sP + v * 12;
+        const float q0 = chain4(P, X, Y, Z), q1 = chain4(P + 4, X, Y, Z), q2 = chain4(P + 8, X, Y, Z);
+        const float zc = fmaxf(q2, 1e-8f);
+        float px = __fdiv_rn(q0, zc), py = __fdiv_rn(q1, zc);
+        px = fminf(fmaxf(px, -1e6f), 1e6f);
+        py = fminf(fmaxf(py, -1e6f), 1e6f);
+        const bool front = q2 > 0.0f;
+        const bool inb = (px <= wm1) && (px >= 0.0f) && (py <= hm1) && (py >= 0.0f);
+        const bool m = inb && front;
+        cnt += m ? 1 : 0;
+        // normalize (projection.py:37-40): 2 * pix / [w - 1, h - 1] - 1
+        const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, px), wm1), 1.0f);
+        const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, py), hm1), 1.0f);
+        ViewSample si = make_sample(gx, gy, hi, wi);
+        ViewSample sf = make_sample(gx, gy, hf, wf);
+        si.inb |= m ? 0x100u : 0u;
+        sI[(size_t)v * kRgThreads + threadIdx.x] = si;
+        sF[(size_t)v * kRgThreads + threadIdx.x] = sf;
+        if (live && view_mask != nullptr) view_mask[p * nv + v] = m ? 1 : 0;
+        if (live && pix_out != nullptr) {
+            pix_out[((int64_t)v * n_pts + p) * 2] = px;
+            pix_out[((int64_t)v * n_pts + p) * 2 + 1] = py;
+        }
+    }
+    if (!live) return;
+    const float denom = __fadd_rn((float)cnt, 1e-8f);
+    const int ct = 3 + d;
+    float *row = glob + p * (int64_t)(2 * ct);
+    if (pixel_mask != nullptr) pixel_mask[p] = cnt > 1 ? 1 : 0;
+
+    auto finish = [&](int ch, float sm, float sa1, float sa2) {
+        const float mean = sm / denom;                                     // sum f * (mask / (c + 1e-8))
+        float ssd = fmaf(-2.0f * mean, sa1, sa2);                          // sum over ALL views of (f - mean)^2
+        ssd = fmaxf(fmaf((float)nv * mean, mean, ssd), 0.0f);
+        row[ch] = mean;
+        row[ct + ch] = expf(-(ssd / denom));
+    };
+    {   // image channels
+        float sm[3] = {0.f, 0.f, 0.f}, sa1[3] = {0.f, 0.f, 0.f}, sa2[3] = {0.f, 0.f, 0.f};
+        for (int v = 0; v < nv; ++v) {
+            const ViewSample s = sI[(size_t)v * kRgThreads + threadIdx.x];
+            const bool m = (s.inb & 0x100u) != 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float f = bilinear<float>(img + v * i_sv + k * i_sc, s, wi);
+                sm[k] += m ? f : 0.0f;
+                sa1[k] += f;
+                sa2[k] = fmaf(f, f, sa2[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) finish(k, sm[k], sa1[k], sa2[k]);
+    }
+    for (int c0 = 0; c0 < d; c0 += kRgChunk) {
+        float sm[kRgChunk], sa1[kRgChunk], sa2[kRgChunk];
+#pragma unroll
+        for (int k = 0; k < kRgChunk; ++k) { sm[k] = 0.f; sa1[k] = 0.f; sa2[k] = 0.f; }
+        for (int v = 0; v < nv; ++v) {
+            const ViewSample s = sF[(size_t)v * kRgThreads + threadIdx.x];
+            const bool m = (sI[(size_t)v * kRgThreads + threadIdx.x].inb & 0x100u) != 0;
+            if (s.inb == 0) continue;                                      // all four corners outside: f = 0
+            const T *plane0 = feat + v * f_sv + (int64_t)c0 * f_sc;
+#pragma unroll
+            for (int k = 0; k < kRgChunk; ++k) {
+                if (c0 + k < d) {
+                    const float f = bilinear<T>(plane0 + k * f_sc, s, wf);
+                    sm[k] += m ? f : 0.0f;
+                    sa1[k] += f;
+                    sa2[k] = fmaf(f, f, sa2[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kRgChunk; ++k)
+            if (c0 + k < d) finish(3 + c0 + k, sm[k], sa1[k], sa2[k]);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// R7
+// -------------------------------------------------------------------------------------------------
+__global__ void k_composite(const float *__restrict__ rgb, const float *__restrict__ sigma, const float *__restrict__ z,
+                            const uint8_t *__restrict__ pmask, int64_t n_rays, int ns, float z_min, float z_max,
+                            int white_bkgd, float *__restrict__ out_rgb, float *__restrict__ depth,
+                            float *__restrict__ weights, float *__restrict__ alpha_o, float *__restrict__ trans_o,
+                            uint8_t *__restrict__ ray_mask) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    float T = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f, wsum = 0.f, dsum = 0.f;
+    int msum = 0;
+    for (int s = 0; s < ns; ++s) {
+        const int64_t i = r * ns + s;
+        const float a = __fsub_rn(1.0f, expf(-sigma[i]));                  // sigma2alpha, no interval term
+        const float wgt = __fmul_rn(a, T);
+        if (alpha_o != nullptr) alpha_o[i] = a;
+        if (trans_o != nullptr) trans_o[i] = T;
+        if (weights != nullptr) weights[i] = wgt;
+        c0 = fmaf(wgt, rgb[i * 3], c0);
+        c1 = fmaf(wgt, rgb[i * 3 + 1], c1);
+        c2 = fmaf(wgt, rgb[i * 3 + 2], c2);
+        wsum += wgt;
+        dsum = fmaf(wgt, z[i], dsum);
+        if (pmask != nullptr) msum += pmask[i] ? 1 : 0;
+        T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, a), 1e-10f));           // cumprod(1 - alpha + 1e-10)
+    }
+    if (white_bkgd) {
+        const float bg = 1.0f - wsum;
+        c0 += bg; c1 += bg; c2 += bg;
+    }
+    out_rgb[r * 3] = c0;
+    out_rgb[r * 3 + 1] = c1;
+    out_rgb[r * 3 + 2] = c2;
+    float dd = dsum / __fadd_rn(wsum, 1e-8f);
+    depth[r] = fminf(fmaxf(dd, z_min), z_max);
+    if (ray_mask != nullptr) ray_mask[r] = msum > 8 ? 1 : 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// R8: ATen grid_sampler_3d, bilinear, border padding, align_corners = True.  The normalised x
+// coordinate indexes the LAST volume axis (D2), y -> D1, z -> D0, applied literally like the reference.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float unnorm_border(float g, int size) {
+    float c = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), (float)(size - 1));
+    return fminf(fmaxf(c, 0.0f), (float)(size - 1));                       // clip_coordinates
+}
+
+__global__ void k_volume_sample(const float *__restrict__ vol, int c, int d0, int d1, int d2,
+                                const float *__restrict__ pts, int64_t n_pts, float3 lo, float3 inv,
+                                float *__restrict__ out, uint8_t *__restrict__ inside) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pts) return;
+    const float nx = __fsub_rn(__fmul_rn(__fsub_rn(pts[p * 3], lo.x), inv.x), 1.0f);
+    const float ny = __fsub_rn(__fmul_rn(__fsub_rn(pts[p * 3 + 1], lo.y), inv.y), 1.0f);
+    const float nz = __fsub_rn(__fmul_rn(__fsub_rn(pts[p * 3 + 2], lo.z), inv.z), 1.0f);
+    if (inside != nullptr)
+        inside[p] = (nx < 1.f && nx > -1.f && ny < 1.f && ny > -1.f && nz < 1.f && nz > -1.f) ? 1 : 0;
+    const float ix = unnorm_border(nx, d2), iy = unnorm_border(ny, d1), iz = unnorm_border(nz, d0);
+    const float x0f = floorf(ix), y0f = floorf(iy), z0f = floorf(iz);
+    const int x0 = (int)x0f, y0 = (int)y0f, z0 = (int)z0f;
+    const float tx = ix - x0f, ty = iy - y0f, tz = iz - z0f;
+    const int64_t plane = (int64_t)d0 * d1 * d2;
+    for (int ch = 0; ch < c; ++ch) {
+        const float *v = vol + ch * plane;
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+            const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+            const float wgt = (dx ? tx : 1.0f - tx) * (dy ? ty : 1.0f - ty) * (dz ? tz : 1.0f - tz);
+            if (xx < d2 && yy < d1 && zz < d0) acc = fmaf(v[((int64_t)zz * d1 + yy) * d2 + xx], wgt, acc);
+        }
+        out[p * c + ch] = acc;
+    }
+}
+
+}  // namespace nd
+
+using namespace nd;
+
+extern "C" {
+
+int nd_sample_rays(const float *ray_o, const float *ray_d, int64_t n_rays, int n_samples, float near_depth,
+                   float far_depth, const float *t_rand, float *pts, float *z_vals, void *stream) {
+    ND_REQUIRE(ray_o && ray_d && pts && z_vals, ND_ERR_BAD_ARG, "nd_sample_rays: null pointer");
+    ND_REQUIRE(n_rays >= 0 && n_samples >= 2, ND_ERR_BAD_SHAPE, "nd_sample_rays: need n_samples >= 2");
+    ND_REQUIRE(near_depth > 0.f && far_depth > near_depth, ND_ERR_BAD_ARG, "nd_sample_rays: need 0 < near < far");
+    if (n_rays == 0) return ND_OK;
+    const int64_t total = n_rays * n_samples;
+    k_sample_rays<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(ray_o, ray_d, n_rays, n_samples,
+                                                                                    near_depth, far_depth, t_rand, pts,
+                                                                                    z_vals);
+    ND_CUDA_LAUNCH_CHECK("k_sample_rays");
+    return ND_OK;
+}
+
+int nd_render_gather_stats(const float *pts, int64_t n_points, const float *cameras, int n_views,
+                           const nd_maps *images, const nd_maps *featmaps, float *globalfeat, uint8_t *view_mask,
+                           uint8_t *pixel_mask, float *pixel_locations, void *stream) {
+    ND_REQUIRE(pts && cameras && images && featmaps && images->data && featmaps->data && globalfeat, ND_ERR_BAD_ARG,
+               "nd_render_gather_stats: null pointer");
+    ND_REQUIRE(n_views > 0 && images->n_views == n_views && featmaps->n_views == n_views, ND_ERR_BAD_SHAPE,
+               "nd_render_gather_stats: view counts differ");
+    ND_REQUIRE(images->dtype == ND_F32 && images->channels == 3, ND_ERR_BAD_SHAPE,
+               "nd_render_gather_stats: images must be f32 [nv,3,H,W]");
+    ND_REQUIRE(images->stride_x == 1 && images->stride_y == images->width && featmaps->stride_x == 1 &&
+                   featmaps->stride_y == featmaps->width,
+               ND_ERR_BAD_SHAPE, "nd_render_gather_stats: planes must be contiguous (the reference samples the whole padded maps)");
+    ND_REQUIRE(n_points >= 0, ND_ERR_BAD_SHAPE, "nd_render_gather_stats: negative point count");
+    if (n_points == 0) return ND_OK;
+    const size_t smem = (size_t)n_views * 12 * sizeof(float) + (size_t)2 * n_views * kRgThreads * sizeof(ViewSample);
+    ND_REQUIRE(smem <= 220 * 1024, ND_ERR_BAD_SHAPE, "nd_render_gather_stats: too many views (%d)", n_views);
+    const unsigned grid = (unsigned)ceil_div(n_points, kRgThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (featmaps->dtype == ND_F32) {
+        auto kern = k_render_gather_stats<float>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            kern<<<grid, kRgThreads, smem, st>>>(pts, n_points, cameras, n_views, (const float *)images->data,
+                                                 images->stride_v, images->stride_c, images->height, images->width,
+                                                 (const float *)featmaps->data, featmaps->stride_v, featmaps->stride_c,
+                                                 featmaps->channels, featmaps->height, featmaps->width, globalfeat,
+                                                 view_mask, pixel_mask, pixel_locations);
+    } else {
+        auto kern = k_render_gather_stats<__nv_bfloat16>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            kern<<<grid, kRgThreads, smem, st>>>(pts, n_points, cameras, n_views, (const float *)images->data,
+                                                 images->stride_v, images->stride_c, images->height, images->width,
+                                                 (const __nv_bfloat16 *)featmaps->data, featmaps->stride_v,
+                                                 featmaps->stride_c, featmaps->channels, featmaps->height,
+                                                 featmaps->width, globalfeat, view_mask, pixel_mask, pixel_locations);
+    }
+    if (e != cudaSuccess) {
+        set_error("nd_render_gather_stats: %s", cudaGetErrorString(e));
+        return ND_ERR_CUDA;
+    }
+    ND_CUDA_LAUNCH_CHECK("k_render_gather_stats");
+    return ND_OK;
+}
+
+int nd_composite(const float *rgb, const float *sigma, const float *z_vals, const uint8_t *pixel_mask, int64_t n_rays,
+                 int n_samples, float z_min, float z_max, int white_bkgd, float *out_rgb, float *out_depth,
+                 float *weights, float *alpha, float *transparency, uint8_t *ray_mask, void *stream) {
+    ND_REQUIRE(rgb && sigma && z_vals && out_rgb && out_depth, ND_ERR_BAD_ARG, "nd_composite: null pointer");
+    ND_REQUIRE(n_rays >= 0 && n_samples >= 1, ND_ERR_BAD_SHAPE, "nd_composite: bad shape");
+    if (n_rays == 0) return ND_OK;
+    k_composite<<<(unsigned)ceil_div(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
+        rgb, sigma, z_vals, pixel_mask, n_rays, n_samples, z_min, z_max, white_bkgd, out_rgb, out_depth, weights, alpha,
+        transparency, ray_mask);
+    ND_CUDA_LAUNCH_CHECK("k_composite");
+    return ND_OK;
+}
+
+int nd_volume_sample_trilinear(const float *volume, int channels, int d0, int d1, int d2, const float *pts,
+                               int64_t n_points, const float *aabb_min_host, const float *aabb_max_host, float *out,
+                               uint8_t *inside, void *stream) {
+    ND_REQUIRE(volume && pts && aabb_min_host && aabb_max_host && out, ND_ERR_BAD_ARG,
+               "nd_volume_sample_trilinear: null pointer");
+    ND_REQUIRE(channels > 0 && d0 > 0 && d1 > 0 && d2 > 0 && n_points >= 0, ND_ERR_BAD_SHAPE,
+               "nd_volume_sample_trilinear: bad shape");
+    if (n_points == 0) return ND_OK;
+    // 1 / (aabb_max - aabb_min) * 2 as the reference evaluates it in fp32 (render_ray.py:34)
+    float3 lo = make_float3(aabb_min_host[0], aabb_min_host[1], aabb_min_host[2]);
+    float3 inv;
+    inv.x = (1.0f / (aabb_max_host[0] - aabb_min_host[0])) * 2.0f;
+    inv.y = (1.0f / (aabb_max_host[1] - aabb_min_host[1])) * 2.0f;
+    inv.z = (1.0f / (aabb_max_host[2] - aabb_min_host[2])) * 2.0f;
+    k_volume_sample<<<(unsigned)ceil_div(n_points, 128), 128, 0, (cudaStream_t)stream>>>(volume, channels, d0, d1, d2, pts,
+                                                                                        n_points, lo, inv, out, inside);
+    ND_CUDA_LAUNCH_CHECK("k_volume_sample");
+    return ND_OK;
+}
+
+}  // extern "C"
