@@ -132,6 +132,92 @@ int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_v
                      int channels, int64_t n_voxels, const float *alpha,
                      float *mean, float *cov, int64_t *count, void *stream);
 
+
+/* ---------------------------------------------------------------------------------------
+ * B8+B9  nerfdet.py:200-210, 232-253  live 35-channel voxel statistics that feed the density MLP.
+ *   mapped  [nv][Cm][Hf][Wf] f32/bf16: the 2-D mapped features (B7, nerfdet.py:190-197), gathered with the
+ *           FEATURE-level projection; an invalid voxel-view contributes map_bias (Linear(0), nerfdet.py:233-237)
+ *   rgb     [nv][3][h][w] f32: denorm_images[:, :, :h, :w], gathered with its own stride-1 projection
+ *           (0 where that projection is invalid; its validity does not enter the count, nerfdet.py:204-210)
+ *   global_volume f32 [N][2*(3+Cm)]: channel-INTERLEAVED rows [m0, c0, m1, c1, ...] exactly as the reference's
+ *           cat(dim=1) + view produces them (nerfdet.py:251-253); mean is NOT zeroed where count == 0
+ *   mean35 / cov35 f32 [3+Cm][N] (optional, may be NULL), count int64 [N] (optional)
+ * ------------------------------------------------------------------------------------- */
+int nd_live_stats(const nd_maps *mapped, const nd_maps *rgb, const float *points, const float *projection,
+                  const float *rgb_projection, int64_t n_voxels, const float *map_bias, float *global_volume,
+                  float *mean35, float *cov35, int64_t *count, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * M  nerf_mlp.py:11-234  VanillaNeRFRadianceField (NerfMLP + SinusoidalEncoder), as instantiated at
+ * nerfdet.py:62-69.  The struct carries the reference state_dict tensors (row-major [out][in] f32 DEVICE
+ * pointers; only the dimensions are read by nd_mlp_packed_bytes / nd_nerf_mlp_fwd).
+ * ------------------------------------------------------------------------------------- */
+typedef struct nd_mlp_weights {
+    const float *base_w[8], *base_b[8];              /* mlp.base.hidden_layers.<i>.{weight,bias} */
+    const float *sigma_w, *sigma_b;                  /* mlp.sigma_layer.output_layer */
+    const float *bottleneck_w, *bottleneck_b;        /* mlp.bottleneck_layer.output_layer */
+    const float *rgb_hidden_w, *rgb_hidden_b;        /* mlp.rgb_layer.hidden_layers.0 */
+    const float *rgb_out_w, *rgb_out_b;              /* mlp.rgb_layer.output_layer */
+    int32_t net_depth, net_width, skip_layer, feature_dim, cond_width, pos_octaves, view_octaves, reserved;
+} nd_mlp_weights;
+
+size_t nd_mlp_packed_bytes(const nd_mlp_weights *w);                       /* 0 = unsupported architecture */
+/* Transposes the weights once into the caller-owned `packed` buffer (k-major, paddings zeroed). */
+int nd_pack_mlp_weights(const nd_mlp_weights *w, void *packed, size_t packed_bytes, void *stream);
+/* forward (nerf_mlp.py:217-234) / query_density (nerf_mlp.py:224-227) for P points:
+ *   x [P][3], features [P][feature_dim], cond [P / samples_per_ray][3] (ray directions, broadcast over the
+ *   samples of a ray, nerf_mlp.py:153-157) ->  sigma [P] (relu'd), alpha [P] = 1 - exp(-sigma) (nerfdet.py:258),
+ *   rgb [P][3] (sigmoid'd).  Any output may be NULL; rgb == NULL or cond == NULL stops after the density head. */
+int nd_nerf_mlp_fwd(const nd_mlp_weights *arch, const void *packed, const float *x, const float *features,
+                    const float *cond, int64_t n_points, int samples_per_ray, float *sigma, float *alpha, float *rgb,
+                    void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * R2  render_ray.py:145-189  sample_along_camera_ray: z_vals [R][S] = near + i * (far - near) / (S - 1), optional
+ * stratified jitter with caller-supplied uniforms t_rand [R][S] (torch.rand_like drawn by the caller; NULL = det),
+ * pts [R][S][3] = z * d + o (mul and add rounded separately).
+ * ------------------------------------------------------------------------------------- */
+int nd_sample_rays(const float *ray_o, const float *ray_d, int64_t n_rays, int n_samples, float near_depth,
+                   float far_depth, const float *t_rand, float *pts, float *z_vals, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * R4+R5+R6  projection.py:24-151 (Projector.compute, grid_sample branch) + render_ray.py:71-93, 301-303.
+ *   pts [P][3]; cameras [nv][34] = [h, w, K 4x4, E 4x4] (render_ray.py:48-69); images [nv][3][Hp][Wp] f32 and
+ *   featmaps [nv][D][Hf][Wf] f32/bf16, both contiguous planes, sampled bilinearly (zeros padding,
+ *   align_corners = True) at the SAME normalised coordinates.
+ *   globalfeat f32 [P][2*(3+D)] = [mean(3+D), exp(-var)(3+D)] (concatenated, render_ray.py:303)
+ *   view_mask u8 [P][nv] (inbound & in-front, optional), pixel_mask u8 [P] = (sum of view_mask > 1, optional),
+ *   pixel_locations f32 [nv][P][2] (optional; clamped like projection.py:61), in_front u8 [nv][P] (optional),
+ *   view_features f32 [P][nv][3+D] (optional): the materialised per-view samples Projector.compute returns
+ *   (projection.py:147, compatibility path only).
+ * The reference's [rays, samples, views, 3+D] tensor is never materialised.
+ * ------------------------------------------------------------------------------------- */
+int nd_render_gather_stats(const float *pts, int64_t n_points, const float *cameras, int n_views,
+                           const nd_maps *images, const nd_maps *featmaps, float *globalfeat, uint8_t *view_mask,
+                           uint8_t *pixel_mask, float *pixel_locations, uint8_t *in_front, float *view_features, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * R7  render_ray.py:196-247  raw2outputs: alpha = 1 - exp(-sigma) (no interval term), T = cumprod(1 - alpha + 1e-10)
+ * shifted, weights = alpha * T, rgb = sum w rgb, depth = sum w z / (sum w + 1e-8) clamped to z_bounds = {min, max} of
+ * the whole batch's z_vals (render_ray.py:236; 2 floats in DEVICE memory so that no host sync is needed),
+ * ray_mask = sum(pixel_mask) > 8.
+ *   rgb [R][S][3], sigma [R][S], z_vals [R][S], pixel_mask u8 [R][S] (optional)
+ *   out_rgb [R][3], out_depth [R]; weights / alpha / transparency [R][S] and ray_mask u8 [R] optional.
+ * ------------------------------------------------------------------------------------- */
+int nd_composite(const float *rgb, const float *sigma, const float *z_vals, const uint8_t *pixel_mask, int64_t n_rays,
+                 int n_samples, const float *z_bounds, int white_bkgd, float *out_rgb, float *out_depth,
+                 float *weights, float *alpha, float *transparency, uint8_t *ray_mask, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * R8  render_ray.py:26-46  volume_sampling: trilinear grid_sample (border padding, align_corners = True) of
+ * volume [C][D0][D1][D2] at (pts - aabb_min) * 2 / (aabb_max - aabb_min) - 1, normalised x indexing the LAST
+ * axis (applied literally like the reference).  out [P][C], inside u8 [P] (all three strictly within (-1, 1)).
+ * aabb_* are HOST pointers to 3 floats.
+ * ------------------------------------------------------------------------------------- */
+int nd_volume_sample_trilinear(const float *volume, int channels, int d0, int d1, int d2, const float *pts,
+                               int64_t n_points, const float *aabb_min_host, const float *aabb_max_host, float *out,
+                               uint8_t *inside, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

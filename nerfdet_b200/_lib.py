@@ -25,6 +25,16 @@ class NdLiftOptions(ctypes.Structure):
                 ('grid_x', c_int32), ('grid_y', c_int32), ('grid_z', c_int32), ('reserved', c_int32)]
 
 
+class NdMlpWeights(ctypes.Structure):
+    _fields_ = [('base_w', c_void_p * 8), ('base_b', c_void_p * 8),
+                ('sigma_w', c_void_p), ('sigma_b', c_void_p),
+                ('bottleneck_w', c_void_p), ('bottleneck_b', c_void_p),
+                ('rgb_hidden_w', c_void_p), ('rgb_hidden_b', c_void_p),
+                ('rgb_out_w', c_void_p), ('rgb_out_b', c_void_p),
+                ('net_depth', c_int32), ('net_width', c_int32), ('skip_layer', c_int32), ('feature_dim', c_int32),
+                ('cond_width', c_int32), ('pos_octaves', c_int32), ('view_octaves', c_int32), ('reserved', c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/nerfdet_lift.h
 SIGNATURES = {
     'nd_version': (c_int, []),
@@ -41,6 +51,20 @@ SIGNATURES = {
                                    c_void_p, c_size_t, POINTER(NdLiftOptions), c_void_p]),
     'nd_lift_finalize': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
+    'nd_live_stats': (c_int, [POINTER(NdMaps), POINTER(NdMaps), c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nd_mlp_packed_bytes': (c_size_t, [POINTER(NdMlpWeights)]),
+    'nd_pack_mlp_weights': (c_int, [POINTER(NdMlpWeights), c_void_p, c_size_t, c_void_p]),
+    'nd_nerf_mlp_fwd': (c_int, [POINTER(NdMlpWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nd_sample_rays': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
+    'nd_render_gather_stats': (c_int, [c_void_p, c_int64, c_void_p, c_int, POINTER(NdMaps), POINTER(NdMaps),
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nd_composite': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nd_volume_sample_trilinear': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64,
+                                           POINTER(c_float), POINTER(c_float), c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

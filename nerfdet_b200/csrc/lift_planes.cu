@@ -5,72 +5,84 @@
 // output rows mean/cov[c][voxel] -- so no transposition is needed, only a fast random-access
 // memory for one (view, channel) plane (18.9 KB at 59x80 fp32).  That memory is shared memory.
 //
-//   Tiling          a RUN is 16 consecutive voxels (one lane's work, 64 B of an output row); a TILE
-//                   is 32 runs (one warp's work).  When the caller passes the grid shape and
-//                   Z % 16 == 0, X % 4 == 0, Y % 8 == 0 a tile is a compact 4 x 8 block of Z-runs,
-//                   so that whole tiles fall outside a camera frustum; otherwise tiles are 512
-//                   consecutive voxels.  Tables below are stored in tile order ("positions").
+//   Octs            an OCT is 32 lanes x 8 consecutive voxels (256 voxels, 32 B of an output row per
+//                   lane); its two QUADS (4 voxels per lane) are the unit of frustum culling.  When the
+//                   caller passes the grid shape and Z % 8 == 0, X % 4 == 0, Y % 8 == 0 an oct is a
+//                   compact 4 x 8 x 8 block of voxels, so that whole octs fall outside a camera frustum;
+//                   otherwise octs are 256 consecutive voxels.
 //   k_plane_index   one pass over (position, view): the bit-exact nearest-pixel projection, stored
 //                   as a uint16 BYTE OFFSET into a plane (invalid -> offset of a zero word behind
-//                   the plane); per-voxel partial view counts (uint8 per 16-view group); and per
-//                   (tile, view) a 4-bit mask saying which quarter of the runs (4 voxels of every
-//                   lane) has any valid voxel.
-//   k_lift_planes   work unit = (channel c, part p of the tiles).  A producer warp streams the nv
-//                   planes of channel c through an S-stage mbarrier ring with TMA bulk copies (each
-//                   plane byte leaves HBM once).  Each compute warp owns one tile and keeps sum /
-//                   sum-of-squares of its 16 voxels per lane in 32 registers across all views; per
-//                   view it loads its 16 offsets (32 B per lane, 1 KB contiguous per warp, L2
-//                   resident), gathers the unmasked quarters from the plane in shared memory and
-//                   accumulates with packed f32x2 adds / FMAs.  The epilogue turns the
-//                   accumulators into mean / exp(-var) (or raw S1 / S2 for the view-sharded path).
+//                   the plane), one 512 B row per (view, oct); per-voxel partial view counts (uint8 per
+//                   16-view group); per (oct, view) a 2-bit mask saying which quad has any valid voxel,
+//                   and the number of active quad-views of every oct (its cost).
+//   k_plane_pack    ranks the octs by cost and pairs the k-th most with the k-th least expensive one
+//                   (one pair per compute warp, so that all warps of a CTA carry the same load); a PART
+//                   is the set of pairs one CTA owns.  Per (part, view) the offset rows of the octs
+//                   that see the view are compacted into one contiguous block, so that the lift kernel
+//                   can fetch them with a single bulk copy, and every warp gets its entry
+//                   (view | quad mask | row slots).
+//   k_lift_planes   work unit = (channel c, part p).  A producer warp streams, per view, the plane of
+//                   channel c AND the part's offset block through an S-stage mbarrier ring with TMA
+//                   bulk copies (each plane byte leaves HBM once; the consumers never touch global
+//                   memory inside the loop).  Each compute warp keeps sum / sum-of-squares of its
+//                   16 voxels per lane in 32 registers across all views; per view that sees it, it
+//                   reads its offsets (16 B per lane and oct) from the stage, gathers the active quads
+//                   from the plane in shared memory and accumulates with packed f32x2 adds / FMAs.
+//                   The epilogue turns the accumulators into mean / exp(-var) (or raw S1 / S2 for
+//                   the view-sharded path).
 //
 // Nothing of size [nv][C][N] (the reference's 1.3 GB volume) or [nv][pixel][C] (a pixel-major
 // staging copy) is ever written.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "nd_common.cuh"
 
 namespace nd {
 
-constexpr int kPV = 16;                 // voxels per lane (one run)
-constexpr int kPTile = 32 * kPV;        // voxels per warp tile
+constexpr int kOV = 8;                  // voxels per lane and oct
+constexpr int kOct = 32 * kOV;          // voxels per oct
+constexpr int kPV = 2 * kOV;            // voxels per lane (two octs per warp)
+constexpr int kRowBytes = kOct * 2;     // one offset row: uint16 per voxel of an oct
 constexpr int kPMaxWarps = 25;          // compute warps per CTA (+1 producer warp)
-constexpr int kPMaxViews = 512;
 constexpr int kPMaxStages = 16;
-constexpr int kPListPitch = 256;        // entries per warp in the active-view list (nv <= 255)
-constexpr int kPRowDepth = 2;           // per-warp ring of offset rows (cp.async prefetch distance 2 views)
-constexpr int kPBx = 4, kPBy = 8;       // compact tile = kPBx x kPBy runs in (x, y)
+constexpr int kPBx = 4, kPBy = 8;       // compact oct = kPBx x kPBy columns in (x, y) x kOV in z
+constexpr int kPMaxOcts = 256;          // cost-balanced oct pairing up to this many octs (else index order)
 
-// run index (first voxel / 16) of lane `lane` of tile `t`
 struct Tiling {
-    int compact;            // 0: tile = 32 consecutive runs
-    int gy, nzr, tiles_y;   // compact: grid Y, runs per Z column, tiles along Y
-    __host__ __device__ __forceinline__ int64_t run(int t, int lane) const {
-        if (!compact) return (int64_t)t * 32 + lane;
-        const int zr = t % nzr, txy = t / nzr;
-        const int ty = txy % tiles_y, tx = txy / tiles_y;
+    int compact;            // 0: oct = 256 consecutive voxels
+    int gy, gz, nzo, tiles_y;   // compact: grid Y and Z, octs per Z column, 4x8 blocks along Y
+    // first voxel of the 8 consecutive voxels of lane `lane` in oct `q`
+    __host__ __device__ __forceinline__ int64_t voxel(int q, int lane) const {
+        if (!compact) return (int64_t)q * kOct + lane * kOV;
+        const int o = q % nzo, b = q / nzo;
+        const int ty = b % tiles_y, tx = b / tiles_y;
         const int ix = tx * kPBx + (lane >> 3), iy = ty * kPBy + (lane & 7);
-        return ((int64_t)ix * gy + iy) * nzr + zr;
+        return ((int64_t)ix * gy + iy) * gz + o * kOV;
     }
 };
 
 struct PlaneArgs {
     Tiling tiling;
-    // geometry tables (workspace), all in position order p = tile * 512 + lane * 16 + j
-    const uint16_t *off16;     // [nv][n_pad]
-    const uint8_t *cnt8;       // [nw16][n_pad] partial view counts
-    const uint64_t *vmask;     // [n_tiles][nw16], 4 bits per view
-    int nv, nw16;
+    // tables (workspace)
+    const uint8_t *cnt8;       // [nw16][n_pad] partial view counts, position p = oct * 256 + lane * 8 + i
+    const uint16_t *offc;      // [n_parts][nv][2 W][256] compacted offset rows of the octs that see the view
+    const uint16_t *rowcnt;    // [n_parts][nvp] rows in each block
+    const uint32_t *ents;      // [n_parts][W][nvp] view | quad mask << 8 | slot A << 16 | slot B << 24 (0: not seen)
+    const uint16_t *pairs;     // [n_parts][W][2] the octs of every warp (0xffff: none)
+    int nv, nvp, nw16;
     int64_t n_vox, n_pad;
-    int n_tiles, n_parts, n_units;   // unit = (channel, part of the tiles); unit u -> c = u / n_parts
+    int n_octs, n_parts, n_units;   // unit = (channel, part); unit u -> c = u / n_parts
     // planes
     const void *feat;
     int64_t sv, sc;            // elements
     uint32_t plane_bytes, plane_pitch;   // smem slot = plane + zero word, padded to plane_pitch
-    int l2_ahead;              // views the producer's L2 prefetch runs ahead of the shared-memory fill
-    int stages, group;         // ring of `stages` stages, `group` consecutive views per stage
+    int stages;                // plane ring: `stages` slots of plane_pitch bytes
+    int ring_rows;             // offset-row ring: `ring_rows` rows of 512 B shared by the stages in flight
     int *trace;                // diagnostics: per-warp per-stage clock trace of CTA 0 (tools/lift_trace.py), or null
-    int debug;                 // diagnostics (tools/lift_probe.py): 1 = no gather, 4 = no plane copies, 16 = no epilogue
+    int debug;                 // diagnostics (tools/lift_probe.py): 1 = no gather, 4 = no plane copies, 16 = no epilogue,
+                               // 32 = index-order pairing (no cost balancing)
     // outputs
     int n_views_total;
     const float *alpha;
@@ -91,16 +103,19 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    // try_wait WITHOUT a suspend-time hint: with a hint ptxas emits TRYWAIT + NANOSLEEP.SYNCS <hint>, and the
+    // sleeping warp was observed to come back only after the full hint (2 us) instead of at phase completion,
+    // which paced the whole ring at one stage per (hint / stages in flight)
     uint32_t done;
     do {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(2000u)   // suspend-time hint (ns): fewer wake-ups of idle warps
+            : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
 }
@@ -165,23 +180,24 @@ __device__ __forceinline__ float2 unpack2(unsigned long long v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Geometry tables.  grid = (tiles, 16-view groups); one thread per position.
+// Geometry tables.  grid = (octs, 16-view groups); one thread per position.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPTile)
-k_plane_index(const Tiling tiling, const float *__restrict__ points, const float *__restrict__ proj, int nv, int nw16,
-              int64_t n_vox, int64_t n_pad, int height, int width, int elt, uint32_t zero_off,
-              uint16_t *__restrict__ off16, uint8_t *__restrict__ cnt8, uint64_t *__restrict__ vmask) {
+__global__ void __launch_bounds__(kOct)
+k_plane_index(const Tiling tiling, const float *__restrict__ points, const float *__restrict__ proj, int nv, int nvp,
+              int n_octs, int64_t n_vox, int64_t n_pad, int height, int width, int elt, uint32_t zero_off,
+              uint16_t *__restrict__ off16, uint8_t *__restrict__ cnt8, uint8_t *__restrict__ omask,
+              uint8_t *__restrict__ cost16) {
     __shared__ float sp[16 * 12];
-    __shared__ unsigned long long smask;
+    __shared__ unsigned smask;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let k_lift_planes start streaming planes
     const int v0 = blockIdx.y * 16;
     const int nvg = min(16, nv - v0);
     if (threadIdx.x < nvg * 12) sp[threadIdx.x] = proj[v0 * 12 + threadIdx.x];
-    if (threadIdx.x == 0) smask = 0ull;
+    if (threadIdx.x == 0) smask = 0u;
     __syncthreads();
-    const int lane_slot = threadIdx.x >> 4, j = threadIdx.x & 15;
-    const int64_t n = tiling.run(blockIdx.x, lane_slot) * kPV + j;
-    const int64_t p = (int64_t)blockIdx.x * kPTile + threadIdx.x;
+    const int lane_slot = threadIdx.x >> 3, i8 = threadIdx.x & 7;
+    const int64_t n = tiling.voxel(blockIdx.x, lane_slot) + i8;
+    const int64_t p = (int64_t)blockIdx.x * kOct + threadIdx.x;
     const bool inside = n < n_vox;
     float X = 0.f, Y = 0.f, Z = 0.f;
     if (inside) {
@@ -190,7 +206,7 @@ k_plane_index(const Tiling tiling, const float *__restrict__ points, const float
         Z = __ldg(points + 2 * n_vox + n);
     }
     int count = 0;
-    unsigned long long m = 0ull;
+    unsigned m = 0u;
 #pragma unroll 4
     for (int i = 0; i < nvg; ++i) {
         float xr, yr, q2;
@@ -198,26 +214,104 @@ k_plane_index(const Tiling tiling, const float *__restrict__ points, const float
         const uint32_t off = ok ? (uint32_t)((int)yr * width + (int)xr) * (uint32_t)elt : zero_off;
         off16[(int64_t)(v0 + i) * n_pad + p] = (uint16_t)off;
         count += ok ? 1 : 0;
-        // warp = 2 lane slots x 16 voxels; quarter g of a run = voxels 4g..4g+3
+        // warp = 4 lane slots x 8 voxels; quad 0 = voxels 0..3, quad 1 = voxels 4..7 of every lane slot
         const unsigned b = __ballot_sync(0xffffffffu, ok);
-        unsigned nib = 0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) nib |= (b & (0x000f000fu << (4 * g))) ? (1u << g) : 0u;
-        m |= (unsigned long long)nib << (4 * i);
+        m |= ((b & 0x0f0f0f0fu) ? 1u : 0u) << (2 * i);
+        m |= ((b & 0xf0f0f0f0u) ? 2u : 0u) << (2 * i);
     }
-    if ((threadIdx.x & 31) == 0 && m != 0ull) atomicOr(&smask, m);
+    if ((threadIdx.x & 31) == 0 && m != 0u) atomicOr(&smask, m);
     cnt8[(int64_t)blockIdx.y * n_pad + p] = (uint8_t)count;
     __syncthreads();
-    if (threadIdx.x == 0) vmask[(int64_t)blockIdx.x * nw16 + blockIdx.y] = smask;
+    const unsigned sm = smask;
+    if (threadIdx.x < 16) omask[(int64_t)blockIdx.x * nvp + v0 + threadIdx.x] = (uint8_t)((sm >> (2 * threadIdx.x)) & 3u);
+    if (threadIdx.x == 16) cost16[(int64_t)blockIdx.y * n_octs + blockIdx.x] = (uint8_t)__popc(sm);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pairing + compaction.  grid = (views, parts); every block recomputes the (cheap) cost ranking.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_plane_pack(int nv, int nvp, int nw16, int n_octs, int n_parts, int W, int64_t n_pad, int balanced,
+             const uint16_t *__restrict__ off16, const uint8_t *__restrict__ omask, const uint8_t *__restrict__ cost16,
+             uint16_t *__restrict__ offc, uint16_t *__restrict__ rowcnt, uint32_t *__restrict__ ents,
+             uint16_t *__restrict__ pairs) {
+    __shared__ uint16_t s_cost[kPMaxOcts];
+    __shared__ uint16_t s_sorted[kPMaxOcts];
+    __shared__ uint16_t s_q[2 * kPMaxWarps];       // octs of this part in slot order (warp w: 2 w, 2 w + 1)
+    __shared__ uint8_t s_m[2 * kPMaxWarps];        // their quad masks in this view
+    __shared__ uint8_t s_slot[2 * kPMaxWarps];     // their row slot in the compacted block (0xff: not seen)
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // tables of k_plane_index
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // k_lift_planes may start streaming planes
+    const int v = blockIdx.x, part = blockIdx.y, tid = threadIdx.x;
+    if (balanced) {
+        for (int t = tid; t < n_octs; t += blockDim.x) {
+            int cst = 0;
+            for (int g = 0; g < nw16; ++g) cst += (int)cost16[(int64_t)g * n_octs + t];
+            s_cost[t] = (uint16_t)cst;
+        }
+        __syncthreads();
+        for (int t = tid; t < n_octs; t += blockDim.x) {
+            const int ct = s_cost[t];
+            int r = 0;
+            for (int j = 0; j < n_octs; ++j) {
+                const int cj = s_cost[j];
+                r += (cj > ct || (cj == ct && j < t)) ? 1 : 0;
+            }
+            s_sorted[r] = (uint16_t)t;               // ties broken by index: every block computes the same ranking
+        }
+        __syncthreads();
+    }
+    const int n_pairs = (n_octs + 1) / 2;
+    if (tid < W) {
+        const int pair = tid * n_parts + part;
+        uint16_t qa = 0xffffu, qb = 0xffffu;
+        if (pair < n_pairs) {
+            const int ia = pair, ib = n_octs - 1 - pair;
+            qa = balanced ? s_sorted[ia] : (uint16_t)ia;
+            if (ib > ia) qb = balanced ? s_sorted[ib] : (uint16_t)ib;
+        }
+        s_q[2 * tid] = qa;
+        s_q[2 * tid + 1] = qb;
+        if (v == 0) {
+            pairs[((int64_t)part * W + tid) * 2] = qa;
+            pairs[((int64_t)part * W + tid) * 2 + 1] = qb;
+        }
+    }
+    __syncthreads();
+    if (tid < 2 * W) {
+        const uint16_t q = s_q[tid];
+        s_m[tid] = q != 0xffffu ? (uint8_t)(omask[(int64_t)q * nvp + v] & 3u) : (uint8_t)0;
+    }
+    __syncthreads();
+    if (tid < 2 * W) {
+        int slot = 0;
+        for (int j = 0; j < tid; ++j) slot += s_m[j] ? 1 : 0;
+        s_slot[tid] = s_m[tid] ? (uint8_t)slot : (uint8_t)0xff;
+        if (tid == 2 * W - 1) rowcnt[(int64_t)part * nvp + v] = (uint16_t)(slot + (s_m[tid] ? 1 : 0));
+    }
+    __syncthreads();
+    if (tid < W) {
+        const uint32_t qm = (uint32_t)s_m[2 * tid] | ((uint32_t)s_m[2 * tid + 1] << 2);
+        const uint32_t e = qm ? ((uint32_t)v | (qm << 8) | ((uint32_t)s_slot[2 * tid] << 16) | ((uint32_t)s_slot[2 * tid + 1] << 24)) : 0u;
+        ents[((int64_t)part * W + tid) * nvp + v] = e;
+    }
+    // compacted rows: one warp per row, 16 B per lane
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < 2 * W; i += (int)(blockDim.x >> 5)) {
+        if (!s_m[i]) continue;
+        const uint4 *src = reinterpret_cast<const uint4 *>(off16 + (int64_t)v * n_pad + (int64_t)s_q[i] * kOct);
+        uint4 *dst = reinterpret_cast<uint4 *>(offc + (((int64_t)part * nv + v) * (2 * W) + s_slot[i]) * kOct);
+        dst[lane] = src[lane];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Gather + statistics with the planes of one channel streamed through shared memory.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ void gather_quarter(uint32_t sb, uint32_t w0, uint32_t w1, unsigned long long &s1a,
-                                               unsigned long long &s2a, unsigned long long &s1b,
-                                               unsigned long long &s2b) {
+__device__ __forceinline__ void gather_quad(uint32_t sb, uint32_t w0, uint32_t w1, unsigned long long &s1a,
+                                            unsigned long long &s2a, unsigned long long &s1b,
+                                            unsigned long long &s2b) {
     const float f0 = lds_elt<T>(sb + (w0 & 0xffffu));
     const float f1 = lds_elt<T>(sb + (w0 >> 16));
     const float f2 = lds_elt<T>(sb + (w1 & 0xffffu));
@@ -226,21 +320,41 @@ __device__ __forceinline__ void gather_quarter(uint32_t sb, uint32_t w0, uint32_
     acc2(s1b, s2b, f2, f3);
 }
 
-template <typename T, bool kRaw>
+__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// Ring bookkeeping shared by the producer and the consumers.  The offset rows of view v occupy eff(v) consecutive
+// (circular) rows of the row ring, eff(v) = rowcnt(v) + pad(v); the pads make the per-unit total a multiple of
+// the ring size R, so that the block of view v starts at the same ring row in every unit and the consumers can
+// bake absolute ring rows into their entries.
+__device__ __forceinline__ int ring_pad(int total_rows, int R, int nv, int v) {
+    const int P = (R - total_rows % R) % R;
+    return P / nv + (v < P % nv ? 1 : 0);
+}
+
+// entry of the active-view list: view | quad mask << 8 | ring row of oct A << 12 | ring row of oct B << 22
+constexpr int kPMaxRingRows = 1023;
+
+template <typename T, bool kRaw, bool kDiag>
 __global__ void __launch_bounds__((kPMaxWarps + 1) * 32, 1)
 k_lift_planes(const PlaneArgs a) {
-    const int S = a.stages, G = a.group;
+    const int S = a.stages;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = (blockDim.x >> 5) - 1;                           // compute warps
     // persistent CTA: units blockIdx.x, blockIdx.x + gridDim.x, ...; gridDim.x is a multiple of n_parts,
-    // so the part (and with it every tile-dependent table) is the same for all units of a CTA
+    // so the part (and with it every oct-dependent table) is the same for all units of a CTA
     const int part = blockIdx.x % a.n_parts;
+    const int list_pitch = a.nv + 1;                               // entries per warp (+ sentinel)
 
-    // ring: S stages x G plane slots; then the barriers, the offset rings and the active-view lists
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + (size_t)S * G * a.plane_pitch);
-    unsigned char *s_rings = smem + (((size_t)S * G * a.plane_pitch + 2 * S * 8 + 15) & ~(size_t)15);   // [W][depth][1 KB]
-    unsigned char *s_lists = s_rings + (size_t)W * kPRowDepth * (kPTile * 2);                              // [W][kPListPitch] u16
+    // plane ring (S slots), offset-row ring (R rows); then the barriers, the per-view row counts and the active-view lists
+    const int R = a.ring_rows;
+    const uint32_t row_base = smem_u32(smem) + (uint32_t)S * a.plane_pitch;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + (size_t)S * a.plane_pitch + (size_t)R * kRowBytes);
+    uint16_t *s_cnt = reinterpret_cast<uint16_t *>(bars + 2 * S);                                          // [nvp] rows to copy
+    uint16_t *s_eff = s_cnt + a.nvp;                                                                        // [nvp] rows of ring space
+    uint32_t *s_lists = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(s_cnt) + (((size_t)a.nvp * 4 + 15) & ~(size_t)15));
     const uint32_t sm_base = smem_u32(smem);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + S);
 
@@ -251,57 +365,100 @@ k_lift_planes(const PlaneArgs a) {
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < S * G; i += blockDim.x)          // the zero word behind every plane slot
+    for (int i = threadIdx.x; i < S; i += blockDim.x)              // the zero word behind every plane slot
         *reinterpret_cast<uint32_t *>(smem + (size_t)i * a.plane_pitch + a.plane_bytes) = 0u;
     __syncthreads();
 
-    const long long t_cta = clock64();
+    const long long t_cta = kDiag ? clock64() : 0;
     if (warp == W) {
-        // ---------------- producer: one elected lane streams the planes of this CTA's units ----------------
-        // (the planes are kernel inputs, not products of k_plane_index: no dependency wait here)
+        // ---------------- producer warp: streams (plane, offset block) per view of this CTA's units ----------------
+        // One lane issues everything; its loop is kept free of integer divisions (a runtime div / mod costs
+        // ~100 cycles of dependent latency, and five of them per view made this thread the bottleneck of the CTA).
+        const int64_t view_bytes = a.sv * (int64_t)sizeof(T);
+        const int n_my = blockIdx.x < a.n_units ? (a.n_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int total = n_my * a.nv;                             // stages this CTA runs through
+        const int pre = min(S, total);
+        const char *feat = reinterpret_cast<const char *>(a.feat);
+        const int64_t chan_bytes = a.sc * (int64_t)sizeof(T);
+        const bool copy_planes = !kDiag || !(a.debug & 4);
+        // the planes are kernel inputs, not products of the index / pack kernels: the first S planes start
+        // streaming before the dependency wait; their barriers get the arrival (and the offset bytes) afterwards
+        if (lane == 0 && copy_planes) {
+            int u = blockIdx.x, v = 0;
+            const char *src = feat + (int64_t)(u / a.n_parts) * chan_bytes;
+            for (int i = 0; i < pre; ++i) {
+                mbar_expect_tx_only(bar_full + 8 * i, a.plane_bytes);
+                bulk_g2s(sm_base + (uint32_t)i * a.plane_pitch, src, a.plane_bytes, bar_full + 8 * i);
+                src += view_bytes;
+                if (++v == a.nv) { v = 0; u += gridDim.x; src = feat + (int64_t)(u / a.n_parts) * chan_bytes; }
+            }
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");         // row counts / offset blocks come from k_plane_pack
+        int tot = 0;
+        for (int v = lane; v < a.nv; v += 32) {
+            const int c = (int)a.rowcnt[(int64_t)part * a.nvp + v];
+            s_cnt[v] = (uint16_t)c;
+            tot += c;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        for (int v = lane; v < a.nv; v += 32) s_eff[v] = (uint16_t)((int)s_cnt[v] + ring_pad(tot, R, a.nv, v));
+        __syncwarp();
         if (lane == 0) {
-            const int64_t view_bytes = a.sv * (int64_t)sizeof(T);
-            int s = 0, n_tr = 0;
-            uint32_t parity = 1;                                   // first pass over the ring: slots are free
-            bool first_pass = true;
-            // L2 prefetch runs `a.l2_ahead` views ahead of the shared-memory fill (it costs no shared memory and
-            // turns the HBM latency of the fill into an L2 hit); pu / pv walk the same (unit, view) sequence
-            int pu = blockIdx.x, pv = 0;
-            auto l2_step = [&]() {
-                if (pu < a.n_units) {
-                    bulk_prefetch_l2(reinterpret_cast<const char *>(a.feat) +
-                                         ((int64_t)(pu / a.n_parts) * a.sc + (int64_t)pv * a.sv) * (int64_t)sizeof(T),
-                                     a.plane_bytes);
-                    if (++pv == a.nv) { pv = 0; pu += gridDim.x; }
+            const char *off_base = reinterpret_cast<const char *>(a.offc) + (int64_t)part * a.nv * (2 * W) * kRowBytes;
+            const uint32_t block_bytes = (uint32_t)(2 * W) * kRowBytes;
+            int n_tr = 0;
+            // stage i: slot s, view v of unit u;  oldest unreleased stage: slot o_s, parity o_par, view o_v
+            int s = 0, v = 0, u = blockIdx.x;
+            const char *psrc = feat + (int64_t)(u / a.n_parts) * chan_bytes;
+            const char *osrc = off_base;
+            int oldest = 0, o_s = 0, o_v = 0;
+            uint32_t o_par = 0;
+            int rows_in_flight = 0, ring_pos = 0;
+            for (int i = 0; i < total; ++i) {
+                const int n_rows = (int)s_cnt[v], n_eff = (int)s_eff[v];
+                const uint32_t fb = bar_full + 8 * s;
+                // the plane slot is free once stage i - S is released; the rows need room in the row ring
+                const long long tp0 = kDiag && a.trace != nullptr ? clock64() : 0;
+                while (oldest <= i - S || rows_in_flight + n_eff > R) {
+                    mbar_wait(bar_empty + 8 * o_s, o_par);
+                    rows_in_flight -= (int)s_eff[o_v];
+                    ++oldest;
+                    if (++o_s == S) { o_s = 0; o_par ^= 1u; }
+                    if (++o_v == a.nv) o_v = 0;
                 }
-            };
-            for (int i = 0; i < a.l2_ahead; ++i) l2_step();
-            for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
-                const int c = u / a.n_parts;
-                const char *src = reinterpret_cast<const char *>(a.feat) + (int64_t)c * a.sc * (int64_t)sizeof(T);
-                for (int v0 = 0; v0 < a.nv; v0 += G) {
-                    const int g_n = min(G, a.nv - v0);
-                    if (a.l2_ahead > 0)
-                        for (int g = 0; g < g_n; ++g) l2_step();
-                    const long long tp0 = clock64();
-                    if (!first_pass) mbar_wait(bar_empty + 8 * s, parity);
-                    if (a.trace != nullptr && blockIdx.x == 0 && n_tr < 256) {
-                        int *t = a.trace + ((size_t)W * 256 + n_tr) * 4;
-                        t[0] = (int)(tp0 - t_cta);
-                        t[1] = (int)(clock64() - t_cta);
-                        t[2] = 0;
-                        t[3] = 0;
-                        ++n_tr;
-                    }
-                    if (a.debug & 4) {
-                        mbar_arrive(bar_full + 8 * s);
-                    } else {
-                        mbar_expect_tx(bar_full + 8 * s, (uint32_t)g_n * a.plane_bytes);
-                        for (int g = 0; g < g_n; ++g)
-                            bulk_g2s(sm_base + (uint32_t)(s * G + g) * a.plane_pitch, src + (v0 + g) * view_bytes,
-                                     a.plane_bytes, bar_full + 8 * s);
-                    }
-                    if (++s == S) { s = 0; parity ^= 1u; first_pass = false; }
+                if (kDiag && a.trace != nullptr && blockIdx.x == 0 && n_tr < 256) {
+                    int *t = a.trace + ((size_t)W * 256 + n_tr) * 4;
+                    t[0] = (int)(tp0 - t_cta);
+                    t[1] = (int)(clock64() - t_cta);
+                    t[2] = rows_in_flight;
+                    t[3] = i - oldest;
+                    ++n_tr;
+                }
+                const uint32_t off_bytes = (uint32_t)n_rows * kRowBytes;
+                if (i >= pre && copy_planes) {
+                    mbar_expect_tx(fb, a.plane_bytes + off_bytes);
+                    bulk_g2s(sm_base + (uint32_t)s * a.plane_pitch, psrc, a.plane_bytes, fb);
+                } else {
+                    mbar_expect_tx(fb, off_bytes);                  // (i < pre: the plane bytes were announced above)
+                }
+                if (n_rows != 0) {
+                    const int first = min(n_rows, R - ring_pos);
+                    bulk_g2s(row_base + (uint32_t)ring_pos * kRowBytes, osrc, (uint32_t)first * kRowBytes, fb);
+                    if (n_rows > first)                             // the block wraps around the end of the ring
+                        bulk_g2s(row_base, osrc + (size_t)first * kRowBytes, (uint32_t)(n_rows - first) * kRowBytes, fb);
+                }
+                ring_pos += n_eff;
+                if (ring_pos >= R) ring_pos -= R;
+                rows_in_flight += n_eff;
+                if (++s == S) s = 0;
+                psrc += view_bytes;
+                osrc += block_bytes;
+                if (++v == a.nv) {                                  // next unit of this CTA: one division per unit
+                    v = 0;
+                    u += gridDim.x;
+                    psrc = feat + (int64_t)(u / a.n_parts) * chan_bytes;
+                    osrc = off_base;
                 }
             }
         }
@@ -309,104 +466,123 @@ k_lift_planes(const PlaneArgs a) {
     }
 
     // ---------------- consumers ----------------
-    asm volatile("griddepcontrol.wait;" ::: "memory");             // tables come from k_plane_index (PDL)
-    const int tile = part * W + warp;
-    const bool tile_ok = tile < a.n_tiles;
-    const int64_t p0 = (int64_t)(tile_ok ? tile : 0) * kPTile + lane * kPV;
-    const char *idx = reinterpret_cast<const char *>(a.off16 + p0);
-    const uint32_t idx_pitch = (uint32_t)(a.n_pad * (int64_t)sizeof(uint16_t));   // bytes per view row
-    const int64_t n0 = a.tiling.run(tile_ok ? tile : 0, lane) * kPV;
-    const bool lane_ok = tile_ok && n0 < a.n_vox;
+    asm volatile("griddepcontrol.wait;" ::: "memory");             // tables come from k_plane_index / k_plane_pack (PDL)
+    const uint16_t qa16 = __ldg(a.pairs + ((int64_t)part * W + warp) * 2);
+    const uint16_t qb16 = __ldg(a.pairs + ((int64_t)part * W + warp) * 2 + 1);
+    const int qa = qa16 == 0xffffu ? -1 : (int)qa16, qb = qb16 == 0xffffu ? -1 : (int)qb16;
+    const int64_t pa = (int64_t)(qa >= 0 ? qa : 0) * kOct + lane * kOV;
+    const int64_t pb = (int64_t)(qb >= 0 ? qb : 0) * kOct + lane * kOV;
+    const int64_t n0a = qa >= 0 ? a.tiling.voxel(qa, lane) : a.n_vox;
+    const int64_t n0b = qb >= 0 ? a.tiling.voxel(qb, lane) : a.n_vox;
 
     // view counts of this lane's 16 voxels (sum of the uint8 partials), packed 4 per word
-    uint4 cw = make_uint4(0, 0, 0, 0);
+    uint32_t cws[4] = {0u, 0u, 0u, 0u};
     for (int g = 0; g < a.nw16; ++g) {
-        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(a.cnt8 + (int64_t)g * a.n_pad + p0));
-        cw.x = __vadd4(cw.x, t.x); cw.y = __vadd4(cw.y, t.y); cw.z = __vadd4(cw.z, t.z); cw.w = __vadd4(cw.w, t.w);
-    }
-
-    // The views that see this warp's tile, as a list (view | quarter mask << 8): views the tile
-    // does not see cost the warp nothing but the stage hand-shake.
-    uint16_t *act = reinterpret_cast<uint16_t *>(s_lists) + warp * kPListPitch;
-    int n_act = 0;
-    for (int vb = 0; vb < a.nv; vb += 32) {
-        const int v = vb + lane;
-        uint32_t nib = 0;
-        if (tile_ok && v < a.nv) nib = (uint32_t)(__ldg(a.vmask + (int64_t)tile * a.nw16 + (v >> 4)) >> ((v & 15) * 4)) & 0xfu;
-        const unsigned b = __ballot_sync(0xffffffffu, nib != 0);
-        if (nib) act[n_act + __popc(b & ((1u << lane) - 1u))] = (uint16_t)(v | (nib << 8));
-        n_act += __popc(b);
-    }
-    if (lane == 0) act[n_act] = 0xffffu;                           // sentinel: view 255 is never reached
-    __syncwarp();
-
-    // this lane's 32 B of offsets per list entry travel through a warp-private ring in shared
-    // memory (cp.async, kPRowDepth - 1 list entries ahead, across unit boundaries)
-    const uint32_t ring = smem_u32(s_rings) + (uint32_t)(warp * kPRowDepth) * (kPTile * 2) + lane * (kPV * 2);
-    int kf = 0;                                                    // next list entry to prefetch
-    auto fetch = [&](int slot) {
-        if (n_act > 0) {
-            const uint32_t v = act[kf] & 0xffu;
-            cp_async16(ring + slot * (kPTile * 2), idx + v * idx_pitch);
-            cp_async16(ring + slot * (kPTile * 2) + 16, idx + v * idx_pitch + 16);
-            if (++kf == n_act) kf = 0;
+        if (qa >= 0) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2 *>(a.cnt8 + (int64_t)g * a.n_pad + pa));
+            cws[0] = __vadd4(cws[0], t.x); cws[1] = __vadd4(cws[1], t.y);
         }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int i = 0; i < kPRowDepth - 1; ++i) fetch(i);
+        if (qb >= 0) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2 *>(a.cnt8 + (int64_t)g * a.n_pad + pb));
+            cws[2] = __vadd4(cws[2], t.x); cws[3] = __vadd4(cws[3], t.y);
+        }
+    }
 
-    int s = 0, d = 0, n_tr = 0;
+    // The views that see this warp's octs, as a list of entries (view | quad mask | ring rows of the two octs):
+    // views that see none of the four quads cost the warp nothing but the stage hand-shake.
+    uint32_t *act = s_lists + warp * list_pitch;
+    {
+        const uint32_t *src = a.ents + ((int64_t)part * W + warp) * a.nvp;
+        const uint16_t *rc = a.rowcnt + (int64_t)part * a.nvp;
+        int tot = 0;
+        for (int v = lane; v < a.nv; v += 32) tot += (int)__ldg(rc + v);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        int n_act = 0, start = 0;                                  // start: ring row of the block of view vb (before lane prefix)
+        for (int vb = 0; vb < a.nv; vb += 32) {
+            const int v = vb + lane;
+            const uint32_t e = v < a.nv ? __ldg(src + v) : 0u;
+            int eff = v < a.nv ? (int)__ldg(rc + v) + ring_pad(tot, R, a.nv, v) : 0;
+            int incl = eff;                                        // inclusive prefix of eff over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int my_start = (start + incl - eff) % R;
+            start = (start + __shfl_sync(0xffffffffu, incl, 31)) % R;
+            const unsigned b = __ballot_sync(0xffffffffu, e != 0u);
+            if (e) {
+                int ra = my_start + (int)((e >> 16) & 0xffu), rb = my_start + (int)(e >> 24);
+                if (ra >= R) ra -= R;
+                if (rb >= R) rb -= R;
+                if (!(e & 0x300u)) ra = 0;
+                if (!(e & 0xc00u)) rb = 0;
+                act[n_act + __popc(b & ((1u << lane) - 1u))] = (e & 0xfffu) | ((uint32_t)ra << 12) | ((uint32_t)rb << 22);
+            }
+            n_act += __popc(b);
+        }
+        if (lane == 0) act[n_act] = 0xffu;                          // sentinel: view 255 is never reached
+        __syncwarp();
+    }
+
+    int s = 0, n_tr = 0;
     uint32_t parity = 0;
+    uint32_t fa = bar_full, ea = bar_empty, sb = sm_base;          // barriers and plane of the current stage
+    const uint32_t lane_row = row_base + lane * (kOV * 2);
+    const bool do_gather = !kDiag || !(a.debug & 1);
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
         const int c = u / a.n_parts;
         unsigned long long s1[kPV / 2], s2[kPV / 2];
 #pragma unroll
         for (int j = 0; j < kPV / 2; ++j) { s1[j] = 0ull; s2[j] = 0ull; }
-        int k = 0;
-        uint32_t ent = act[0];
+        const uint32_t *ap = act;
+        uint32_t ent = *ap;
 
-        for (int v0 = 0; v0 < a.nv; v0 += G) {
-            const long long tc0 = a.trace != nullptr ? clock64() : 0;
-            mbar_wait(bar_full + 8 * s, parity);
-            const long long tc1 = a.trace != nullptr ? clock64() : 0;
-            const int k_before = k;
-            const uint32_t v_end = (uint32_t)min(v0 + G, a.nv);
-            while ((ent & 0xffu) < v_end) {                        // warp-uniform: the list is per warp
-                fetch(d == 0 ? kPRowDepth - 1 : d - 1);            // refill the slot consumed last
-                cp_async_wait<kPRowDepth - 1>();                   // this entry's offsets have landed
-                if (!(a.debug & 1)) {
-                    const uint32_t sb = sm_base + (uint32_t)(s * G + (int)(ent & 0xffu) - v0) * a.plane_pitch;
-                    const uint4 c0 = lds_u4(ring + d * (kPTile * 2)), c1 = lds_u4(ring + d * (kPTile * 2) + 16);
-                    if (ent & 0x100u) gather_quarter<T>(sb, c0.x, c0.y, s1[0], s2[0], s1[1], s2[1]);
-                    if (ent & 0x200u) gather_quarter<T>(sb, c0.z, c0.w, s1[2], s2[2], s1[3], s2[3]);
-                    if (ent & 0x400u) gather_quarter<T>(sb, c1.x, c1.y, s1[4], s2[4], s1[5], s2[5]);
-                    if (ent & 0x800u) gather_quarter<T>(sb, c1.z, c1.w, s1[6], s2[6], s1[7], s2[7]);
+        for (int v = 0; v < a.nv; ++v) {
+            const long long tc0 = kDiag && a.trace != nullptr ? clock64() : 0;
+            mbar_wait(fa, parity);
+            const long long tc1 = kDiag && a.trace != nullptr ? clock64() : 0;
+            int n_ent = 0;
+            if ((ent & 0xffu) == (uint32_t)v) {                    // warp-uniform: the list is per warp
+                if (do_gather) {
+                    if (ent & 0x300u) {
+                        const uint4 c0 = lds_u4(lane_row + ((ent >> 12) & 0x3ffu) * kRowBytes);
+                        if (ent & 0x100u) gather_quad<T>(sb, c0.x, c0.y, s1[0], s2[0], s1[1], s2[1]);
+                        if (ent & 0x200u) gather_quad<T>(sb, c0.z, c0.w, s1[2], s2[2], s1[3], s2[3]);
+                    }
+                    if (ent & 0xc00u) {
+                        const uint4 c1 = lds_u4(lane_row + (ent >> 22) * kRowBytes);
+                        if (ent & 0x400u) gather_quad<T>(sb, c1.x, c1.y, s1[4], s2[4], s1[5], s2[5]);
+                        if (ent & 0x800u) gather_quad<T>(sb, c1.z, c1.w, s1[6], s2[6], s1[7], s2[7]);
+                    }
                 }
-                if (++d == kPRowDepth) d = 0;
-                ent = act[++k];
+                ent = *++ap;
+                n_ent = 1;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8 * s);
-            if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && n_tr < 256) {
+            if (lane == 0) mbar_arrive(ea);
+            if (kDiag && a.trace != nullptr && blockIdx.x == 0 && lane == 0 && n_tr < 256) {
                 int *t = a.trace + ((size_t)warp * 256 + n_tr) * 4;
                 t[0] = (int)(tc0 - t_cta);
                 t[1] = (int)(tc1 - t_cta);
                 t[2] = (int)(clock64() - t_cta);
-                t[3] = k - k_before;
+                t[3] = n_ent;
                 ++n_tr;
             }
-            if (++s == S) { s = 0; parity ^= 1u; }
+            fa += 8; ea += 8; sb += a.plane_pitch;
+            if (++s == S) { s = 0; parity ^= 1u; fa = bar_full; ea = bar_empty; sb = sm_base; }
         }
-        if (!lane_ok || (a.debug & 16)) continue;
+        if (kDiag && (a.debug & 16)) continue;
 
         // ---------------- epilogue of unit (c, part): the producer is already streaming the next unit ----------------
         const int64_t row = (int64_t)c * a.n_vox;
-        const bool vec_ok = (n0 + kPV <= a.n_vox) && ((row + n0) % 4 == 0) &&
-                            ((reinterpret_cast<uintptr_t>(a.out_a) | reinterpret_cast<uintptr_t>(a.out_b)) % 16 == 0);
-        const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
+        const bool base_ok = (row % 4 == 0) &&
+                             ((reinterpret_cast<uintptr_t>(a.out_a) | reinterpret_cast<uintptr_t>(a.out_b)) % 16 == 0);
 #pragma unroll
         for (int g = 0; g < kPV / 4; ++g) {
+            const int64_t nb = (g < 2 ? n0a : n0b) + 4 * (g & 1);  // first of this quad's 4 voxels
+            if (nb >= a.n_vox) continue;
             int cnv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) cnv[j] = (int)((cws[g] >> (8 * j)) & 0xffu);
@@ -417,32 +593,33 @@ k_lift_planes(const PlaneArgs a) {
             float oa[4], ob[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float cf = (float)cnv[j];
                 if (kRaw) {
                     oa[j] = v1[j];
                     ob[j] = v2[j];
                 } else if (cnv[j] > 0) {
-                    const float m = v1[j] / cf;                                   // == S1 / (count + 1e-8) in fp32
+                    const float cf = (float)cnv[j];                               // count + 1e-8 == count in fp32
+                    const float m = v1[j] / cf;                                   // IEEE divide: the mean is bit-equal to the reference's
+                    const float rc = __frcp_rn(cf);
                     float ssd = fmaxf(fmaf(-m, v1[j], v2[j]), 0.0f);              // sum over valid views of (f - m)^2
                     ssd = fmaf((float)(a.n_views_total - cnv[j]) * m, m, ssd);    // invalid views contribute m^2 each
                     float al = 1.0f;
-                    if (a.alpha != nullptr && n0 + 4 * g + j < a.n_vox) al = __ldg(a.alpha + n0 + 4 * g + j);
+                    if (a.alpha != nullptr && nb + j < a.n_vox) al = __ldg(a.alpha + nb + j);
                     oa[j] = m * al;
-                    ob[j] = expf(-(ssd / cf));
+                    ob[j] = exp2f(ssd * rc * -1.4426950408889634f);               // exp(-var); ex2.approx, rel. error ~1e-7 (1 + var)
                 } else {
                     oa[j] = 0.0f;                                                 // nerfdet.py:176
                     ob[j] = 0.0f;                                                 // exp(-1e6) == 0 (nerfdet.py:180-181)
                 }
             }
-            const int64_t o = row + n0 + 4 * g;
-            if (vec_ok) {
+            const int64_t o = row + nb;
+            if (base_ok && nb + 4 <= a.n_vox && nb % 4 == 0) {
                 __stcs(reinterpret_cast<float4 *>(a.out_a + o), make_float4(oa[0], oa[1], oa[2], oa[3]));
                 if (a.out_b != nullptr)
                     __stcs(reinterpret_cast<float4 *>(a.out_b + o), make_float4(ob[0], ob[1], ob[2], ob[3]));
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (n0 + 4 * g + j < a.n_vox) {
+                    if (nb + j < a.n_vox) {
                         a.out_a[o + j] = oa[j];
                         if (a.out_b != nullptr) a.out_b[o + j] = ob[j];
                     }
@@ -451,7 +628,7 @@ k_lift_planes(const PlaneArgs a) {
             if (c == 0) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int64_t n = n0 + 4 * g + j;
+                    const int64_t n = nb + j;
                     if (n < a.n_vox) {
                         if (a.count_i64 != nullptr) a.count_i64[n] = (int64_t)cnv[j];
                         if (a.count_f32 != nullptr) a.count_f32[n] = (float)cnv[j];
@@ -468,14 +645,14 @@ k_lift_planes(const PlaneArgs a) {
 static int *g_trace = nullptr;   // device buffer [(warps + 1)][256][4] int32 set by nd_debug_set_trace (tools only)
 void set_lift_trace(int *buf) { g_trace = buf; }
 
-// ---------------------------------------------------------------------------------------------
-// ---------------------------------------------------------------------------------------------
 struct PlaneGeom {
     Tiling tiling;
-    int elt, n_pix, nw16, n_tiles, n_parts, warps, stages, group, grid;
+    int elt, n_pix, nw16, nvp, n_octs, n_pairs, n_parts, warps, stages, grid;
     int64_t n_pad;
     uint32_t plane_bytes, plane_pitch;
-    size_t off_bytes, cnt_bytes, mask_bytes, total_bytes, smem_bytes;
+    int ring_rows;
+    size_t off_bytes, cnt_bytes, mask_bytes, cost_bytes, offc_bytes, rowcnt_bytes, ents_bytes, pairs_bytes, total_bytes,
+        smem_bytes;
 };
 
 static bool plane_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *opt, PlaneGeom &g) {
@@ -487,41 +664,50 @@ static bool plane_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *o
     if ((reinterpret_cast<uintptr_t>(f->data) & 15) != 0 || (f->stride_v * g.elt) % 16 != 0 ||
         (f->stride_c * g.elt) % 16 != 0)
         return false;
-    if (f->n_views > 255) return false;                                     // uint8 view counts
+    if (f->n_views > 254) return false;                                     // uint8 view counts, view 255 = list sentinel
     g.plane_bytes = (uint32_t)pb;
     g.nw16 = (f->n_views + 15) / 16;
-    g.n_tiles = (int)ceil_div(n_vox, kPTile);
-    g.n_pad = (int64_t)g.n_tiles * kPTile;
-    g.tiling = Tiling{0, 0, 0, 0};
+    g.nvp = g.nw16 * 16;
+    g.tiling = Tiling{0, 0, 0, 0, 0};
+    g.n_octs = (int)ceil_div(n_vox, kOct);
+    if (g.n_octs > 65000) return false;                                     // uint16 oct ids
     if (opt != nullptr && opt->grid_x > 0 && opt->grid_y > 0 && opt->grid_z > 0 &&
-        (int64_t)opt->grid_x * opt->grid_y * opt->grid_z == n_vox && opt->grid_z % kPV == 0 &&
+        (int64_t)opt->grid_x * opt->grid_y * opt->grid_z == n_vox && opt->grid_z % kOV == 0 &&
         opt->grid_x % kPBx == 0 && opt->grid_y % kPBy == 0) {
         g.tiling.compact = 1;
         g.tiling.gy = opt->grid_y;
-        g.tiling.nzr = opt->grid_z / kPV;
+        g.tiling.gz = opt->grid_z;
+        g.tiling.nzo = opt->grid_z / kOV;
         g.tiling.tiles_y = opt->grid_y / kPBy;
     }
-    int max_warps = kPMaxWarps, stages = 2, group = 4;
+    g.n_pad = (int64_t)g.n_octs * kOct;
+    g.n_pairs = (g.n_octs + 1) / 2;
+    int max_warps = kPMaxWarps, stages = 0;
     if (const char *e = getenv("ND_LIFT_STAGES")) stages = atoi(e);         // tuning knobs for tools/lift_probe.py
-    if (const char *e = getenv("ND_LIFT_GROUP")) group = atoi(e);
     if (const char *e = getenv("ND_LIFT_WARPS")) {
         const int v = atoi(e);
         if (v >= 1 && v < max_warps) max_warps = v;
     }
-    g.n_parts = (int)ceil_div(g.n_tiles, max_warps);
-    g.warps = (int)ceil_div(g.n_tiles, g.n_parts);
+    g.n_parts = (int)ceil_div(g.n_pairs, max_warps);
+    g.warps = (int)ceil_div(g.n_pairs, g.n_parts);
     g.plane_pitch = (uint32_t)align_up((size_t)pb + 16, 128);
-    const size_t fixed = 2 * kPMaxStages * 8 + 16 + (size_t)g.warps * (kPRowDepth * kPTile * 2 + kPListPitch * 2);
-    const int slots = (int)(((size_t)(224 * 1024) - fixed) / g.plane_pitch);   // plane slots that fit one SM
-    if (slots < 2) return false;
-    if (group < 1) group = 1;
+    const size_t fixed = 2 * kPMaxStages * 8 + align_up((size_t)g.nvp * 4, 16) + (size_t)g.warps * (f->n_views + 1) * 4 + 16;
+    const size_t avail = (size_t)(227 * 1024) - fixed;
+    // plane slots S and offset rows R share the rest: R must hold the largest block (2 W rows); by default every
+    // stage in flight gets room for about half of the part's octs (the typical share that sees a view)
+    const size_t min_rows = (size_t)2 * g.warps;
+    if (avail < 2 * (size_t)g.plane_pitch + min_rows * kRowBytes) return false;
+    if (stages <= 0) {
+        stages = 2;
+        while (stages < 8 && (size_t)(stages + 1) * g.plane_pitch + std::max(min_rows, (size_t)(stages + 1) * g.warps) * kRowBytes <= avail)
+            ++stages;
+    }
     if (stages < 2) stages = 2;
     if (stages > kPMaxStages) stages = kPMaxStages;
-    while (stages * group > slots) {                                        // shrink the ring to what fits
-        if (group > 1 && (group >= stages || stages == 2)) --group; else --stages;
-    }
+    while (stages > 2 && (size_t)stages * g.plane_pitch + min_rows * kRowBytes > avail) --stages;
+    g.ring_rows = (int)((avail - (size_t)stages * g.plane_pitch) / kRowBytes);
+    if (g.ring_rows > kPMaxRingRows) g.ring_rows = kPMaxRingRows;
     g.stages = stages;
-    g.group = group;
     // persistent grid: one CTA per SM, a multiple of n_parts (see k_lift_planes)
     int sms = 148;
     {
@@ -535,10 +721,16 @@ static bool plane_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *o
     g.grid = (int)grid;
     g.off_bytes = align_up((size_t)f->n_views * g.n_pad * sizeof(uint16_t), 256);
     g.cnt_bytes = align_up((size_t)g.nw16 * g.n_pad, 256);
-    g.mask_bytes = align_up((size_t)g.n_tiles * g.nw16 * sizeof(uint64_t), 256);
-    g.total_bytes = g.off_bytes + g.cnt_bytes + g.mask_bytes;
-    g.smem_bytes = (size_t)g.stages * g.group * g.plane_pitch + 2 * g.stages * 8 + 16 +
-                   (size_t)g.warps * (kPRowDepth * kPTile * 2 + kPListPitch * 2);
+    g.mask_bytes = align_up((size_t)g.n_octs * g.nvp, 256);
+    g.cost_bytes = align_up((size_t)g.nw16 * g.n_octs, 256);
+    g.offc_bytes = align_up((size_t)g.n_parts * f->n_views * 2 * g.warps * kRowBytes, 256);
+    g.rowcnt_bytes = align_up((size_t)g.n_parts * g.nvp * sizeof(uint16_t), 256);
+    g.ents_bytes = align_up((size_t)g.n_parts * g.warps * g.nvp * sizeof(uint32_t), 256);
+    g.pairs_bytes = align_up((size_t)g.n_parts * g.warps * 2 * sizeof(uint16_t), 256);
+    g.total_bytes = g.off_bytes + g.cnt_bytes + g.mask_bytes + g.cost_bytes + g.offc_bytes + g.rowcnt_bytes + g.ents_bytes +
+                    g.pairs_bytes;
+    g.smem_bytes = (size_t)g.stages * g.plane_pitch + (size_t)g.ring_rows * kRowBytes + 2 * g.stages * 8 +
+                   align_up((size_t)g.nvp * 4, 16) + (size_t)g.warps * (f->n_views + 1) * 4;
     return true;
 }
 
@@ -553,32 +745,21 @@ size_t lift_planes_workspace_bytes(const nd_maps *f, int64_t n_vox, const nd_lif
     return g.total_bytes;
 }
 
-template <typename T, bool kRaw>
-static nd_status launch_planes(const PlaneArgs &a, const PlaneGeom &g, int channels, cudaStream_t st) {
-    auto kern = k_lift_planes<T, kRaw>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
-    if (e != cudaSuccess) {
-        set_error("k_lift_planes: cannot reserve %zu bytes of shared memory: %s", g.smem_bytes, cudaGetErrorString(e));
-        return ND_ERR_CUDA;
-    }
-    // programmatic dependent launch: prologue and plane streaming overlap the tail of k_plane_index;
-    // the consumers execute griddepcontrol.wait before touching its tables
+// launch with programmatic stream serialization: the kernel may start while its predecessor drains and
+// executes griddepcontrol.wait before touching the predecessor's results
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)g.grid);
-    cfg.blockDim = dim3((unsigned)(g.warps + 1) * 32);
-    cfg.dynamicSmemBytes = g.smem_bytes;
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, a);
-    if (e != cudaSuccess) {
-        set_error("k_lift_planes: CUDA error %s", cudaGetErrorString(e));
-        return ND_ERR_CUDA;
-    }
-    return ND_OK;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 template <typename T, bool kRaw>
@@ -591,45 +772,73 @@ nd_status run_lift_planes(const nd_maps *f, const float *points, const float *pr
                ws_bytes, g.total_bytes);
     ND_REQUIRE((reinterpret_cast<uintptr_t>(ws) % 256) == 0, ND_ERR_BAD_ALIGNMENT, "lift: workspace not 256-byte aligned");
     char *wsb = reinterpret_cast<char *>(ws);
-    uint16_t *off16 = reinterpret_cast<uint16_t *>(wsb);
-    uint8_t *cnt8 = reinterpret_cast<uint8_t *>(wsb + g.off_bytes);
-    uint64_t *vmask = reinterpret_cast<uint64_t *>(wsb + g.off_bytes + g.cnt_bytes);
+    uint16_t *off16 = reinterpret_cast<uint16_t *>(wsb);            wsb += g.off_bytes;
+    uint8_t *cnt8 = reinterpret_cast<uint8_t *>(wsb);               wsb += g.cnt_bytes;
+    uint8_t *omask = reinterpret_cast<uint8_t *>(wsb);              wsb += g.mask_bytes;
+    uint8_t *cost16 = reinterpret_cast<uint8_t *>(wsb);             wsb += g.cost_bytes;
+    uint16_t *offc = reinterpret_cast<uint16_t *>(wsb);             wsb += g.offc_bytes;
+    uint16_t *rowcnt = reinterpret_cast<uint16_t *>(wsb);           wsb += g.rowcnt_bytes;
+    uint32_t *ents = reinterpret_cast<uint32_t *>(wsb);             wsb += g.ents_bytes;
+    uint16_t *pairs = reinterpret_cast<uint16_t *>(wsb);
 
-    k_plane_index<<<dim3((unsigned)g.n_tiles, (unsigned)g.nw16), kPTile, 0, st>>>(
-        g.tiling, points, proj, f->n_views, g.nw16, n_vox, g.n_pad, f->height, f->width, g.elt, g.plane_bytes, off16,
-        cnt8, vmask);
+    int debug = 0;
+    if (const char *e = getenv("ND_LIFT_DEBUG")) debug = atoi(e);
+    k_plane_index<<<dim3((unsigned)g.n_octs, (unsigned)g.nw16), kOct, 0, st>>>(
+        g.tiling, points, proj, f->n_views, g.nvp, g.n_octs, n_vox, g.n_pad, f->height, f->width, g.elt, g.plane_bytes,
+        off16, cnt8, omask, cost16);
     ND_CUDA_LAUNCH_CHECK("k_plane_index");
+    const int balanced = (g.n_octs <= kPMaxOcts && !(debug & 32)) ? 1 : 0;
+    cudaError_t e = launch_pdl(k_plane_pack, dim3((unsigned)f->n_views, (unsigned)g.n_parts), dim3(256), 0, st, (int)f->n_views,
+                               g.nvp, g.nw16, g.n_octs, g.n_parts, g.warps, g.n_pad, balanced, (const uint16_t *)off16,
+                               (const uint8_t *)omask, (const uint8_t *)cost16, offc, rowcnt, ents, pairs);
+    if (e != cudaSuccess) {
+        set_error("k_plane_pack: CUDA error %s", cudaGetErrorString(e));
+        return ND_ERR_CUDA;
+    }
 
     PlaneArgs a{};
     a.tiling = g.tiling;
-    a.off16 = off16;
     a.cnt8 = cnt8;
-    a.vmask = vmask;
+    a.offc = offc;
+    a.rowcnt = rowcnt;
+    a.ents = ents;
+    a.pairs = pairs;
     a.nv = f->n_views;
+    a.nvp = g.nvp;
     a.nw16 = g.nw16;
     a.n_vox = n_vox;
     a.n_pad = g.n_pad;
-    a.n_tiles = g.n_tiles;
+    a.n_octs = g.n_octs;
     a.n_parts = g.n_parts;
+    a.n_units = f->channels * g.n_parts;
     a.feat = f->data;
     a.sv = f->stride_v;
     a.sc = f->stride_c;
     a.plane_bytes = g.plane_bytes;
     a.plane_pitch = g.plane_pitch;
-    a.n_units = f->channels * g.n_parts;
-    a.group = g.group;
-    a.l2_ahead = 0;
+    a.stages = g.stages;
+    a.ring_rows = g.ring_rows;
     a.trace = g_trace;
-    if (const char *e = getenv("ND_LIFT_L2AHEAD")) a.l2_ahead = atoi(e);
+    a.debug = debug;
     a.n_views_total = f->n_views;
     a.alpha = alpha;
     a.out_a = out_a;
     a.out_b = out_b;
     a.count_i64 = count_i64;
     a.count_f32 = count_f32;
-    a.stages = g.stages;
-    if (const char *e = getenv("ND_LIFT_DEBUG")) a.debug = atoi(e);
-    return launch_planes<T, kRaw>(a, g, f->channels, st);
+    // the diagnostics build (debug switches, clock trace) is a separate instantiation: the product kernel carries none of it
+    auto kern = (debug != 0 || g_trace != nullptr) ? k_lift_planes<T, kRaw, true> : k_lift_planes<T, kRaw, false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
+    if (e != cudaSuccess) {
+        set_error("k_lift_planes: cannot reserve %zu bytes of shared memory: %s", g.smem_bytes, cudaGetErrorString(e));
+        return ND_ERR_CUDA;
+    }
+    e = launch_pdl(kern, dim3((unsigned)g.grid), dim3((unsigned)(g.warps + 1) * 32), g.smem_bytes, st, a);
+    if (e != cudaSuccess) {
+        set_error("k_lift_planes: CUDA error %s", cudaGetErrorString(e));
+        return ND_ERR_CUDA;
+    }
+    return ND_OK;
 }
 
 #define ND_INSTANTIATE_PLANES(T, R)                                                                                   \

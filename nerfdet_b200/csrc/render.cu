@@ -87,19 +87,21 @@ k_render_gather_stats(const float *__restrict__ pts, int64_t n_pts, const float 
                       const float *__restrict__ img, int64_t i_sv, int64_t i_sc, int hi, int wi,
                       const T *__restrict__ feat, int64_t f_sv, int64_t f_sc, int d, int hf, int wf,
                       float *__restrict__ glob, uint8_t *__restrict__ view_mask, uint8_t *__restrict__ pixel_mask,
-                      float *__restrict__ pix_out) {
+                      float *__restrict__ pix_out, uint8_t *__restrict__ front_out, float *__restrict__ view_feat) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *sP = reinterpret_cast<float *>(smem_raw);                       // [nv][12] rows 0-2 of K @ E
     ViewSample *sI = reinterpret_cast<ViewSample *>(sP + nv * 12);        // [nv][threads] image samples
     ViewSample *sF = sI + (size_t)nv * kRgThreads;                        // [nv][threads] feature-map samples
-    // P = K4 @ E (projection.py:57, a 4x4 bmm): the K = 4 FMA chain in k order, rows 0-2
+    // P = K4 @ E (projection.py:57, a 4x4 bmm), rows 0-2
     for (int i = threadIdx.x; i < nv * 12; i += blockDim.x) {
         const int v = i / 12, rc = i - v * 12, r = rc >> 2, c = rc & 3;
         const float *K = cams + v * 34 + 2, *E = cams + v * 34 + 18;
+        // torch's 4x4 @ 4x4 bmm rounds every product and every sum (no FMA contraction), k ascending -- checked
+        // bit for bit against the reference run on the CPU; the 4x4 @ 4xN product below IS an FMA chain
         float t = __fmul_rn(K[r * 4 + 0], E[0 * 4 + c]);
-        t = __fmaf_rn(K[r * 4 + 1], E[1 * 4 + c], t);
-        t = __fmaf_rn(K[r * 4 + 2], E[2 * 4 + c], t);
-        t = __fmaf_rn(K[r * 4 + 3], E[3 * 4 + c], t);
+        t = __fadd_rn(t, __fmul_rn(K[r * 4 + 1], E[1 * 4 + c]));
+        t = __fadd_rn(t, __fmul_rn(K[r * 4 + 2], E[2 * 4 + c]));
+        t = __fadd_rn(t, __fmul_rn(K[r * 4 + 3], E[3 * 4 + c]));
         sP[i] = t;
     }
     __syncthreads();
@@ -130,6 +132,7 @@ k_render_gather_stats(const float *__restrict__ pts, int64_t n_pts, const float 
         sI[(size_t)v * kRgThreads + threadIdx.x] = si;
         sF[(size_t)v * kRgThreads + threadIdx.x] = sf;
         if (live && view_mask != nullptr) view_mask[p * nv + v] = m ? 1 : 0;
+        if (live && front_out != nullptr) front_out[(int64_t)v * n_pts + p] = front ? 1 : 0;
         if (live && pix_out != nullptr) {
             pix_out[((int64_t)v * n_pts + p) * 2] = px;
             pix_out[((int64_t)v * n_pts + p) * 2 + 1] = py;
@@ -156,6 +159,7 @@ k_render_gather_stats(const float *__restrict__ pts, int64_t n_pts, const float 
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const float f = bilinear<float>(img + v * i_sv + k * i_sc, s, wi);
+                if (view_feat != nullptr) view_feat[(p * nv + v) * (int64_t)ct + k] = f;
                 sm[k] += m ? f : 0.0f;
                 sa1[k] += f;
                 sa2[k] = fmaf(f, f, sa2[k]);
@@ -171,12 +175,13 @@ k_render_gather_stats(const float *__restrict__ pts, int64_t n_pts, const float 
         for (int v = 0; v < nv; ++v) {
             const ViewSample s = sF[(size_t)v * kRgThreads + threadIdx.x];
             const bool m = (sI[(size_t)v * kRgThreads + threadIdx.x].inb & 0x100u) != 0;
-            if (s.inb == 0) continue;                                      // all four corners outside: f = 0
+            if (s.inb == 0 && view_feat == nullptr) continue;              // all four corners outside: f = 0
             const T *plane0 = feat + v * f_sv + (int64_t)c0 * f_sc;
 #pragma unroll
             for (int k = 0; k < kRgChunk; ++k) {
                 if (c0 + k < d) {
                     const float f = bilinear<T>(plane0 + k * f_sc, s, wf);
+                    if (view_feat != nullptr) view_feat[(p * nv + v) * (int64_t)ct + 3 + c0 + k] = f;
                     sm[k] += m ? f : 0.0f;
                     sa1[k] += f;
                     sa2[k] = fmaf(f, f, sa2[k]);
@@ -193,7 +198,7 @@ k_render_gather_stats(const float *__restrict__ pts, int64_t n_pts, const float 
 // R7
 // -------------------------------------------------------------------------------------------------
 __global__ void k_composite(const float *__restrict__ rgb, const float *__restrict__ sigma, const float *__restrict__ z,
-                            const uint8_t *__restrict__ pmask, int64_t n_rays, int ns, float z_min, float z_max,
+                            const uint8_t *__restrict__ pmask, int64_t n_rays, int ns, const float *__restrict__ z_bounds,
                             int white_bkgd, float *__restrict__ out_rgb, float *__restrict__ depth,
                             float *__restrict__ weights, float *__restrict__ alpha_o, float *__restrict__ trans_o,
                             uint8_t *__restrict__ ray_mask) {
@@ -224,7 +229,7 @@ __global__ void k_composite(const float *__restrict__ rgb, const float *__restri
     out_rgb[r * 3 + 1] = c1;
     out_rgb[r * 3 + 2] = c2;
     float dd = dsum / __fadd_rn(wsum, 1e-8f);
-    depth[r] = fminf(fmaxf(dd, z_min), z_max);
+    depth[r] = fminf(fmaxf(dd, __ldg(z_bounds)), __ldg(z_bounds + 1));
     if (ray_mask != nullptr) ray_mask[r] = msum > 8 ? 1 : 0;
 }
 
@@ -288,9 +293,10 @@ int nd_sample_rays(const float *ray_o, const float *ray_d, int64_t n_rays, int n
 
 int nd_render_gather_stats(const float *pts, int64_t n_points, const float *cameras, int n_views,
                            const nd_maps *images, const nd_maps *featmaps, float *globalfeat, uint8_t *view_mask,
-                           uint8_t *pixel_mask, float *pixel_locations, void *stream) {
-    ND_REQUIRE(pts && cameras && images && featmaps && images->data && featmaps->data && globalfeat, ND_ERR_BAD_ARG,
-               "nd_render_gather_stats: null pointer");
+                           uint8_t *pixel_mask, float *pixel_locations, uint8_t *in_front, float *view_features, void *stream) {
+    ND_REQUIRE(pts && cameras && images && featmaps && images->data && (featmaps->data || featmaps->channels == 0) &&
+                   globalfeat,
+               ND_ERR_BAD_ARG, "nd_render_gather_stats: null pointer");
     ND_REQUIRE(n_views > 0 && images->n_views == n_views && featmaps->n_views == n_views, ND_ERR_BAD_SHAPE,
                "nd_render_gather_stats: view counts differ");
     ND_REQUIRE(images->dtype == ND_F32 && images->channels == 3, ND_ERR_BAD_SHAPE,
@@ -313,7 +319,7 @@ int nd_render_gather_stats(const float *pts, int64_t n_points, const float *came
                                                  images->stride_v, images->stride_c, images->height, images->width,
                                                  (const float *)featmaps->data, featmaps->stride_v, featmaps->stride_c,
                                                  featmaps->channels, featmaps->height, featmaps->width, globalfeat,
-                                                 view_mask, pixel_mask, pixel_locations);
+                                                 view_mask, pixel_mask, pixel_locations, in_front, view_features);
     } else {
         auto kern = k_render_gather_stats<__nv_bfloat16>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -322,7 +328,7 @@ int nd_render_gather_stats(const float *pts, int64_t n_points, const float *came
                                                  images->stride_v, images->stride_c, images->height, images->width,
                                                  (const __nv_bfloat16 *)featmaps->data, featmaps->stride_v,
                                                  featmaps->stride_c, featmaps->channels, featmaps->height,
-                                                 featmaps->width, globalfeat, view_mask, pixel_mask, pixel_locations);
+                                                 featmaps->width, globalfeat, view_mask, pixel_mask, pixel_locations, in_front, view_features);
     }
     if (e != cudaSuccess) {
         set_error("nd_render_gather_stats: %s", cudaGetErrorString(e));
@@ -333,13 +339,13 @@ int nd_render_gather_stats(const float *pts, int64_t n_points, const float *came
 }
 
 int nd_composite(const float *rgb, const float *sigma, const float *z_vals, const uint8_t *pixel_mask, int64_t n_rays,
-                 int n_samples, float z_min, float z_max, int white_bkgd, float *out_rgb, float *out_depth,
+                 int n_samples, const float *z_bounds, int white_bkgd, float *out_rgb, float *out_depth,
                  float *weights, float *alpha, float *transparency, uint8_t *ray_mask, void *stream) {
-    ND_REQUIRE(rgb && sigma && z_vals && out_rgb && out_depth, ND_ERR_BAD_ARG, "nd_composite: null pointer");
+    ND_REQUIRE(rgb && sigma && z_vals && z_bounds && out_rgb && out_depth, ND_ERR_BAD_ARG, "nd_composite: null pointer");
     ND_REQUIRE(n_rays >= 0 && n_samples >= 1, ND_ERR_BAD_SHAPE, "nd_composite: bad shape");
     if (n_rays == 0) return ND_OK;
     k_composite<<<(unsigned)ceil_div(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
-        rgb, sigma, z_vals, pixel_mask, n_rays, n_samples, z_min, z_max, white_bkgd, out_rgb, out_depth, weights, alpha,
+        rgb, sigma, z_vals, pixel_mask, n_rays, n_samples, z_bounds, white_bkgd, out_rgb, out_depth, weights, alpha,
         transparency, ray_mask);
     ND_CUDA_LAUNCH_CHECK("k_composite");
     return ND_OK;

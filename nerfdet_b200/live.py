@@ -1,0 +1,80 @@
+"""The live voxel side of ``nerfdet.extract_feat`` (reference ``nerfdet.py:152-261``, the
+``nerf_mode='image'``, ``nerf_density=True`` branch -- the only one that runs):
+
+    B7   map_features_2d      Linear(C -> 32) per pixel of the sliced feature maps          nerfdet.py:190-197
+    B8+9 live_statistics      RGB + mapped-feature gathers, 35-ch mean / exp(-var)         nerfdet.py:200-210, 232-253
+    B10  density_volume       alpha = 1 - exp(-relu(sigma));  x = alpha * mean             nerfdet.py:254-261
+
+``lift_scene`` chains them with the fused 256-channel lift (lifting.lift_mean_var) and returns what
+``extract_feat`` hands to ``neck_3d`` (the ``[C, X, Y, Z]`` volume) and to the head (``valids``).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import lifting, ops
+
+
+def map_features_2d(feature_2d: torch.Tensor, mapping) -> torch.Tensor:
+    """``self.mapping`` applied per pixel (nerfdet.py:190-197): ``[nv, C, h, w] -> [nv, 32, h, w]``.
+    ``mapping`` is the reference's ``nn.Sequential(nn.Linear(256, 32))`` (nerfdet.py:103-105) or any
+    callable on ``[nv, h*w, C]``.  One plain cuBLAS SGEMM through torch, exactly the reference's op sequence."""
+    nv, c, h, w = feature_2d.shape
+    flat = feature_2d.reshape(nv, c, h * w).permute(0, 2, 1).contiguous()
+    return mapping(flat).permute(0, 2, 1).contiguous().view(nv, -1, h, w)
+
+
+def _mapping_bias(mapping) -> torch.Tensor:
+    lin = mapping[0] if isinstance(mapping, torch.nn.Sequential) else mapping
+    return lin.bias.detach()
+
+
+def live_statistics(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias, want_planes=False):
+    """B8 + B9.  ``mapped_2d [nv, 32, h, w]`` (B7 output), ``rgb_images [nv, 3, H, W]`` = the
+    ``denorm_images[:, :, :img_h, :img_w]`` slice, projections at feature level (stride 4) and image level
+    (stride 1).  Returns ``global_volume [N, 70]`` (interleaved rows), the feature-level
+    count ``[1, X, Y, Z]`` and, on request, ``mean35`` / ``cov35 [35, X, Y, Z]``."""
+    gx, gy, gz = points.shape[-3:]
+    glob, mean35, cov35, count = ops.live_stats(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias,
+                                                want_planes)
+    out = dict(global_volume=glob, count=count.view(1, gx, gy, gz))
+    if want_planes:
+        out['mean35'] = mean35.view(-1, gx, gy, gz)
+        out['cov35'] = cov35.view(-1, gx, gy, gz)
+    return out
+
+
+def lift_scene(feature: torch.Tensor, img_meta: Dict, n_voxels, voxel_size, mapping=None, nerf_mlp=None,
+               denorm_images: Optional[torch.Tensor] = None, stride: int = 4, want_cov: bool = False) -> Dict:
+    """One scene of ``extract_feat``'s loop body (nerfdet.py:152-261) without ``render_rays``.
+
+    ``feature [nv, C, Hf, Wf]`` is the un-sliced FPN output of the scene's views.  With ``mapping``,
+    ``nerf_mlp`` and ``denorm_images [nv, 3, Hp, Wp]`` given, the returned ``volume`` is
+    ``alpha * volume_mean`` (the density-weighted volume ``neck_3d`` receives); without them it is the plain
+    ``volume_mean``.  Keys: volume [C,X,Y,Z], valid [1,X,Y,Z] int64, and, when available, volume_cov,
+    feature_2d [nv,32,h,w], global_volume [N,70], alpha [N]."""
+    dev = feature.device
+    projection = lifting.compute_projection(img_meta, stride).to(dev)
+    points = lifting.get_points(n_voxels, voxel_size, img_meta['lidar2img']['origin']).to(dev)
+    height = img_meta['img_shape'][0] // stride
+    width = img_meta['img_shape'][1] // stride
+    sliced = feature[:, :, :height, :width]
+    out = {}
+    alpha = None
+    if mapping is not None and nerf_mlp is not None and denorm_images is not None:
+        feature_2d = map_features_2d(sliced, mapping)
+        rgb_projection = lifting.compute_projection(img_meta, 1).to(dev)
+        rgb = denorm_images[:, :, :img_meta['img_shape'][0], :img_meta['img_shape'][1]]
+        live = live_statistics(feature_2d, rgb, points, projection, rgb_projection, _mapping_bias(mapping))
+        pts = points.view(3, -1).permute(1, 0).contiguous()
+        _, alpha = nerf_mlp.query_density(pts, live['global_volume'], return_alpha=True)
+        out.update(feature_2d=feature_2d, global_volume=live['global_volume'], alpha=alpha.view(-1),
+                   rgb_projection=rgb_projection)
+    mean, cov, valid = lifting.lift_mean_var(sliced, points, projection, alpha=alpha, want_cov=want_cov)
+    out.update(volume=mean, valid=valid, points=points, projection=projection)
+    if want_cov:
+        out['volume_cov'] = cov
+    return out

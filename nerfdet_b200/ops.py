@@ -6,7 +6,7 @@ on ``torch.cuda.current_stream()``.  CUDA tensors only -- there is no CPU path."
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -231,3 +231,270 @@ def lift_launch_count(features: Tensor, n_voxels: int, scratch_budget_bytes: int
     m = _maps(features)
     opt = _options(scratch_budget_bytes)
     return int(_lib.load().nd_lift_launch_count(ctypes.byref(m), n_voxels, ctypes.byref(opt)))
+
+
+# ==========================================================================================
+# Live 35-channel statistics, shared MLP and the render branch
+# ==========================================================================================
+def _maps_contig(t: Tensor, what: str, allow_bf16: bool = True) -> NdMaps:
+    m = _maps(t)
+    if t.dtype == torch.bfloat16 and not allow_bf16:
+        raise TypeError(f'{what} must be float32')
+    return m
+
+
+@torch.library.custom_op(f'{_NS}::live_stats', mutates_args=())
+def live_stats(mapped: Tensor, rgb: Tensor, points: Tensor, projection: Tensor, rgb_projection: Tensor,
+               map_bias: Tensor, want_planes: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """B8 + B9 (reference nerfdet.py:200-210, 232-253).  Returns ``global_volume [N, 2*(3+Cm)]``
+    (channel-interleaved rows), ``mean35`` / ``cov35 [3+Cm, N]`` (empty unless ``want_planes``) and the
+    feature-level view count ``int64 [N]``."""
+    _need_cuda(mapped, rgb, points, projection, rgb_projection, map_bias)
+    mm = _maps(mapped)
+    mr = _maps(rgb)
+    if rgb.dtype != torch.float32 or mr.channels != 3:
+        raise ValueError('rgb must be float32 [n_views, 3, h, w]')
+    _check_geometry(points, projection, mm.n_views)
+    if tuple(rgb_projection.shape) != (mm.n_views, 3, 4) or rgb_projection.dtype != torch.float32:
+        raise ValueError('rgb_projection must be float32 [n_views, 3, 4]')
+    if map_bias.dtype != torch.float32 or map_bias.numel() != mm.channels:
+        raise ValueError('map_bias must be float32 with one value per mapped channel')
+    points, _ = _flat_points(points)
+    n = points.shape[1]
+    ct = 3 + mm.channels
+    dev = mapped.device
+    glob = torch.empty((n, 2 * ct), dtype=torch.float32, device=dev)
+    mean35 = torch.empty((ct, n) if want_planes else (0,), dtype=torch.float32, device=dev)
+    cov35 = torch.empty((ct, n) if want_planes else (0,), dtype=torch.float32, device=dev)
+    count = torch.empty((n,), dtype=torch.int64, device=dev)
+    projection = projection.contiguous()
+    rgb_projection = rgb_projection.contiguous()
+    map_bias = map_bias.contiguous()
+    lib = _lib.load()
+    _lib.check(lib.nd_live_stats(ctypes.byref(mm), ctypes.byref(mr), _ptr(points), _ptr(projection),
+                                 _ptr(rgb_projection), n, _ptr(map_bias), _ptr(glob),
+                                 _ptr(mean35) if want_planes else None, _ptr(cov35) if want_planes else None,
+                                 _ptr(count), _stream()), 'nd_live_stats')
+    return glob, mean35, cov35, count
+
+
+@live_stats.register_fake
+def _(mapped, rgb, points, projection, rgb_projection, map_bias, want_planes):
+    n = points[0].numel()
+    ct = 3 + mapped.shape[1]
+    f = lambda *s: mapped.new_empty(s, dtype=torch.float32)
+    return (f(n, 2 * ct), f(ct, n) if want_planes else f(0), f(ct, n) if want_planes else f(0),
+            mapped.new_empty((n,), dtype=torch.int64))
+
+
+def mlp_arch(weights, dims) -> _lib.NdMlpWeights:
+    """ctypes view of the reference state_dict tensors (``weights``: dict name -> CUDA tensor or None)."""
+    w = _lib.NdMlpWeights()
+    for i in range(8):
+        t = weights.get(f'base_w{i}')
+        w.base_w[i] = t.data_ptr() if t is not None else None
+        t = weights.get(f'base_b{i}')
+        w.base_b[i] = t.data_ptr() if t is not None else None
+    for name in ('sigma_w', 'sigma_b', 'bottleneck_w', 'bottleneck_b', 'rgb_hidden_w', 'rgb_hidden_b',
+                 'rgb_out_w', 'rgb_out_b'):
+        t = weights.get(name)
+        setattr(w, name, t.data_ptr() if t is not None else None)
+    (w.net_depth, w.net_width, w.skip_layer, w.feature_dim, w.cond_width, w.pos_octaves,
+     w.view_octaves) = [int(v) for v in dims]
+    return w
+
+
+def pack_mlp_weights(weights, dims) -> Tensor:
+    """One-time transposition of the reference weights into the kernel's layout (``nd_pack_mlp_weights``)."""
+    tensors = [t for t in weights.values() if t is not None]
+    _need_cuda(*tensors)
+    for t in tensors:
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError('MLP weights must be contiguous float32 tensors')
+    lib = _lib.load()
+    arch = mlp_arch(weights, dims)
+    nbytes = lib.nd_mlp_packed_bytes(ctypes.byref(arch))
+    if nbytes == 0:
+        raise RuntimeError('nd_mlp_packed_bytes: unsupported MLP architecture ' + str(tuple(dims)))
+    packed = torch.empty((nbytes,), dtype=torch.uint8, device=tensors[0].device)
+    _lib.check(lib.nd_pack_mlp_weights(ctypes.byref(arch), _ptr(packed), nbytes, _stream()), 'nd_pack_mlp_weights')
+    return packed
+
+
+@torch.library.custom_op(f'{_NS}::nerf_mlp_fwd', mutates_args=())
+def nerf_mlp_fwd(packed: Tensor, dims: List[int], x: Tensor, features: Tensor, cond: Optional[Tensor],
+                 samples_per_ray: int, want_rgb: bool, want_alpha: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """sigma [P], rgb [P, 3] (empty unless ``want_rgb``), alpha = 1 - exp(-sigma) [P] (empty unless
+    ``want_alpha``) for P points (reference nerf_mlp.py:217-234)."""
+    _need_cuda(packed, x, features, cond)
+    if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != 3:
+        raise ValueError('x must be float32 [P, 3]')
+    p = x.shape[0]
+    if features.dtype != torch.float32 or tuple(features.shape) != (p, dims[3]):
+        raise ValueError(f'features must be float32 [{p}, {dims[3]}], got {tuple(features.shape)}')
+    if want_rgb:
+        if cond is None or cond.dtype != torch.float32 or cond.dim() != 2 or cond.shape[1] != 3 or \
+                samples_per_ray < 1 or cond.shape[0] * samples_per_ray != p:
+            raise ValueError('cond must be float32 [P / samples_per_ray, 3]')
+        cond = cond.contiguous()
+    x = x.contiguous()
+    features = features.contiguous()
+    dev = x.device
+    sigma = torch.empty((p,), dtype=torch.float32, device=dev)
+    rgb = torch.empty((p, 3) if want_rgb else (0,), dtype=torch.float32, device=dev)
+    alpha = torch.empty((p,) if want_alpha else (0,), dtype=torch.float32, device=dev)
+    arch = mlp_arch({}, dims)
+    lib = _lib.load()
+    _lib.check(lib.nd_nerf_mlp_fwd(ctypes.byref(arch), _ptr(packed), _ptr(x), _ptr(features),
+                                   _ptr(cond) if want_rgb else None, p, max(int(samples_per_ray), 1), _ptr(sigma),
+                                   _ptr(alpha) if want_alpha else None, _ptr(rgb) if want_rgb else None, _stream()),
+               'nd_nerf_mlp_fwd')
+    return sigma, rgb, alpha
+
+
+@nerf_mlp_fwd.register_fake
+def _(packed, dims, x, features, cond, samples_per_ray, want_rgb, want_alpha):
+    p = x.shape[0]
+    return (x.new_empty((p,)), x.new_empty((p, 3) if want_rgb else (0,)), x.new_empty((p,) if want_alpha else (0,)))
+
+
+@torch.library.custom_op(f'{_NS}::sample_rays', mutates_args=())
+def sample_rays(ray_o: Tensor, ray_d: Tensor, near: float, far: float, n_samples: int,
+                t_rand: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """pts [R, S, 3], z_vals [R, S] (reference render_ray.py:145-189; ``t_rand`` None = deterministic)."""
+    _need_cuda(ray_o, ray_d, t_rand)
+    if ray_o.dtype != torch.float32 or ray_d.dtype != torch.float32 or ray_o.shape != ray_d.shape or \
+            ray_o.dim() != 2 or ray_o.shape[1] != 3:
+        raise ValueError('ray_o / ray_d must be float32 [R, 3]')
+    r = ray_o.shape[0]
+    if t_rand is not None:
+        if t_rand.dtype != torch.float32 or tuple(t_rand.shape) != (r, n_samples):
+            raise ValueError('t_rand must be float32 [R, S]')
+        t_rand = t_rand.contiguous()
+    ray_o, ray_d = ray_o.contiguous(), ray_d.contiguous()
+    pts = torch.empty((r, n_samples, 3), dtype=torch.float32, device=ray_o.device)
+    z = torch.empty((r, n_samples), dtype=torch.float32, device=ray_o.device)
+    lib = _lib.load()
+    _lib.check(lib.nd_sample_rays(_ptr(ray_o), _ptr(ray_d), r, int(n_samples), float(near), float(far), _ptr(t_rand),
+                                  _ptr(pts), _ptr(z), _stream()), 'nd_sample_rays')
+    return pts, z
+
+
+@sample_rays.register_fake
+def _(ray_o, ray_d, near, far, n_samples, t_rand):
+    r = ray_o.shape[0]
+    return ray_o.new_empty((r, n_samples, 3)), ray_o.new_empty((r, n_samples))
+
+
+@torch.library.custom_op(f'{_NS}::render_gather_stats', mutates_args=())
+def render_gather_stats(pts: Tensor, cameras: Tensor, images: Tensor, featmaps: Tensor, want_pixels: bool,
+                        want_view_features: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """R4 + R5 + R6 for P points: ``globalfeat [P, 2*(3+D)]``, ``view_mask bool [P, nv]``,
+    ``pixel_mask bool [P]``, ``pixel_locations [nv, P, 2]``, ``in_front bool [nv, P]`` and
+    ``view_features [P, nv, 3+D]`` (the last three empty unless requested).  Reference projection.py:24-151 + render_ray.py:71-93, 301-303."""
+    _need_cuda(pts, cameras, images, featmaps)
+    if pts.dtype != torch.float32 or pts.dim() != 2 or pts.shape[1] != 3:
+        raise ValueError('pts must be float32 [P, 3]')
+    if cameras.dtype != torch.float32 or cameras.dim() != 2 or cameras.shape[1] != 34:
+        raise ValueError('cameras must be float32 [n_views, 34]')
+    nv = cameras.shape[0]
+    if images.dtype != torch.float32 or images.dim() != 4 or images.shape[0] != nv or images.shape[1] != 3:
+        raise ValueError('images must be float32 [n_views, 3, H, W]')
+    images = images.contiguous()
+    featmaps = featmaps.contiguous()          # the reference samples the whole (contiguous) maps
+    mi, mf = _maps(images), _maps(featmaps)
+    if mf.channels == 0:
+        mf.data = None
+    if mf.n_views != nv:
+        raise ValueError('featmaps must have one map stack per view')
+    pts, cameras = pts.contiguous(), cameras.contiguous()
+    p = pts.shape[0]
+    ct = 3 + mf.channels
+    dev = pts.device
+    glob = torch.empty((p, 2 * ct), dtype=torch.float32, device=dev)
+    view_mask = torch.empty((p, nv), dtype=torch.bool, device=dev)
+    pixel_mask = torch.empty((p,), dtype=torch.bool, device=dev)
+    pix = torch.empty((nv, p, 2) if want_pixels else (0,), dtype=torch.float32, device=dev)
+    front = torch.empty((nv, p) if want_pixels else (0,), dtype=torch.bool, device=dev)
+    vf = torch.empty((p, nv, ct) if want_view_features else (0,), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.nd_render_gather_stats(_ptr(pts), p, _ptr(cameras), nv, ctypes.byref(mi), ctypes.byref(mf),
+                                          _ptr(glob), _ptr(view_mask), _ptr(pixel_mask),
+                                          _ptr(pix) if want_pixels else None, _ptr(front) if want_pixels else None,
+                                          _ptr(vf) if want_view_features else None, _stream()),
+               'nd_render_gather_stats')
+    return glob, view_mask, pixel_mask, pix, front, vf
+
+
+@render_gather_stats.register_fake
+def _(pts, cameras, images, featmaps, want_pixels, want_view_features):
+    p, nv, ct = pts.shape[0], cameras.shape[0], 3 + featmaps.shape[1]
+    return (pts.new_empty((p, 2 * ct)), pts.new_empty((p, nv), dtype=torch.bool),
+            pts.new_empty((p,), dtype=torch.bool), pts.new_empty((nv, p, 2) if want_pixels else (0,)),
+            pts.new_empty((nv, p) if want_pixels else (0,), dtype=torch.bool),
+            pts.new_empty((p, nv, ct) if want_view_features else (0,)))
+
+
+@torch.library.custom_op(f'{_NS}::composite', mutates_args=())
+def composite(rgb: Tensor, sigma: Tensor, z_vals: Tensor, pixel_mask: Optional[Tensor], z_bounds: Tensor,
+              white_bkgd: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """raw2outputs (reference render_ray.py:196-247): rgb [R,3], depth [R], weights, alpha, transparency [R,S],
+    ray mask bool [R].  ``z_bounds`` = float32 [2] device tensor {min, max} of the batch's z_vals."""
+    _need_cuda(rgb, sigma, z_vals, pixel_mask, z_bounds)
+    r, s = z_vals.shape
+    if rgb.dtype != torch.float32 or tuple(rgb.shape) != (r, s, 3) or sigma.dtype != torch.float32 or \
+            sigma.numel() != r * s or z_vals.dtype != torch.float32:
+        raise ValueError('composite: rgb [R,S,3], sigma [R,S], z_vals [R,S] float32 expected')
+    if z_bounds.dtype != torch.float32 or z_bounds.numel() != 2:
+        raise ValueError('z_bounds must be a float32 tensor {min, max}')
+    rgb, sigma, z_vals, z_bounds = rgb.contiguous(), sigma.contiguous(), z_vals.contiguous(), z_bounds.contiguous()
+    pm = None
+    if pixel_mask is not None:
+        if pixel_mask.dtype != torch.bool or pixel_mask.numel() != r * s:
+            raise ValueError('pixel_mask must be bool [R, S]')
+        pm = pixel_mask.contiguous()
+    dev = rgb.device
+    out_rgb = torch.empty((r, 3), dtype=torch.float32, device=dev)
+    depth = torch.empty((r,), dtype=torch.float32, device=dev)
+    weights = torch.empty((r, s), dtype=torch.float32, device=dev)
+    alpha = torch.empty_like(weights)
+    trans = torch.empty_like(weights)
+    mask = torch.zeros((r,), dtype=torch.bool, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.nd_composite(_ptr(rgb), _ptr(sigma), _ptr(z_vals), _ptr(pm), r, s, _ptr(z_bounds),
+                                1 if white_bkgd else 0, _ptr(out_rgb), _ptr(depth), _ptr(weights), _ptr(alpha),
+                                _ptr(trans), _ptr(mask) if pm is not None else None, _stream()), 'nd_composite')
+    return out_rgb, depth, weights, alpha, trans, mask
+
+
+@composite.register_fake
+def _(rgb, sigma, z_vals, pixel_mask, z_bounds, white_bkgd):
+    r, s = z_vals.shape
+    f = lambda *sh: rgb.new_empty(sh)
+    return f(r, 3), f(r), f(r, s), f(r, s), f(r, s), rgb.new_empty((r,), dtype=torch.bool)
+
+
+@torch.library.custom_op(f'{_NS}::volume_sample', mutates_args=())
+def volume_sample(volume: Tensor, pts: Tensor, aabb_min: List[float], aabb_max: List[float]) -> Tuple[Tensor, Tensor]:
+    """Trilinear lookup (reference render_ray.py:26-46): features [P, C], inside bool [P]."""
+    _need_cuda(volume, pts)
+    if volume.dtype != torch.float32 or volume.dim() != 4:
+        raise ValueError('volume must be float32 [C, D0, D1, D2]')
+    if pts.dtype != torch.float32 or pts.dim() != 2 or pts.shape[1] != 3:
+        raise ValueError('pts must be float32 [P, 3]')
+    volume, pts = volume.contiguous(), pts.contiguous()
+    c, d0, d1, d2 = volume.shape
+    p = pts.shape[0]
+    out = torch.empty((p, c), dtype=torch.float32, device=pts.device)
+    inside = torch.empty((p,), dtype=torch.bool, device=pts.device)
+    lo = (ctypes.c_float * 3)(*[float(v) for v in aabb_min])
+    hi = (ctypes.c_float * 3)(*[float(v) for v in aabb_max])
+    lib = _lib.load()
+    _lib.check(lib.nd_volume_sample_trilinear(_ptr(volume), c, d0, d1, d2, _ptr(pts), p, lo, hi, _ptr(out),
+                                              _ptr(inside), _stream()), 'nd_volume_sample_trilinear')
+    return out, inside
+
+
+@volume_sample.register_fake
+def _(volume, pts, aabb_min, aabb_max):
+    return pts.new_empty((pts.shape[0], volume.shape[0])), pts.new_empty((pts.shape[0],), dtype=torch.bool)

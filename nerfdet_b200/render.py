@@ -1,0 +1,149 @@
+"""The NeRF rendering branch with the reference call signatures
+(``mmdet3d/models/model_utils/render_ray.py``): ``render_rays`` / ``render_rays_func`` and their helpers.
+
+Host code keeps what the reference keeps on the host -- ray selection with a numpy ``RandomState(234)``
+(render_ray.py:20, 422), ``torch.rand_like`` for the stratified jitter (so both random streams match the
+reference's), camera packing (render_ray.py:48-69); everything per ray sample runs in the CUDA kernels of
+``csrc/render.cu`` and ``csrc/mlp.cu``.  The reference's ``[rays, samples, views, 35]`` tensor is not built."""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import ops
+from .projection import Projector  # noqa: F401  (re-exported like the reference module layout)
+
+rng = np.random.RandomState(234)          # render_ray.py:20
+
+
+def _compute_projection(img_meta) -> torch.Tensor:
+    """[1, n_views, 34] = [h, w, K 4x4 (rows 0-1 / (ori_h / img_h)), E 4x4] on the CPU (render_ray.py:48-69)."""
+    views = len(img_meta['lidar2img']['extrinsic'])
+    intrinsic = torch.tensor(img_meta['lidar2img']['intrinsic'][:4, :4])
+    ratio = img_meta['ori_shape'][0] / img_meta['img_shape'][0]
+    intrinsic[:2] /= ratio
+    intrinsic = intrinsic.unsqueeze(0).view(1, 16).repeat(views, 1)
+    img_size = torch.Tensor(img_meta['img_shape'][:2]).unsqueeze(0).repeat(views, 1)
+    extrinsic = torch.stack([torch.Tensor(img_meta['lidar2img']['extrinsic'][v]) for v in range(views)]).view(views, 16)
+    return torch.cat([img_size, intrinsic, extrinsic], dim=-1).unsqueeze(0)
+
+
+def sample_along_camera_ray(ray_o, ray_d, depth_range, N_samples, inv_uniform=False, det=False):
+    """pts [rays, samples, 3], z_vals [rays, samples] (render_ray.py:145-189)."""
+    if inv_uniform:
+        raise NotImplementedError('inv_uniform=True is never used by NeRF-Det')
+    t_rand = None
+    if not det:
+        t_rand = torch.rand((ray_o.shape[0], N_samples), dtype=torch.float32, device=ray_o.device)   # == rand_like(z_vals)
+    return ops.sample_rays(ray_o, ray_d, float(depth_range[0]), float(depth_range[1]), int(N_samples), t_rand)
+
+
+def volume_sampling(sample_pts, features, aabb):
+    """Trilinear lookup of ``features [1, C, D0, D1, D2]`` at ``sample_pts [rays, samples, 3]``
+    (render_ray.py:26-46): ``[rays, samples, C]`` and the strict in-box mask."""
+    assert features.shape[0] == 1
+    r, s = sample_pts.shape[:2]
+    out, inside = ops.volume_sample(features[0], sample_pts.reshape(-1, 3), [float(v) for v in aabb[0]],
+                                    [float(v) for v in aabb[1]])
+    return out.view(r, s, -1), inside.view(r, s)
+
+
+def raw2outputs(raw, z_vals, mask, white_bkgd=False):
+    """Alpha compositing (render_ray.py:196-247) of ``raw [rays, samples, 4]`` = (rgb, sigma)."""
+    bounds = torch.stack(torch.aminmax(z_vals))          # batch-global clamp bounds, stays on the device
+    rgb, depth, weights, alpha, trans, ray_mask = ops.composite(raw[..., :3].contiguous(), raw[..., 3].contiguous(),
+                                                                z_vals, mask, bounds, bool(white_bkgd))
+    return OrderedDict([('rgb', rgb), ('depth', depth), ('weights', weights),
+                        ('mask', ray_mask if mask is not None else None), ('alpha', alpha), ('z_vals', z_vals),
+                        ('transparency', trans)])
+
+
+def render_rays_func(ray_o, ray_d, mean_volume, cov_volume, features_2D, img, aabb, near_far_range, N_samples,
+                     N_rand=4096, nerf_mlp=None, img_meta=None, projector=None, mode='volume', nerf_sample_view=3,
+                     inv_uniform=False, N_importance=0, det=False, is_train=True, white_bkgd=False, gt_rgb=None,
+                     gt_depth=None):
+    """render_ray.py:250-367 (coarse pass; the ``N_importance > 0`` fine pass references undefined names in the
+    reference and is not built)."""
+    if N_importance > 0:
+        raise NotImplementedError('the fine pass (N_importance > 0) is dead code in the reference')
+    ret = {'outputs_coarse': None, 'outputs_fine': None, 'gt_rgb': gt_rgb, 'gt_depth': gt_depth}
+    pts, z_vals = sample_along_camera_ray(ray_o, ray_d, near_far_range, N_samples, inv_uniform, det)
+    n_rays, n_samples = pts.shape[:2]
+    cameras = _compute_projection(img_meta)[0].to(pts.device)
+    flat = pts.view(-1, 3)
+    if mode == 'image':
+        glob, _, pixel_mask, _, _, _ = ops.render_gather_stats(flat, cameras, img, features_2D, False, False)
+        rgb_pts, density_pts = nerf_mlp(pts, ray_d, glob.view(n_rays, n_samples, -1))
+        ret['sigma'] = density_pts
+    elif mode == 'volume':
+        mean_pts, inbound = volume_sampling(pts, mean_volume, aabb)
+        cov_pts, inbound = volume_sampling(pts, cov_volume, aabb)
+        empty = img.new_zeros((img.shape[0], 0) + tuple(img.shape[2:]))
+        _, _, pixel_mask, _, _, _ = ops.render_gather_stats(flat, cameras, img, empty, False, False)
+        rgb_pts, density_pts = nerf_mlp(pts, ray_d, torch.cat([mean_pts, cov_pts], dim=-1))
+        density_pts = density_pts * inbound.unsqueeze(dim=-1)
+    else:
+        raise ValueError(f'unknown mode {mode!r}')
+    raw = torch.cat([rgb_pts, density_pts], dim=-1)
+    ret['outputs_coarse'] = raw2outputs(raw, z_vals, pixel_mask.view(n_rays, n_samples), white_bkgd=white_bkgd)
+    return ret
+
+
+def render_rays(ray_batch, mean_volume, cov_volume, features_2D, img, aabb, near_far_range, N_samples, N_rand=4096,
+                nerf_mlp=None, img_meta=None, projector=None, mode='volume', nerf_sample_view=3, inv_uniform=False,
+                N_importance=0, det=False, is_train=True, white_bkgd=False, render_testing=False):
+    """render_ray.py:371-520.  ``img [nv, 3, Hp, Wp]`` are the de-normalised source images, ``features_2D
+    [nv, D, h, w]`` the mapped feature maps; tensors of ``ray_batch`` may live on the host or the device."""
+    dev = img.device
+    ray_o = ray_batch['ray_o']
+    ray_d = ray_batch['ray_d']
+    gt_rgb = ray_batch['gt_rgb']
+    gt_depth = ray_batch['gt_depth']
+    nerf_sizes = ray_batch['nerf_sizes']
+
+    def common(extra_det):
+        return dict(nerf_mlp=nerf_mlp, img_meta=img_meta, projector=projector, mode=mode,
+                    nerf_sample_view=nerf_sample_view, inv_uniform=inv_uniform, N_importance=N_importance,
+                    det=extra_det, is_train=is_train, white_bkgd=white_bkgd)
+
+    if is_train:
+        ray_o = ray_o.view(-1, 3)
+        ray_d = ray_d.view(-1, 3)
+        gt_rgb = gt_rgb.view(-1, 3)
+        if len(gt_depth) != 0:
+            gt_depth = gt_depth.view(-1, 1)
+            keep = (gt_depth > 0).squeeze(-1)
+            ray_o, ray_d, gt_rgb, gt_depth = ray_o[keep], ray_d[keep], gt_rgb[keep], gt_depth[keep]
+        else:
+            gt_depth = None
+        total_rays = ray_d.shape[0]
+        select_inds = rng.choice(total_rays, size=(N_rand,), replace=False)
+        ray_o, ray_d, gt_rgb = ray_o[select_inds], ray_d[select_inds], gt_rgb[select_inds]
+        if gt_depth is not None:
+            gt_depth = gt_depth[select_inds]
+        return render_rays_func(ray_o.to(dev).float(), ray_d.to(dev).float(), mean_volume, cov_volume, features_2D, img,
+                                aabb, near_far_range, N_samples, N_rand, gt_rgb=gt_rgb.to(dev),
+                                gt_depth=gt_depth.to(dev) if gt_depth is not None else None, **common(det))
+    if render_testing:
+        nerf_size = nerf_sizes[0]
+        view_num = ray_o.shape[1]
+        H, W = int(nerf_size[0][0]), int(nerf_size[0][1])
+        ray_o = ray_o.view(-1, 3).to(dev).float()
+        ray_d = ray_d.view(-1, 3).to(dev).float()
+        gt_rgb = gt_rgb.view(-1, 3)
+        gt_depth = gt_depth.view(-1, 1) if len(gt_depth) != 0 else None
+        assert view_num * H * W == ray_o.shape[0]
+        rgbs, depths = [], []
+        for i in range(0, ray_o.shape[0], N_rand):
+            ret = render_rays_func(ray_o[i:i + N_rand], ray_d[i:i + N_rand], mean_volume, cov_volume, features_2D, img,
+                                   aabb, near_far_range, N_samples, N_rand, gt_rgb=gt_rgb, gt_depth=gt_depth,
+                                   **common(True))
+            rgbs.append(ret['outputs_coarse']['rgb'])
+            depths.append(ret['outputs_coarse']['depth'])
+        return {'outputs_coarse': {'rgb': torch.cat(rgbs, dim=0).view(view_num, H, W, 3),
+                                   'depth': torch.cat(depths, dim=0).view(view_num, H, W, 1)},
+                'gt_rgb': gt_rgb.view(view_num, H, W, 3),
+                'gt_depth': gt_depth.view(view_num, H, W, 1) if gt_depth is not None else None}
+    return None

@@ -1,0 +1,110 @@
+"""CPU tier for the host-side mirror of the reference interface: what the reference keeps on the host
+(camera packing, ray selection, module / state_dict layout) must match fixtures made by the reference, and
+every op must refuse to run without a CUDA device (no fallback)."""
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+from nerfdet_b200 import lifting, live, nerf_mlp, ops, projection, render
+from nerfdet_b200.synthetic import make_mlp_state
+from oracle import golden_cases as gc
+
+
+def test_camera_packing_matches_reference():
+    inp = gc.render_inputs(gc.CASES['render_det'])
+    g = gc.load_golden('render_det')
+    cams = render._compute_projection(inp['img_meta'])
+    assert cams.shape == (1, 6, 34)
+    assert np.array_equal(cams.numpy(), g['cameras'])
+
+
+def test_module_tree_has_reference_state_dict_keys():
+    field = nerf_mlp.VanillaNeRFRadianceField(net_depth=4, net_width=256, skip_layer=3, feature_dim=70,
+                                              net_depth_condition=1, net_width_condition=128)
+    ref_state = {k: v for k, v in make_mlp_state(1).items() if not k.startswith('mapping.')}
+    own = field.state_dict()
+    assert sorted(own.keys()) == sorted(ref_state.keys())
+    for k, v in ref_state.items():
+        assert tuple(own[k].shape) == tuple(v.shape), k
+    field.load_state_dict(ref_state)                     # strict
+    # reference initialisation: zero biases (nerf_mlp.py:60-78)
+    fresh = nerf_mlp.VanillaNeRFRadianceField(4, 256, 3, 70)
+    assert all(float(p.detach().abs().max()) == 0.0 for n, p in fresh.named_parameters() if n.endswith('bias'))
+    # deeper trunk with a mid-network skip (nerf_mlp.py:80-90): layer after the skip takes width + input
+    deep = nerf_mlp.VanillaNeRFRadianceField(net_depth=8, net_width=256, skip_layer=4, feature_dim=0)
+    assert deep.mlp.base.hidden_layers[5].in_features == 256 + 63
+    assert deep.mlp.sigma_layer.output_layer.in_features == 256
+
+
+def test_signatures_mirror_the_reference():
+    """Argument names / order of the reference callables."""
+    assert list(inspect.signature(lifting.backproject).parameters) == ['features', 'points', 'projection', 'depth', 'voxel_size']
+    assert list(inspect.signature(lifting.get_points).parameters) == ['n_voxels', 'voxel_size', 'origin']
+    want = ['ray_batch', 'mean_volume', 'cov_volume', 'features_2D', 'img', 'aabb', 'near_far_range', 'N_samples',
+            'N_rand', 'nerf_mlp', 'img_meta', 'projector', 'mode', 'nerf_sample_view', 'inv_uniform', 'N_importance',
+            'det', 'is_train', 'white_bkgd', 'render_testing']
+    assert list(inspect.signature(render.render_rays).parameters) == want
+    assert list(inspect.signature(projection.Projector.compute).parameters) == ['self', 'xyz', 'train_imgs', 'train_cameras',
+                                                                               'featmaps', 'grid_sample']
+    assert list(inspect.signature(nerf_mlp.VanillaNeRFRadianceField.forward).parameters) == ['self', 'x', 'condition', 'features']
+    assert render.rng.randint(1 << 30) == np.random.RandomState(234).randint(1 << 30)
+
+
+def test_training_ray_selection_matches_reference():
+    """R1: flatten, drop gt_depth <= 0, numpy RandomState(234).choice -- checked up to the first CUDA call."""
+    case = gc.CASES['extract_small']
+    g = gc.load_golden('extract_small')
+    inp = gc.extract_inputs(case)
+    seen = {}
+
+    def stop(ray_o, ray_d, *args, **kw):
+        seen.update(ray_o=ray_o, ray_d=ray_d, gt_rgb=kw['gt_rgb'], gt_depth=kw['gt_depth'])
+        raise StopIteration
+
+    render.rng = np.random.RandomState(234)
+    orig = render.render_rays_func
+    render.render_rays_func = stop
+    try:
+        with pytest.raises(StopIteration):
+            render.render_rays(inp['ray_batch'], None, None, torch.zeros(5, 32, 14, 20), torch.zeros(5, 3, 60, 80), None,
+                               inp['near_far_range'], inp['N_samples'], inp['N_rand'], None, inp['img_meta'], None, 'image')
+    finally:
+        render.render_rays_func = orig
+    rb = inp['ray_batch']
+    keep = rb['gt_depth'].view(-1) > 0
+    sel = g['select_inds']
+    assert torch.equal(seen['ray_o'], rb['ray_o'].view(-1, 3)[keep][sel].float())
+    assert np.allclose(seen['gt_rgb'].numpy(), g['gt_rgb'])
+    assert np.allclose(seen['gt_depth'].numpy(), g['gt_depth'])
+
+
+def test_new_ops_refuse_cpu_tensors():
+    z = torch.zeros
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.sample_rays(z(4, 3), z(4, 3), 0.2, 8.0, 8, None)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.render_gather_stats(z(4, 3), z(2, 34), z(2, 3, 8, 8), z(2, 4, 4, 4), False, False)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.composite(z(2, 4, 3), z(2, 4), z(2, 4), None, z(2), False)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.volume_sample(z(2, 3, 3, 3), z(5, 3), [0., 0., 0.], [1., 1., 1.])
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.live_stats(z(2, 32, 4, 4), z(2, 3, 16, 16), z(3, 8), z(2, 3, 4), z(2, 3, 4), z(32), False)
+    field = nerf_mlp.VanillaNeRFRadianceField(4, 256, 3, 70)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        field.query_density(z(4, 3), z(4, 70))
+
+
+def test_mlp_packed_size_and_unsupported_architectures():
+    import ctypes
+    from nerfdet_b200 import _lib
+    lib = _lib.load()
+    arch = ops.mlp_arch({}, [4, 256, 3, 70, 128, 10, 4])
+    # 4 hidden layers (136 / 256 / 256 / 256 rows) + heads with the [h, in] concatenation (392 rows)
+    floats = (136 * 256 + 256) + 3 * (256 * 256 + 256) + (392 + 4) + (392 * 256 + 256) + (284 * 128 + 128) + (3 * 128 + 4)
+    assert lib.nd_mlp_packed_bytes(ctypes.byref(arch)) == 4 * floats
+    assert lib.nd_mlp_packed_bytes(ctypes.byref(ops.mlp_arch({}, [4, 128, 3, 70, 128, 10, 4]))) == 0
+    with pytest.raises(NotImplementedError):
+        nerf_mlp.VanillaNeRFRadianceField(4, 256, 3, 70, net_depth_condition=2)
