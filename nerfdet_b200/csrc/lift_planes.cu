@@ -48,6 +48,7 @@ constexpr int kRowBytes = kOct * 2;     // one offset row: uint16 per voxel of a
 constexpr int kPMaxWarps = 25;          // compute warps per CTA (+1 producer warp)
 constexpr int kPMaxStages = 16;
 constexpr int kPBx = 4, kPBy = 8;       // compact oct = kPBx x kPBy columns in (x, y) x kOV in z
+constexpr int kIdxViews = 4;            // views per block of k_plane_index (more, smaller blocks: the pass is latency bound)
 constexpr int kPMaxOcts = 256;          // cost-balanced oct pairing up to this many octs (else index order)
 
 struct Tiling {
@@ -66,8 +67,9 @@ struct Tiling {
 struct PlaneArgs {
     Tiling tiling;
     // tables (workspace)
-    const uint8_t *cnt8;       // [nw16][n_pad] partial view counts, position p = oct * 256 + lane * 8 + i
-    const uint16_t *offc;      // [n_parts][nv][2 W][256] compacted offset rows of the octs that see the view
+    const uint8_t *cnt8;       // [nw16][n_pad] partial view counts per group of kIdxViews views, position p = oct * 256 + lane * 8 + i
+    const uint16_t *offc;      // [n_parts][part_rows][256] offset rows of the octs that see a view, view after view in ring order
+    int64_t part_rows;
     const uint16_t *rowcnt;    // [n_parts][nvp] rows in each block
     const uint32_t *ents;      // [n_parts][W][nvp] view | quad mask << 8 | slot A << 16 | slot B << 24 (0: not seen)
     const uint16_t *pairs;     // [n_parts][W][2] the octs of every warp (0xffff: none)
@@ -78,7 +80,8 @@ struct PlaneArgs {
     const void *feat;
     int64_t sv, sc;            // elements
     uint32_t plane_bytes, plane_pitch;   // smem slot = plane + zero word, padded to plane_pitch
-    int stages;                // plane ring: `stages` slots of plane_pitch bytes
+    int stages;                // plane ring: `stages` stages of `group` plane slots (plane_pitch bytes each)
+    int group;                 // views per stage (compile-time kG of the kernel instantiation)
     int ring_rows;             // offset-row ring: `ring_rows` rows of 512 B shared by the stages in flight
     int *trace;                // diagnostics: per-warp per-stage clock trace of CTA 0 (tools/lift_trace.py), or null
     int debug;                 // diagnostics (tools/lift_probe.py): 1 = no gather, 4 = no plane copies, 16 = no epilogue,
@@ -187,11 +190,11 @@ k_plane_index(const Tiling tiling, const float *__restrict__ points, const float
               int n_octs, int64_t n_vox, int64_t n_pad, int height, int width, int elt, uint32_t zero_off,
               uint16_t *__restrict__ off16, uint8_t *__restrict__ cnt8, uint8_t *__restrict__ omask,
               uint8_t *__restrict__ cost16) {
-    __shared__ float sp[16 * 12];
+    __shared__ float sp[kIdxViews * 12];
     __shared__ unsigned smask;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let k_lift_planes start streaming planes
-    const int v0 = blockIdx.y * 16;
-    const int nvg = min(16, nv - v0);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the dependent kernels start their prologues
+    const int v0 = blockIdx.y * kIdxViews;
+    const int nvg = min(kIdxViews, nv - v0);
     if (threadIdx.x < nvg * 12) sp[threadIdx.x] = proj[v0 * 12 + threadIdx.x];
     if (threadIdx.x == 0) smask = 0u;
     __syncthreads();
@@ -207,87 +210,155 @@ k_plane_index(const Tiling tiling, const float *__restrict__ points, const float
     }
     int count = 0;
     unsigned m = 0u;
-#pragma unroll 4
-    for (int i = 0; i < nvg; ++i) {
-        float xr, yr, q2;
-        const bool ok = project_nearest(sp + i * 12, X, Y, Z, height, width, xr, yr, q2) && inside;
-        const uint32_t off = ok ? (uint32_t)((int)yr * width + (int)xr) * (uint32_t)elt : zero_off;
-        off16[(int64_t)(v0 + i) * n_pad + p] = (uint16_t)off;
-        count += ok ? 1 : 0;
-        // warp = 4 lane slots x 8 voxels; quad 0 = voxels 0..3, quad 1 = voxels 4..7 of every lane slot
-        const unsigned b = __ballot_sync(0xffffffffu, ok);
-        m |= ((b & 0x0f0f0f0fu) ? 1u : 0u) << (2 * i);
-        m |= ((b & 0xf0f0f0f0u) ? 2u : 0u) << (2 * i);
+#pragma unroll
+    for (int i = 0; i < kIdxViews; ++i) {
+        if (i < nvg) {
+            float xr, yr, q2;
+            const bool ok = project_nearest(sp + i * 12, X, Y, Z, height, width, xr, yr, q2) && inside;
+            const uint32_t off = ok ? (uint32_t)((int)yr * width + (int)xr) * (uint32_t)elt : zero_off;
+            off16[(int64_t)(v0 + i) * n_pad + p] = (uint16_t)off;
+            count += ok ? 1 : 0;
+            // warp = 4 lane slots x 8 voxels; quad 0 = voxels 0..3, quad 1 = voxels 4..7 of every lane slot
+            const unsigned b = __ballot_sync(0xffffffffu, ok);
+            m |= ((b & 0x0f0f0f0fu) ? 1u : 0u) << (2 * i);
+            m |= ((b & 0xf0f0f0f0u) ? 2u : 0u) << (2 * i);
+        }
     }
     if ((threadIdx.x & 31) == 0 && m != 0u) atomicOr(&smask, m);
     cnt8[(int64_t)blockIdx.y * n_pad + p] = (uint8_t)count;
     __syncthreads();
     const unsigned sm = smask;
-    if (threadIdx.x < 16) omask[(int64_t)blockIdx.x * nvp + v0 + threadIdx.x] = (uint8_t)((sm >> (2 * threadIdx.x)) & 3u);
-    if (threadIdx.x == 16) cost16[(int64_t)blockIdx.y * n_octs + blockIdx.x] = (uint8_t)__popc(sm);
+    if (threadIdx.x < kIdxViews) omask[(int64_t)blockIdx.x * nvp + v0 + threadIdx.x] = (uint8_t)((sm >> (2 * threadIdx.x)) & 3u);
+    if (threadIdx.x == 32) cost16[(int64_t)blockIdx.y * n_octs + blockIdx.x] = (uint8_t)__popc(sm);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pairing + compaction.  grid = (views, parts); every block recomputes the (cheap) cost ranking.
+// Pairing (one block): ranks the octs by cost, pairs the k-th most with the k-th least expensive one, and tabulates
+// per (part, view) how many of the part's octs see the view and where the view's block of offset rows starts.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_plane_pack(int nv, int nvp, int nw16, int n_octs, int n_parts, int W, int64_t n_pad, int balanced,
-             const uint16_t *__restrict__ off16, const uint8_t *__restrict__ omask, const uint8_t *__restrict__ cost16,
-             uint16_t *__restrict__ offc, uint16_t *__restrict__ rowcnt, uint32_t *__restrict__ ents,
-             uint16_t *__restrict__ pairs) {
+__global__ void __launch_bounds__(1024)
+k_plane_rank(int nv, int nvp, int nw16, int n_octs, int n_parts, int W, int balanced, int ring_rows,
+             const uint8_t *__restrict__ omask, const uint8_t *__restrict__ cost16, uint16_t *__restrict__ pairs,
+             uint16_t *__restrict__ rowcnt, uint32_t *__restrict__ gstart) {
     __shared__ uint16_t s_cost[kPMaxOcts];
     __shared__ uint16_t s_sorted[kPMaxOcts];
-    __shared__ uint16_t s_q[2 * kPMaxWarps];       // octs of this part in slot order (warp w: 2 w, 2 w + 1)
-    __shared__ uint8_t s_m[2 * kPMaxWarps];        // their quad masks in this view
-    __shared__ uint8_t s_slot[2 * kPMaxWarps];     // their row slot in the compacted block (0xff: not seen)
+    extern __shared__ uint16_t s_dyn[];            // [n_parts][2 W] octs of every part, [n_parts][nvp] row counts
+    uint16_t *s_q = s_dyn, *s_c = s_dyn + (size_t)n_parts * 2 * W;
     asm volatile("griddepcontrol.wait;" ::: "memory");               // tables of k_plane_index
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // k_lift_planes may start streaming planes
-    const int v = blockIdx.x, part = blockIdx.y, tid = threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n_warps = (int)(blockDim.x >> 5);
     if (balanced) {
         for (int t = tid; t < n_octs; t += blockDim.x) {
             int cst = 0;
-            for (int g = 0; g < nw16; ++g) cst += (int)cost16[(int64_t)g * n_octs + t];
+            for (int g0 = 0; g0 < nw16; g0 += 8) {       // 8 independent loads in flight
+                uint8_t c8[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) c8[k] = g0 + k < nw16 ? __ldg(cost16 + (int64_t)(g0 + k) * n_octs + t) : (uint8_t)0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) cst += (int)c8[k];
+            }
             s_cost[t] = (uint16_t)cst;
         }
         __syncthreads();
-        for (int t = tid; t < n_octs; t += blockDim.x) {
+        // rank(t) = number of octs that come before t (higher cost, ties by index): one warp per oct, lanes over j
+        for (int t = warp; t < n_octs; t += n_warps) {
             const int ct = s_cost[t];
             int r = 0;
-            for (int j = 0; j < n_octs; ++j) {
-                const int cj = s_cost[j];
-                r += (cj > ct || (cj == ct && j < t)) ? 1 : 0;
+            for (int j0 = 0; j0 < n_octs; j0 += 32) {
+                const int j = j0 + lane;
+                const bool before = j < n_octs && (s_cost[j] > ct || (s_cost[j] == ct && j < t));
+                r += __popc(__ballot_sync(0xffffffffu, before));
             }
-            s_sorted[r] = (uint16_t)t;               // ties broken by index: every block computes the same ranking
+            if (lane == 0) s_sorted[r] = (uint16_t)t;
         }
         __syncthreads();
     }
     const int n_pairs = (n_octs + 1) / 2;
-    if (tid < W) {
-        const int pair = tid * n_parts + part;
+    for (int k = tid; k < n_parts * W; k += blockDim.x) {            // k = part * W + warp slot
+        const int part = k / W, w = k - part * W;
+        const int pair = w * n_parts + part;
         uint16_t qa = 0xffffu, qb = 0xffffu;
         if (pair < n_pairs) {
             const int ia = pair, ib = n_octs - 1 - pair;
             qa = balanced ? s_sorted[ia] : (uint16_t)ia;
             if (ib > ia) qb = balanced ? s_sorted[ib] : (uint16_t)ib;
         }
-        s_q[2 * tid] = qa;
-        s_q[2 * tid + 1] = qb;
-        if (v == 0) {
-            pairs[((int64_t)part * W + tid) * 2] = qa;
-            pairs[((int64_t)part * W + tid) * 2 + 1] = qb;
+        s_q[2 * k] = qa;
+        s_q[2 * k + 1] = qb;
+        pairs[2 * k] = qa;
+        pairs[2 * k + 1] = qb;
+    }
+    __syncthreads();
+    // rows per (part, view): thread = (part, view), loads in batches of 10 so that they overlap
+    for (int k = tid; k < n_parts * nv; k += blockDim.x) {
+        const int part = k / nv, v = k - part * nv;
+        const uint16_t *q = s_q + (size_t)part * 2 * W;
+        int c = 0;
+        for (int i0 = 0; i0 < 2 * W; i0 += 10) {
+            uint8_t m8[10];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                const uint16_t qq = i0 + j < 2 * W ? q[i0 + j] : (uint16_t)0xffffu;
+                m8[j] = qq != 0xffffu ? __ldg(omask + (int64_t)qq * nvp + v) : (uint8_t)0;
+            }
+#pragma unroll
+            for (int j = 0; j < 10; ++j) c += (m8[j] & 3u) ? 1 : 0;
+        }
+        s_c[(size_t)part * nvp + v] = (uint16_t)c;
+        rowcnt[(int64_t)part * nvp + v] = (uint16_t)c;
+    }
+    __syncthreads();
+    // first row of every view's block: rows + ring paddings (ring_pad) of the views before it; one warp per part
+    for (int part = warp; part < n_parts; part += n_warps) {
+        int tot = 0;
+        for (int v = lane; v < nv; v += 32) tot += (int)s_c[(size_t)part * nvp + v];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        const int pad_total = (ring_rows - tot % ring_rows) % ring_rows;
+        int base = 0;
+        for (int vb = 0; vb < nv; vb += 32) {
+            const int v = vb + lane;
+            const int eff = v < nv ? (int)s_c[(size_t)part * nvp + v] + pad_total / nv + (v < pad_total % nv ? 1 : 0) : 0;
+            int incl = eff;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (v < nv) gstart[(int64_t)part * nvp + v] = (uint32_t)(base + incl - eff);
+            base += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
-    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Compaction.  grid = (views, parts): the offset rows of the part's octs that see the view are copied into the
+// view's block (so that k_lift_planes fetches them with one bulk copy) and every warp gets its entry.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_plane_pack(int nv, int nvp, int W, int64_t n_pad, int64_t part_rows, const uint16_t *__restrict__ off16,
+             const uint8_t *__restrict__ omask, const uint16_t *__restrict__ pairs, const uint32_t *__restrict__ gstart,
+             uint16_t *__restrict__ offc, uint32_t *__restrict__ ents) {
+    __shared__ uint16_t s_q[2 * kPMaxWarps];       // octs of this part in slot order (warp w: 2 w, 2 w + 1)
+    __shared__ uint8_t s_m[2 * kPMaxWarps];        // their quad masks in this view
+    __shared__ uint8_t s_slot[2 * kPMaxWarps];     // their row slot in the view's block (0xff: not seen)
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // tables of k_plane_index / k_plane_rank
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // k_lift_planes may start streaming planes
+    const int v = blockIdx.x, part = blockIdx.y, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, n_warps = (int)(blockDim.x >> 5);
     if (tid < 2 * W) {
-        const uint16_t q = s_q[tid];
-        s_m[tid] = q != 0xffffu ? (uint8_t)(omask[(int64_t)q * nvp + v] & 3u) : (uint8_t)0;
+        const uint16_t q = __ldg(pairs + (int64_t)part * 2 * W + tid);
+        s_q[tid] = q;
+        s_m[tid] = q != 0xffffu ? (uint8_t)(__ldg(omask + (int64_t)q * nvp + v) & 3u) : (uint8_t)0;
     }
+    const int64_t g_start = (int64_t)__ldg(gstart + (int64_t)part * nvp + v);
     __syncthreads();
-    if (tid < 2 * W) {
-        int slot = 0;
-        for (int j = 0; j < tid; ++j) slot += s_m[j] ? 1 : 0;
-        s_slot[tid] = s_m[tid] ? (uint8_t)slot : (uint8_t)0xff;
-        if (tid == 2 * W - 1) rowcnt[(int64_t)part * nvp + v] = (uint16_t)(slot + (s_m[tid] ? 1 : 0));
+    if (warp == 0) {                                     // slot = number of active octs before this one (2 W <= 64)
+        const bool a0 = lane < 2 * W && s_m[lane] != 0, a1 = lane + 32 < 2 * W && s_m[lane + 32] != 0;
+        const unsigned b0 = __ballot_sync(0xffffffffu, a0), b1 = __ballot_sync(0xffffffffu, a1);
+        const unsigned below = (1u << lane) - 1u;
+        if (lane < 2 * W) s_slot[lane] = a0 ? (uint8_t)__popc(b0 & below) : (uint8_t)0xff;
+        if (lane + 32 < 2 * W) s_slot[lane + 32] = a1 ? (uint8_t)(__popc(b0) + __popc(b1 & below)) : (uint8_t)0xff;
     }
     __syncthreads();
     if (tid < W) {
@@ -295,12 +366,11 @@ k_plane_pack(int nv, int nvp, int nw16, int n_octs, int n_parts, int W, int64_t 
         const uint32_t e = qm ? ((uint32_t)v | (qm << 8) | ((uint32_t)s_slot[2 * tid] << 16) | ((uint32_t)s_slot[2 * tid + 1] << 24)) : 0u;
         ents[((int64_t)part * W + tid) * nvp + v] = e;
     }
-    // compacted rows: one warp per row, 16 B per lane
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int i = warp; i < 2 * W; i += (int)(blockDim.x >> 5)) {
+    // rows: one warp per row, 16 B per lane
+    for (int i = warp; i < 2 * W; i += n_warps) {
         if (!s_m[i]) continue;
         const uint4 *src = reinterpret_cast<const uint4 *>(off16 + (int64_t)v * n_pad + (int64_t)s_q[i] * kOct);
-        uint4 *dst = reinterpret_cast<uint4 *>(offc + (((int64_t)part * nv + v) * (2 * W) + s_slot[i]) * kOct);
+        uint4 *dst = reinterpret_cast<uint4 *>(offc + ((int64_t)part * part_rows + g_start + s_slot[i]) * kOct);
         dst[lane] = src[lane];
     }
 }
@@ -308,6 +378,22 @@ k_plane_pack(int nv, int nvp, int nw16, int n_octs, int n_parts, int W, int64_t 
 // ---------------------------------------------------------------------------------------------
 // Gather + statistics with the planes of one channel streamed through shared memory.
 // ---------------------------------------------------------------------------------------------
+// flag words in shared memory (release / acquire at CTA scope): the per-stage hand-shake between 25 consumer warps
+// and the producers goes through these instead of mbarriers -- 50 mbarrier operations per stage (25 arrivals plus
+// 25 waits on one barrier word) were measured at ~700 cycles per stage and paced the whole ring
+// Plain volatile accesses, no fences: a warp's shared-memory instructions execute in program order in the SM's
+// load/store pipeline, so the flag store follows the warp's gathers of the stage, and data written by a bulk copy
+// is in shared memory before the copy's mbarrier completes (which the forwarder observes before it raises `ready`).
+// (st.release / ld.acquire cost ~200 / ~130 cycles each here -- a fence per stage and warp.)
+__device__ __forceinline__ void st_release(uint32_t addr, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 template <typename T>
 __device__ __forceinline__ void gather_quad(uint32_t sb, uint32_t w0, uint32_t w1, unsigned long long &s1a,
                                             unsigned long long &s2a, unsigned long long &s1b,
@@ -336,13 +422,13 @@ __device__ __forceinline__ int ring_pad(int total_rows, int R, int nv, int v) {
 // entry of the active-view list: view | quad mask << 8 | ring row of oct A << 12 | ring row of oct B << 22
 constexpr int kPMaxRingRows = 1023;
 
-template <typename T, bool kRaw, bool kDiag>
-__global__ void __launch_bounds__((kPMaxWarps + 1) * 32, 1)
+template <typename T, bool kRaw, bool kDiag, int kG>
+__global__ void __launch_bounds__((kPMaxWarps + 3) * 32, 1)
 k_lift_planes(const PlaneArgs a) {
-    const int S = a.stages;
+    const int S = a.stages;                                        // stages of kG consecutive views each
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int W = (blockDim.x >> 5) - 1;                           // compute warps
+    const int W = (blockDim.x >> 5) - 3;                           // compute warps (+ plane producer, row producer, forwarder)
     // persistent CTA: units blockIdx.x, blockIdx.x + gridDim.x, ...; gridDim.x is a multiple of n_parts,
     // so the part (and with it every oct-dependent table) is the same for all units of a CTA
     const int part = blockIdx.x % a.n_parts;
@@ -350,50 +436,78 @@ k_lift_planes(const PlaneArgs a) {
 
     // plane ring (S slots), offset-row ring (R rows); then the barriers, the per-view row counts and the active-view lists
     const int R = a.ring_rows;
-    const uint32_t row_base = smem_u32(smem) + (uint32_t)S * a.plane_pitch;
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + (size_t)S * a.plane_pitch + (size_t)R * kRowBytes);
-    uint16_t *s_cnt = reinterpret_cast<uint16_t *>(bars + 2 * S);                                          // [nvp] rows to copy
+    const uint32_t stage_pitch = (uint32_t)kG * a.plane_pitch;
+    const uint32_t row_base = smem_u32(smem) + (uint32_t)S * stage_pitch;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + (size_t)S * stage_pitch + (size_t)R * kRowBytes);
+    uint32_t *s_flags = reinterpret_cast<uint32_t *>(bars + 2 * S);                                        // [32] progress of the warps, [32] ready
+    uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_flags + 64);                                          // [nvp] rows to copy
     uint16_t *s_eff = s_cnt + a.nvp;                                                                        // [nvp] rows of ring space
-    uint32_t *s_lists = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(s_cnt) + (((size_t)a.nvp * 4 + 15) & ~(size_t)15));
+    uint16_t *s_pos = s_eff + a.nvp;                                                                        // [stages per unit] first ring row
+    uint16_t *s_sn = s_pos + a.nvp;                                                                         // [stages per unit] ring rows
+    uint16_t *s_lag = s_sn + a.nvp;                                                                         // [stages per unit] see below
+    uint32_t *s_grow = reinterpret_cast<uint32_t *>(s_lag + a.nvp);                                         // [stages per unit] first row in the part's table
+    uint32_t *s_lists = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(s_cnt) + (((size_t)a.nvp * 14 + 15) & ~(size_t)15));
     const uint32_t sm_base = smem_u32(smem);
-    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + S);
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t f_progress = smem_u32(s_flags), f_ready = smem_u32(s_flags + 32);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, (uint32_t)W);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < S; i += blockDim.x)              // the zero word behind every plane slot
+    if (threadIdx.x < 64) s_flags[threadIdx.x] = 0u;
+    for (int i = threadIdx.x; i < S * kG; i += blockDim.x)         // the zero word behind every plane slot
         *reinterpret_cast<uint32_t *>(smem + (size_t)i * a.plane_pitch + a.plane_bytes) = 0u;
     __syncthreads();
 
     const long long t_cta = kDiag ? clock64() : 0;
-    if (warp == W) {
-        // ---------------- producer warp: streams (plane, offset block) per view of this CTA's units ----------------
-        // One lane issues everything; its loop is kept free of integer divisions (a runtime div / mod costs
-        // ~100 cycles of dependent latency, and five of them per view made this thread the bottleneck of the CTA).
+    if (warp == W + 2) {
+        // ---------------- forwarder: turns the completion of a stage's bulk copies (mbarrier) into a flag word ----------------
+        const int n_my = blockIdx.x < a.n_units ? (a.n_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int total = n_my * ((a.nv + kG - 1) / kG);
+        int s = 0;
+        uint32_t par = 0;
+        for (int i = 0; i < total; ++i) {
+            mbar_wait(bar_full + 8 * s, par);
+            if (lane == 0) st_release(f_ready, (uint32_t)(i + 1));
+            if (++s == S) { s = 0; par ^= 1u; }
+        }
+        return;
+    }
+    if (warp >= W) {
+        // ---------------- two producer warps: warp W streams the planes, warp W + 1 the offset rows ----------------
+        // Their loops are kept free of integer divisions and of everything that can be tabulated: one elected
+        // thread issuing ~100 dependent instructions per view was the bottleneck of the whole CTA.
+        const bool plane_warp = warp == W;
         const int64_t view_bytes = a.sv * (int64_t)sizeof(T);
         const int n_my = blockIdx.x < a.n_units ? (a.n_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-        const int total = n_my * a.nv;                             // stages this CTA runs through
+        const int spu = (a.nv + kG - 1) / kG;                      // stages per unit
+        const int total = n_my * spu;                              // stages this CTA runs through
         const int pre = min(S, total);
         const char *feat = reinterpret_cast<const char *>(a.feat);
         const int64_t chan_bytes = a.sc * (int64_t)sizeof(T);
         const bool copy_planes = !kDiag || !(a.debug & 4);
-        // the planes are kernel inputs, not products of the index / pack kernels: the first S planes start
-        // streaming before the dependency wait; their barriers get the arrival (and the offset bytes) afterwards
-        if (lane == 0 && copy_planes) {
+        // the planes are kernel inputs, not products of the index / pack kernels: the planes of the first S stages
+        // start streaming before the dependency wait; their barriers get the arrival (and the offset bytes) afterwards
+        if (plane_warp && lane == 0 && copy_planes) {
             int u = blockIdx.x, v = 0;
             const char *src = feat + (int64_t)(u / a.n_parts) * chan_bytes;
             for (int i = 0; i < pre; ++i) {
-                mbar_expect_tx_only(bar_full + 8 * i, a.plane_bytes);
-                bulk_g2s(sm_base + (uint32_t)i * a.plane_pitch, src, a.plane_bytes, bar_full + 8 * i);
-                src += view_bytes;
-                if (++v == a.nv) { v = 0; u += gridDim.x; src = feat + (int64_t)(u / a.n_parts) * chan_bytes; }
+                const int nvs = min(kG, a.nv - v);
+                mbar_expect_tx_only(bar_full + 8 * i, (uint32_t)nvs * a.plane_bytes);
+                for (int g = 0; g < nvs; ++g)
+                    bulk_g2s(sm_base + (uint32_t)(i * kG + g) * a.plane_pitch, src + g * view_bytes, a.plane_bytes, bar_full + 8 * i);
+                src += nvs * view_bytes;
+                v += nvs;
+                if (v == a.nv) { v = 0; u += gridDim.x; src = feat + (int64_t)(u / a.n_parts) * chan_bytes; }
             }
         }
         asm volatile("griddepcontrol.wait;" ::: "memory");         // row counts / offset blocks come from k_plane_pack
+        // Per-stage tables (both warps compute the same values): ring rows s_sn (rows + paddings of the stage's views),
+        // first ring row s_pos, first row in the part's table s_grow, and s_lag = how many of the preceding stages may
+        // still be unreleased when the stage's rows are written (they must fit the ring together; < S).
         int tot = 0;
         for (int v = lane; v < a.nv; v += 32) {
             const int c = (int)a.rowcnt[(int64_t)part * a.nvp + v];
@@ -405,61 +519,76 @@ k_lift_planes(const PlaneArgs a) {
         for (int v = lane; v < a.nv; v += 32) s_eff[v] = (uint16_t)((int)s_cnt[v] + ring_pad(tot, R, a.nv, v));
         __syncwarp();
         if (lane == 0) {
-            const char *off_base = reinterpret_cast<const char *>(a.offc) + (int64_t)part * a.nv * (2 * W) * kRowBytes;
-            const uint32_t block_bytes = (uint32_t)(2 * W) * kRowBytes;
-            int n_tr = 0;
-            // stage i: slot s, view v of unit u;  oldest unreleased stage: slot o_s, parity o_par, view o_v
-            int s = 0, v = 0, u = blockIdx.x;
-            const char *psrc = feat + (int64_t)(u / a.n_parts) * chan_bytes;
-            const char *osrc = off_base;
-            int oldest = 0, o_s = 0, o_v = 0;
-            uint32_t o_par = 0;
-            int rows_in_flight = 0, ring_pos = 0;
-            for (int i = 0; i < total; ++i) {
-                const int n_rows = (int)s_cnt[v], n_eff = (int)s_eff[v];
-                const uint32_t fb = bar_full + 8 * s;
-                // the plane slot is free once stage i - S is released; the rows need room in the row ring
-                const long long tp0 = kDiag && a.trace != nullptr ? clock64() : 0;
-                while (oldest <= i - S || rows_in_flight + n_eff > R) {
-                    mbar_wait(bar_empty + 8 * o_s, o_par);
-                    rows_in_flight -= (int)s_eff[o_v];
-                    ++oldest;
-                    if (++o_s == S) { o_s = 0; o_par ^= 1u; }
-                    if (++o_v == a.nv) o_v = 0;
+            int g_row = 0;
+            for (int j = 0; j < spu; ++j) {
+                int n = 0;
+                for (int g = 0; g < kG && j * kG + g < a.nv; ++g) n += (int)s_eff[j * kG + g];
+                s_sn[j] = (uint16_t)n;
+                s_grow[j] = (uint32_t)g_row;
+                s_pos[j] = (uint16_t)(g_row % R);
+                g_row += n;
+            }
+            for (int j = 0; j < spu; ++j) {
+                int sum = (int)s_sn[j], d = 0, k = j;
+                while (d < S - 1) {
+                    k = k == 0 ? spu - 1 : k - 1;
+                    if (sum + (int)s_sn[k] > R) break;
+                    sum += (int)s_sn[k];
+                    ++d;
                 }
-                if (kDiag && a.trace != nullptr && blockIdx.x == 0 && n_tr < 256) {
-                    int *t = a.trace + ((size_t)W * 256 + n_tr) * 4;
-                    t[0] = (int)(tp0 - t_cta);
-                    t[1] = (int)(clock64() - t_cta);
-                    t[2] = rows_in_flight;
-                    t[3] = i - oldest;
-                    ++n_tr;
-                }
-                const uint32_t off_bytes = (uint32_t)n_rows * kRowBytes;
-                if (i >= pre && copy_planes) {
-                    mbar_expect_tx(fb, a.plane_bytes + off_bytes);
-                    bulk_g2s(sm_base + (uint32_t)s * a.plane_pitch, psrc, a.plane_bytes, fb);
-                } else {
-                    mbar_expect_tx(fb, off_bytes);                  // (i < pre: the plane bytes were announced above)
-                }
-                if (n_rows != 0) {
-                    const int first = min(n_rows, R - ring_pos);
-                    bulk_g2s(row_base + (uint32_t)ring_pos * kRowBytes, osrc, (uint32_t)first * kRowBytes, fb);
-                    if (n_rows > first)                             // the block wraps around the end of the ring
-                        bulk_g2s(row_base, osrc + (size_t)first * kRowBytes, (uint32_t)(n_rows - first) * kRowBytes, fb);
-                }
-                ring_pos += n_eff;
-                if (ring_pos >= R) ring_pos -= R;
-                rows_in_flight += n_eff;
-                if (++s == S) s = 0;
-                psrc += view_bytes;
-                osrc += block_bytes;
-                if (++v == a.nv) {                                  // next unit of this CTA: one division per unit
-                    v = 0;
-                    u += gridDim.x;
-                    psrc = feat + (int64_t)(u / a.n_parts) * chan_bytes;
-                    osrc = off_base;
-                }
+                s_lag[j] = (uint16_t)d;
+            }
+        }
+        __syncwarp();
+        const char *off_part = reinterpret_cast<const char *>(a.offc) + (int64_t)part * a.part_rows * kRowBytes;
+        int n_tr = 0;
+        // stage i = (unit u, stage j of the unit): slot s
+        int s = 0, j = 0, u = blockIdx.x;
+        const char *psrc = feat + (int64_t)(u / a.n_parts) * chan_bytes;
+        int released = 0;                                          // stages every consumer warp is done with
+        for (int i = 0; i < total; ++i) {
+            const int n = (int)s_sn[j];
+            const uint32_t fb = bar_full + 8 * s;
+            // planes: the slots are free once stage i - S is released; rows: stages older than i - lag released
+            const int need = plane_warp ? i - S + 1 : i - (int)s_lag[j];
+            const long long tp0 = kDiag && a.trace != nullptr ? clock64() : 0;
+            if (released < need) {
+                do {                                                // lane w reads the progress word of consumer warp w
+                    const uint32_t pr = lane < W ? ld_acquire(f_progress + 4 * lane) : 0x7fffffffu;
+                    released = (int)__reduce_min_sync(0xffffffffu, pr);
+                } while (released < need);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // their reads before our async-proxy writes
+            }
+            if (kDiag && a.trace != nullptr && blockIdx.x == 0 && lane == 0 && plane_warp && n_tr < 256) {
+                int *t = a.trace + ((size_t)W * 256 + n_tr) * 4;
+                t[0] = (int)(tp0 - t_cta);
+                t[1] = (int)(clock64() - t_cta);
+                t[2] = n;
+                t[3] = i - released;
+                ++n_tr;
+            }
+            if (plane_warp) {
+                const int nvs = min(kG, a.nv - j * kG);
+                const bool with_planes = i >= pre && copy_planes;   // (i < pre: the plane bytes were announced above)
+                if (lane == 0)
+                    mbar_expect_tx(fb, (with_planes ? (uint32_t)nvs * a.plane_bytes : 0u) + (uint32_t)n * kRowBytes);
+                __syncwarp();
+                if (with_planes && lane < nvs)
+                    bulk_g2s(sm_base + (uint32_t)(s * kG + lane) * a.plane_pitch, psrc + lane * view_bytes, a.plane_bytes, fb);
+                psrc += nvs * view_bytes;
+            } else if (lane == 0 && n != 0) {
+                const char *src = off_part + (size_t)s_grow[j] * kRowBytes;
+                const int pos = (int)s_pos[j];
+                const int first = min(n, R - pos);
+                bulk_g2s(row_base + (uint32_t)pos * kRowBytes, src, (uint32_t)first * kRowBytes, fb);
+                if (n > first)                                      // the block wraps around the end of the ring
+                    bulk_g2s(row_base, src + (size_t)first * kRowBytes, (uint32_t)(n - first) * kRowBytes, fb);
+            }
+            if (++s == S) s = 0;
+            if (++j == spu) {                                       // next unit of this CTA: one division per unit
+                j = 0;
+                u += gridDim.x;
+                psrc = feat + (int64_t)(u / a.n_parts) * chan_bytes;
             }
         }
         return;
@@ -527,8 +656,9 @@ k_lift_planes(const PlaneArgs a) {
     }
 
     int s = 0, n_tr = 0;
-    uint32_t parity = 0;
-    uint32_t fa = bar_full, ea = bar_empty, sb = sm_base;          // barriers and plane of the current stage
+    uint32_t sb = sm_base;                                         // planes of the current stage
+    uint32_t gi = 0, ready = 0;                                    // stages this warp is done with / known to have landed
+    const uint32_t my_progress = f_progress + 4 * warp;
     const uint32_t lane_row = row_base + lane * (kOV * 2);
     const bool do_gather = !kDiag || !(a.debug & 1);
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
@@ -539,29 +669,34 @@ k_lift_planes(const PlaneArgs a) {
         const uint32_t *ap = act;
         uint32_t ent = *ap;
 
-        for (int v = 0; v < a.nv; ++v) {
+        for (int v0 = 0; v0 < a.nv; v0 += kG) {
             const long long tc0 = kDiag && a.trace != nullptr ? clock64() : 0;
-            mbar_wait(fa, parity);
+            while (ready <= gi) ready = ld_acquire(f_ready);       // the forwarder publishes the number of landed stages
             const long long tc1 = kDiag && a.trace != nullptr ? clock64() : 0;
             int n_ent = 0;
-            if ((ent & 0xffu) == (uint32_t)v) {                    // warp-uniform: the list is per warp
-                if (do_gather) {
-                    if (ent & 0x300u) {
-                        const uint4 c0 = lds_u4(lane_row + ((ent >> 12) & 0x3ffu) * kRowBytes);
-                        if (ent & 0x100u) gather_quad<T>(sb, c0.x, c0.y, s1[0], s2[0], s1[1], s2[1]);
-                        if (ent & 0x200u) gather_quad<T>(sb, c0.z, c0.w, s1[2], s2[2], s1[3], s2[3]);
+#pragma unroll
+            for (int g = 0; g < kG; ++g) {
+                if ((ent & 0xffu) == (uint32_t)(v0 + g)) {         // warp-uniform: the list is per warp
+                    if (do_gather) {
+                        const uint32_t pb = sb + (uint32_t)g * a.plane_pitch;
+                        if (ent & 0x300u) {
+                            const uint4 c0 = lds_u4(lane_row + ((ent >> 12) & 0x3ffu) * kRowBytes);
+                            if (ent & 0x100u) gather_quad<T>(pb, c0.x, c0.y, s1[0], s2[0], s1[1], s2[1]);
+                            if (ent & 0x200u) gather_quad<T>(pb, c0.z, c0.w, s1[2], s2[2], s1[3], s2[3]);
+                        }
+                        if (ent & 0xc00u) {
+                            const uint4 c1 = lds_u4(lane_row + (ent >> 22) * kRowBytes);
+                            if (ent & 0x400u) gather_quad<T>(pb, c1.x, c1.y, s1[4], s2[4], s1[5], s2[5]);
+                            if (ent & 0x800u) gather_quad<T>(pb, c1.z, c1.w, s1[6], s2[6], s1[7], s2[7]);
+                        }
                     }
-                    if (ent & 0xc00u) {
-                        const uint4 c1 = lds_u4(lane_row + (ent >> 22) * kRowBytes);
-                        if (ent & 0x400u) gather_quad<T>(sb, c1.x, c1.y, s1[4], s2[4], s1[5], s2[5]);
-                        if (ent & 0x800u) gather_quad<T>(sb, c1.z, c1.w, s1[6], s2[6], s1[7], s2[7]);
-                    }
+                    ent = *++ap;
+                    ++n_ent;
                 }
-                ent = *++ap;
-                n_ent = 1;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(ea);
+            ++gi;
+            if (lane == 0) st_release(my_progress, gi);
             if (kDiag && a.trace != nullptr && blockIdx.x == 0 && lane == 0 && n_tr < 256) {
                 int *t = a.trace + ((size_t)warp * 256 + n_tr) * 4;
                 t[0] = (int)(tc0 - t_cta);
@@ -570,8 +705,8 @@ k_lift_planes(const PlaneArgs a) {
                 t[3] = n_ent;
                 ++n_tr;
             }
-            fa += 8; ea += 8; sb += a.plane_pitch;
-            if (++s == S) { s = 0; parity ^= 1u; fa = bar_full; ea = bar_empty; sb = sm_base; }
+            sb += stage_pitch;
+            if (++s == S) { s = 0; sb = sm_base; }
         }
         if (kDiag && (a.debug & 16)) continue;
 
@@ -647,12 +782,12 @@ void set_lift_trace(int *buf) { g_trace = buf; }
 
 struct PlaneGeom {
     Tiling tiling;
-    int elt, n_pix, nw16, nvp, n_octs, n_pairs, n_parts, warps, stages, grid;
-    int64_t n_pad;
+    int elt, n_pix, nw16, nvp, n_octs, n_pairs, n_parts, warps, stages, group, grid;
+    int64_t n_pad, part_rows;
     uint32_t plane_bytes, plane_pitch;
     int ring_rows;
-    size_t off_bytes, cnt_bytes, mask_bytes, cost_bytes, offc_bytes, rowcnt_bytes, ents_bytes, pairs_bytes, total_bytes,
-        smem_bytes;
+    size_t off_bytes, cnt_bytes, mask_bytes, cost_bytes, offc_bytes, rowcnt_bytes, ents_bytes, pairs_bytes, gstart_bytes,
+        total_bytes, smem_bytes;
 };
 
 static bool plane_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *opt, PlaneGeom &g) {
@@ -666,8 +801,8 @@ static bool plane_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *o
         return false;
     if (f->n_views > 254) return false;                                     // uint8 view counts, view 255 = list sentinel
     g.plane_bytes = (uint32_t)pb;
-    g.nw16 = (f->n_views + 15) / 16;
-    g.nvp = g.nw16 * 16;
+    g.nw16 = (f->n_views + kIdxViews - 1) / kIdxViews;      // view groups of the index pass
+    g.nvp = g.nw16 * kIdxViews;
     g.tiling = Tiling{0, 0, 0, 0, 0};
     g.n_octs = (int)ceil_div(n_vox, kOct);
     if (g.n_octs > 65000) return false;                                     // uint16 oct ids
@@ -682,8 +817,10 @@ static bool plane_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *o
     }
     g.n_pad = (int64_t)g.n_octs * kOct;
     g.n_pairs = (g.n_octs + 1) / 2;
-    int max_warps = kPMaxWarps, stages = 0;
+    int max_warps = kPMaxWarps, stages = 0, group = 2;
     if (const char *e = getenv("ND_LIFT_STAGES")) stages = atoi(e);         // tuning knobs for tools/lift_probe.py
+    if (const char *e = getenv("ND_LIFT_GROUP")) group = atoi(e);
+    if (group != 1 && group != 2 && group != 4) group = 2;
     if (const char *e = getenv("ND_LIFT_WARPS")) {
         const int v = atoi(e);
         if (v >= 1 && v < max_warps) max_warps = v;
@@ -691,22 +828,35 @@ static bool plane_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *o
     g.n_parts = (int)ceil_div(g.n_pairs, max_warps);
     g.warps = (int)ceil_div(g.n_pairs, g.n_parts);
     g.plane_pitch = (uint32_t)align_up((size_t)pb + 16, 128);
-    const size_t fixed = 2 * kPMaxStages * 8 + align_up((size_t)g.nvp * 4, 16) + (size_t)g.warps * (f->n_views + 1) * 4 + 16;
+    const size_t fixed = 2 * kPMaxStages * 8 + 256 + align_up((size_t)g.nvp * 14, 16) + (size_t)g.warps * (f->n_views + 1) * 4 + 16;
     const size_t avail = (size_t)(227 * 1024) - fixed;
     // plane slots S and offset rows R share the rest: R must hold the largest block (2 W rows); by default every
     // stage in flight gets room for about half of the part's octs (the typical share that sees a view)
-    const size_t min_rows = (size_t)2 * g.warps;
-    if (avail < 2 * (size_t)g.plane_pitch + min_rows * kRowBytes) return false;
+    const size_t min_rows = (size_t)2 * g.warps * group;                        // one stage's worst case
+    const size_t stage_bytes = (size_t)group * g.plane_pitch;
+    while (group > 1 && avail < 2 * stage_bytes + min_rows * kRowBytes) group >>= 1;
+    if (avail < 2 * (size_t)group * g.plane_pitch + (size_t)2 * g.warps * group * kRowBytes) return false;
+    const size_t sb = (size_t)group * g.plane_pitch, mr = (size_t)2 * g.warps * group;
     if (stages <= 0) {
+        // default: as many stages as fit (at most 8 plane slots) while the row ring keeps room for about half of
+        // the part's octs (the typical share that sees a view) per view in flight
         stages = 2;
-        while (stages < 8 && (size_t)(stages + 1) * g.plane_pitch + std::max(min_rows, (size_t)(stages + 1) * g.warps) * kRowBytes <= avail)
+        while ((stages + 1) * group <= 8 &&
+               (size_t)(stages + 1) * sb + std::max(mr, (size_t)(stages + 1) * group * g.warps) * kRowBytes <= avail)
             ++stages;
     }
     if (stages < 2) stages = 2;
     if (stages > kPMaxStages) stages = kPMaxStages;
-    while (stages > 2 && (size_t)stages * g.plane_pitch + min_rows * kRowBytes > avail) --stages;
-    g.ring_rows = (int)((avail - (size_t)stages * g.plane_pitch) / kRowBytes);
-    if (g.ring_rows > kPMaxRingRows) g.ring_rows = kPMaxRingRows;
+    while (stages > 2 && (size_t)stages * sb + mr * kRowBytes > avail) --stages;
+    g.group = group;
+    for (;;) {
+        g.ring_rows = (int)((avail - (size_t)stages * sb) / kRowBytes);
+        if (g.ring_rows > kPMaxRingRows) g.ring_rows = kPMaxRingRows;
+        // one stage (rows of all the part's octs plus the ring paddings of its views) must fit the ring
+        if (g.ring_rows >= group * (2 * g.warps + g.ring_rows / f->n_views + 1)) break;
+        if (stages <= 2) return false;
+        --stages;
+    }
     g.stages = stages;
     // persistent grid: one CTA per SM, a multiple of n_parts (see k_lift_planes)
     int sms = 148;
@@ -723,14 +873,16 @@ static bool plane_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *o
     g.cnt_bytes = align_up((size_t)g.nw16 * g.n_pad, 256);
     g.mask_bytes = align_up((size_t)g.n_octs * g.nvp, 256);
     g.cost_bytes = align_up((size_t)g.nw16 * g.n_octs, 256);
-    g.offc_bytes = align_up((size_t)g.n_parts * f->n_views * 2 * g.warps * kRowBytes, 256);
+    g.part_rows = (int64_t)f->n_views * 2 * g.warps + g.ring_rows;      // rows + paddings of one part, upper bound
+    g.offc_bytes = align_up((size_t)g.n_parts * (size_t)g.part_rows * kRowBytes, 256);
     g.rowcnt_bytes = align_up((size_t)g.n_parts * g.nvp * sizeof(uint16_t), 256);
     g.ents_bytes = align_up((size_t)g.n_parts * g.warps * g.nvp * sizeof(uint32_t), 256);
     g.pairs_bytes = align_up((size_t)g.n_parts * g.warps * 2 * sizeof(uint16_t), 256);
+    g.gstart_bytes = align_up((size_t)g.n_parts * g.nvp * sizeof(uint32_t), 256);
     g.total_bytes = g.off_bytes + g.cnt_bytes + g.mask_bytes + g.cost_bytes + g.offc_bytes + g.rowcnt_bytes + g.ents_bytes +
-                    g.pairs_bytes;
-    g.smem_bytes = (size_t)g.stages * g.plane_pitch + (size_t)g.ring_rows * kRowBytes + 2 * g.stages * 8 +
-                   align_up((size_t)g.nvp * 4, 16) + (size_t)g.warps * (f->n_views + 1) * 4;
+                    g.pairs_bytes + g.gstart_bytes;
+    g.smem_bytes = (size_t)g.stages * g.group * g.plane_pitch + (size_t)g.ring_rows * kRowBytes + 2 * g.stages * 8 + 256 +
+                   align_up((size_t)g.nvp * 14, 16) + (size_t)g.warps * (f->n_views + 1) * 4;
     return true;
 }
 
@@ -779,7 +931,8 @@ nd_status run_lift_planes(const nd_maps *f, const float *points, const float *pr
     uint16_t *offc = reinterpret_cast<uint16_t *>(wsb);             wsb += g.offc_bytes;
     uint16_t *rowcnt = reinterpret_cast<uint16_t *>(wsb);           wsb += g.rowcnt_bytes;
     uint32_t *ents = reinterpret_cast<uint32_t *>(wsb);             wsb += g.ents_bytes;
-    uint16_t *pairs = reinterpret_cast<uint16_t *>(wsb);
+    uint16_t *pairs = reinterpret_cast<uint16_t *>(wsb);            wsb += g.pairs_bytes;
+    uint32_t *gstart = reinterpret_cast<uint32_t *>(wsb);
 
     int debug = 0;
     if (const char *e = getenv("ND_LIFT_DEBUG")) debug = atoi(e);
@@ -788,11 +941,17 @@ nd_status run_lift_planes(const nd_maps *f, const float *points, const float *pr
         off16, cnt8, omask, cost16);
     ND_CUDA_LAUNCH_CHECK("k_plane_index");
     const int balanced = (g.n_octs <= kPMaxOcts && !(debug & 32)) ? 1 : 0;
-    cudaError_t e = launch_pdl(k_plane_pack, dim3((unsigned)f->n_views, (unsigned)g.n_parts), dim3(256), 0, st, (int)f->n_views,
-                               g.nvp, g.nw16, g.n_octs, g.n_parts, g.warps, g.n_pad, balanced, (const uint16_t *)off16,
-                               (const uint8_t *)omask, (const uint8_t *)cost16, offc, rowcnt, ents, pairs);
+    const size_t rank_smem = ((size_t)g.n_parts * 2 * g.warps + (size_t)g.n_parts * g.nvp) * sizeof(uint16_t);
+    ND_REQUIRE(rank_smem <= 40 * 1024, ND_ERR_BAD_SHAPE, "lift: too many parts x views for the pairing pass (%zu bytes)", rank_smem);
+    cudaError_t e = launch_pdl(k_plane_rank, dim3(1), dim3(1024), rank_smem, st, (int)f->n_views, g.nvp, g.nw16, g.n_octs,
+                               g.n_parts, g.warps, balanced, g.ring_rows, (const uint8_t *)omask, (const uint8_t *)cost16, pairs,
+                               rowcnt, gstart);
+    if (e == cudaSuccess)
+        e = launch_pdl(k_plane_pack, dim3((unsigned)f->n_views, (unsigned)g.n_parts), dim3(256), 0, st, (int)f->n_views, g.nvp,
+                       g.warps, g.n_pad, g.part_rows, (const uint16_t *)off16, (const uint8_t *)omask, (const uint16_t *)pairs,
+                       (const uint32_t *)gstart, offc, ents);
     if (e != cudaSuccess) {
-        set_error("k_plane_pack: CUDA error %s", cudaGetErrorString(e));
+        set_error("k_plane_rank / k_plane_pack: CUDA error %s", cudaGetErrorString(e));
         return ND_ERR_CUDA;
     }
 
@@ -800,6 +959,7 @@ nd_status run_lift_planes(const nd_maps *f, const float *points, const float *pr
     a.tiling = g.tiling;
     a.cnt8 = cnt8;
     a.offc = offc;
+    a.part_rows = g.part_rows;
     a.rowcnt = rowcnt;
     a.ents = ents;
     a.pairs = pairs;
@@ -817,6 +977,7 @@ nd_status run_lift_planes(const nd_maps *f, const float *points, const float *pr
     a.plane_bytes = g.plane_bytes;
     a.plane_pitch = g.plane_pitch;
     a.stages = g.stages;
+    a.group = g.group;
     a.ring_rows = g.ring_rows;
     a.trace = g_trace;
     a.debug = debug;
@@ -827,13 +988,19 @@ nd_status run_lift_planes(const nd_maps *f, const float *points, const float *pr
     a.count_i64 = count_i64;
     a.count_f32 = count_f32;
     // the diagnostics build (debug switches, clock trace) is a separate instantiation: the product kernel carries none of it
-    auto kern = (debug != 0 || g_trace != nullptr) ? k_lift_planes<T, kRaw, true> : k_lift_planes<T, kRaw, false>;
+    const bool diag = debug != 0 || g_trace != nullptr;
+    void (*kern)(const PlaneArgs) = nullptr;
+    switch (g.group) {
+        case 1: kern = diag ? k_lift_planes<T, kRaw, true, 1> : k_lift_planes<T, kRaw, false, 1>; break;
+        case 2: kern = diag ? k_lift_planes<T, kRaw, true, 2> : k_lift_planes<T, kRaw, false, 2>; break;
+        default: kern = diag ? k_lift_planes<T, kRaw, true, 4> : k_lift_planes<T, kRaw, false, 4>; break;
+    }
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
     if (e != cudaSuccess) {
         set_error("k_lift_planes: cannot reserve %zu bytes of shared memory: %s", g.smem_bytes, cudaGetErrorString(e));
         return ND_ERR_CUDA;
     }
-    e = launch_pdl(kern, dim3((unsigned)g.grid), dim3((unsigned)(g.warps + 1) * 32), g.smem_bytes, st, a);
+    e = launch_pdl(kern, dim3((unsigned)g.grid), dim3((unsigned)(g.warps + 3) * 32), g.smem_bytes, st, a);
     if (e != cudaSuccess) {
         set_error("k_lift_planes: CUDA error %s", cudaGetErrorString(e));
         return ND_ERR_CUDA;

@@ -46,3 +46,9 @@ for w in range(25):
 print('stage end time of the slowest warp, first 30 stages:', cons[:, :30, 2].max(axis=0).tolist())
 print('producer: (wait begin, wait end) first 12 stages:', t[25, :12, :2].tolist())
 np.save(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'gpurun_out', 'lift_trace.npy'), t)
+# producer (plane warp) per-stage detail: wait begin, wait end, gap to the next wait begin
+pr = t[25, :n_st if n_st < 256 else 255]
+print('producer stages 20..40: (wait, issue-to-next-wait):', [(int(pr[i, 1] - pr[i, 0]), int(pr[i + 1, 0] - pr[i, 1])) for i in range(20, 40)])
+c0 = t[0]
+print('consumer warp 0 stages 20..40: (wait, work):', [(int(c0[i, 1] - c0[i, 0]), int(c0[i, 2] - c0[i, 1])) for i in range(20, 40)])
+print('consumer warp 0 stage period:', [int(c0[i + 1, 0] - c0[i, 0]) for i in range(20, 40)])
