@@ -172,6 +172,18 @@ int nd_nerf_mlp_fwd(const nd_mlp_weights *arch, const void *packed, const float 
                     const float *cond, int64_t n_points, int samples_per_ray, float *sigma, float *alpha, float *rgb,
                     void *stream);
 
+/* The same network on the tcgen05 tensor cores: bf16 operands, fp32 accumulation in tensor memory (csrc/mlp_tc.cu).
+ * This is the path BASELINE.json's 1e-2 (bf16) tolerance applies to; nd_nerf_mlp_fwd stays the 1e-4 (fp32) one.
+ * Own packed layout (every 64-column K block of every layer stored as the shared-memory image of a K-major
+ * 128-byte-swizzled UMMA operand, then biases / head rows in fp32); `packed` must be 256-byte aligned.
+ * Supported: net_width 256, net_width_condition 128, 63 + feature_dim <= 144, octaves 10 / 4, net_depth <= 8
+ * (nd_mlp_tc_packed_bytes returns 0 otherwise).  Same arguments and outputs as nd_nerf_mlp_fwd. */
+size_t nd_mlp_tc_packed_bytes(const nd_mlp_weights *w);
+int nd_pack_mlp_weights_tc(const nd_mlp_weights *w, void *packed, size_t packed_bytes, void *stream);
+int nd_nerf_mlp_fwd_tc(const nd_mlp_weights *arch, const void *packed, const float *x, const float *features,
+                       const float *cond, int64_t n_points, int samples_per_ray, float *sigma, float *alpha, float *rgb,
+                       void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * R2  render_ray.py:145-189  sample_along_camera_ray: z_vals [R][S] = near + i * (far - near) / (S - 1), optional
  * stratified jitter with caller-supplied uniforms t_rand [R][S] (torch.rand_like drawn by the caller; NULL = det),

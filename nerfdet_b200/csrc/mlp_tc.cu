@@ -1,0 +1,712 @@
+// The shared NeRF / geometry MLP on the 5th-generation tensor cores (row M of SURVEY.md section 8a;
+// reference nerf_mlp.py:11-234 as instantiated at nerfdet.py:62-69).  bf16 operands, fp32 accumulation
+// in tensor memory: this is the path BASELINE.json's 1e-2 (bf16) tolerance applies to; the FFMA path
+// in mlp.cu stays the 1e-4 (fp32) one.
+//
+// One persistent CTA per SM walks tiles of 128 points through the whole network:
+//
+//   activations   never leave the SM.  H [128][256] bf16 and IN [128][192] bf16 (posenc 63 | features |
+//                 zero pad to 144 | view encoding 27 at column 144) live in shared memory as K-major
+//                 128-byte-swizzled blocks of 64 columns -- directly the A operand of tcgen05.mma.
+//   weights       nd_pack_mlp_weights_tc stores every (layer, 64-column K block) as the exact shared-memory
+//                 image of a K-major SWIZZLE_128B B operand, so the producer warp streams one block with ONE
+//                 cp.async.bulk (TMA) into a 3-stage mbarrier ring; the weights stay L2-resident (0.8 MB).
+//   accumulators  two 128 x 256 fp32 buffers in TMEM (all 512 columns).  Jobs (layers) alternate between
+//                 them, so the epilogue of layer i (tcgen05.ld -> bias, relu -> bf16 -> swizzled st.shared)
+//                 runs while layer i + 1 already accumulates: the epilogue publishes H in chunks of 64
+//                 columns and the MMA warp starts the next layer's K block j as soon as chunk j is there.
+//   roles         warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-7 input encoding of the NEXT
+//                 tile (held in registers until the IN buffer is released), warp 8 weight producer,
+//                 warp 9 MMA issuer (one elected thread) and TMEM owner.
+//   heads         sigma (K -> 1) and the RGB output layer (128 -> 3) are dot products of the fp32 rows the
+//                 epilogue threads already hold (thread = point); the [h, in] skip input of the heads is
+//                 extra K blocks of the same job, the `in` share of sigma is computed in fp32 by the
+//                 encoding warps.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nd_common.cuh"
+
+namespace nd {
+
+constexpr int kTcTile = 128;            // points per tile = UMMA M
+constexpr int kTcWidth = 256;           // net_width
+constexpr int kTcCondWidth = 128;       // net_width_condition
+constexpr int kTcPosOct = 10, kTcViewOct = 4;
+constexpr int kTcPosDim = 3 + 6 * kTcPosOct;     // 63
+constexpr int kTcViewDim = 3 + 6 * kTcViewOct;   // 27
+constexpr int kTcInPad = 144;           // [posenc | features | 0] columns of the IN buffer (9 K steps)
+constexpr int kTcCondCol = 144;         // view encoding: IN columns 144 .. 175 (2 K steps)
+constexpr int kTcInChunks = 22;         // 16-byte chunks (8 bf16) a point's IN row is written in
+constexpr int kTcBlockBytes = 16384;    // 128 rows x 128 B: one A block
+constexpr int kTcStageBytes = 32768;    // 256 rows x 128 B: one B block
+constexpr int kTcStages = 3;
+constexpr int kTcMaxUnits = 64, kTcMaxJobs = 12, kTcMaxDepth = 8;
+constexpr int kTcThreads = 320;
+constexpr uint32_t kOffH = 0, kOffIn = 4 * kTcBlockBytes, kOffB = kOffIn + 3 * kTcBlockBytes,
+                   kOffTail = kOffB + kTcStages * kTcStageBytes;   // 212992
+constexpr uint32_t kTailBars = 0, kTailTmem = 256, kTailSigIn = 512, kTailPar = 512 + 4 * kTcTile * 4;
+
+enum : uint8_t { kJobRelu = 1, kJobWritesH = 2, kJobSigma = 4, kJobRgb = 8, kJobFreesIn = 16 };
+
+struct TcUnit {                 // one K block of one job = one B stage
+    uint32_t src_off;           // byte offset of the block in the weight image
+    uint16_t bytes16;           // bytes / 16
+    uint8_t a_blk;              // A operand: 0..3 = H chunk, 4..6 = IN block
+    uint8_t k0, nk;             // first K step (16 columns each) inside the block and number of steps
+    uint8_t pad[3];
+};
+struct TcJob {
+    uint8_t first_unit, n_units, flags, pad;
+    uint16_t n, bias_off;       // output width (UMMA N), float offset of the bias in the small-parameter block
+};
+struct TcPlan {
+    int n_jobs, n_units;        // jobs per tile in the mode at hand
+    TcJob jobs[kTcMaxJobs];
+    TcUnit units[kTcMaxUnits];
+};
+struct TcPackUnit {             // source of one block for the packing kernel
+    const float *w;             // reference weight [n][k_ref]
+    int n, k_ref, col_base, lo, hi;   // block column kk in [lo, hi) <- reference column col_base + kk, others zero
+    uint32_t dst_off;
+};
+struct TcLayout {
+    TcPlan full, density;       // with / without the colour branch
+    TcPackUnit pack[kTcMaxUnits];
+    int n_pack;
+    size_t image_bytes;         // weight image
+    int n_par;                  // small parameters (floats): biases, sigma row, rgb output layer
+    int off_ws_h, off_ws_in, off_bsig, off_wo, off_bo;
+    size_t total_bytes;
+    int in_dim, feat;
+};
+
+struct TcArgs {
+    TcPlan plan;
+    const uint8_t *wimg;
+    const float *par;
+    int n_par, off_ws_h, off_ws_in, off_bsig, off_wo, off_bo;
+    const float *x, *feat, *cond;
+    int64_t n_points;
+    int samples_per_ray, feat_dim, n_tiles;
+    float *sigma, *alpha, *rgb;
+};
+
+// ---- plan / layout (host) -------------------------------------------------------------------------------
+static bool tc_layout(const nd_mlp_weights *w, TcLayout &L, bool report) {
+    const int depth = w->net_depth, feat = w->feature_dim, skip = w->skip_layer;
+    const int in_dim = kTcPosDim + feat;
+    if (depth < 1 || depth > kTcMaxDepth || w->net_width != kTcWidth || w->cond_width != kTcCondWidth || feat < 0 ||
+        in_dim > kTcInPad || w->pos_octaves != kTcPosOct || w->view_octaves != kTcViewOct || skip < 0) {
+        if (report)
+            set_error("nerf_mlp (tensor-core path): unsupported architecture (depth %d, width %d, cond width %d, feature_dim %d, "
+                      "octaves %d/%d): needs net_width 256, net_width_condition 128, 63 + feature_dim <= 144, octaves 10/4",
+                      depth, w->net_width, w->cond_width, feat, w->pos_octaves, w->view_octaves);
+        return false;
+    }
+    memset(&L, 0, sizeof(L));
+    L.in_dim = in_dim;
+    L.feat = feat;
+    TcPlan &P = L.full;
+    uint32_t img = 0;
+    int par = 0;
+    auto add_job = [&](int n, uint8_t flags) -> TcJob & {
+        TcJob &j = P.jobs[P.n_jobs++];
+        j.first_unit = (uint8_t)P.n_units;
+        j.n_units = 0;
+        j.flags = flags;
+        j.n = (uint16_t)n;
+        j.bias_off = (uint16_t)par;
+        par += n;
+        return j;
+    };
+    auto add_unit = [&](TcJob &j, const float *wsrc, int k_ref, int a_blk, int k0, int nk, int col_base, int lo, int hi) {
+        TcUnit &u = P.units[P.n_units];
+        TcPackUnit &pu = L.pack[P.n_units];
+        ++P.n_units;
+        ++j.n_units;
+        const uint32_t bytes = (uint32_t)j.n * 128u;
+        u.src_off = img;
+        u.bytes16 = (uint16_t)(bytes / 16);
+        u.a_blk = (uint8_t)a_blk;
+        u.k0 = (uint8_t)k0;
+        u.nk = (uint8_t)nk;
+        pu.w = wsrc;
+        pu.n = j.n;
+        pu.k_ref = k_ref;
+        pu.col_base = col_base;
+        pu.lo = lo;
+        pu.hi = hi;
+        pu.dst_off = img;
+        img += bytes;
+    };
+    auto add_h_units = [&](TcJob &j, const float *wsrc, int k_ref) {
+        for (int c = 0; c < 4; ++c) add_unit(j, wsrc, k_ref, c, 0, 4, c * 64, 0, 64);
+    };
+    auto add_in_units = [&](TcJob &j, const float *wsrc, int k_ref, int ref0) {   // ref0: reference column of in[0]
+        for (int b = 0; b < 3; ++b) {
+            const int cols = b < 2 ? 64 : kTcInPad - 128;
+            int hi = in_dim - b * 64;
+            hi = hi < 0 ? 0 : (hi > cols ? cols : hi);
+            add_unit(j, wsrc, k_ref, 4 + b, 0, cols / 16, ref0 + b * 64, 0, hi);
+        }
+    };
+    bool cat = false;
+    for (int i = 0; i < depth; ++i) {
+        TcJob &j = add_job(kTcWidth, kJobRelu | kJobWritesH);
+        const int k_ref = i == 0 ? in_dim : kTcWidth + (cat ? in_dim : 0);
+        if (i == 0) {
+            add_in_units(j, w->base_w[0], k_ref, 0);
+        } else {
+            add_h_units(j, w->base_w[i], k_ref);
+            if (cat) add_in_units(j, w->base_w[i], k_ref, kTcWidth);
+        }
+        cat = skip > 0 && i % skip == 0 && i > 0;
+    }
+    P.jobs[P.n_jobs - 1].flags |= kJobSigma;
+    const int head_ref = kTcWidth + (cat ? in_dim : 0);
+    // the density-only plan stops here: its last job does not publish H, and IN is free after the last job reading it
+    L.density = P;
+    {
+        TcPlan &D = L.density;
+        D.jobs[D.n_jobs - 1].flags &= (uint8_t)~kJobWritesH;
+        int last_in = 0;
+        for (int j = 0; j < D.n_jobs; ++j)
+            for (int u = 0; u < D.jobs[j].n_units; ++u)
+                if (D.units[D.jobs[j].first_unit + u].a_blk >= 4) last_in = j;
+        D.jobs[last_in].flags |= kJobFreesIn;
+    }
+    {   // bottleneck (no activation) and the colour hidden layer
+        TcJob &jb = add_job(kTcWidth, kJobWritesH);
+        add_h_units(jb, w->bottleneck_w, head_ref);
+        if (cat) add_in_units(jb, w->bottleneck_w, head_ref, kTcWidth);
+        TcJob &jr = add_job(kTcCondWidth, kJobRelu | kJobRgb | kJobFreesIn);
+        add_h_units(jr, w->rgb_hidden_w, kTcWidth + kTcViewDim);
+        // view encoding: IN block 2, block columns 16 .. 47 (IN columns 144 .. 175)
+        add_unit(jr, w->rgb_hidden_w, kTcWidth + kTcViewDim, 6, 1, 2, kTcWidth - 16, 16, 16 + kTcViewDim);
+    }
+    L.n_pack = P.n_units;
+    L.image_bytes = img;
+    L.off_ws_h = par;  par += kTcWidth;
+    L.off_ws_in = par; par += kTcInPad;
+    L.off_bsig = par;  par += 4;
+    L.off_wo = par;    par += 3 * kTcCondWidth;
+    L.off_bo = par;    par += 4;
+    L.n_par = par;
+    L.total_bytes = align_up(L.image_bytes, 256) + (size_t)par * sizeof(float);
+    (void)head_ref;
+    return true;
+}
+
+// ---- packing --------------------------------------------------------------------------------------------
+struct TcPackArgs {
+    TcPackUnit u[kTcMaxUnits];
+};
+
+// K-major SWIZZLE_128B image of an [n][64] bf16 block: row r at (r / 8) * 1024 + (r % 8) * 128, its 16-byte chunk c
+// at position c ^ (r % 8)
+__device__ __host__ __forceinline__ uint32_t sw128_offset(int r, int col) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((col >> 3) ^ (r & 7)) & 7) << 4) + (col & 7) * 2);
+}
+
+__global__ void k_pack_tc_units(const __grid_constant__ TcPackArgs a, uint8_t *__restrict__ img) {
+    const TcPackUnit &u = a.u[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= u.n * 64) return;
+    const int r = i >> 6, kk = i & 63;
+    float v = 0.0f;
+    if (kk >= u.lo && kk < u.hi) v = u.w[(size_t)r * u.k_ref + u.col_base + kk];
+    *reinterpret_cast<__nv_bfloat16 *>(img + u.dst_off + sw128_offset(r, kk)) = __float2bfloat16_rn(v);
+}
+
+struct TcParSrc {
+    const float *bias[kTcMaxJobs];
+    int bias_off[kTcMaxJobs], bias_n[kTcMaxJobs], n_jobs;
+    const float *sigma_w, *sigma_b, *wo, *bo;
+    int head_ref, in_dim, cat;
+    int off_ws_h, off_ws_in, off_bsig, off_wo, off_bo, n_par;
+};
+
+__global__ void k_pack_tc_params(const __grid_constant__ TcParSrc s, float *__restrict__ par) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n_par) return;
+    float v = 0.0f;
+    for (int j = 0; j < s.n_jobs; ++j)
+        if (i >= s.bias_off[j] && i < s.bias_off[j] + s.bias_n[j]) v = s.bias[j][i - s.bias_off[j]];
+    if (i >= s.off_ws_h && i < s.off_ws_h + kTcWidth) v = s.sigma_w[i - s.off_ws_h];
+    if (i >= s.off_ws_in && i < s.off_ws_in + kTcInPad) {
+        const int k = i - s.off_ws_in;
+        v = (s.cat && k < s.in_dim) ? s.sigma_w[kTcWidth + k] : 0.0f;
+    }
+    if (i == s.off_bsig) v = s.sigma_b[0];
+    if (i >= s.off_wo && i < s.off_wo + 3 * kTcCondWidth) v = s.wo[i - s.off_wo];
+    if (i >= s.off_bo && i < s.off_bo + 3) v = s.bo[i - s.off_bo];
+    par[i] = v;
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+namespace tc {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier once every tcgen05 operation issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+    return r;
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    uint64_t d = (uint64_t)((addr & 0x3ffffu) >> 4);   // start address, bits [0, 14)
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major), bits [16, 30)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset, bits [32, 46)
+    d |= (uint64_t)1 << 46;                            // descriptor version 1 (sm_100), bits [46, 48)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B, bits [61, 64)
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16, both K-major, M = 128
+__device__ __forceinline__ uint32_t instr_desc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
+}
+}  // namespace tc
+
+// ---- input encoding -----------------------------------------------------------------------------------
+// [x, sin(2^k x) (k outer, xyz inner), sin(2^k x + pi/2)] (nerf_mlp.py:181-197) by angle doubling from one accurate
+// sincos per coordinate: the doubling error (2^k * 6e-8) and the reference's fp32 rounding of 2^k x + pi/2
+// (|delta arg| <= 1.3e-4) are both far below the bf16 rounding the values get on their way into the tensor core.
+template <int kOct>
+__device__ __forceinline__ void encode_doubling(const float (&x)[3], float *dst) {
+    float s[3], c[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        dst[i] = x[i];
+        sincosf(x[i], &s[i], &c[i]);
+    }
+#pragma unroll
+    for (int k = 0; k < kOct; ++k) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            dst[3 + k * 3 + i] = s[i];
+            dst[3 + kOct * 3 + k * 3 + i] = c[i];
+            const float s2 = 2.0f * s[i] * c[i];
+            const float c2 = fmaf(-2.0f * s[i], s[i], 1.0f);
+            s[i] = s2;
+            c[i] = c2;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = tc::smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B operands need 1024-byte alignment
+    uint8_t *sm = smem_raw + (base - raw);
+    const uint32_t sH = base + kOffH, sIN = base + kOffIn, sB = base + kOffB;
+    const uint32_t bars = base + kOffTail + kTailBars;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(sm + kOffTail + kTailTmem);
+    // [4][128]: slot t % 4.  The encoding warps may run ahead of the epilogue by the tile whose first job is in
+    // flight plus the one they hold in registers; four slots keep the writer of tile t + 4 behind the reader of tile t
+    // in every job plan (two would race in the density-only plan, where IN is released after the first job).
+    float *s_sig_in = reinterpret_cast<float *>(sm + kOffTail + kTailSigIn);
+    float *s_par = reinterpret_cast<float *>(sm + kOffTail + kTailPar);
+    const uint32_t b_full = bars, b_empty = bars + 8 * 3, d_full = bars + 8 * 6, d_empty = bars + 8 * 8,
+                   h_ready = bars + 8 * 10, in_ready = bars + 8 * 14, in_free = bars + 8 * 15;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 3; ++i) { tc::mbar_init(b_full + 8 * i, 1); tc::mbar_init(b_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(d_full + 8 * i, 1); tc::mbar_init(d_empty + 8 * i, 128); }
+        for (int i = 0; i < 4; ++i) tc::mbar_init(h_ready + 8 * i, 128);
+        tc::mbar_init(in_ready, 128);
+        tc::mbar_init(in_free, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) tc::tmem_alloc(tc::smem_u32(s_tmem), 512);
+    for (int i = threadIdx.x; i < a.n_par; i += kTcThreads) s_par[i] = a.par[i];
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const TcPlan &P = a.plan;
+
+    if (warp == 8) {
+        // ---------------- weight producer ----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                for (int u = 0; u < P.n_units; ++u) {
+                    tc::mbar_wait(b_empty + 8 * stage, ph ^ 1u);
+                    const uint32_t bytes = (uint32_t)P.units[u].bytes16 * 16u;
+                    tc::mbar_expect_tx(b_full + 8 * stage, bytes);
+                    tc::bulk_g2s(sB + stage * kTcStageBytes, a.wimg + P.units[u].src_off, bytes, b_full + 8 * stage);
+                    if (++stage == kTcStages) { stage = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t ph = 0, hpar = 0, in_par = 0, dpar = 3u;       // dpar bit d: parity to wait for on d_empty[d]
+            uint32_t jc = 0;                                           // running job counter -> accumulator buffer
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                bool in_ok = false;
+                for (int j = 0; j < P.n_jobs; ++j, ++jc) {
+                    const TcJob job = P.jobs[j];
+                    const uint32_t d = jc & 1u;
+                    tc::mbar_wait(d_empty + 8 * d, (dpar >> d) & 1u);
+                    dpar ^= 1u << d;
+                    const uint32_t idesc = tc::instr_desc(job.n);
+                    const uint32_t d_tmem = tmem + d * 256u;
+                    for (int uu = 0; uu < job.n_units; ++uu) {
+                        const TcUnit u = P.units[job.first_unit + uu];
+                        uint32_t a_addr;
+                        if (u.a_blk < 4) {
+                            tc::mbar_wait(h_ready + 8 * u.a_blk, (hpar >> u.a_blk) & 1u);
+                            hpar ^= 1u << u.a_blk;
+                            a_addr = sH + u.a_blk * kTcBlockBytes;
+                        } else {
+                            if (!in_ok) {
+                                tc::mbar_wait(in_ready, in_par);
+                                in_par ^= 1u;
+                                in_ok = true;
+                            }
+                            a_addr = sIN + (u.a_blk - 4) * kTcBlockBytes;
+                        }
+                        tc::mbar_wait(b_full + 8 * stage, ph);
+                        tc::tc_fence_after();
+                        const uint64_t ad = tc::smem_desc(a_addr), bd = tc::smem_desc(sB + stage * kTcStageBytes);
+                        for (int s = 0; s < u.nk; ++s) {
+                            const uint64_t ko = (uint64_t)(2 * (u.k0 + s));        // 32 B per K step, in 16-byte units
+                            tc::umma_bf16(d_tmem, ad + ko, bd + ko, idesc, (uu | s) != 0 ? 1u : 0u);
+                        }
+                        tc::umma_commit(b_empty + 8 * stage);                       // frees the B stage once these MMAs are done
+                        if (++stage == kTcStages) { stage = 0; ph ^= 1u; }
+                    }
+                    tc::umma_commit(d_full + 8 * d);
+                    if (job.flags & kJobFreesIn) tc::umma_commit(in_free);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- input encoding of the next tile (thread = point) ----------------
+        const int r = threadIdx.x - 128;
+        const uint32_t row_addr = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+        const float *ws_in = s_par + a.off_ws_in;
+        int t = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++t) {
+            const int64_t gp = (int64_t)tile * kTcTile + r;
+            const bool ok = gp < a.n_points;
+            uint32_t pk[kTcInChunks * 4];
+            float sig_in = 0.0f;
+            {
+                float enc[kTcPosDim];
+                float xyz[3] = {0.f, 0.f, 0.f};
+                if (ok) { xyz[0] = a.x[gp * 3]; xyz[1] = a.x[gp * 3 + 1]; xyz[2] = a.x[gp * 3 + 2]; }
+                encode_doubling<kTcPosOct>(xyz, enc);
+                const float *fr = a.feat + gp * a.feat_dim;
+#pragma unroll
+                for (int c = 0; c < kTcInPad / 8; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int idx = c * 8 + e;
+                        if (idx < kTcPosDim) v[e] = ok ? enc[idx] : 0.0f;
+                        else v[e] = (ok && idx - kTcPosDim < a.feat_dim) ? __ldg(fr + (idx - kTcPosDim)) : 0.0f;
+                        sig_in = fmaf(v[e], ws_in[idx], sig_in);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pk[c * 4 + e] = tc::pack_bf16(v[2 * e], v[2 * e + 1]);
+                }
+            }
+            {
+                float enc[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) enc[i] = 0.0f;
+                if (a.cond != nullptr && ok) {
+                    const int64_t ray = gp / a.samples_per_ray;
+                    const float dir[3] = {a.cond[ray * 3], a.cond[ray * 3 + 1], a.cond[ray * 3 + 2]};
+                    encode_doubling<kTcViewOct>(dir, enc);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pk[(kTcInPad / 8 + c) * 4 + e] = tc::pack_bf16(enc[c * 8 + 2 * e], enc[c * 8 + 2 * e + 1]);
+            }
+            if (t > 0) tc::mbar_wait(in_free, (uint32_t)(t - 1) & 1u);     // the previous tile's last reader of IN is done
+#pragma unroll
+            for (int c = 0; c < kTcInChunks; ++c) {
+                const int blk = c >> 3, cc = c & 7;
+                tc::sts_u4(sIN + blk * kTcBlockBytes + row_addr + (uint32_t)((cc ^ (r & 7)) << 4), pk[c * 4], pk[c * 4 + 1],
+                           pk[c * 4 + 2], pk[c * 4 + 3]);
+            }
+            s_sig_in[(t & 3) * kTcTile + r] = sig_in;
+            tc::fence_proxy_async();
+            tc::mbar_arrive(in_ready);
+        }
+    } else {
+        // ---------------- epilogue (thread = point = TMEM lane) ----------------
+        const int r = threadIdx.x;
+        const uint32_t row_addr = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const float *ws_h = s_par + a.off_ws_h, *wo = s_par + a.off_wo;
+        uint32_t dfull_par = 0, jc = 0;
+        int t = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++t) {
+            const int64_t gp = (int64_t)tile * kTcTile + r;
+            for (int j = 0; j < P.n_jobs; ++j, ++jc) {
+                const TcJob job = P.jobs[j];
+                const uint32_t d = jc & 1u;
+                tc::mbar_wait(d_full + 8 * d, (dfull_par >> d) & 1u);
+                dfull_par ^= 1u << d;
+                tc::tc_fence_after();
+                const float *bias = s_par + job.bias_off;
+                const bool relu = job.flags & kJobRelu, writes_h = job.flags & kJobWritesH;
+                const bool sig_head = job.flags & kJobSigma, rgb_head = job.flags & kJobRgb;
+                float sig = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+                const int n_chunks = job.n >> 6;
+                for (int ch = 0; ch < n_chunks; ++ch) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int col = ch * 64 + half * 32;
+                        uint32_t v[32];
+                        tc::tmem_ld32(tmem + lane_base + d * 256u + (uint32_t)col, v);
+                        tc::tmem_ld_wait();
+                        float f[32];
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4 *>(bias + col + i);
+                            f[i] = __uint_as_float(v[i]) + b4.x;
+                            f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
+                            f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
+                            f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+                        }
+                        if (relu) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+                        }
+                        if (sig_head) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 w4 = *reinterpret_cast<const float4 *>(ws_h + col + i);
+                                sig = fmaf(f[i], w4.x, sig); sig = fmaf(f[i + 1], w4.y, sig);
+                                sig = fmaf(f[i + 2], w4.z, sig); sig = fmaf(f[i + 3], w4.w, sig);
+                            }
+                        }
+                        if (rgb_head) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 w0 = *reinterpret_cast<const float4 *>(wo + col + i);
+                                const float4 w1 = *reinterpret_cast<const float4 *>(wo + kTcCondWidth + col + i);
+                                const float4 w2 = *reinterpret_cast<const float4 *>(wo + 2 * kTcCondWidth + col + i);
+                                c0 = fmaf(f[i], w0.x, c0); c0 = fmaf(f[i + 1], w0.y, c0); c0 = fmaf(f[i + 2], w0.z, c0); c0 = fmaf(f[i + 3], w0.w, c0);
+                                c1 = fmaf(f[i], w1.x, c1); c1 = fmaf(f[i + 1], w1.y, c1); c1 = fmaf(f[i + 2], w1.z, c1); c1 = fmaf(f[i + 3], w1.w, c1);
+                                c2 = fmaf(f[i], w2.x, c2); c2 = fmaf(f[i + 1], w2.y, c2); c2 = fmaf(f[i + 2], w2.z, c2); c2 = fmaf(f[i + 3], w2.w, c2);
+                            }
+                        }
+                        if (writes_h) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int cc = half * 4 + q;
+                                tc::sts_u4(sH + ch * kTcBlockBytes + row_addr + (uint32_t)((cc ^ (r & 7)) << 4),
+                                           tc::pack_bf16(f[q * 8], f[q * 8 + 1]), tc::pack_bf16(f[q * 8 + 2], f[q * 8 + 3]),
+                                           tc::pack_bf16(f[q * 8 + 4], f[q * 8 + 5]), tc::pack_bf16(f[q * 8 + 6], f[q * 8 + 7]));
+                            }
+                        }
+                    }
+                    if (writes_h) {
+                        tc::fence_proxy_async();               // generic-proxy stores -> visible to the tensor core's async proxy
+                        tc::mbar_arrive(h_ready + 8 * ch);
+                    }
+                }
+                tc::tc_fence_before();
+                tc::mbar_arrive(d_empty + 8 * d);              // this accumulator buffer may be overwritten
+                if (sig_head && gp < a.n_points) {
+                    const float sg = fmaxf(sig + s_sig_in[(t & 3) * kTcTile + r] + s_par[a.off_bsig], 0.0f);
+                    if (a.sigma != nullptr) a.sigma[gp] = sg;
+                    if (a.alpha != nullptr) a.alpha[gp] = 1.0f - expf(-sg);        // nerfdet.py:258
+                }
+                if (rgb_head && gp < a.n_points) {
+                    const float *bo = s_par + a.off_bo;
+                    a.rgb[gp * 3] = 1.0f / (1.0f + expf(-(c0 + bo[0])));
+                    a.rgb[gp * 3 + 1] = 1.0f / (1.0f + expf(-(c1 + bo[1])));
+                    a.rgb[gp * 3 + 2] = 1.0f / (1.0f + expf(-(c2 + bo[2])));
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem, 512);
+    }
+}
+
+}  // namespace nd
+
+using namespace nd;
+
+extern "C" {
+
+size_t nd_mlp_tc_packed_bytes(const nd_mlp_weights *w) {
+    TcLayout L;
+    if (w == nullptr || !tc_layout(w, L, false)) return 0;
+    return L.total_bytes;
+}
+
+int nd_pack_mlp_weights_tc(const nd_mlp_weights *w, void *packed, size_t packed_bytes, void *stream) {
+    ND_REQUIRE(w != nullptr && packed != nullptr, ND_ERR_BAD_ARG, "nd_pack_mlp_weights_tc: null pointer");
+    TcLayout L;
+    if (!tc_layout(w, L, true)) return ND_ERR_BAD_SHAPE;
+    ND_REQUIRE(packed_bytes >= L.total_bytes, ND_ERR_WORKSPACE, "nd_pack_mlp_weights_tc: buffer too small (%zu < %zu)",
+               packed_bytes, L.total_bytes);
+    ND_REQUIRE((reinterpret_cast<uintptr_t>(packed) % 256) == 0, ND_ERR_BAD_ALIGNMENT,
+               "nd_pack_mlp_weights_tc: buffer not 256-byte aligned");
+    for (int i = 0; i < w->net_depth; ++i)
+        ND_REQUIRE(w->base_w[i] != nullptr && w->base_b[i] != nullptr, ND_ERR_BAD_ARG, "nd_pack_mlp_weights_tc: layer %d missing", i);
+    ND_REQUIRE(w->sigma_w && w->sigma_b && w->bottleneck_w && w->bottleneck_b && w->rgb_hidden_w && w->rgb_hidden_b &&
+                   w->rgb_out_w && w->rgb_out_b,
+               ND_ERR_BAD_ARG, "nd_pack_mlp_weights_tc: head weights missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *img = reinterpret_cast<uint8_t *>(packed);
+    float *par = reinterpret_cast<float *>(img + align_up(L.image_bytes, 256));
+    TcPackArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    for (int i = 0; i < L.n_pack; ++i) pa.u[i] = L.pack[i];
+    k_pack_tc_units<<<dim3((unsigned)ceil_div(kTcWidth * 64, 256), (unsigned)L.n_pack), 256, 0, st>>>(pa, img);
+    ND_CUDA_LAUNCH_CHECK("k_pack_tc_units");
+    TcParSrc ps;
+    memset(&ps, 0, sizeof(ps));
+    const TcPlan &P = L.full;
+    ps.n_jobs = P.n_jobs;
+    for (int j = 0; j < P.n_jobs; ++j) {
+        ps.bias_off[j] = P.jobs[j].bias_off;
+        ps.bias_n[j] = P.jobs[j].n;
+        ps.bias[j] = j < w->net_depth ? w->base_b[j] : (j == w->net_depth ? w->bottleneck_b : w->rgb_hidden_b);
+    }
+    ps.sigma_w = w->sigma_w; ps.sigma_b = w->sigma_b; ps.wo = w->rgb_out_w; ps.bo = w->rgb_out_b;
+    ps.in_dim = L.in_dim;
+    {
+        const int skip = w->skip_layer, i = w->net_depth - 1;
+        ps.cat = (skip > 0 && i % skip == 0 && i > 0) ? 1 : 0;
+    }
+    ps.off_ws_h = L.off_ws_h; ps.off_ws_in = L.off_ws_in; ps.off_bsig = L.off_bsig; ps.off_wo = L.off_wo; ps.off_bo = L.off_bo;
+    ps.n_par = L.n_par;
+    k_pack_tc_params<<<(unsigned)ceil_div(L.n_par, 256), 256, 0, st>>>(ps, par);
+    ND_CUDA_LAUNCH_CHECK("k_pack_tc_params");
+    return ND_OK;
+}
+
+int nd_nerf_mlp_fwd_tc(const nd_mlp_weights *arch, const void *packed, const float *x, const float *features,
+                       const float *cond, int64_t n_points, int samples_per_ray, float *sigma, float *alpha, float *rgb,
+                       void *stream) {
+    ND_REQUIRE(n_points >= 0, ND_ERR_BAD_SHAPE, "nd_nerf_mlp_fwd_tc: negative point count");
+    if (n_points == 0) return ND_OK;
+    ND_REQUIRE(arch != nullptr && packed != nullptr && x != nullptr, ND_ERR_BAD_ARG, "nd_nerf_mlp_fwd_tc: null pointer");
+    TcLayout L;
+    if (!tc_layout(arch, L, true)) return ND_ERR_BAD_SHAPE;
+    ND_REQUIRE(L.feat == 0 || features != nullptr, ND_ERR_BAD_ARG, "nd_nerf_mlp_fwd_tc: features missing");
+    ND_REQUIRE(rgb == nullptr || (cond != nullptr && samples_per_ray > 0 && n_points % samples_per_ray == 0),
+               ND_ERR_BAD_SHAPE, "nd_nerf_mlp_fwd_tc: rgb needs cond [P / samples_per_ray][3]");
+    ND_REQUIRE((reinterpret_cast<uintptr_t>(packed) % 256) == 0, ND_ERR_BAD_ALIGNMENT,
+               "nd_nerf_mlp_fwd_tc: packed buffer not 256-byte aligned");
+    const bool want_rgb = rgb != nullptr && cond != nullptr;
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.plan = want_rgb ? L.full : L.density;
+    a.wimg = reinterpret_cast<const uint8_t *>(packed);
+    a.par = reinterpret_cast<const float *>(a.wimg + align_up(L.image_bytes, 256));
+    a.n_par = L.n_par;
+    a.off_ws_h = L.off_ws_h; a.off_ws_in = L.off_ws_in; a.off_bsig = L.off_bsig; a.off_wo = L.off_wo; a.off_bo = L.off_bo;
+    a.x = x; a.feat = features; a.cond = want_rgb ? cond : nullptr;
+    a.n_points = n_points;
+    a.samples_per_ray = samples_per_ray > 0 ? samples_per_ray : 1;
+    a.feat_dim = L.feat;
+    a.n_tiles = (int)ceil_div(n_points, kTcTile);
+    a.sigma = sigma; a.alpha = alpha; a.rgb = want_rgb ? rgb : nullptr;
+    const size_t smem = 1024 + kOffTail + kTailPar + (size_t)L.n_par * sizeof(float);
+    ND_REQUIRE(smem <= 227 * 1024, ND_ERR_BAD_SHAPE, "nd_nerf_mlp_fwd_tc: %zu bytes of shared memory needed", smem);
+    cudaError_t e = cudaFuncSetAttribute(k_nerf_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("k_nerf_mlp_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+        return ND_ERR_CUDA;
+    }
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = a.n_tiles < sms ? a.n_tiles : sms;
+    k_nerf_mlp_tc<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(a);
+    ND_CUDA_LAUNCH_CHECK("k_nerf_mlp_tc");
+    return ND_OK;
+}
+
+}  // extern "C"

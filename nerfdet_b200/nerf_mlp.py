@@ -4,7 +4,9 @@
 ``VanillaNeRFRadianceField`` keeps the reference constructor, ``forward(x, condition, features)``,
 ``query_density(x, features)`` and -- through an identical sub-module tree -- the reference
 ``state_dict`` keys (``mlp.base.hidden_layers.<i>.weight`` ...), so reference checkpoints load
-unchanged.  The arithmetic runs in ``nd_nerf_mlp_fwd`` (csrc/mlp.cu); there is no eager fallback.
+unchanged.  The arithmetic runs in ``nd_nerf_mlp_fwd`` (csrc/mlp.cu, fp32 FFMA, 1e-4) or, with
+``precision='bf16'``, in ``nd_nerf_mlp_fwd_tc`` (csrc/mlp_tc.cu: tcgen05 tensor cores, bf16 operands,
+fp32 accumulation in tensor memory, 1e-2); there is no eager fallback.
 Forward only (autograd is row N1 of SURVEY.md section 8f).
 """
 from __future__ import annotations
@@ -72,8 +74,11 @@ class _Encoder(nn.Module):
 
 class VanillaNeRFRadianceField(nn.Module):
     def __init__(self, net_depth: int = 8, net_width: int = 256, skip_layer: int = 4, feature_dim: int = 0,
-                 net_depth_condition: int = 1, net_width_condition: int = 128) -> None:
+                 net_depth_condition: int = 1, net_width_condition: int = 128, *, precision: str = 'fp32') -> None:
         super().__init__()
+        if precision not in ('fp32', 'bf16'):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision                 # may be switched at any time; the packed copy follows
         if net_depth_condition != 1:
             raise NotImplementedError('net_depth_condition != 1 is not used by NeRF-Det and not built')
         self.posi_encoder = _Encoder(3, 0, 10)
@@ -100,9 +105,10 @@ class VanillaNeRFRadianceField(nn.Module):
     def packed_weights(self) -> torch.Tensor:
         """Kernel-layout copy of the weights, rebuilt whenever a parameter was modified or moved."""
         w = self._weights()
-        key = tuple((t.data_ptr(), t._version) for t in w.values())
+        key = (self.precision,) + tuple((t.data_ptr(), t._version) for t in w.values())
         if self._packed is None or key != self._packed_key:
-            self._packed = ops.pack_mlp_weights({k: t.detach().contiguous() for k, t in w.items()}, self.dims)
+            self._packed = ops.pack_mlp_weights({k: t.detach().contiguous() for k, t in w.items()}, self.dims,
+                                                self.precision)
             self._packed_key = key
         return self._packed
 
@@ -113,7 +119,7 @@ class VanillaNeRFRadianceField(nn.Module):
         lead = x.shape[:-1]
         feats = self._features(x, features)
         sigma, _, alpha = ops.nerf_mlp_fwd(self.packed_weights(), self.dims, x.reshape(-1, 3), feats, None, 1, False,
-                                           return_alpha)
+                                           return_alpha, self.precision)
         sigma = sigma.view(*lead, 1)
         return (sigma, alpha.view(*lead, 1)) if return_alpha else sigma
 
@@ -132,7 +138,8 @@ class VanillaNeRFRadianceField(nn.Module):
             if condition.dim() != 2 or condition.shape[0] != lead[0]:
                 raise ValueError(f'condition {tuple(condition.shape)} does not broadcast over x {tuple(x.shape)}')
             cond, spr = condition, p // condition.shape[0]
-        sigma, rgb, _ = ops.nerf_mlp_fwd(self.packed_weights(), self.dims, x.reshape(-1, 3), feats, cond, spr, True, False)
+        sigma, rgb, _ = ops.nerf_mlp_fwd(self.packed_weights(), self.dims, x.reshape(-1, 3), feats, cond, spr, True, False,
+                                         self.precision)
         return rgb.view(*lead, 3), sigma.view(*lead, 1)
 
     def _features(self, x, features):

@@ -304,8 +304,9 @@ def mlp_arch(weights, dims) -> _lib.NdMlpWeights:
     return w
 
 
-def pack_mlp_weights(weights, dims) -> Tensor:
-    """One-time transposition of the reference weights into the kernel's layout (``nd_pack_mlp_weights``)."""
+def pack_mlp_weights(weights, dims, precision: str = 'fp32') -> Tensor:
+    """One-time re-layout of the reference weights for the kernel at hand: ``nd_pack_mlp_weights`` (fp32 FFMA path,
+    k-major transposition) or ``nd_pack_mlp_weights_tc`` (bf16 tcgen05 path, swizzled UMMA operand images)."""
     tensors = [t for t in weights.values() if t is not None]
     _need_cuda(*tensors)
     for t in tensors:
@@ -313,19 +314,30 @@ def pack_mlp_weights(weights, dims) -> Tensor:
             raise TypeError('MLP weights must be contiguous float32 tensors')
     lib = _lib.load()
     arch = mlp_arch(weights, dims)
-    nbytes = lib.nd_mlp_packed_bytes(ctypes.byref(arch))
+    size_fn, pack_fn = _mlp_entry(lib, precision)[:2]
+    nbytes = size_fn(ctypes.byref(arch))
     if nbytes == 0:
-        raise RuntimeError('nd_mlp_packed_bytes: unsupported MLP architecture ' + str(tuple(dims)))
+        raise RuntimeError(f'unsupported MLP architecture {tuple(dims)} for precision {precision!r}')
     packed = torch.empty((nbytes,), dtype=torch.uint8, device=tensors[0].device)
-    _lib.check(lib.nd_pack_mlp_weights(ctypes.byref(arch), _ptr(packed), nbytes, _stream()), 'nd_pack_mlp_weights')
+    _lib.check(pack_fn(ctypes.byref(arch), _ptr(packed), nbytes, _stream()), 'nd_pack_mlp_weights')
     return packed
+
+
+def _mlp_entry(lib, precision: str):
+    if precision == 'fp32':
+        return lib.nd_mlp_packed_bytes, lib.nd_pack_mlp_weights, lib.nd_nerf_mlp_fwd
+    if precision == 'bf16':
+        return lib.nd_mlp_tc_packed_bytes, lib.nd_pack_mlp_weights_tc, lib.nd_nerf_mlp_fwd_tc
+    raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
 
 
 @torch.library.custom_op(f'{_NS}::nerf_mlp_fwd', mutates_args=())
 def nerf_mlp_fwd(packed: Tensor, dims: List[int], x: Tensor, features: Tensor, cond: Optional[Tensor],
-                 samples_per_ray: int, want_rgb: bool, want_alpha: bool) -> Tuple[Tensor, Tensor, Tensor]:
+                 samples_per_ray: int, want_rgb: bool, want_alpha: bool,
+                 precision: str = 'fp32') -> Tuple[Tensor, Tensor, Tensor]:
     """sigma [P], rgb [P, 3] (empty unless ``want_rgb``), alpha = 1 - exp(-sigma) [P] (empty unless
-    ``want_alpha``) for P points (reference nerf_mlp.py:217-234)."""
+    ``want_alpha``) for P points (reference nerf_mlp.py:217-234).  ``precision``: 'fp32' (FFMA kernel, 1e-4) or
+    'bf16' (tcgen05 kernel, 1e-2); ``packed`` must come from ``pack_mlp_weights`` with the same precision."""
     _need_cuda(packed, x, features, cond)
     if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != 3:
         raise ValueError('x must be float32 [P, 3]')
@@ -345,15 +357,16 @@ def nerf_mlp_fwd(packed: Tensor, dims: List[int], x: Tensor, features: Tensor, c
     alpha = torch.empty((p,) if want_alpha else (0,), dtype=torch.float32, device=dev)
     arch = mlp_arch({}, dims)
     lib = _lib.load()
-    _lib.check(lib.nd_nerf_mlp_fwd(ctypes.byref(arch), _ptr(packed), _ptr(x), _ptr(features),
-                                   _ptr(cond) if want_rgb else None, p, max(int(samples_per_ray), 1), _ptr(sigma),
-                                   _ptr(alpha) if want_alpha else None, _ptr(rgb) if want_rgb else None, _stream()),
+    fwd = _mlp_entry(lib, precision)[2]
+    _lib.check(fwd(ctypes.byref(arch), _ptr(packed), _ptr(x), _ptr(features),
+                   _ptr(cond) if want_rgb else None, p, max(int(samples_per_ray), 1), _ptr(sigma),
+                   _ptr(alpha) if want_alpha else None, _ptr(rgb) if want_rgb else None, _stream()),
                'nd_nerf_mlp_fwd')
     return sigma, rgb, alpha
 
 
 @nerf_mlp_fwd.register_fake
-def _(packed, dims, x, features, cond, samples_per_ray, want_rgb, want_alpha):
+def _(packed, dims, x, features, cond, samples_per_ray, want_rgb, want_alpha, precision='fp32'):
     p = x.shape[0]
     return (x.new_empty((p,)), x.new_empty((p, 3) if want_rgb else (0,)), x.new_empty((p,) if want_alpha else (0,)))
 

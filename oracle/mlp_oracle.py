@@ -62,3 +62,41 @@ class FieldOracle:
         t = torch.relu(self._lin('mlp.rgb_layer.hidden_layers.0', torch.cat([bott, cond], dim=-1)))
         rgb = torch.sigmoid(self._lin('mlp.rgb_layer.output_layer', t))
         return rgb, sigma
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+class FieldOracleBf16(FieldOracle):
+    """The same network with the operand roundings of the tensor-core kernel (nerfdet_b200/csrc/mlp_tc.cu): inputs,
+    weights and hidden activations rounded to bf16 where they enter a matrix product, products accumulated in fp32;
+    the sigma row and the 128 -> 3 output layer stay fp32 on the un-rounded rows.  Used by the GPU tests to tell a
+    layout / pipeline bug (differs from this by > 1e-3) from bf16 rounding (differs from ``FieldOracle`` by ~1e-2)."""
+
+    def _lin16(self, key, x):
+        return F.linear(_bf16(x), _bf16(self.s[key + '.weight']), self.s[key + '.bias'])
+
+    def _trunk16(self, x, features):
+        inp = torch.cat([sinusoidal_encode(x, 10), features], dim=-1)
+        h = inp
+        for i in range(self.net_depth):
+            h = torch.relu(self._lin16(f'mlp.base.hidden_layers.{i}', h))
+        return h, inp
+
+    def query_density(self, x, features):
+        h, inp = self._trunk16(x, features)
+        return torch.relu(self._lin('mlp.sigma_layer.output_layer', torch.cat([h, inp], dim=-1)))
+
+    def __call__(self, x, condition, features):
+        h, inp = self._trunk16(x, features)
+        cat = torch.cat([h, inp], dim=-1)
+        sigma = torch.relu(self._lin('mlp.sigma_layer.output_layer', cat))
+        bott = self._lin16('mlp.bottleneck_layer.output_layer', cat)
+        cond = sinusoidal_encode(condition, 4)
+        if cond.shape[:-1] != bott.shape[:-1]:
+            cond = cond.view([cond.shape[0]] + [1] * (bott.dim() - cond.dim()) + [cond.shape[-1]]
+                             ).expand(*bott.shape[:-1], cond.shape[-1])
+        t = torch.relu(self._lin16('mlp.rgb_layer.hidden_layers.0', torch.cat([bott, cond], dim=-1)))
+        rgb = torch.sigmoid(self._lin('mlp.rgb_layer.output_layer', t))
+        return rgb, sigma

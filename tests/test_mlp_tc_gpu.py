@@ -1,0 +1,130 @@
+"""GPU tier for the tensor-core (tcgen05, bf16 operands / fp32 accumulation) build of the shared MLP
+(nerfdet_b200/csrc/mlp_tc.cu), called through the reference module interface
+with ``precision='bf16'``.
+
+Two bars, both written here:
+  * against the unmodified reference (tests/golden/mlp_small.npz, render_det.npz) and the fp32 CPU oracle:
+    BASELINE.json's bf16 tolerance, max |a - b| <= 1e-2 * max |ref| per output tensor (bf16 rounding of every
+    layer's operands makes a purely element-wise relative test ill-posed next to the relu / near-zero outputs);
+  * against the CPU oracle that applies the SAME bf16 operand roundings (oracle/mlp_oracle.py:FieldOracleBf16):
+    max |a - b| <= 2e-3 * max |ref| -- what is left is accumulation order and the rare activation that rounds to
+    the neighbouring bf16 value, so a wrong swizzle, descriptor or pipeline hazard cannot hide behind the tolerance.
+"""
+import numpy as np
+import pytest
+import torch
+
+from nerfdet_b200 import render
+from nerfdet_b200.nerf_mlp import VanillaNeRFRadianceField
+from nerfdet_b200.projection import Projector
+from oracle import golden_cases as gc
+from oracle import mlp_oracle as mo
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def assert_norm_close(a, b, tol, name=''):
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    assert np.isfinite(a).all(), f'{name}: non-finite values'
+    scale = max(float(np.abs(b).max()), 1e-30)
+    err = float(np.abs(a - b).max())
+    assert err <= tol * scale, f'{name}: max abs err {err:.3e} > {tol:g} * max|ref| ({scale:.3e})'
+
+
+def make_field(state, precision='bf16') -> VanillaNeRFRadianceField:
+    field = VanillaNeRFRadianceField(net_depth=4, net_width=256, skip_layer=3, feature_dim=70,
+                                     net_depth_condition=1, net_width_condition=128, precision=precision)
+    field.load_state_dict({k: v for k, v in state.items() if not k.startswith('mapping.')})
+    return field.to(DEV)
+
+
+def test_tc_mlp_vs_reference_golden():
+    g = gc.load_golden('mlp_small')
+    inp = gc.mlp_inputs(gc.CASES['mlp_small'])
+    field = make_field(inp['state'])
+    rgb, sigma = field(inp['pts'].to(DEV), inp['ray_d'].to(DEV), inp['feats'].to(DEV))
+    assert rgb.shape == (32, 8, 3) and sigma.shape == (32, 8, 1)
+    assert_norm_close(rgb, g['rgb'], 1e-2, 'rgb vs reference')
+    assert_norm_close(sigma, g['sigma'], 1e-2, 'sigma vs reference')
+    dens = field.query_density(inp['pts'].reshape(-1, 3).to(DEV), inp['feats'].reshape(-1, 70).to(DEV))
+    assert_norm_close(dens, g['density'], 1e-2, 'density vs reference')
+    # same roundings on the CPU: tight
+    o16 = mo.FieldOracleBf16(inp['state'])
+    r16, s16 = o16(inp['pts'], inp['ray_d'], inp['feats'])
+    assert_norm_close(rgb, r16, 2e-3, 'rgb vs bf16 oracle')
+    assert_norm_close(sigma, s16, 2e-3, 'sigma vs bf16 oracle')
+    assert_norm_close(dens, o16.query_density(inp['pts'].reshape(-1, 3), inp['feats'].reshape(-1, 70)), 2e-3,
+                      'density vs bf16 oracle')
+    # the fp32 build of the same module is unaffected by the switch
+    f32 = make_field(inp['state'], 'fp32')
+    rgb32, sigma32 = f32(inp['pts'].to(DEV), inp['ray_d'].to(DEV), inp['feats'].to(DEV))
+    assert_norm_close(rgb32, g['rgb'], 1e-4, 'fp32 rgb')
+    assert_norm_close(rgb, rgb32, 1e-2, 'bf16 vs fp32 build')
+    assert_norm_close(sigma, sigma32, 1e-2, 'bf16 vs fp32 build (sigma)')
+
+
+@pytest.mark.parametrize('p', [1, 127, 129, 300, 19000, 40001])
+def test_tc_mlp_ragged_and_persistent(p):
+    """Point counts around the 128-point tile and beyond 148 tiles (several tiles per persistent CTA: the
+    accumulator / IN-buffer hand-over between consecutive tiles)."""
+    inp = gc.mlp_inputs(gc.CASES['mlp_small'])
+    field = make_field(inp['state'])
+    o32, o16 = mo.FieldOracle(inp['state']), mo.FieldOracleBf16(inp['state'])
+    rs = np.random.RandomState(11 + p)
+    x = torch.from_numpy(rs.uniform(-3.5, 3.5, (p, 3)).astype(np.float32))
+    f = torch.from_numpy(np.concatenate([rs.normal(0, 1, (p, 35)), rs.uniform(0, 1, (p, 35))], axis=-1).astype(np.float32))
+    d = torch.from_numpy(rs.normal(0, 0.7, (p, 3)).astype(np.float32))
+    rgb, sigma = field(x.to(DEV), d.to(DEV), f.to(DEV))
+    torch.cuda.synchronize()
+    r32, s32 = o32(x, d, f)
+    r16, s16 = o16(x, d, f)
+    assert_norm_close(rgb, r32, 1e-2, f'rgb p={p}')
+    assert_norm_close(sigma, s32, 1e-2, f'sigma p={p}')
+    assert_norm_close(rgb, r16, 2e-3, f'rgb vs bf16 oracle p={p}')
+    assert_norm_close(sigma, s16, 2e-3, f'sigma vs bf16 oracle p={p}')
+    dens, alpha = field.query_density(x.to(DEV), f.to(DEV), return_alpha=True)
+    assert_norm_close(dens, s16, 2e-3, f'density-only p={p}')
+    assert_norm_close(alpha, 1.0 - torch.exp(-s16), 2e-3, f'alpha p={p}')
+    # idempotence: a second launch on the same inputs gives the same bits
+    rgb2, sigma2 = field(x.to(DEV), d.to(DEV), f.to(DEV))
+    assert torch.equal(rgb2, rgb) and torch.equal(sigma2, sigma)
+
+
+def test_tc_mlp_weight_update_and_empty():
+    inp = gc.mlp_inputs(gc.CASES['mlp_small'])
+    field = make_field(inp['state'])
+    rs = np.random.RandomState(3)
+    x = torch.from_numpy(rs.uniform(-3.5, 3.5, (200, 3)).astype(np.float32))
+    f = torch.from_numpy(rs.normal(0, 1, (200, 70)).astype(np.float32))
+    s1 = field.query_density(x.to(DEV), f.to(DEV))
+    with torch.no_grad():
+        field.mlp.sigma_layer.output_layer.bias.add_(0.25)
+    state2 = {k: v.clone() for k, v in inp['state'].items()}
+    state2['mlp.sigma_layer.output_layer.bias'] = state2['mlp.sigma_layer.output_layer.bias'] + 0.25
+    s2 = field.query_density(x.to(DEV), f.to(DEV))
+    assert_norm_close(s2, mo.FieldOracleBf16(state2).query_density(x, f), 2e-3, 'sigma after update')
+    assert not torch.equal(s1, s2)
+    assert field.query_density(x[:0].to(DEV), f[:0].to(DEV)).shape == (0, 1)
+
+
+def test_tc_render_vs_reference():
+    """render_rays_func with the tensor-core MLP against the unmodified reference (bf16 tolerance on the floats,
+    masks and depths samples still bit-exact)."""
+    case = gc.CASES['render_det']
+    g = gc.load_golden('render_det')
+    inp = gc.render_inputs(case)
+    ray_o, ray_d = inp['ray_o'].to(DEV), inp['ray_d'].to(DEV)
+    images, featmaps = inp['images'].to(DEV), inp['featmaps'].to(DEV)
+    field = make_field(inp['state'])
+    ret = render.render_rays_func(ray_o, ray_d, None, None, featmaps, images, inp['aabb'], inp['near_far_range'],
+                                  inp['N_samples'], ray_o.shape[0], field, inp['img_meta'], Projector(), 'image', 3,
+                                  False, 0, True)
+    oc = ret['outputs_coarse']
+    assert np.array_equal(oc['mask'].cpu().numpy(), g['mask'])
+    assert np.array_equal(oc['z_vals'].cpu().numpy(), g['z_vals'])
+    for k in ('rgb', 'depth', 'weights', 'alpha', 'transparency'):
+        assert_norm_close(oc[k], g[k], 1e-2, k)
+    assert_norm_close(ret['sigma'], g['sigma'], 1e-2, 'sigma')

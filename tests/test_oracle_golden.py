@@ -130,3 +130,17 @@ def test_extract_feat_oracle_matches_reference():
         _close(oc[k], g[k], rtol=1e-4, atol_scale=1e-5, name=k)
     _close(gt_rgb, g['gt_rgb'], name='gt_rgb')
     _close(gt_depth, g['gt_depth'], name='gt_depth')
+
+
+def test_bf16_mlp_oracle_within_bf16_tolerance_of_reference():
+    """oracle/mlp_oracle.py:FieldOracleBf16 (the operand roundings of the tensor-core kernel) stays within
+    BASELINE.json's bf16 tolerance (1e-2, normalised by the tensor's max) of the reference fixture."""
+    import numpy as np
+    from oracle import golden_cases as gc
+    from oracle import mlp_oracle as mo
+    g = gc.load_golden('mlp_small')
+    inp = gc.mlp_inputs(gc.CASES['mlp_small'])
+    rgb, sigma = mo.FieldOracleBf16(inp['state'])(inp['pts'], inp['ray_d'], inp['feats'])
+    for name, a, b in (('rgb', rgb.numpy(), g['rgb']), ('sigma', sigma.numpy(), g['sigma'])):
+        err = np.abs(a - b).max()
+        assert 0 < err <= 1e-2 * np.abs(b).max(), (name, err)
