@@ -5,19 +5,24 @@
 //
 // One persistent CTA per SM walks tiles of 128 points through the whole network:
 //
-//   activations   never leave the SM.  H [128][256] bf16 and IN [128][192] bf16 (posenc 63 | features |
-//                 zero pad to 144 | view encoding 27 at column 144) live in shared memory as K-major
-//                 128-byte-swizzled blocks of 64 columns -- directly the A operand of tcgen05.mma.
+//   activations   never leave the SM, and the hidden activations never leave TENSOR MEMORY: the epilogue of
+//                 layer i reads its fp32 accumulator row (tcgen05.ld), applies bias / relu, packs to bf16 and
+//                 stores the result back IN PLACE (tcgen05.st: the 8 packed columns of K step s over the first
+//                 8 of the 16 accumulator columns they came from), where layer i + 1 reads it as the A operand
+//                 of tcgen05.mma (A-from-TMEM form).  Shared-memory bandwidth, the limiter of the first version
+//                 (A re-read from shared memory for every MMA), is left to the weights alone.
+//                 IN [128][192] bf16 (posenc 63 | features | zero pad to 144 | view encoding 27 at column
+//                 144) lives in shared memory as K-major 128-byte-swizzled blocks of 64 columns (A-from-smem).
 //   weights       nd_pack_mlp_weights_tc stores every (layer, 64-column K block) as the exact shared-memory
 //                 image of a K-major SWIZZLE_128B B operand, so the producer warp streams one block with ONE
-//                 cp.async.bulk (TMA) into a 3-stage mbarrier ring; the weights stay L2-resident (0.8 MB).
-//   accumulators  two 128 x 256 fp32 buffers in TMEM (all 512 columns).  Jobs (layers) alternate between
-//                 them, so the epilogue of layer i (tcgen05.ld -> bias, relu -> bf16 -> swizzled st.shared)
-//                 runs while layer i + 1 already accumulates: the epilogue publishes H in chunks of 64
-//                 columns and the MMA warp starts the next layer's K block j as soon as chunk j is there.
-//   roles         warps 0-3 epilogue (TMEM lane quarter = warp id), warps 4-7 input encoding of the NEXT
-//                 tile (held in registers until the IN buffer is released), warp 8 weight producer,
-//                 warp 9 MMA issuer (one elected thread) and TMEM owner.
+//                 cp.async.bulk (TMA) into a 5-stage mbarrier ring; the weights stay L2-resident (0.8 MB).
+//   accumulators  two 128 x 256 fp32 regions in TMEM (all 512 columns).  Jobs (layers) alternate between
+//                 them, so the epilogue of layer i runs while layer i + 1 already accumulates into the other
+//                 region: the epilogue publishes its A operand in chunks of 64 K columns and the MMA warp
+//                 starts the next layer's K block j as soon as chunk j is there.
+//   roles         warps 0-7 epilogue (TMEM lane quarter = warp % 4, 32-column half of a chunk = warp / 4),
+//                 warps 8-11 input encoding of the NEXT tile (held in registers until the IN buffer is
+//                 released), warp 12 weight producer, warp 13 MMA issuer (one elected thread), TMEM owner.
 //   heads         sigma (K -> 1) and the RGB output layer (128 -> 3) are dot products of the fp32 rows the
 //                 epilogue threads already hold (thread = point); the [h, in] skip input of the heads is
 //                 extra K blocks of the same job, the `in` share of sigma is computed in fp32 by the
@@ -40,22 +45,25 @@ constexpr int kTcInPad = 144;           // [posenc | features | 0] columns of th
 constexpr int kTcCondCol = 144;         // view encoding: IN columns 144 .. 175 (2 K steps)
 constexpr int kTcInChunks = 22;         // 16-byte chunks (8 bf16) a point's IN row is written in
 constexpr int kTcBlockBytes = 16384;    // 128 rows x 128 B: one A block
-constexpr int kTcStageBytes = 32768;    // 256 rows x 128 B: one B block
-constexpr int kTcStages = 3;
-constexpr int kTcMaxUnits = 64, kTcMaxJobs = 12, kTcMaxDepth = 8;
-constexpr int kTcThreads = 320;
-constexpr uint32_t kOffH = 0, kOffIn = 4 * kTcBlockBytes, kOffB = kOffIn + 3 * kTcBlockBytes,
-                   kOffTail = kOffB + kTcStages * kTcStageBytes;   // 212992
-constexpr uint32_t kTailBars = 0, kTailTmem = 256, kTailSigIn = 512, kTailPar = 512 + 4 * kTcTile * 4;
+constexpr int kTcUnitN = 256;           // output columns per B unit = UMMA N (128: a 256-wide layer is two units per K block)
+constexpr int kTcStageBytes = kTcUnitN * 128;    // rows x 128 B: one B unit
+constexpr int kTcStages = 160 * 1024 / kTcStageBytes;
+constexpr int kTcMaxUnits = 128, kTcMaxJobs = 12, kTcMaxDepth = 8;
+constexpr int kTcEpiThreads = 256;      // warps 0-7: TMEM lane quarter = warp % 4, column half of a 64-column chunk = warp / 4
+constexpr int kTcThreads = 448;         // + warps 8-11 input encoding, warp 12 weight producer, warp 13 MMA issuer
+constexpr uint32_t kOffIn = 0, kOffB = kOffIn + 3 * kTcBlockBytes, kOffTail = kOffB + kTcStages * kTcStageBytes;   // 212992
+constexpr uint32_t kTailBars = 0, kTailTmem = 256, kTailHead = 512, kTailSigIn = kTailHead + 2 * kTcTile * 16,
+                   kTailPar = kTailSigIn + 4 * kTcTile * 4;
 
 enum : uint8_t { kJobRelu = 1, kJobWritesH = 2, kJobSigma = 4, kJobRgb = 8, kJobFreesIn = 16 };
 
-struct TcUnit {                 // one K block of one job = one B stage
-    uint32_t src_off;           // byte offset of the block in the weight image
-    uint16_t bytes16;           // bytes / 16
-    uint8_t a_blk;              // A operand: 0..3 = H chunk, 4..6 = IN block
+struct TcUnit {                 // kTcUnitN (or 128) output columns x one K block of one job = one B stage
+    uint32_t src_off;           // byte offset of the unit in the weight image
+    uint8_t a_blk;              // A operand: 0..3 = chunk of the previous job's output (TMEM), 4..6 = IN block (smem)
     uint8_t k0, nk;             // first K step (16 columns each) inside the block and number of steps
-    uint8_t pad[3];
+    uint8_t flags;              // 1: first unit of its K block (wait for the A operand), 2: first K block (overwrite D)
+    uint16_t d_col;             // accumulator column of the unit's first output
+    uint16_t n;                 // output columns (UMMA N)
 };
 struct TcJob {
     uint8_t first_unit, n_units, flags, pad;
@@ -68,7 +76,7 @@ struct TcPlan {
 };
 struct TcPackUnit {             // source of one block for the packing kernel
     const float *w;             // reference weight [n][k_ref]
-    int n, k_ref, col_base, lo, hi;   // block column kk in [lo, hi) <- reference column col_base + kk, others zero
+    int n, row0, k_ref, col_base, lo, hi;   // rows row0 .. row0 + n; block column kk in [lo, hi) <- reference column col_base + kk
     uint32_t dst_off;
 };
 struct TcLayout {
@@ -122,24 +130,30 @@ static bool tc_layout(const nd_mlp_weights *w, TcLayout &L, bool report) {
         return j;
     };
     auto add_unit = [&](TcJob &j, const float *wsrc, int k_ref, int a_blk, int k0, int nk, int col_base, int lo, int hi) {
-        TcUnit &u = P.units[P.n_units];
-        TcPackUnit &pu = L.pack[P.n_units];
-        ++P.n_units;
-        ++j.n_units;
-        const uint32_t bytes = (uint32_t)j.n * 128u;
-        u.src_off = img;
-        u.bytes16 = (uint16_t)(bytes / 16);
-        u.a_blk = (uint8_t)a_blk;
-        u.k0 = (uint8_t)k0;
-        u.nk = (uint8_t)nk;
-        pu.w = wsrc;
-        pu.n = j.n;
-        pu.k_ref = k_ref;
-        pu.col_base = col_base;
-        pu.lo = lo;
-        pu.hi = hi;
-        pu.dst_off = img;
-        img += bytes;
+        const bool first_kb = j.n_units == 0;
+        const int un = j.n < kTcUnitN ? j.n : kTcUnitN;
+        for (int nh = 0; nh < j.n / un; ++nh) {
+            TcUnit &u = P.units[P.n_units];
+            TcPackUnit &pu = L.pack[P.n_units];
+            ++P.n_units;
+            ++j.n_units;
+            u.src_off = img;
+            u.a_blk = (uint8_t)a_blk;
+            u.k0 = (uint8_t)k0;
+            u.nk = (uint8_t)nk;
+            u.flags = (uint8_t)((nh == 0 ? 1 : 0) | (first_kb ? 2 : 0));
+            u.d_col = (uint16_t)(nh * un);
+            u.n = (uint16_t)un;
+            pu.w = wsrc;
+            pu.n = un;
+            pu.row0 = nh * un;
+            pu.k_ref = k_ref;
+            pu.col_base = col_base;
+            pu.lo = lo;
+            pu.hi = hi;
+            pu.dst_off = img;
+            img += (uint32_t)un * 128u;
+        }
     };
     auto add_h_units = [&](TcJob &j, const float *wsrc, int k_ref) {
         for (int c = 0; c < 4; ++c) add_unit(j, wsrc, k_ref, c, 0, 4, c * 64, 0, 64);
@@ -200,8 +214,8 @@ static bool tc_layout(const nd_mlp_weights *w, TcLayout &L, bool report) {
 }
 
 // ---- packing --------------------------------------------------------------------------------------------
-struct TcPackArgs {
-    TcPackUnit u[kTcMaxUnits];
+struct TcPackArgs {                // kernel parameters are limited to 4 KB: 64 units per launch
+    TcPackUnit u[64];
 };
 
 // K-major SWIZZLE_128B image of an [n][64] bf16 block: row r at (r / 8) * 1024 + (r % 8) * 128, its 16-byte chunk c
@@ -216,7 +230,7 @@ __global__ void k_pack_tc_units(const __grid_constant__ TcPackArgs a, uint8_t *_
     if (i >= u.n * 64) return;
     const int r = i >> 6, kk = i & 63;
     float v = 0.0f;
-    if (kk >= u.lo && kk < u.hi) v = u.w[(size_t)r * u.k_ref + u.col_base + kk];
+    if (kk >= u.lo && kk < u.hi) v = u.w[(size_t)(u.row0 + r) * u.k_ref + u.col_base + kk];
     *reinterpret_cast<__nv_bfloat16 *>(img + u.dst_off + sw128_offset(r, kk)) = __float2bfloat16_rn(v);
 }
 
@@ -335,6 +349,30 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
 __device__ __forceinline__ uint32_t instr_desc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcTile >> 4) << 24);
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: A rows = TMEM lanes, K pairs packed into 32-bit columns
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// relu fused into the bf16 conversion
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 }  // namespace tc
 
 // ---- input encoding -----------------------------------------------------------------------------------
@@ -369,27 +407,28 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
     const uint32_t raw = tc::smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B operands need 1024-byte alignment
     uint8_t *sm = smem_raw + (base - raw);
-    const uint32_t sH = base + kOffH, sIN = base + kOffIn, sB = base + kOffB;
+    const uint32_t sIN = base + kOffIn, sB = base + kOffB;
     const uint32_t bars = base + kOffTail + kTailBars;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(sm + kOffTail + kTailTmem);
+    float *s_head = reinterpret_cast<float *>(sm + kOffTail + kTailHead);          // [2][128][4] (slot t % 2): sigma | rgb partials of column half 1
     // [4][128]: slot t % 4.  The encoding warps may run ahead of the epilogue by the tile whose first job is in
     // flight plus the one they hold in registers; four slots keep the writer of tile t + 4 behind the reader of tile t
     // in every job plan (two would race in the density-only plan, where IN is released after the first job).
     float *s_sig_in = reinterpret_cast<float *>(sm + kOffTail + kTailSigIn);
     float *s_par = reinterpret_cast<float *>(sm + kOffTail + kTailPar);
-    const uint32_t b_full = bars, b_empty = bars + 8 * 3, d_full = bars + 8 * 6, d_empty = bars + 8 * 8,
-                   h_ready = bars + 8 * 10, in_ready = bars + 8 * 14, in_free = bars + 8 * 15;
+    const uint32_t b_full = bars, b_empty = bars + 8 * kTcStages, d_full = bars + 8 * 2 * kTcStages,
+                   d_empty = d_full + 8 * 2, h_ready = d_full + 8 * 4, in_ready = d_full + 8 * 8, in_free = d_full + 8 * 9;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 3; ++i) { tc::mbar_init(b_full + 8 * i, 1); tc::mbar_init(b_empty + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(d_full + 8 * i, 1); tc::mbar_init(d_empty + 8 * i, 128); }
-        for (int i = 0; i < 4; ++i) tc::mbar_init(h_ready + 8 * i, 128);
+        for (int i = 0; i < kTcStages; ++i) { tc::mbar_init(b_full + 8 * i, 1); tc::mbar_init(b_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(d_full + 8 * i, 1); tc::mbar_init(d_empty + 8 * i, kTcEpiThreads); }
+        for (int i = 0; i < 4; ++i) tc::mbar_init(h_ready + 8 * i, kTcEpiThreads);
         tc::mbar_init(in_ready, 128);
         tc::mbar_init(in_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) tc::tmem_alloc(tc::smem_u32(s_tmem), 512);
+    if (warp == 13) tc::tmem_alloc(tc::smem_u32(s_tmem), 512);
     for (int i = threadIdx.x; i < a.n_par; i += kTcThreads) s_par[i] = a.par[i];
     tc::tc_fence_before();
     __syncthreads();
@@ -397,7 +436,7 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
     const uint32_t tmem = *s_tmem;
     const TcPlan &P = a.plan;
 
-    if (warp == 8) {
+    if (warp == 12) {
         // ---------------- weight producer ----------------
         if (lane == 0) {
             int stage = 0;
@@ -405,14 +444,14 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 for (int u = 0; u < P.n_units; ++u) {
                     tc::mbar_wait(b_empty + 8 * stage, ph ^ 1u);
-                    const uint32_t bytes = (uint32_t)P.units[u].bytes16 * 16u;
+                    const uint32_t bytes = (uint32_t)P.units[u].n * 128u;
                     tc::mbar_expect_tx(b_full + 8 * stage, bytes);
                     tc::bulk_g2s(sB + stage * kTcStageBytes, a.wimg + P.units[u].src_off, bytes, b_full + 8 * stage);
                     if (++stage == kTcStages) { stage = 0; ph ^= 1u; }
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 13) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             int stage = 0;
@@ -425,29 +464,37 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                     const uint32_t d = jc & 1u;
                     tc::mbar_wait(d_empty + 8 * d, (dpar >> d) & 1u);
                     dpar ^= 1u << d;
-                    const uint32_t idesc = tc::instr_desc(job.n);
-                    const uint32_t d_tmem = tmem + d * 256u;
+                    const uint32_t a_region = tmem + (d ^ 1u) * 256u;             // the previous job's region holds this job's A
                     for (int uu = 0; uu < job.n_units; ++uu) {
                         const TcUnit u = P.units[job.first_unit + uu];
-                        uint32_t a_addr;
-                        if (u.a_blk < 4) {
-                            tc::mbar_wait(h_ready + 8 * u.a_blk, (hpar >> u.a_blk) & 1u);
-                            hpar ^= 1u << u.a_blk;
-                            a_addr = sH + u.a_blk * kTcBlockBytes;
-                        } else {
-                            if (!in_ok) {
-                                tc::mbar_wait(in_ready, in_par);
-                                in_par ^= 1u;
-                                in_ok = true;
+                        const bool from_tmem = u.a_blk < 4;
+                        if (from_tmem) {
+                            if (u.flags & 1) {
+                                tc::mbar_wait(h_ready + 8 * u.a_blk, (hpar >> u.a_blk) & 1u);
+                                hpar ^= 1u << u.a_blk;
                             }
-                            a_addr = sIN + (u.a_blk - 4) * kTcBlockBytes;
+                        } else if (!in_ok) {
+                            tc::mbar_wait(in_ready, in_par);
+                            in_par ^= 1u;
+                            in_ok = true;
                         }
                         tc::mbar_wait(b_full + 8 * stage, ph);
                         tc::tc_fence_after();
-                        const uint64_t ad = tc::smem_desc(a_addr), bd = tc::smem_desc(sB + stage * kTcStageBytes);
-                        for (int s = 0; s < u.nk; ++s) {
-                            const uint64_t ko = (uint64_t)(2 * (u.k0 + s));        // 32 B per K step, in 16-byte units
-                            tc::umma_bf16(d_tmem, ad + ko, bd + ko, idesc, (uu | s) != 0 ? 1u : 0u);
+                        const uint32_t idesc = tc::instr_desc(u.n);
+                        const uint64_t bd = tc::smem_desc(sB + stage * kTcStageBytes);
+                        const uint32_t d_tmem = tmem + d * 256u + u.d_col;
+                        if (from_tmem) {
+                            // K step s of chunk c: 8 packed columns at column 64 c + 16 s of the previous region
+                            const uint32_t a_tmem = a_region + (uint32_t)u.a_blk * 64u;
+                            for (int s = 0; s < u.nk; ++s)
+                                tc::umma_bf16_ts(d_tmem, a_tmem + 16u * (uint32_t)(u.k0 + s), bd + (uint64_t)(2 * (u.k0 + s)), idesc,
+                                                 ((u.flags & 2) && s == 0) ? 0u : 1u);
+                        } else {
+                            const uint64_t ad = tc::smem_desc(sIN + (u.a_blk - 4) * kTcBlockBytes);
+                            for (int s = 0; s < u.nk; ++s) {
+                                const uint64_t ko = (uint64_t)(2 * (u.k0 + s));    // 32 B per K step, in 16-byte units
+                                tc::umma_bf16(d_tmem, ad + ko, bd + ko, idesc, ((u.flags & 2) && s == 0) ? 0u : 1u);
+                            }
                         }
                         tc::umma_commit(b_empty + 8 * stage);                       // frees the B stage once these MMAs are done
                         if (++stage == kTcStages) { stage = 0; ph ^= 1u; }
@@ -457,9 +504,9 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 8) {
         // ---------------- input encoding of the next tile (thread = point) ----------------
-        const int r = threadIdx.x - 128;
+        const int r = threadIdx.x - kTcEpiThreads;
         const uint32_t row_addr = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
         const float *ws_in = s_par + a.off_ws_in;
         int t = 0;
@@ -514,10 +561,10 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
             tc::mbar_arrive(in_ready);
         }
     } else {
-        // ---------------- epilogue (thread = point = TMEM lane) ----------------
-        const int r = threadIdx.x;
-        const uint32_t row_addr = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        // ---------------- epilogue: thread = (point = TMEM lane, 32-column half of every 64-column chunk) ----------------
+        const int q = warp & 3, half = warp >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const float *ws_h = s_par + a.off_ws_h, *wo = s_par + a.off_wo;
         uint32_t dfull_par = 0, jc = 0;
         int t = 0;
@@ -535,78 +582,82 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                 float sig = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
                 const int n_chunks = job.n >> 6;
                 for (int ch = 0; ch < n_chunks; ++ch) {
+                    const int col = ch * 64 + half * 32;
+                    uint32_t v[32];
+                    tc::tmem_ld32(tmem + lane_base + d * 256u + (uint32_t)col, v);
+                    tc::tmem_ld_wait();
+                    float f[32];
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const int col = ch * 64 + half * 32;
-                        uint32_t v[32];
-                        tc::tmem_ld32(tmem + lane_base + d * 256u + (uint32_t)col, v);
-                        tc::tmem_ld_wait();
-                        float f[32];
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(bias + col + i);
+                        f[i] = __uint_as_float(v[i]) + b4.x;
+                        f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
+                        f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
+                        f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+                    }
+                    if (sig_head) {                            // fp32 row x fp32 sigma weights, relu'd values
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4 *>(bias + col + i);
-                            f[i] = __uint_as_float(v[i]) + b4.x;
-                            f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
-                            f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
-                            f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+                            const float4 w4 = *reinterpret_cast<const float4 *>(ws_h + col + i);
+                            sig = fmaf(fmaxf(f[i], 0.f), w4.x, sig); sig = fmaf(fmaxf(f[i + 1], 0.f), w4.y, sig);
+                            sig = fmaf(fmaxf(f[i + 2], 0.f), w4.z, sig); sig = fmaf(fmaxf(f[i + 3], 0.f), w4.w, sig);
                         }
-                        if (relu) {
+                    }
+                    if (rgb_head) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-                        }
-                        if (sig_head) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                const float4 w4 = *reinterpret_cast<const float4 *>(ws_h + col + i);
-                                sig = fmaf(f[i], w4.x, sig); sig = fmaf(f[i + 1], w4.y, sig);
-                                sig = fmaf(f[i + 2], w4.z, sig); sig = fmaf(f[i + 3], w4.w, sig);
-                            }
-                        }
-                        if (rgb_head) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                const float4 w0 = *reinterpret_cast<const float4 *>(wo + col + i);
-                                const float4 w1 = *reinterpret_cast<const float4 *>(wo + kTcCondWidth + col + i);
-                                const float4 w2 = *reinterpret_cast<const float4 *>(wo + 2 * kTcCondWidth + col + i);
-                                c0 = fmaf(f[i], w0.x, c0); c0 = fmaf(f[i + 1], w0.y, c0); c0 = fmaf(f[i + 2], w0.z, c0); c0 = fmaf(f[i + 3], w0.w, c0);
-                                c1 = fmaf(f[i], w1.x, c1); c1 = fmaf(f[i + 1], w1.y, c1); c1 = fmaf(f[i + 2], w1.z, c1); c1 = fmaf(f[i + 3], w1.w, c1);
-                                c2 = fmaf(f[i], w2.x, c2); c2 = fmaf(f[i + 1], w2.y, c2); c2 = fmaf(f[i + 2], w2.z, c2); c2 = fmaf(f[i + 3], w2.w, c2);
-                            }
-                        }
-                        if (writes_h) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int cc = half * 4 + q;
-                                tc::sts_u4(sH + ch * kTcBlockBytes + row_addr + (uint32_t)((cc ^ (r & 7)) << 4),
-                                           tc::pack_bf16(f[q * 8], f[q * 8 + 1]), tc::pack_bf16(f[q * 8 + 2], f[q * 8 + 3]),
-                                           tc::pack_bf16(f[q * 8 + 4], f[q * 8 + 5]), tc::pack_bf16(f[q * 8 + 6], f[q * 8 + 7]));
-                            }
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 w0 = *reinterpret_cast<const float4 *>(wo + col + i);
+                            const float4 w1 = *reinterpret_cast<const float4 *>(wo + kTcCondWidth + col + i);
+                            const float4 w2 = *reinterpret_cast<const float4 *>(wo + 2 * kTcCondWidth + col + i);
+                            const float t0 = fmaxf(f[i], 0.f), t1 = fmaxf(f[i + 1], 0.f), t2 = fmaxf(f[i + 2], 0.f), t3 = fmaxf(f[i + 3], 0.f);
+                            c0 = fmaf(t0, w0.x, c0); c0 = fmaf(t1, w0.y, c0); c0 = fmaf(t2, w0.z, c0); c0 = fmaf(t3, w0.w, c0);
+                            c1 = fmaf(t0, w1.x, c1); c1 = fmaf(t1, w1.y, c1); c1 = fmaf(t2, w1.z, c1); c1 = fmaf(t3, w1.w, c1);
+                            c2 = fmaf(t0, w2.x, c2); c2 = fmaf(t1, w2.y, c2); c2 = fmaf(t2, w2.z, c2); c2 = fmaf(t3, w2.w, c2);
                         }
                     }
                     if (writes_h) {
-                        tc::fence_proxy_async();               // generic-proxy stores -> visible to the tensor core's async proxy
+                        // bf16 pairs back into the columns they came from: K step s at column 16 s of this region
+                        uint32_t pkd[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            pkd[i] = relu ? tc::pack_bf16_relu(f[2 * i], f[2 * i + 1]) : tc::pack_bf16(f[2 * i], f[2 * i + 1]);
+                        const uint32_t t0 = tmem + lane_base + d * 256u + (uint32_t)col;
+                        tc::tmem_st8(t0, pkd);
+                        tc::tmem_st8(t0 + 16u, pkd + 8);
+                        tc::tmem_st_wait();
+                        tc::tc_fence_before();
                         tc::mbar_arrive(h_ready + 8 * ch);
                     }
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(d_empty + 8 * d);              // this accumulator buffer may be overwritten
-                if (sig_head && gp < a.n_points) {
-                    const float sg = fmaxf(sig + s_sig_in[(t & 3) * kTcTile + r] + s_par[a.off_bsig], 0.0f);
-                    if (a.sigma != nullptr) a.sigma[gp] = sg;
-                    if (a.alpha != nullptr) a.alpha[gp] = 1.0f - expf(-sg);        // nerfdet.py:258
-                }
-                if (rgb_head && gp < a.n_points) {
-                    const float *bo = s_par + a.off_bo;
-                    a.rgb[gp * 3] = 1.0f / (1.0f + expf(-(c0 + bo[0])));
-                    a.rgb[gp * 3 + 1] = 1.0f / (1.0f + expf(-(c1 + bo[1])));
-                    a.rgb[gp * 3 + 2] = 1.0f / (1.0f + expf(-(c2 + bo[2])));
+                if (sig_head || rgb_head) {
+                    // the two column halves of a point sit in warps q and q + 4: half 1 hands its partial sums over
+                    float *slot = s_head + ((t & 1) * kTcTile + r) * 4;
+                    if (half == 1) {
+                        if (sig_head) slot[0] = sig;
+                        else { slot[1] = c0; slot[2] = c1; slot[3] = c2; }
+                    }
+                    tc::bar_sync(1 + q, 64);
+                    if (half == 0 && gp < a.n_points) {
+                        if (sig_head) {
+                            const float sg = fmaxf(sig + slot[0] + s_sig_in[(t & 3) * kTcTile + r] + s_par[a.off_bsig], 0.0f);
+                            if (a.sigma != nullptr) a.sigma[gp] = sg;
+                            if (a.alpha != nullptr) a.alpha[gp] = 1.0f - expf(-sg);        // nerfdet.py:258
+                        } else {
+                            const float *bo = s_par + a.off_bo;
+                            a.rgb[gp * 3] = 1.0f / (1.0f + expf(-(c0 + slot[1] + bo[0])));
+                            a.rgb[gp * 3 + 1] = 1.0f / (1.0f + expf(-(c1 + slot[2] + bo[1])));
+                            a.rgb[gp * 3 + 2] = 1.0f / (1.0f + expf(-(c2 + slot[3] + bo[2])));
+                        }
+                    }
                 }
             }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 13) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem, 512);
     }
@@ -640,11 +691,14 @@ int nd_pack_mlp_weights_tc(const nd_mlp_weights *w, void *packed, size_t packed_
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *img = reinterpret_cast<uint8_t *>(packed);
     float *par = reinterpret_cast<float *>(img + align_up(L.image_bytes, 256));
-    TcPackArgs pa;
-    memset(&pa, 0, sizeof(pa));
-    for (int i = 0; i < L.n_pack; ++i) pa.u[i] = L.pack[i];
-    k_pack_tc_units<<<dim3((unsigned)ceil_div(kTcWidth * 64, 256), (unsigned)L.n_pack), 256, 0, st>>>(pa, img);
-    ND_CUDA_LAUNCH_CHECK("k_pack_tc_units");
+    for (int u0 = 0; u0 < L.n_pack; u0 += 64) {
+        TcPackArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        const int nb = L.n_pack - u0 < 64 ? L.n_pack - u0 : 64;
+        for (int i = 0; i < nb; ++i) pa.u[i] = L.pack[u0 + i];
+        k_pack_tc_units<<<dim3((unsigned)ceil_div(kTcWidth * 64, 256), (unsigned)nb), 256, 0, st>>>(pa, img);
+        ND_CUDA_LAUNCH_CHECK("k_pack_tc_units");
+    }
     TcParSrc ps;
     memset(&ps, 0, sizeof(ps));
     const TcPlan &P = L.full;

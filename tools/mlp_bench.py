@@ -40,9 +40,28 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / n * 1e3
+            # the same launches replayed from a CUDA graph: no host launch overhead between kernels
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                run()
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(10):
+                        run()
+            torch.cuda.current_stream().wait_stream(side)
+            g.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            us_graph = e0.elapsed_time(e1) / 50 * 1e3
             flop = p * (FLOP_FULL if full else FLOP_DENSITY)
-            print(json.dumps({'shape': name, 'precision': prec, 'points': p, 'us': round(us, 1),
-                              'tflops': round(flop / us / 1e6, 1), 'mpoints_per_s': round(p / us, 1)}), flush=True)
+            print(json.dumps({'shape': name, 'precision': prec, 'points': p, 'us_eager': round(us, 1),
+                              'us': round(us_graph, 1), 'tflops': round(flop / us_graph / 1e6, 1),
+                              'mpoints_per_s': round(p / us_graph, 1)}), flush=True)
 
 
 if __name__ == '__main__':
