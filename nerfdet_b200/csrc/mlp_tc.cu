@@ -99,6 +99,8 @@ struct TcArgs {
     int64_t n_points;
     int samples_per_ray, feat_dim, n_tiles;
     float *sigma, *alpha, *rgb;
+    int debug;                  // diagnostics (ND_MLP_TC_DEBUG): 1 = no weight copies, 2 = no MMAs, 4 = no epilogue math,
+                                // 8 = MMA warp ignores the epilogue hand-shakes, 16 = ... and the weight / input barriers (timing only)
 };
 
 // ---- plan / layout (host) -------------------------------------------------------------------------------
@@ -401,8 +403,12 @@ __device__ __forceinline__ void encode_doubling(const float (&x)[3], float *dst)
     }
 }
 
+// kDiag: the diagnostics build honours TcArgs::debug (tools/mlp_bench.py with ND_MLP_TC_DEBUG); the product
+// instantiation carries none of it.
+template <bool kDiag>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
+    const int dbg = kDiag ? a.debug : 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = tc::smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B operands need 1024-byte alignment
@@ -422,9 +428,9 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kTcStages; ++i) { tc::mbar_init(b_full + 8 * i, 1); tc::mbar_init(b_empty + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(d_full + 8 * i, 1); tc::mbar_init(d_empty + 8 * i, kTcEpiThreads); }
-        for (int i = 0; i < 4; ++i) tc::mbar_init(h_ready + 8 * i, kTcEpiThreads);
-        tc::mbar_init(in_ready, 128);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(d_full + 8 * i, 1); tc::mbar_init(d_empty + 8 * i, kTcEpiThreads / 32); }
+        for (int i = 0; i < 4; ++i) tc::mbar_init(h_ready + 8 * i, kTcEpiThreads / 32);   // one arrival per warp
+        tc::mbar_init(in_ready, 4);
         tc::mbar_init(in_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -445,8 +451,11 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                 for (int u = 0; u < P.n_units; ++u) {
                     tc::mbar_wait(b_empty + 8 * stage, ph ^ 1u);
                     const uint32_t bytes = (uint32_t)P.units[u].n * 128u;
+                    if (dbg & 1) { tc::mbar_arrive(b_full + 8 * stage); }
+                    else {
                     tc::mbar_expect_tx(b_full + 8 * stage, bytes);
                     tc::bulk_g2s(sB + stage * kTcStageBytes, a.wimg + P.units[u].src_off, bytes, b_full + 8 * stage);
+                    }
                     if (++stage == kTcStages) { stage = 0; ph ^= 1u; }
                 }
             }
@@ -462,28 +471,29 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                 for (int j = 0; j < P.n_jobs; ++j, ++jc) {
                     const TcJob job = P.jobs[j];
                     const uint32_t d = jc & 1u;
-                    tc::mbar_wait(d_empty + 8 * d, (dpar >> d) & 1u);
+                    if (!(dbg & 8)) tc::mbar_wait(d_empty + 8 * d, (dpar >> d) & 1u);
                     dpar ^= 1u << d;
                     const uint32_t a_region = tmem + (d ^ 1u) * 256u;             // the previous job's region holds this job's A
                     for (int uu = 0; uu < job.n_units; ++uu) {
                         const TcUnit u = P.units[job.first_unit + uu];
                         const bool from_tmem = u.a_blk < 4;
                         if (from_tmem) {
-                            if (u.flags & 1) {
+                            if ((u.flags & 1) && !(dbg & 8)) {
                                 tc::mbar_wait(h_ready + 8 * u.a_blk, (hpar >> u.a_blk) & 1u);
                                 hpar ^= 1u << u.a_blk;
                             }
-                        } else if (!in_ok) {
+                        } else if (!in_ok && !(dbg & 16)) {
                             tc::mbar_wait(in_ready, in_par);
                             in_par ^= 1u;
                             in_ok = true;
                         }
-                        tc::mbar_wait(b_full + 8 * stage, ph);
+                        if (!(dbg & 16)) tc::mbar_wait(b_full + 8 * stage, ph);
                         tc::tc_fence_after();
                         const uint32_t idesc = tc::instr_desc(u.n);
                         const uint64_t bd = tc::smem_desc(sB + stage * kTcStageBytes);
                         const uint32_t d_tmem = tmem + d * 256u + u.d_col;
-                        if (from_tmem) {
+                        if (dbg & 2) {
+                        } else if (from_tmem) {
                             // K step s of chunk c: 8 packed columns at column 64 c + 16 s of the previous region
                             const uint32_t a_tmem = a_region + (uint32_t)u.a_blk * 64u;
                             for (int s = 0; s < u.nk; ++s)
@@ -558,7 +568,8 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
             }
             s_sig_in[(t & 3) * kTcTile + r] = sig_in;
             tc::fence_proxy_async();
-            tc::mbar_arrive(in_ready);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(in_ready);
         }
     } else {
         // ---------------- epilogue: thread = (point = TMEM lane, 32-column half of every 64-column chunk) ----------------
@@ -583,6 +594,14 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                 const int n_chunks = job.n >> 6;
                 for (int ch = 0; ch < n_chunks; ++ch) {
                     const int col = ch * 64 + half * 32;
+                    if (dbg & 4) {
+                        if (writes_h) {
+                            tc::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) tc::mbar_arrive(h_ready + 8 * ch);
+                        }
+                        continue;
+                    }
                     uint32_t v[32];
                     tc::tmem_ld32(tmem + lane_base + d * 256u + (uint32_t)col, v);
                     tc::tmem_ld_wait();
@@ -626,11 +645,13 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                         tc::tmem_st8(t0 + 16u, pkd + 8);
                         tc::tmem_st_wait();
                         tc::tc_fence_before();
-                        tc::mbar_arrive(h_ready + 8 * ch);
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(h_ready + 8 * ch);
                     }
                 }
                 tc::tc_fence_before();
-                tc::mbar_arrive(d_empty + 8 * d);              // this accumulator buffer may be overwritten
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(d_empty + 8 * d);   // this accumulator region may be overwritten
                 if (sig_head || rgb_head) {
                     // the two column halves of a point sit in warps q and q + 4: half 1 hands its partial sums over
                     float *slot = s_head + ((t & 1) * kTcTile + r) * 4;
@@ -748,17 +769,23 @@ int nd_nerf_mlp_fwd_tc(const nd_mlp_weights *arch, const void *packed, const flo
     a.feat_dim = L.feat;
     a.n_tiles = (int)ceil_div(n_points, kTcTile);
     a.sigma = sigma; a.alpha = alpha; a.rgb = want_rgb ? rgb : nullptr;
+    if (const char *e = getenv("ND_MLP_TC_DEBUG")) a.debug = atoi(e);
     const size_t smem = 1024 + kOffTail + kTailPar + (size_t)L.n_par * sizeof(float);
     ND_REQUIRE(smem <= 227 * 1024, ND_ERR_BAD_SHAPE, "nd_nerf_mlp_fwd_tc: %zu bytes of shared memory needed", smem);
-    cudaError_t e = cudaFuncSetAttribute(k_nerf_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    void (*kern)(const TcArgs) = a.debug != 0 ? k_nerf_mlp_tc<true> : k_nerf_mlp_tc<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         set_error("k_nerf_mlp_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
         return ND_ERR_CUDA;
     }
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (const char *g = getenv("ND_MLP_TC_GRID")) {              // diagnostics: fewer CTAs (L2 contention probe)
+        const int v = atoi(g);
+        if (v >= 1 && v < sms) sms = v;
+    }
     const int grid = a.n_tiles < sms ? a.n_tiles : sms;
-    k_nerf_mlp_tc<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(a);
+    kern<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(a);
     ND_CUDA_LAUNCH_CHECK("k_nerf_mlp_tc");
     return ND_OK;
 }
