@@ -134,6 +134,16 @@ int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_v
 
 
 /* ---------------------------------------------------------------------------------------
+ * B7  nerfdet.py:190-197  the per-pixel Linear(C -> 32) ("mapping") on the sliced 2-D features:
+ *   mapped[v][y][x][j] = bias[j] + sum_c weight[j][c] * features[v][c][y][x]      (fp32 FMA, channels ascending)
+ * features: NCHW planes read in place (contiguous planes, 16-byte aligned; f32 or bf16); weight f32 [32][C]
+ * row-major (the reference nn.Linear.weight), bias f32 [32] or NULL; mapped f32 [nv][h][w][32] -- the
+ * CHANNELS-LAST layout nd_live_stats and nd_render_gather_stats gather from (stride_c == 1).
+ * ------------------------------------------------------------------------------------- */
+int nd_map_features(const nd_maps *features, const float *weight, const float *bias, int out_channels,
+                    float *mapped, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * B8+B9  nerfdet.py:200-210, 232-253  live 35-channel voxel statistics that feed the density MLP.
  *   mapped  [nv][Cm][Hf][Wf] f32/bf16: the 2-D mapped features (B7, nerfdet.py:190-197), gathered with the
  *           FEATURE-level projection; an invalid voxel-view contributes map_bias (Linear(0), nerfdet.py:233-237)

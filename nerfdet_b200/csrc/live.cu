@@ -88,6 +88,96 @@ k_live_stats(const T *__restrict__ mapped, int64_t m_sv, int64_t m_sc, int64_t m
     if (count_out != nullptr) count_out[n] = cnt;
 }
 
+// Channels-last build (the product path; `mapped` as [nv][h][w][Cm], which is what the per-pixel Linear of B7
+// produces): one WARP per voxel, lane = mapped channel (lanes 0-2 also carry RGB).  The two projections run with
+// lane = view; only the valid views are visited, each mapped gather is one coalesced row of Cm elements.  Invalid
+// views contribute the bias (mapped) or 0 (RGB); their share is added in closed form after the loop.
+constexpr int kLcWarps = 8, kLcPerWarp = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kLcWarps * 32)
+k_live_stats_cl(const T *__restrict__ mapped, int64_t m_sv, int64_t m_sy, int64_t m_sx, int cm, int hf, int wf,
+                const float *__restrict__ rgb, int64_t r_sv, int64_t r_sc, int64_t r_sy, int64_t r_sx, int hr, int wr,
+                const float *__restrict__ points, const float *__restrict__ proj_f, const float *__restrict__ proj_r, int nv,
+                int64_t n_vox, const float *__restrict__ bias, float *__restrict__ glob, float *__restrict__ mean_out,
+                float *__restrict__ cov_out, int64_t *__restrict__ count_out) {
+    extern __shared__ float sp[];                       // [nv][12] feature-level, [nv][12] rgb-level
+    float *spr = sp + nv * 12;
+    for (int i = threadIdx.x; i < nv * 12; i += blockDim.x) {
+        sp[i] = proj_f[i];
+        spr[i] = proj_r[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const float b = lane < cm ? bias[lane] : 0.0f;
+    const int ct = 3 + cm;
+    for (int it = 0; it < kLcPerWarp; ++it) {
+        const int64_t n = ((int64_t)blockIdx.x * kLcWarps + warp) * kLcPerWarp + it;
+        if (n >= n_vox) break;                                             // warp-uniform
+        const float X = __ldg(points + n), Y = __ldg(points + n_vox + n), Z = __ldg(points + 2 * n_vox + n);
+        float s1 = 0.f, s2 = 0.f, r1 = 0.f, r2 = 0.f;
+        int cnt = 0;
+        for (int v0 = 0; v0 < nv; v0 += 32) {
+            const int v = v0 + lane;
+            bool ok_f = false, ok_r = false;
+            int off_f = 0, off_r = 0;
+            if (v < nv) {
+                float xr, yr, q2;
+                ok_f = project_nearest(sp + v * 12, X, Y, Z, hf, wf, xr, yr, q2);
+                if (ok_f) off_f = (int)((int)yr * m_sy + (int)xr * m_sx);
+                ok_r = project_nearest(spr + v * 12, X, Y, Z, hr, wr, xr, yr, q2);
+                if (ok_r) off_r = (int)((int)yr * r_sy + (int)xr * r_sx);
+            }
+            const unsigned bf = __ballot_sync(full, ok_f), br = __ballot_sync(full, ok_r);
+            cnt += __popc(bf);
+            unsigned act = bf | br;
+            while (act) {
+                const int src = __ffs(act) - 1;
+                act &= act - 1;
+                const int64_t vv = v0 + src;
+                if ((bf >> src) & 1u) {
+                    const int of = __shfl_sync(full, off_f, src);
+                    if (lane < cm) {
+                        const float hv = to_f32<T>(mapped[vv * m_sv + of + lane]);
+                        s1 += hv;
+                        s2 = fmaf(hv, hv, s2);
+                    }
+                }
+                if ((br >> src) & 1u) {
+                    const int orr = __shfl_sync(full, off_r, src);
+                    if (lane < 3) {
+                        const float hv = __ldg(rgb + vv * r_sv + lane * r_sc + orr);
+                        r1 += hv;
+                        r2 = fmaf(hv, hv, r2);
+                    }
+                }
+            }
+        }
+        // invalid views enter the mapped statistics as the Linear bias
+        const float n_inv = (float)(nv - cnt);
+        s1 = fmaf(n_inv, b, s1);
+        s2 = fmaf(n_inv * b, b, s2);
+        const float denom = __fadd_rn((float)cnt, 1e-8f);
+        float *row = glob + n * (int64_t)(2 * ct);
+        auto finish = [&](int k, float a1, float a2) {
+            const float m = a1 / denom;
+            float cv = 0.0f;
+            if (cnt > 0) {
+                float ssd = fmaf(-2.0f * m, a1, a2);
+                ssd = fmaxf(fmaf((float)nv * m, m, ssd), 0.0f);
+                cv = expf(-(ssd / denom));
+            }
+            *reinterpret_cast<float2 *>(row + 2 * k) = make_float2(m, cv);
+            if (mean_out != nullptr) mean_out[(int64_t)k * n_vox + n] = m;
+            if (cov_out != nullptr) cov_out[(int64_t)k * n_vox + n] = cv;
+        };
+        if (lane < 3) finish(lane, r1, r2);
+        if (lane < cm) finish(3 + lane, s1, s2);
+        if (lane == 0 && count_out != nullptr) count_out[n] = cnt;
+    }
+}
+
 }  // namespace nd
 
 using namespace nd;
@@ -108,8 +198,26 @@ extern "C" int nd_live_stats(const nd_maps *mapped, const nd_maps *rgb, const fl
     const int nv = mapped->n_views;
     const size_t smem = ((size_t)nv * 24 + mapped->channels) * sizeof(float);
     ND_REQUIRE(smem <= 48 * 1024, ND_ERR_BAD_SHAPE, "nd_live_stats: too many views (%d)", nv);
-    const unsigned grid = (unsigned)ceil_div(n_voxels, 128);
     cudaStream_t st = (cudaStream_t)stream;
+    if (mapped->stride_c == 1 && (reinterpret_cast<uintptr_t>(global_volume) & 7) == 0) {      // channels-last: warp per voxel
+        const size_t sm = (size_t)nv * 24 * sizeof(float);
+        const unsigned g = (unsigned)ceil_div(n_voxels, (int64_t)kLcWarps * kLcPerWarp);
+        if (mapped->dtype == ND_F32)
+            k_live_stats_cl<float><<<g, kLcWarps * 32, sm, st>>>(
+                (const float *)mapped->data, mapped->stride_v, mapped->stride_y, mapped->stride_x, mapped->channels,
+                mapped->height, mapped->width, (const float *)rgb->data, rgb->stride_v, rgb->stride_c, rgb->stride_y,
+                rgb->stride_x, rgb->height, rgb->width, points, projection, rgb_projection, nv, n_voxels, map_bias,
+                global_volume, mean35, cov35, count);
+        else
+            k_live_stats_cl<__nv_bfloat16><<<g, kLcWarps * 32, sm, st>>>(
+                (const __nv_bfloat16 *)mapped->data, mapped->stride_v, mapped->stride_y, mapped->stride_x, mapped->channels,
+                mapped->height, mapped->width, (const float *)rgb->data, rgb->stride_v, rgb->stride_c, rgb->stride_y,
+                rgb->stride_x, rgb->height, rgb->width, points, projection, rgb_projection, nv, n_voxels, map_bias,
+                global_volume, mean35, cov35, count);
+        ND_CUDA_LAUNCH_CHECK("k_live_stats_cl");
+        return ND_OK;
+    }
+    const unsigned grid = (unsigned)ceil_div(n_voxels, 128);
     if (mapped->dtype == ND_F32)
         k_live_stats<float><<<grid, 128, smem, st>>>(
             (const float *)mapped->data, mapped->stride_v, mapped->stride_c, mapped->stride_y, mapped->stride_x,

@@ -194,6 +194,155 @@ k_render_gather_stats(const float *__restrict__ pts, int64_t n_pts, const float 
     }
 }
 
+// Channels-last build of the same statistics (the product path): one WARP per ray sample, lane = mapped-feature
+// channel (lanes 0-2 also carry the three image channels).  The projection of the sample into the views runs with
+// lane = view; only views with at least one bilinear corner in bounds (~25 %) are visited afterwards, their
+// sample parameters broadcast with shuffles, and each corner of the feature map is ONE coalesced 128-byte row
+// [pixel][D] instead of D scattered 4-byte loads from D planes.  Same arithmetic (corner order nw, ne, sw, se;
+// views ascending) as the thread-per-sample kernel above, which stays for the materialising compatibility outputs.
+constexpr int kRcWarps = 8, kRcPerWarp = 4;
+
+struct ViewSampleG {         // like ViewSample, for arbitrary strides
+    int32_t x0, y0;
+    float fx, fy;
+    uint32_t inb;
+};
+
+__device__ __forceinline__ ViewSampleG make_sample_g(float gx, float gy, int hs, int ws) {
+    const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), (float)(ws - 1));
+    const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), (float)(hs - 1));
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    ViewSampleG s;
+    s.fx = ix - x0f;
+    s.fy = iy - y0f;
+    s.x0 = (int)fminf(fmaxf(x0f, -4.0f), (float)(ws + 2));
+    s.y0 = (int)fminf(fmaxf(y0f, -4.0f), (float)(hs + 2));
+    const bool xin0 = s.x0 >= 0 && s.x0 < ws, xin1 = s.x0 + 1 >= 0 && s.x0 + 1 < ws;
+    const bool yin0 = s.y0 >= 0 && s.y0 < hs, yin1 = s.y0 + 1 >= 0 && s.y0 + 1 < hs;
+    s.inb = (xin0 && yin0 ? 1u : 0u) | (xin1 && yin0 ? 2u : 0u) | (xin0 && yin1 ? 4u : 0u) | (xin1 && yin1 ? 8u : 0u);
+    if (!(ix == ix) || !(iy == iy)) s.inb = 0;
+    return s;
+}
+
+template <typename T>
+__device__ __forceinline__ float bilinear_g(const T *__restrict__ p, int64_t sx, int64_t sy, float fx, float fy, uint32_t inb) {
+    const float nw = (1.0f - fx) * (1.0f - fy), ne = fx * (1.0f - fy);
+    const float sw = (1.0f - fx) * fy, se = fx * fy;
+    // the four loads are independent: issue them together, then the fma chain in the reference's corner order
+    const float v0 = (inb & 1u) ? to_f32<T>(p[0]) : 0.0f;
+    const float v1 = (inb & 2u) ? to_f32<T>(p[sx]) : 0.0f;
+    const float v2 = (inb & 4u) ? to_f32<T>(p[sy]) : 0.0f;
+    const float v3 = (inb & 8u) ? to_f32<T>(p[sy + sx]) : 0.0f;
+    float acc = 0.0f;
+    if (inb & 1u) acc = fmaf(v0, nw, acc);
+    if (inb & 2u) acc = fmaf(v1, ne, acc);
+    if (inb & 4u) acc = fmaf(v2, sw, acc);
+    if (inb & 8u) acc = fmaf(v3, se, acc);
+    return acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRcWarps * 32)
+k_render_gather_stats_cl(const float *__restrict__ pts, int64_t n_pts, const float *__restrict__ cams, int nv,
+                         const float *__restrict__ img, int64_t i_sv, int64_t i_sc, int64_t i_sy, int64_t i_sx, int hi, int wi,
+                         const T *__restrict__ feat, int64_t f_sv, int64_t f_sy, int64_t f_sx, int d, int hf, int wf,
+                         float *__restrict__ glob, uint8_t *__restrict__ view_mask, uint8_t *__restrict__ pixel_mask) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sP = reinterpret_cast<float *>(smem_raw);                       // [nv][12] rows 0-2 of K @ E
+    for (int i = threadIdx.x; i < nv * 12; i += blockDim.x) {
+        const int v = i / 12, rc = i - v * 12, r = rc >> 2, c = rc & 3;
+        const float *K = cams + v * 34 + 2, *E = cams + v * 34 + 18;
+        float t = __fmul_rn(K[r * 4 + 0], E[0 * 4 + c]);                   // see k_render_gather_stats
+        t = __fadd_rn(t, __fmul_rn(K[r * 4 + 1], E[1 * 4 + c]));
+        t = __fadd_rn(t, __fmul_rn(K[r * 4 + 2], E[2 * 4 + c]));
+        t = __fadd_rn(t, __fmul_rn(K[r * 4 + 3], E[3 * 4 + c]));
+        sP[i] = t;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float h = cams[0], w = cams[1];
+    const float wm1 = __fsub_rn(w, 1.0f), hm1 = __fsub_rn(h, 1.0f);
+    const int ct = 3 + d;
+    const unsigned full = 0xffffffffu;
+    for (int it = 0; it < kRcPerWarp; ++it) {
+        const int64_t p = ((int64_t)blockIdx.x * kRcWarps + warp) * kRcPerWarp + it;
+        if (p >= n_pts) break;                                             // warp-uniform
+        const float X = __ldg(pts + p * 3), Y = __ldg(pts + p * 3 + 1), Z = __ldg(pts + p * 3 + 2);
+        int cnt = 0;
+        float smF = 0.f, s1F = 0.f, s2F = 0.f, smI = 0.f, s1I = 0.f, s2I = 0.f;
+        for (int v0 = 0; v0 < nv; v0 += 32) {
+            const int v = v0 + lane;
+            ViewSampleG si{0, 0, 0.f, 0.f, 0u}, sf{0, 0, 0.f, 0.f, 0u};
+            bool m = false;
+            if (v < nv) {
+                const float *P = sP + v * 12;
+                const float q0 = chain4(P, X, Y, Z), q1 = chain4(P + 4, X, Y, Z), q2 = chain4(P + 8, X, Y, Z);
+                const float zc = fmaxf(q2, 1e-8f);
+                float px = __fdiv_rn(q0, zc), py = __fdiv_rn(q1, zc);
+                px = fminf(fmaxf(px, -1e6f), 1e6f);
+                py = fminf(fmaxf(py, -1e6f), 1e6f);
+                const bool front = q2 > 0.0f;
+                const bool inb = (px <= wm1) && (px >= 0.0f) && (py <= hm1) && (py >= 0.0f);
+                m = inb && front;
+                const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, px), wm1), 1.0f);
+                const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, py), hm1), 1.0f);
+                si = make_sample_g(gx, gy, hi, wi);
+                sf = make_sample_g(gx, gy, hf, wf);
+                if (d == 0) sf.inb = 0u;
+                if (view_mask != nullptr) view_mask[p * nv + v] = m ? 1 : 0;
+            }
+            cnt += __popc(__ballot_sync(full, m));
+            const uint32_t bits = si.inb | (sf.inb << 4) | (m ? 0x100u : 0u);
+            const int offI = (int)(si.y0 * i_sy + si.x0 * i_sx), offF = (int)(sf.y0 * f_sy + sf.x0 * f_sx);
+            unsigned act = __ballot_sync(full, (bits & 0xffu) != 0u);
+            while (act) {
+                const int src = __ffs(act) - 1;
+                act &= act - 1;
+                const uint32_t b = __shfl_sync(full, bits, src);
+                const bool mv = (b & 0x100u) != 0;
+                const int64_t vv = v0 + src;
+                if (b & 0xfu) {
+                    const int oi = __shfl_sync(full, offI, src);
+                    const float fx = __shfl_sync(full, si.fx, src), fy = __shfl_sync(full, si.fy, src);
+                    if (lane < 3) {
+                        const float f = bilinear_g<float>(img + vv * i_sv + lane * i_sc + oi, i_sx, i_sy, fx, fy, b & 0xfu);
+                        smI += mv ? f : 0.0f;
+                        s1I += f;
+                        s2I = fmaf(f, f, s2I);
+                    }
+                }
+                if (b & 0xf0u) {
+                    const int of = __shfl_sync(full, offF, src);
+                    const float fx = __shfl_sync(full, sf.fx, src), fy = __shfl_sync(full, sf.fy, src);
+                    if (lane < d) {
+                        const float f = bilinear_g<T>(feat + vv * f_sv + of + lane, f_sx, f_sy, fx, fy, (b >> 4) & 0xfu);
+                        smF += mv ? f : 0.0f;
+                        s1F += f;
+                        s2F = fmaf(f, f, s2F);
+                    }
+                }
+            }
+        }
+        const float denom = __fadd_rn((float)cnt, 1e-8f);
+        float *row = glob + p * (int64_t)(2 * ct);
+        if (lane == 0 && pixel_mask != nullptr) pixel_mask[p] = cnt > 1 ? 1 : 0;
+        if (lane < 3) {
+            const float mean = smI / denom;
+            float ssd = fmaf(-2.0f * mean, s1I, s2I);
+            ssd = fmaxf(fmaf((float)nv * mean, mean, ssd), 0.0f);
+            row[lane] = mean;
+            row[ct + lane] = expf(-(ssd / denom));
+        }
+        if (lane < d) {
+            const float mean = smF / denom;
+            float ssd = fmaf(-2.0f * mean, s1F, s2F);
+            ssd = fmaxf(fmaf((float)nv * mean, mean, ssd), 0.0f);
+            row[3 + lane] = mean;
+            row[ct + 3 + lane] = expf(-(ssd / denom));
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // R7
 // -------------------------------------------------------------------------------------------------
@@ -301,11 +450,33 @@ int nd_render_gather_stats(const float *pts, int64_t n_points, const float *came
                "nd_render_gather_stats: view counts differ");
     ND_REQUIRE(images->dtype == ND_F32 && images->channels == 3, ND_ERR_BAD_SHAPE,
                "nd_render_gather_stats: images must be f32 [nv,3,H,W]");
-    ND_REQUIRE(images->stride_x == 1 && images->stride_y == images->width && featmaps->stride_x == 1 &&
-                   featmaps->stride_y == featmaps->width,
-               ND_ERR_BAD_SHAPE, "nd_render_gather_stats: planes must be contiguous (the reference samples the whole padded maps)");
     ND_REQUIRE(n_points >= 0, ND_ERR_BAD_SHAPE, "nd_render_gather_stats: negative point count");
     if (n_points == 0) return ND_OK;
+    // product path: channels-last feature maps ([nv][h][w][D], D <= 32) and nothing materialised per view
+    if ((featmaps->channels == 0 || (featmaps->stride_c == 1 && featmaps->channels <= 32)) && pixel_locations == nullptr &&
+        in_front == nullptr && view_features == nullptr) {
+        const size_t sm = (size_t)n_views * 12 * sizeof(float);
+        ND_REQUIRE(sm <= 48 * 1024, ND_ERR_BAD_SHAPE, "nd_render_gather_stats: too many views (%d)", n_views);
+        const unsigned g = (unsigned)ceil_div(n_points, (int64_t)kRcWarps * kRcPerWarp);
+        cudaStream_t s0 = (cudaStream_t)stream;
+        if (featmaps->dtype == ND_F32)
+            k_render_gather_stats_cl<float><<<g, kRcWarps * 32, sm, s0>>>(
+                pts, n_points, cameras, n_views, (const float *)images->data, images->stride_v, images->stride_c,
+                images->stride_y, images->stride_x, images->height, images->width, (const float *)featmaps->data,
+                featmaps->stride_v, featmaps->stride_y, featmaps->stride_x, featmaps->channels, featmaps->height,
+                featmaps->width, globalfeat, view_mask, pixel_mask);
+        else
+            k_render_gather_stats_cl<__nv_bfloat16><<<g, kRcWarps * 32, sm, s0>>>(
+                pts, n_points, cameras, n_views, (const float *)images->data, images->stride_v, images->stride_c,
+                images->stride_y, images->stride_x, images->height, images->width, (const __nv_bfloat16 *)featmaps->data,
+                featmaps->stride_v, featmaps->stride_y, featmaps->stride_x, featmaps->channels, featmaps->height,
+                featmaps->width, globalfeat, view_mask, pixel_mask);
+        ND_CUDA_LAUNCH_CHECK("k_render_gather_stats_cl");
+        return ND_OK;
+    }
+    ND_REQUIRE(images->stride_x == 1 && images->stride_y == images->width && featmaps->stride_x == 1 &&
+                   featmaps->stride_y == featmaps->width,
+               ND_ERR_BAD_SHAPE, "nd_render_gather_stats: the materialising path needs contiguous NCHW planes");
     const size_t smem = (size_t)n_views * 12 * sizeof(float) + (size_t)2 * n_views * kRgThreads * sizeof(ViewSample);
     ND_REQUIRE(smem <= 220 * 1024, ND_ERR_BAD_SHAPE, "nd_render_gather_stats: too many views (%d)", n_views);
     const unsigned grid = (unsigned)ceil_div(n_points, kRgThreads);

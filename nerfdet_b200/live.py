@@ -21,10 +21,24 @@ from . import lifting, ops
 def map_features_2d(feature_2d: torch.Tensor, mapping) -> torch.Tensor:
     """``self.mapping`` applied per pixel (nerfdet.py:190-197): ``[nv, C, h, w] -> [nv, 32, h, w]``.
     ``mapping`` is the reference's ``nn.Sequential(nn.Linear(256, 32))`` (nerfdet.py:103-105) or any
-    callable on ``[nv, h*w, C]``.  One plain cuBLAS SGEMM through torch, exactly the reference's op sequence."""
+    callable on ``[nv, h*w, C]``.
+
+    For the reference's ``Linear(C, 32)`` this is ``nd_map_features`` (csrc/mapping.cu): one fp32 FFMA kernel that
+    reads the NCHW planes in place -- the reference's 242 MB ``permute(0, 2, 1).contiguous()`` copy is not made -- and
+    writes the channels-last layout the gather kernels want: the returned tensor has the reference's logical shape
+    ``[nv, 32, h, w]`` with channels-last strides.  Other mappings go through torch."""
     nv, c, h, w = feature_2d.shape
-    flat = feature_2d.reshape(nv, c, h * w).permute(0, 2, 1).contiguous()
-    return mapping(flat).permute(0, 2, 1).contiguous().view(nv, -1, h, w)
+    lin = mapping[0] if isinstance(mapping, torch.nn.Sequential) and len(mapping) == 1 else mapping
+    elt = feature_2d.element_size()
+    if (isinstance(lin, torch.nn.Linear) and lin.out_features == 32 and c % 16 == 0 and feature_2d.is_cuda
+            and (h * w * elt) % 16 == 0):
+        sv, sc, sy, sx = feature_2d.stride()
+        if not (sx == 1 and sy == w and (sc * elt) % 16 == 0 and (sv * elt) % 16 == 0 and feature_2d.data_ptr() % 16 == 0):
+            feature_2d = feature_2d.contiguous()
+        y = ops.map_features(feature_2d, lin.weight.detach(), lin.bias.detach() if lin.bias is not None else None)
+        return y.permute(0, 3, 1, 2)
+    flat = feature_2d.reshape(nv, c, h * w).permute(0, 2, 1).contiguous().float()
+    return mapping(flat).view(nv, h, w, -1).permute(0, 3, 1, 2)
 
 
 def _mapping_bias(mapping) -> torch.Tensor:

@@ -243,6 +243,31 @@ def _maps_contig(t: Tensor, what: str, allow_bf16: bool = True) -> NdMaps:
     return m
 
 
+@torch.library.custom_op(f'{_NS}::map_features', mutates_args=())
+def map_features(features: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """B7 (reference nerfdet.py:190-197): per-pixel ``Linear(C -> 32)`` of NCHW ``features [nv, C, h, w]`` read in
+    place; returns the mapped maps as a contiguous channels-last buffer ``[nv, h, w, 32]`` float32."""
+    _need_cuda(features, weight, bias)
+    m = _maps(features)
+    if weight.dtype != torch.float32 or weight.dim() != 2 or weight.shape[1] != m.channels:
+        raise ValueError(f'weight must be float32 [out, {m.channels}]')
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != weight.shape[0]):
+        raise ValueError('bias must be float32 [out]')
+    weight = weight.contiguous()
+    bias = bias.contiguous() if bias is not None else None
+    out = torch.empty((m.n_views, m.height, m.width, weight.shape[0]), dtype=torch.float32, device=features.device)
+    lib = _lib.load()
+    _lib.check(lib.nd_map_features(ctypes.byref(m), _ptr(weight), _ptr(bias) if bias is not None else None,
+                                   int(weight.shape[0]), _ptr(out), _stream()), 'nd_map_features')
+    return out
+
+
+@map_features.register_fake
+def _(features, weight, bias):
+    nv, _, h, w = features.shape
+    return features.new_empty((nv, h, w, weight.shape[0]), dtype=torch.float32)
+
+
 @torch.library.custom_op(f'{_NS}::live_stats', mutates_args=())
 def live_stats(mapped: Tensor, rgb: Tensor, points: Tensor, projection: Tensor, rgb_projection: Tensor,
                map_bias: Tensor, want_planes: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
@@ -414,7 +439,11 @@ def render_gather_stats(pts: Tensor, cameras: Tensor, images: Tensor, featmaps: 
     if images.dtype != torch.float32 or images.dim() != 4 or images.shape[0] != nv or images.shape[1] != 3:
         raise ValueError('images must be float32 [n_views, 3, H, W]')
     images = images.contiguous()
-    featmaps = featmaps.contiguous()          # the reference samples the whole (contiguous) maps
+    if want_pixels or want_view_features or featmaps.shape[1] > 32:
+        featmaps = featmaps.contiguous()      # materialising kernel: NCHW planes
+    elif featmaps.shape[1] > 0 and (featmaps.stride(1) != 1 or featmaps.stride(3) != featmaps.shape[1]):
+        # product kernel: channels-last maps [nv, h, w, D] (what live.map_features_2d hands over; converted otherwise)
+        featmaps = featmaps.contiguous(memory_format=torch.channels_last)
     mi, mf = _maps(images), _maps(featmaps)
     if mf.channels == 0:
         mf.data = None
