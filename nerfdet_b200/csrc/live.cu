@@ -92,7 +92,8 @@ k_live_stats(const T *__restrict__ mapped, int64_t m_sv, int64_t m_sc, int64_t m
 // produces): one WARP per voxel, lane = mapped channel (lanes 0-2 also carry RGB).  The two projections run with
 // lane = view; only the valid views are visited, each mapped gather is one coalesced row of Cm elements.  Invalid
 // views contribute the bias (mapped) or 0 (RGB); their share is added in closed form after the loop.
-constexpr int kLcWarps = 8, kLcPerWarp = 4;
+constexpr int kLcWarps = 4, kLcPerWarp = 1;     // small blocks: per-voxel cost varies 10x across the room, the
+                                                // hardware block scheduler does the balancing
 
 template <typename T>
 __global__ void __launch_bounds__(kLcWarps * 32)

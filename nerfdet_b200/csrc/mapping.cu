@@ -53,9 +53,9 @@ k_map_features(const T *__restrict__ feat, int64_t sv, int64_t sc, int n_pix, in
         if (kb < n_k) load_stage(kb);
         else asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    for (int i = tid; i < channels * kMapN; i += kMapThreads) {     // Wt[c][j] = weight[j][c]
-        const int j = i / channels, c = i - j * channels;
-        sW[c * kMapN + j] = weight[i];
+    for (int i = tid; i < channels * kMapN; i += kMapThreads) {     // Wt[c][j] = weight[j][c]; conflict-free stores
+        const int c = i / kMapN, j = i - c * kMapN;
+        sW[i] = __ldg(weight + (size_t)j * channels + c);
     }
     float acc[8][8];
 #pragma unroll

@@ -208,9 +208,10 @@ struct ViewSampleG {         // like ViewSample, for arbitrary strides
     uint32_t inb;
 };
 
+// ATen grid_sampler_2d unnormalisation ((g + 1) / 2 * (size - 1); the halving is exact) + corner bookkeeping
 __device__ __forceinline__ ViewSampleG make_sample_g(float gx, float gy, int hs, int ws) {
-    const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), (float)(ws - 1));
-    const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), (float)(hs - 1));
+    const float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(ws - 1));
+    const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(hs - 1));
     const float x0f = floorf(ix), y0f = floorf(iy);
     ViewSampleG s;
     s.fx = ix - x0f;
@@ -224,31 +225,36 @@ __device__ __forceinline__ ViewSampleG make_sample_g(float gx, float gy, int hs,
     return s;
 }
 
-template <typename T>
-__device__ __forceinline__ float bilinear_g(const T *__restrict__ p, int64_t sx, int64_t sy, float fx, float fy, uint32_t inb) {
-    const float nw = (1.0f - fx) * (1.0f - fy), ne = fx * (1.0f - fy);
-    const float sw = (1.0f - fx) * fy, se = fx * fy;
-    // the four loads are independent: issue them together, then the fma chain in the reference's corner order
-    const float v0 = (inb & 1u) ? to_f32<T>(p[0]) : 0.0f;
-    const float v1 = (inb & 2u) ? to_f32<T>(p[sx]) : 0.0f;
-    const float v2 = (inb & 4u) ? to_f32<T>(p[sy]) : 0.0f;
-    const float v3 = (inb & 8u) ? to_f32<T>(p[sy + sx]) : 0.0f;
-    float acc = 0.0f;
-    if (inb & 1u) acc = fmaf(v0, nw, acc);
-    if (inb & 2u) acc = fmaf(v1, ne, acc);
-    if (inb & 4u) acc = fmaf(v2, sw, acc);
-    if (inb & 8u) acc = fmaf(v3, se, acc);
-    return acc;
+// per (warp, view) sample parameters parked in shared memory by the lane that projected the view and read back by
+// the quarter-warp that gathers the view (broadcast LDS.128)
+struct __align__(16) ViewParams {
+    int32_t offI, offF;      // element offsets of the north-west corners (view base included)
+    uint32_t bits;           // image corners | feature corners << 4 | view mask << 8
+    float fxI, fyI, fxF, fyF;
+    int32_t pad;
+};
+
+template <typename T> __device__ __forceinline__ float4 load4(const T *p);
+template <> __device__ __forceinline__ float4 load4<float>(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                       __uint_as_float(r.y & 0xffff0000u));
 }
 
+// One WARP per ray sample.  Projection: lane = view.  Gather: four views per step, one per QUARTER-warp; the 8 lanes
+// of a quarter fetch the 32 mapped channels of a bilinear corner as one coalesced 128-byte row (4 channels per lane),
+// lanes 0-2 of the quarter also fetch the three image channels.  Each lane keeps the masked sum / sum / sum of
+// squares of its channels over the views its quarter visited; the quarters are combined with shuffles at the end.
 template <typename T>
 __global__ void __launch_bounds__(kRcWarps * 32)
 k_render_gather_stats_cl(const float *__restrict__ pts, int64_t n_pts, const float *__restrict__ cams, int nv,
-                         const float *__restrict__ img, int64_t i_sv, int64_t i_sc, int64_t i_sy, int64_t i_sx, int hi, int wi,
-                         const T *__restrict__ feat, int64_t f_sv, int64_t f_sy, int64_t f_sx, int d, int hf, int wf,
+                         const float *__restrict__ img, int i_sv, int i_sc, int i_sy, int i_sx, int hi, int wi,
+                         const T *__restrict__ feat, int f_sv, int f_sy, int f_sx, int d, int hf, int wf,
                          float *__restrict__ glob, uint8_t *__restrict__ view_mask, uint8_t *__restrict__ pixel_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *sP = reinterpret_cast<float *>(smem_raw);                       // [nv][12] rows 0-2 of K @ E
+    ViewParams *sV = reinterpret_cast<ViewParams *>(smem_raw) + (threadIdx.x >> 5) * 32;      // [warps][32]
+    float *sP = reinterpret_cast<float *>(smem_raw + sizeof(ViewParams) * 32 * kRcWarps);     // [nv][12] rows 0-2 of K @ E
     for (int i = threadIdx.x; i < nv * 12; i += blockDim.x) {
         const int v = i / 12, rc = i - v * 12, r = rc >> 2, c = rc & 3;
         const float *K = cams + v * 34 + 2, *E = cams + v * 34 + 18;
@@ -259,26 +265,30 @@ k_render_gather_stats_cl(const float *__restrict__ pts, int64_t n_pts, const flo
         sP[i] = t;
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, quarter = lane >> 3, l8 = lane & 7;
     const float h = cams[0], w = cams[1];
     const float wm1 = __fsub_rn(w, 1.0f), hm1 = __fsub_rn(h, 1.0f);
     const int ct = 3 + d;
     const unsigned full = 0xffffffffu;
+    const bool feat_lane = 4 * l8 < d, img_lane = l8 < 3;
+    const float *img_l = img + (img_lane ? l8 * i_sc : 0);
+    const T *feat_l = feat + (feat_lane ? 4 * l8 : 0);
     for (int it = 0; it < kRcPerWarp; ++it) {
         const int64_t p = ((int64_t)blockIdx.x * kRcWarps + warp) * kRcPerWarp + it;
         if (p >= n_pts) break;                                             // warp-uniform
         const float X = __ldg(pts + p * 3), Y = __ldg(pts + p * 3 + 1), Z = __ldg(pts + p * 3 + 2);
         int cnt = 0;
-        float smF = 0.f, s1F = 0.f, s2F = 0.f, smI = 0.f, s1I = 0.f, s2I = 0.f;
+        float smF[4] = {0.f, 0.f, 0.f, 0.f}, s1F[4] = {0.f, 0.f, 0.f, 0.f}, s2F[4] = {0.f, 0.f, 0.f, 0.f};
+        float smI = 0.f, s1I = 0.f, s2I = 0.f;
         for (int v0 = 0; v0 < nv; v0 += 32) {
             const int v = v0 + lane;
-            ViewSampleG si{0, 0, 0.f, 0.f, 0u}, sf{0, 0, 0.f, 0.f, 0u};
+            ViewParams vp{0, 0, 0u, 0.f, 0.f, 0.f, 0.f, 0};
             bool m = false;
             if (v < nv) {
                 const float *P = sP + v * 12;
                 const float q0 = chain4(P, X, Y, Z), q1 = chain4(P + 4, X, Y, Z), q2 = chain4(P + 8, X, Y, Z);
                 const float zc = fmaxf(q2, 1e-8f);
-                float px = __fdiv_rn(q0, zc), py = __fdiv_rn(q1, zc);
+                float px = __fdiv_rn(q0, zc), py = __fdiv_rn(q1, zc);      // IEEE: the masks are bit-exact
                 px = fminf(fmaxf(px, -1e6f), 1e6f);
                 py = fminf(fmaxf(py, -1e6f), 1e6f);
                 const bool front = q2 > 0.0f;
@@ -286,59 +296,104 @@ k_render_gather_stats_cl(const float *__restrict__ pts, int64_t n_pts, const flo
                 m = inb && front;
                 const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, px), wm1), 1.0f);
                 const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, py), hm1), 1.0f);
-                si = make_sample_g(gx, gy, hi, wi);
-                sf = make_sample_g(gx, gy, hf, wf);
+                const ViewSampleG si = make_sample_g(gx, gy, hi, wi);
+                ViewSampleG sf = make_sample_g(gx, gy, hf, wf);
                 if (d == 0) sf.inb = 0u;
+                vp.offI = v * i_sv + si.y0 * i_sy + si.x0 * i_sx;
+                vp.offF = v * f_sv + sf.y0 * f_sy + sf.x0 * f_sx;
+                vp.bits = si.inb | (sf.inb << 4) | (m ? 0x100u : 0u);
+                vp.fxI = si.fx; vp.fyI = si.fy; vp.fxF = sf.fx; vp.fyF = sf.fy;
                 if (view_mask != nullptr) view_mask[p * nv + v] = m ? 1 : 0;
             }
             cnt += __popc(__ballot_sync(full, m));
-            const uint32_t bits = si.inb | (sf.inb << 4) | (m ? 0x100u : 0u);
-            const int offI = (int)(si.y0 * i_sy + si.x0 * i_sx), offF = (int)(sf.y0 * f_sy + sf.x0 * f_sx);
-            unsigned act = __ballot_sync(full, (bits & 0xffu) != 0u);
+            unsigned act = __ballot_sync(full, (vp.bits & 0xffu) != 0u);
+            if (act == 0u) continue;
+            __syncwarp();                                                  // the previous round's readers are done
+            sV[lane] = vp;
+            __syncwarp();
             while (act) {
-                const int src = __ffs(act) - 1;
-                act &= act - 1;
-                const uint32_t b = __shfl_sync(full, bits, src);
-                const bool mv = (b & 0x100u) != 0;
-                const int64_t vv = v0 + src;
-                if (b & 0xfu) {
-                    const int oi = __shfl_sync(full, offI, src);
-                    const float fx = __shfl_sync(full, si.fx, src), fy = __shfl_sync(full, si.fy, src);
-                    if (lane < 3) {
-                        const float f = bilinear_g<float>(img + vv * i_sv + lane * i_sc + oi, i_sx, i_sy, fx, fy, b & 0xfu);
-                        smI += mv ? f : 0.0f;
-                        s1I += f;
-                        s2I = fmaf(f, f, s2I);
-                    }
+                // the next four active views, one per quarter-warp (ascending within a quarter over the steps)
+                int src = -1;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const int sbit = act ? __ffs(act) - 1 : -1;
+                    if (act) act &= act - 1;
+                    if (qq == quarter) src = sbit;
                 }
-                if (b & 0xf0u) {
-                    const int of = __shfl_sync(full, offF, src);
-                    const float fx = __shfl_sync(full, sf.fx, src), fy = __shfl_sync(full, sf.fy, src);
-                    if (lane < d) {
-                        const float f = bilinear_g<T>(feat + vv * f_sv + of + lane, f_sx, f_sy, fx, fy, (b >> 4) & 0xfu);
-                        smF += mv ? f : 0.0f;
-                        s1F += f;
-                        s2F = fmaf(f, f, s2F);
+                if (src < 0) continue;
+                const int4 a4 = *reinterpret_cast<const int4 *>(&sV[src]);             // offI, offF, bits, fxI
+                const float4 b4 = *reinterpret_cast<const float4 *>(&sV[src].fyI);     // fyI, fxF, fyF, pad
+                const uint32_t b = (uint32_t)a4.z;
+                const bool mv = (b & 0x100u) != 0;
+                if ((b & 0xfu) && img_lane) {
+                    const float fx = __int_as_float(a4.w), fy = b4.x;
+                    const float *q = img_l + a4.x;
+                    const float v0 = (b & 1u) ? __ldg(q) : 0.0f, v1 = (b & 2u) ? __ldg(q + i_sx) : 0.0f;
+                    const float v2 = (b & 4u) ? __ldg(q + i_sy) : 0.0f, v3 = (b & 8u) ? __ldg(q + i_sy + i_sx) : 0.0f;
+                    float f = 0.0f;
+                    if (b & 1u) f = fmaf(v0, (1.0f - fx) * (1.0f - fy), f);
+                    if (b & 2u) f = fmaf(v1, fx * (1.0f - fy), f);
+                    if (b & 4u) f = fmaf(v2, (1.0f - fx) * fy, f);
+                    if (b & 8u) f = fmaf(v3, fx * fy, f);
+                    smI += mv ? f : 0.0f;
+                    s1I += f;
+                    s2I = fmaf(f, f, s2I);
+                }
+                if ((b & 0xf0u) && feat_lane) {
+                    const float fx = b4.y, fy = b4.z;
+                    const T *q = feat_l + a4.y;
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 c0 = (b & 0x10u) ? load4<T>(q) : z4, c1 = (b & 0x20u) ? load4<T>(q + f_sx) : z4;
+                    const float4 c2 = (b & 0x40u) ? load4<T>(q + f_sy) : z4, c3 = (b & 0x80u) ? load4<T>(q + f_sy + f_sx) : z4;
+                    const float nw = (1.0f - fx) * (1.0f - fy), ne = fx * (1.0f - fy), sw = (1.0f - fx) * fy, se = fx * fy;
+                    const float a0[4] = {c0.x, c0.y, c0.z, c0.w}, a1[4] = {c1.x, c1.y, c1.z, c1.w};
+                    const float a2[4] = {c2.x, c2.y, c2.z, c2.w}, a3[4] = {c3.x, c3.y, c3.z, c3.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float f = 0.0f;                                    // corner order nw, ne, sw, se like ATen
+                        if (b & 0x10u) f = fmaf(a0[k], nw, f);
+                        if (b & 0x20u) f = fmaf(a1[k], ne, f);
+                        if (b & 0x40u) f = fmaf(a2[k], sw, f);
+                        if (b & 0x80u) f = fmaf(a3[k], se, f);
+                        smF[k] += mv ? f : 0.0f;
+                        s1F[k] += f;
+                        s2F[k] = fmaf(f, f, s2F[k]);
                     }
                 }
             }
+        }
+        // combine the four quarters (lanes l8, l8 + 8, l8 + 16, l8 + 24 hold the same channels)
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                smF[k] += __shfl_xor_sync(full, smF[k], o);
+                s1F[k] += __shfl_xor_sync(full, s1F[k], o);
+                s2F[k] += __shfl_xor_sync(full, s2F[k], o);
+            }
+            smI += __shfl_xor_sync(full, smI, o);
+            s1I += __shfl_xor_sync(full, s1I, o);
+            s2I += __shfl_xor_sync(full, s2I, o);
         }
         const float denom = __fadd_rn((float)cnt, 1e-8f);
         float *row = glob + p * (int64_t)(2 * ct);
         if (lane == 0 && pixel_mask != nullptr) pixel_mask[p] = cnt > 1 ? 1 : 0;
-        if (lane < 3) {
+        if (quarter == 0 && img_lane) {
             const float mean = smI / denom;
             float ssd = fmaf(-2.0f * mean, s1I, s2I);
             ssd = fmaxf(fmaf((float)nv * mean, mean, ssd), 0.0f);
-            row[lane] = mean;
-            row[ct + lane] = expf(-(ssd / denom));
+            row[l8] = mean;
+            row[ct + l8] = expf(-(ssd / denom));
         }
-        if (lane < d) {
-            const float mean = smF / denom;
-            float ssd = fmaf(-2.0f * mean, s1F, s2F);
-            ssd = fmaxf(fmaf((float)nv * mean, mean, ssd), 0.0f);
-            row[3 + lane] = mean;
-            row[ct + 3 + lane] = expf(-(ssd / denom));
+        if (quarter == 1 && feat_lane) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float mean = smF[k] / denom;
+                float ssd = fmaf(-2.0f * mean, s1F[k], s2F[k]);
+                ssd = fmaxf(fmaf((float)nv * mean, mean, ssd), 0.0f);
+                row[3 + 4 * l8 + k] = mean;
+                row[ct + 3 + 4 * l8 + k] = expf(-(ssd / denom));
+            }
         }
     }
 }
@@ -453,24 +508,31 @@ int nd_render_gather_stats(const float *pts, int64_t n_points, const float *came
     ND_REQUIRE(n_points >= 0, ND_ERR_BAD_SHAPE, "nd_render_gather_stats: negative point count");
     if (n_points == 0) return ND_OK;
     // product path: channels-last feature maps ([nv][h][w][D], D <= 32) and nothing materialised per view
-    if ((featmaps->channels == 0 || (featmaps->stride_c == 1 && featmaps->channels <= 32)) && pixel_locations == nullptr &&
+    if ((featmaps->channels == 0 || (featmaps->stride_c == 1 && featmaps->channels <= 32 && featmaps->channels % 4 == 0 &&
+                                     featmaps->stride_x % 4 == 0 && featmaps->stride_y % 4 == 0 && featmaps->stride_v % 4 == 0 &&
+                                     (reinterpret_cast<uintptr_t>(featmaps->data) & 15) == 0)) &&
+        pixel_locations == nullptr &&
         in_front == nullptr && view_features == nullptr) {
-        const size_t sm = (size_t)n_views * 12 * sizeof(float);
+        const size_t sm = (size_t)n_views * 12 * sizeof(float) + sizeof(ViewParams) * 32 * kRcWarps;
         ND_REQUIRE(sm <= 48 * 1024, ND_ERR_BAD_SHAPE, "nd_render_gather_stats: too many views (%d)", n_views);
+        const int64_t span_i = (int64_t)n_views * images->stride_v, span_f = (int64_t)n_views * featmaps->stride_v;
+        ND_REQUIRE(span_i < (1ll << 31) && span_f < (1ll << 31) && images->stride_v >= 0 && featmaps->stride_v >= 0,
+                   ND_ERR_BAD_SHAPE, "nd_render_gather_stats: source stacks beyond 2^31 elements");
         const unsigned g = (unsigned)ceil_div(n_points, (int64_t)kRcWarps * kRcPerWarp);
         cudaStream_t s0 = (cudaStream_t)stream;
         if (featmaps->dtype == ND_F32)
             k_render_gather_stats_cl<float><<<g, kRcWarps * 32, sm, s0>>>(
-                pts, n_points, cameras, n_views, (const float *)images->data, images->stride_v, images->stride_c,
-                images->stride_y, images->stride_x, images->height, images->width, (const float *)featmaps->data,
-                featmaps->stride_v, featmaps->stride_y, featmaps->stride_x, featmaps->channels, featmaps->height,
-                featmaps->width, globalfeat, view_mask, pixel_mask);
+                pts, n_points, cameras, n_views, (const float *)images->data, (int)images->stride_v, (int)images->stride_c,
+                (int)images->stride_y, (int)images->stride_x, images->height, images->width, (const float *)featmaps->data,
+                (int)featmaps->stride_v, (int)featmaps->stride_y, (int)featmaps->stride_x, featmaps->channels,
+                featmaps->height, featmaps->width, globalfeat, view_mask, pixel_mask);
         else
             k_render_gather_stats_cl<__nv_bfloat16><<<g, kRcWarps * 32, sm, s0>>>(
-                pts, n_points, cameras, n_views, (const float *)images->data, images->stride_v, images->stride_c,
-                images->stride_y, images->stride_x, images->height, images->width, (const __nv_bfloat16 *)featmaps->data,
-                featmaps->stride_v, featmaps->stride_y, featmaps->stride_x, featmaps->channels, featmaps->height,
-                featmaps->width, globalfeat, view_mask, pixel_mask);
+                pts, n_points, cameras, n_views, (const float *)images->data, (int)images->stride_v, (int)images->stride_c,
+                (int)images->stride_y, (int)images->stride_x, images->height, images->width,
+                (const __nv_bfloat16 *)featmaps->data, (int)featmaps->stride_v, (int)featmaps->stride_y,
+                (int)featmaps->stride_x, featmaps->channels, featmaps->height, featmaps->width, globalfeat, view_mask,
+                pixel_mask);
         ND_CUDA_LAUNCH_CHECK("k_render_gather_stats_cl");
         return ND_OK;
     }

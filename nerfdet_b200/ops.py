@@ -439,7 +439,7 @@ def render_gather_stats(pts: Tensor, cameras: Tensor, images: Tensor, featmaps: 
     if images.dtype != torch.float32 or images.dim() != 4 or images.shape[0] != nv or images.shape[1] != 3:
         raise ValueError('images must be float32 [n_views, 3, H, W]')
     images = images.contiguous()
-    if want_pixels or want_view_features or featmaps.shape[1] > 32:
+    if want_pixels or want_view_features or featmaps.shape[1] > 32 or featmaps.shape[1] % 4 != 0:
         featmaps = featmaps.contiguous()      # materialising kernel: NCHW planes
     elif featmaps.shape[1] > 0 and (featmaps.stride(1) != 1 or featmaps.stride(3) != featmaps.shape[1]):
         # product kernel: channels-last maps [nv, h, w, D] (what live.map_features_2d hands over; converted otherwise)
