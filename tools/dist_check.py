@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Multi-GPU check of the view-sharded lift, run under torchrun with one rank per GPU:
+every rank lifts its slice of the views, the accumulators are summed with one NCCL all-reduce, and the finalised
+mean / all-view variance / count are compared with the single-GPU fused lift over ALL views run on the same device.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nerfdet_b200 import distributed as nd_dist  # noqa: E402
+from nerfdet_b200 import lifting  # noqa: E402
+from nerfdet_b200.synthetic import SceneConfig, make_scene  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist.init_process_group('nccl', device_id=dev)
+    nv = 100                                              # BASELINE configs[3]: ~100 views at test time
+    cfg = SceneConfig(n_views=nv, n_voxels=(40, 40, 16), voxel_size=(.16, .16, .2), channels=256)
+    sc = make_scene(cfg, seed=77, with_images=False, with_features=True)      # same seed -> same scene on every rank
+    proj = lifting.compute_projection(sc.img_meta, 4).to(dev)
+    pts = lifting.get_points(cfg.n_voxels, cfg.voxel_size, sc.img_meta['lidar2img']['origin']).to(dev)
+    feats = sc.features.to(dev)[:, :, :59, :80]
+    b, e = nd_dist.view_shard(nv, rank, world)
+    mean, cov, cnt = nd_dist.lift_mean_var_view_sharded(feats[b:e], pts, proj[b:e], n_views_total=nv)
+    m1, c1, n1 = lifting.lift_mean_var(feats, pts, proj)
+    torch.cuda.synchronize()
+    ok_cnt = torch.equal(cnt, n1)
+
+    def err(a, r):
+        a, r = a.double(), r.double()
+        tol = 1e-4 * r.abs() + 1e-5 * r.abs().max()
+        return float((a - r).abs().max()), int(((a - r).abs() > tol).sum())
+    e_mean, bad_mean = err(mean, m1)
+    e_cov, bad_cov = err(cov, c1)
+    res = torch.tensor([int(ok_cnt), bad_mean, bad_cov], device=dev)
+    dist.all_reduce(res, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(f'view-sharded lift on {world} GPUs vs single-GPU lift over {nv} views: counts equal on {int(res[0])}/{world} ranks, '
+              f'mean max abs err {e_mean:.3e} ({int(res[1])} outside 1e-4), cov max abs err {e_cov:.3e} ({int(res[2])} outside 1e-4)',
+              flush=True)
+    assert int(res[0]) == world and int(res[1]) == 0 and int(res[2]) == 0
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
