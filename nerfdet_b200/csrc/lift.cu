@@ -632,7 +632,7 @@ size_t nd_lift_workspace_bytes(const nd_maps *f, int64_t n_voxels, const nd_lift
 int nd_lift_launch_count(const nd_maps *f, int64_t n_voxels, const nd_lift_options *opt) {
     if (validate_maps(f, "nd_lift_launch_count") != ND_OK || n_voxels < 0) return -1;
     const LiftPlan p = make_plan(f, n_voxels, opt);
-    if (p.planes) return 4;   // k_plane_index, k_plane_rank, k_plane_pack, k_lift_planes
+    if (p.planes) return 3;   // k_plane_index, k_plane_pack, k_lift_planes
     if (p.direct) return 2;
     return 1 + 2 * p.n_chunks;
 }

@@ -15,7 +15,7 @@
 //                   the plane), one 512 B row per (view, oct); per-voxel partial view counts (uint8 per
 //                   16-view group); per (oct, view) a 2-bit mask saying which quad has any valid voxel,
 //                   and the number of active quad-views of every oct (its cost).
-//   k_plane_pack    ranks the octs by cost and pairs the k-th most with the k-th least expensive one
+//   k_plane_pack    (every block, redundantly) ranks the octs by cost and pairs the k-th most with the k-th least expensive one
 //                   (one pair per compute warp, so that all warps of a CTA carry the same load); a PART
 //                   is the set of pairs one CTA owns.  Per (part, view) the offset rows of the octs
 //                   that see the view are compacted into one contiguous block, so that the lift kernel
@@ -233,142 +233,122 @@ k_plane_index(const Tiling tiling, const float *__restrict__ points, const float
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pairing (one block): ranks the octs by cost, pairs the k-th most with the k-th least expensive one, and tabulates
-// per (part, view) how many of the part's octs see the view and where the view's block of offset rows starts.
+// Pairing + compaction.  grid = (views, parts).  Every block repeats the (tiny) pairing for its part -- ranks the
+// octs by cost, pairs the k-th most with the k-th least expensive one (one pair per compute warp), counts per view
+// how many of the part's octs see it and where the view's block of offset rows starts -- and then compacts the offset
+// rows of ITS view: the rows of the part's octs that see the view are copied into one contiguous block (so that
+// k_lift_planes fetches them with a single bulk copy) and every warp gets its entry.  The blocks of view 0 publish the
+// per-part tables (pairs, row counts) the lift kernel needs.  (A separate single-block ranking kernel cost 21 us of
+// pure latency on the critical path.)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_plane_rank(int nv, int nvp, int nw16, int n_octs, int n_parts, int W, int balanced, int ring_rows,
-             const uint8_t *__restrict__ omask, const uint8_t *__restrict__ cost16, uint16_t *__restrict__ pairs,
-             uint16_t *__restrict__ rowcnt, uint32_t *__restrict__ gstart) {
+__global__ void __launch_bounds__(256)
+k_plane_pack(int nv, int nvp, int nw16, int n_octs, int n_parts, int W, int balanced, int ring_rows, int64_t n_pad,
+             int64_t part_rows, const uint16_t *__restrict__ off16, const uint8_t *__restrict__ omask,
+             const uint8_t *__restrict__ cost16, uint16_t *__restrict__ pairs, uint16_t *__restrict__ rowcnt,
+             uint16_t *__restrict__ offc, uint32_t *__restrict__ ents) {
     __shared__ uint16_t s_cost[kPMaxOcts];
     __shared__ uint16_t s_sorted[kPMaxOcts];
-    extern __shared__ uint16_t s_dyn[];            // [n_parts][2 W] octs of every part, [n_parts][nvp] row counts
-    uint16_t *s_q = s_dyn, *s_c = s_dyn + (size_t)n_parts * 2 * W;
+    __shared__ uint16_t s_q[2 * kPMaxWarps];       // octs of this part in slot order (warp w: 2 w, 2 w + 1)
+    __shared__ uint8_t s_slot[2 * kPMaxWarps];     // their row slot in the view's block (0xff: not seen)
+    __shared__ uint32_t s_gstart;                  // first row of this view's block in the part's table
+    extern __shared__ uint8_t s_dyn[];             // [2 W][nvp] quad masks of the part's octs, then uint16 [nvp] row counts
+    uint8_t *s_m = s_dyn;
+    uint16_t *s_c = reinterpret_cast<uint16_t *>(s_dyn + (((size_t)2 * W * nvp + 15) & ~(size_t)15));
     asm volatile("griddepcontrol.wait;" ::: "memory");               // tables of k_plane_index
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, n_warps = (int)(blockDim.x >> 5);
-    if (balanced) {
-        for (int t = tid; t < n_octs; t += blockDim.x) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // k_lift_planes may start streaming planes
+    const int v = blockIdx.x, part = blockIdx.y, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, n_warps = (int)(blockDim.x >> 5);
+    if (balanced) {                                                  // n_octs <= kPMaxOcts == blockDim.x
+        if (tid < n_octs) {
             int cst = 0;
-            for (int g0 = 0; g0 < nw16; g0 += 8) {       // 8 independent loads in flight
+            for (int g0 = 0; g0 < nw16; g0 += 8) {                   // 8 independent loads in flight
                 uint8_t c8[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) c8[k] = g0 + k < nw16 ? __ldg(cost16 + (int64_t)(g0 + k) * n_octs + t) : (uint8_t)0;
+                for (int k = 0; k < 8; ++k) c8[k] = g0 + k < nw16 ? __ldg(cost16 + (int64_t)(g0 + k) * n_octs + tid) : (uint8_t)0;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) cst += (int)c8[k];
             }
-            s_cost[t] = (uint16_t)cst;
+            s_cost[tid] = (uint16_t)cst;
         }
         __syncthreads();
-        // rank(t) = number of octs that come before t (higher cost, ties by index): one warp per oct, lanes over j
-        for (int t = warp; t < n_octs; t += n_warps) {
-            const int ct = s_cost[t];
+        if (tid < n_octs) {                                          // rank = number of octs that come before this one
+            const int ct = s_cost[tid];
             int r = 0;
-            for (int j0 = 0; j0 < n_octs; j0 += 32) {
-                const int j = j0 + lane;
-                const bool before = j < n_octs && (s_cost[j] > ct || (s_cost[j] == ct && j < t));
-                r += __popc(__ballot_sync(0xffffffffu, before));
+            for (int j = 0; j < n_octs; ++j) {
+                const int cj = s_cost[j];
+                r += (cj > ct || (cj == ct && j < tid)) ? 1 : 0;
             }
-            if (lane == 0) s_sorted[r] = (uint16_t)t;
+            s_sorted[r] = (uint16_t)tid;
         }
         __syncthreads();
     }
     const int n_pairs = (n_octs + 1) / 2;
-    for (int k = tid; k < n_parts * W; k += blockDim.x) {            // k = part * W + warp slot
-        const int part = k / W, w = k - part * W;
-        const int pair = w * n_parts + part;
+    if (tid < W) {
+        const int pair = tid * n_parts + part;
         uint16_t qa = 0xffffu, qb = 0xffffu;
         if (pair < n_pairs) {
             const int ia = pair, ib = n_octs - 1 - pair;
             qa = balanced ? s_sorted[ia] : (uint16_t)ia;
             if (ib > ia) qb = balanced ? s_sorted[ib] : (uint16_t)ib;
         }
-        s_q[2 * k] = qa;
-        s_q[2 * k + 1] = qb;
-        pairs[2 * k] = qa;
-        pairs[2 * k + 1] = qb;
-    }
-    __syncthreads();
-    // rows per (part, view): thread = (part, view), loads in batches of 10 so that they overlap
-    for (int k = tid; k < n_parts * nv; k += blockDim.x) {
-        const int part = k / nv, v = k - part * nv;
-        const uint16_t *q = s_q + (size_t)part * 2 * W;
-        int c = 0;
-        for (int i0 = 0; i0 < 2 * W; i0 += 10) {
-            uint8_t m8[10];
-#pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                const uint16_t qq = i0 + j < 2 * W ? q[i0 + j] : (uint16_t)0xffffu;
-                m8[j] = qq != 0xffffu ? __ldg(omask + (int64_t)qq * nvp + v) : (uint8_t)0;
-            }
-#pragma unroll
-            for (int j = 0; j < 10; ++j) c += (m8[j] & 3u) ? 1 : 0;
+        s_q[2 * tid] = qa;
+        s_q[2 * tid + 1] = qb;
+        if (v == 0) {
+            pairs[((int64_t)part * W + tid) * 2] = qa;
+            pairs[((int64_t)part * W + tid) * 2 + 1] = qb;
         }
-        s_c[(size_t)part * nvp + v] = (uint16_t)c;
-        rowcnt[(int64_t)part * nvp + v] = (uint16_t)c;
     }
     __syncthreads();
-    // first row of every view's block: rows + ring paddings (ring_pad) of the views before it; one warp per part
-    for (int part = warp; part < n_parts; part += n_warps) {
+    for (int idx = tid; idx < 2 * W * nv; idx += blockDim.x) {       // quad masks of the part's octs in every view
+        const int i = idx / nv, vv = idx - i * nv;
+        const uint16_t q = s_q[i];
+        s_m[i * nvp + vv] = q != 0xffffu ? (uint8_t)(__ldg(omask + (int64_t)q * nvp + vv) & 3u) : (uint8_t)0;
+    }
+    __syncthreads();
+    for (int vv = tid; vv < nv; vv += blockDim.x) {                  // rows per view
+        int c = 0;
+        for (int i = 0; i < 2 * W; ++i) c += s_m[i * nvp + vv] ? 1 : 0;
+        s_c[vv] = (uint16_t)c;
+        if (v == 0) rowcnt[(int64_t)part * nvp + vv] = (uint16_t)c;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // first row of every view's block: rows + ring paddings (ring_pad) of the views before it
         int tot = 0;
-        for (int v = lane; v < nv; v += 32) tot += (int)s_c[(size_t)part * nvp + v];
+        for (int vv = lane; vv < nv; vv += 32) tot += (int)s_c[vv];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         const int pad_total = (ring_rows - tot % ring_rows) % ring_rows;
         int base = 0;
         for (int vb = 0; vb < nv; vb += 32) {
-            const int v = vb + lane;
-            const int eff = v < nv ? (int)s_c[(size_t)part * nvp + v] + pad_total / nv + (v < pad_total % nv ? 1 : 0) : 0;
+            const int vv = vb + lane;
+            const int eff = vv < nv ? (int)s_c[vv] + pad_total / nv + (vv < pad_total % nv ? 1 : 0) : 0;
             int incl = eff;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
-            if (v < nv) gstart[(int64_t)part * nvp + v] = (uint32_t)(base + incl - eff);
+            if (vv == v) s_gstart = (uint32_t)(base + incl - eff);
             base += __shfl_sync(0xffffffffu, incl, 31);
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Compaction.  grid = (views, parts): the offset rows of the part's octs that see the view are copied into the
-// view's block (so that k_lift_planes fetches them with one bulk copy) and every warp gets its entry.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_plane_pack(int nv, int nvp, int W, int64_t n_pad, int64_t part_rows, const uint16_t *__restrict__ off16,
-             const uint8_t *__restrict__ omask, const uint16_t *__restrict__ pairs, const uint32_t *__restrict__ gstart,
-             uint16_t *__restrict__ offc, uint32_t *__restrict__ ents) {
-    __shared__ uint16_t s_q[2 * kPMaxWarps];       // octs of this part in slot order (warp w: 2 w, 2 w + 1)
-    __shared__ uint8_t s_m[2 * kPMaxWarps];        // their quad masks in this view
-    __shared__ uint8_t s_slot[2 * kPMaxWarps];     // their row slot in the view's block (0xff: not seen)
-    asm volatile("griddepcontrol.wait;" ::: "memory");               // tables of k_plane_index / k_plane_rank
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // k_lift_planes may start streaming planes
-    const int v = blockIdx.x, part = blockIdx.y, tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31, n_warps = (int)(blockDim.x >> 5);
-    if (tid < 2 * W) {
-        const uint16_t q = __ldg(pairs + (int64_t)part * 2 * W + tid);
-        s_q[tid] = q;
-        s_m[tid] = q != 0xffffu ? (uint8_t)(__ldg(omask + (int64_t)q * nvp + v) & 3u) : (uint8_t)0;
-    }
-    const int64_t g_start = (int64_t)__ldg(gstart + (int64_t)part * nvp + v);
-    __syncthreads();
-    if (warp == 0) {                                     // slot = number of active octs before this one (2 W <= 64)
-        const bool a0 = lane < 2 * W && s_m[lane] != 0, a1 = lane + 32 < 2 * W && s_m[lane + 32] != 0;
+        // slot = number of active octs before this one in view v (2 W <= 64)
+        const bool a0 = lane < 2 * W && s_m[lane * nvp + v] != 0, a1 = lane + 32 < 2 * W && s_m[(lane + 32) * nvp + v] != 0;
         const unsigned b0 = __ballot_sync(0xffffffffu, a0), b1 = __ballot_sync(0xffffffffu, a1);
         const unsigned below = (1u << lane) - 1u;
         if (lane < 2 * W) s_slot[lane] = a0 ? (uint8_t)__popc(b0 & below) : (uint8_t)0xff;
         if (lane + 32 < 2 * W) s_slot[lane + 32] = a1 ? (uint8_t)(__popc(b0) + __popc(b1 & below)) : (uint8_t)0xff;
     }
     __syncthreads();
+    const int64_t g_start = (int64_t)s_gstart;
     if (tid < W) {
-        const uint32_t qm = (uint32_t)s_m[2 * tid] | ((uint32_t)s_m[2 * tid + 1] << 2);
+        const uint32_t qm = (uint32_t)s_m[(2 * tid) * nvp + v] | ((uint32_t)s_m[(2 * tid + 1) * nvp + v] << 2);
         const uint32_t e = qm ? ((uint32_t)v | (qm << 8) | ((uint32_t)s_slot[2 * tid] << 16) | ((uint32_t)s_slot[2 * tid + 1] << 24)) : 0u;
         ents[((int64_t)part * W + tid) * nvp + v] = e;
     }
     // rows: one warp per row, 16 B per lane
     for (int i = warp; i < 2 * W; i += n_warps) {
-        if (!s_m[i]) continue;
+        if (!s_m[i * nvp + v]) continue;
         const uint4 *src = reinterpret_cast<const uint4 *>(off16 + (int64_t)v * n_pad + (int64_t)s_q[i] * kOct);
         uint4 *dst = reinterpret_cast<uint4 *>(offc + ((int64_t)part * part_rows + g_start + s_slot[i]) * kOct);
         dst[lane] = src[lane];
@@ -941,19 +921,17 @@ nd_status run_lift_planes(const nd_maps *f, const float *points, const float *pr
         off16, cnt8, omask, cost16);
     ND_CUDA_LAUNCH_CHECK("k_plane_index");
     const int balanced = (g.n_octs <= kPMaxOcts && !(debug & 32)) ? 1 : 0;
-    const size_t rank_smem = ((size_t)g.n_parts * 2 * g.warps + (size_t)g.n_parts * g.nvp) * sizeof(uint16_t);
-    ND_REQUIRE(rank_smem <= 40 * 1024, ND_ERR_BAD_SHAPE, "lift: too many parts x views for the pairing pass (%zu bytes)", rank_smem);
-    cudaError_t e = launch_pdl(k_plane_rank, dim3(1), dim3(1024), rank_smem, st, (int)f->n_views, g.nvp, g.nw16, g.n_octs,
-                               g.n_parts, g.warps, balanced, g.ring_rows, (const uint8_t *)omask, (const uint8_t *)cost16, pairs,
-                               rowcnt, gstart);
-    if (e == cudaSuccess)
-        e = launch_pdl(k_plane_pack, dim3((unsigned)f->n_views, (unsigned)g.n_parts), dim3(256), 0, st, (int)f->n_views, g.nvp,
-                       g.warps, g.n_pad, g.part_rows, (const uint16_t *)off16, (const uint8_t *)omask, (const uint16_t *)pairs,
-                       (const uint32_t *)gstart, offc, ents);
+    const size_t pack_smem = (((size_t)2 * g.warps * g.nvp + 15) & ~(size_t)15) + (size_t)g.nvp * sizeof(uint16_t);
+    ND_REQUIRE(pack_smem <= 40 * 1024, ND_ERR_BAD_SHAPE, "lift: too many views for the pairing pass (%zu bytes)", pack_smem);
+    cudaError_t e = launch_pdl(k_plane_pack, dim3((unsigned)f->n_views, (unsigned)g.n_parts), dim3(256), pack_smem, st,
+                               (int)f->n_views, g.nvp, g.nw16, g.n_octs, g.n_parts, g.warps, balanced, g.ring_rows, g.n_pad,
+                               g.part_rows, (const uint16_t *)off16, (const uint8_t *)omask, (const uint8_t *)cost16, pairs,
+                               rowcnt, offc, ents);
     if (e != cudaSuccess) {
-        set_error("k_plane_rank / k_plane_pack: CUDA error %s", cudaGetErrorString(e));
+        set_error("k_plane_pack: CUDA error %s", cudaGetErrorString(e));
         return ND_ERR_CUDA;
     }
+    (void)gstart;
 
     PlaneArgs a{};
     a.tiling = g.tiling;
