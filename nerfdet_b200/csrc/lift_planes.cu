@@ -85,7 +85,7 @@ struct PlaneArgs {
     int ring_rows;             // offset-row ring: `ring_rows` rows of 512 B shared by the stages in flight
     int *trace;                // diagnostics: per-warp per-stage clock trace of CTA 0 (tools/lift_trace.py), or null
     int debug;                 // diagnostics (tools/lift_probe.py): 1 = no gather, 4 = no plane copies, 16 = no epilogue,
-                               // 32 = index-order pairing (no cost balancing)
+                               // 32 = index-order pairing (no cost balancing), 8 = no offset-row copies
     // outputs
     int n_views_total;
     const float *alpha;
@@ -550,13 +550,14 @@ k_lift_planes(const PlaneArgs a) {
             if (plane_warp) {
                 const int nvs = min(kG, a.nv - j * kG);
                 const bool with_planes = i >= pre && copy_planes;   // (i < pre: the plane bytes were announced above)
+                const bool copy_rows = !kDiag || !(a.debug & 8);
                 if (lane == 0)
-                    mbar_expect_tx(fb, (with_planes ? (uint32_t)nvs * a.plane_bytes : 0u) + (uint32_t)n * kRowBytes);
+                    mbar_expect_tx(fb, (with_planes ? (uint32_t)nvs * a.plane_bytes : 0u) + (copy_rows ? (uint32_t)n * kRowBytes : 0u));
                 __syncwarp();
                 if (with_planes && lane < nvs)
                     bulk_g2s(sm_base + (uint32_t)(s * kG + lane) * a.plane_pitch, psrc + lane * view_bytes, a.plane_bytes, fb);
                 psrc += nvs * view_bytes;
-            } else if (lane == 0 && n != 0) {
+            } else if (lane == 0 && n != 0 && (!kDiag || !(a.debug & 8))) {
                 const char *src = off_part + (size_t)s_grow[j] * kRowBytes;
                 const int pos = (int)s_pos[j];
                 const int first = min(n, R - pos);
