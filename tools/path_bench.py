@@ -79,11 +79,20 @@ def lift_sweep():
         sets = [torch.randn(nv, 256, 60, 80, device=DEV) for _ in range(3)]
         eager, graph = timed(lambda i: lifting.lift_mean_var(sets[i][:, :, :59, :80], pts, proj))
         n = int(np.prod(grid))
-        byts = nv * 256 * 59 * 80 * 4 + 2 * 256 * n * 4 + n * 8 + nv * 48
-        t = graph if graph == graph else eager
-        print(json.dumps({'what': 'lift', 'views': nv, 'grid': list(grid), 'us': round(t, 1), 'us_eager': round(eager, 1),
-                          'gsamples_per_s': round(nv * n / t / 1e3, 2), 'algorithmic_mb': round(byts / 1e6, 1),
-                          'gbs': round(byts / t / 1e3, 1), 'frac_of_hbm_peak': round(byts / t / 1e3 / PEAK, 3)}), flush=True)
+
+        def report(dtype, elt, eager, graph):
+            byts = nv * 256 * 59 * 80 * elt + 2 * 256 * n * 4 + n * 8 + nv * 48
+            t = graph if graph == graph else eager
+            print(json.dumps({'what': 'lift', 'features': dtype, 'views': nv, 'grid': list(grid), 'us': round(t, 1),
+                              'us_eager': round(eager, 1), 'gsamples_per_s': round(nv * n / t / 1e3, 2),
+                              'algorithmic_mb': round(byts / 1e6, 1), 'gbs': round(byts / t / 1e3, 1),
+                              'frac_of_hbm_peak': round(byts / t / 1e3 / PEAK, 3)}), flush=True)
+        report('f32', 4, eager, graph)
+        if nv == 50 and grid == (40, 40, 16):                    # bf16 feature variant of configs[1]
+            sets16 = [s.to(torch.bfloat16) for s in sets]
+            e16, g16 = timed(lambda i: lifting.lift_mean_var(sets16[i][:, :, :59, :80], pts, proj))
+            report('bf16', 2, e16, g16)
+            del sets16
         del sets
 
 
