@@ -256,24 +256,47 @@ def main():
     e2e = None
     if not args.no_e2e:
         e2e_steps = min(steps, 30)
-        stage = torch.empty_like(dev_sets[0])
-        host_out = [torch.empty((CHANNELS, n_vox), dtype=torch.float32).pin_memory() for _ in range(2)]
-        host_cnt = torch.empty((n_vox,), dtype=torch.int64).pin_memory()
+        # two streams, each with its own device staging buffer and pinned result buffers: step i + 1's host->device copy
+        # runs while step i computes and copies its results back (the copies of EVERY step are inside the timed region;
+        # this is how a streaming caller would drive the op)
+        lanes = []
+        for _ in range(2):
+            lanes.append({
+                'stream': torch.cuda.Stream(device=dev),
+                'stage': torch.empty_like(dev_sets[0]),
+                'host_out': [torch.empty((CHANNELS, n_vox), dtype=torch.float32).pin_memory() for _ in range(2)],
+                'host_cnt': torch.empty((n_vox,), dtype=torch.int64).pin_memory(),
+            })
 
         def e2e_step(i):
-            stage.copy_(host_sets[i % N_INPUT_SETS], non_blocking=True)
-            mean, cov, cnt = step(stage)
-            host_out[0].copy_(mean.view(CHANNELS, -1), non_blocking=True)
-            host_out[1].copy_(cov.view(CHANNELS, -1), non_blocking=True)
-            host_cnt.copy_(cnt.view(-1), non_blocking=True)
+            ln = lanes[i % 2]
+            with torch.cuda.stream(ln['stream']):
+                ln['stage'].copy_(host_sets[i % N_INPUT_SETS], non_blocking=True)
+                mean, cov, cnt = step(ln['stage'])
+                ln['host_out'][0].copy_(mean.view(CHANNELS, -1), non_blocking=True)
+                ln['host_out'][1].copy_(cov.view(CHANNELS, -1), non_blocking=True)
+                ln['host_cnt'].copy_(cnt.view(-1), non_blocking=True)
+                # the outputs were allocated on this side stream: keep them alive until it has used them
+                for t in (mean, cov, cnt):
+                    t.record_stream(ln['stream'])
 
-        for i in range(3):
+        def e2e_join():
+            for ln in lanes:
+                torch.cuda.current_stream().wait_stream(ln['stream'])
+
+        for ln in lanes:
+            ln['stream'].wait_stream(torch.cuda.current_stream())
+        for i in range(4):
             e2e_step(i)
+        e2e_join()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        for ln in lanes:
+            ln['stream'].wait_event(e0)
         for i in range(e2e_steps):
             e2e_step(i)
+        e2e_join()
         e1.record()
         barrier()
         ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -283,7 +306,9 @@ def main():
         e2e = {'value': views_total * n_vox / (e2e_ms * 1e-3), 'unit': 'samples/s',
                'h2d_bytes_per_step': int(host_sets[0].numel() * 4) * n_gpus,
                'd2h_bytes_per_step': int(2 * CHANNELS * n_vox * 4 + n_vox * 8) * n_gpus,
-               'ms_per_step': e2e_ms, 'steps': e2e_steps}
+               'ms_per_step': e2e_ms, 'steps': e2e_steps,
+               'note': 'pinned host features -> device, fused lift through the Python API, mean / cov / count -> pinned host, '
+                       'every step; two streams so that consecutive steps overlap copy and compute'}
 
     clocks = sampler.stop() if rank == 0 else None
 
