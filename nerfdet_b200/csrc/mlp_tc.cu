@@ -48,12 +48,12 @@ constexpr int kTcBlockBytes = 16384;    // 128 rows x 128 B: one A block
 constexpr int kTcUnitN = 256;           // output columns per B unit = UMMA N (128: a 256-wide layer is two units per K block)
 constexpr int kTcStageBytes = kTcUnitN * 128;    // rows x 128 B: one B unit
 constexpr int kTcStages = 160 * 1024 / kTcStageBytes;
-constexpr int kTcMaxUnits = 128, kTcMaxJobs = 12, kTcMaxDepth = 8;
+constexpr int kTcMaxUnits = 64, kTcMaxJobs = 12, kTcMaxDepth = 8;
 constexpr int kTcEpiThreads = 256;      // warps 0-7: TMEM lane quarter = warp % 4, column half of a 64-column chunk = warp / 4
 constexpr int kTcThreads = 448;         // + warps 8-11 input encoding, warp 12 weight producer, warp 13 MMA issuer
 constexpr uint32_t kOffIn = 0, kOffB = kOffIn + 3 * kTcBlockBytes, kOffTail = kOffB + kTcStages * kTcStageBytes;   // 212992
 constexpr uint32_t kTailBars = 0, kTailTmem = 256, kTailHead = 512, kTailSigIn = kTailHead + 2 * kTcTile * 16,
-                   kTailPar = kTailSigIn + 4 * kTcTile * 4;
+                   kTailUnits = kTailSigIn + 4 * kTcTile * 4, kTailPar = kTailUnits + kTcMaxUnits * 16;
 
 enum : uint8_t { kJobRelu = 1, kJobWritesH = 2, kJobSigma = 4, kJobRgb = 8, kJobFreesIn = 16 };
 
@@ -329,6 +329,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// one lane of a converged warp (lets ptxas keep the MMA operands in uniform registers and drop its per-lane issue loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -436,6 +442,24 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
     }
     if (warp == 13) tc::tmem_alloc(tc::smem_u32(s_tmem), 512);
     for (int i = threadIdx.x; i < a.n_par; i += kTcThreads) s_par[i] = a.par[i];
+    // The MMA warp's per-unit record, precomputed once: one LDS.128 per unit instead of dependent constant-bank loads
+    // and descriptor arithmetic between the MMAs (the issuing thread, not the tensor pipe, paced the first version:
+    // ~224 cycles per M128 x N256 x K16 instruction against 138 for the same instruction issued back to back,
+    // tools/microbench7.cu).
+    //   x: A operand of the first K step -- TMEM column offset inside the previous job's region, or the low word of the
+    //      shared-memory descriptor of the IN block;  y: instruction descriptor;  z: 2 * k0 | nk << 8 | flags << 16 |
+    //      a_blk << 24;  w: accumulator column
+    uint4 *s_units = reinterpret_cast<uint4 *>(sm + kOffTail + kTailUnits);
+    for (int i = threadIdx.x; i < a.plan.n_units; i += kTcThreads) {
+        const TcUnit u = a.plan.units[i];
+        uint4 r;
+        r.x = u.a_blk < 4 ? (uint32_t)u.a_blk * 64u + 16u * u.k0
+                          : (uint32_t)tc::smem_desc(base + kOffIn + (uint32_t)(u.a_blk - 4) * kTcBlockBytes) + 2u * u.k0;
+        r.y = tc::instr_desc(u.n);
+        r.z = 2u * u.k0 | ((uint32_t)u.nk << 8) | ((uint32_t)u.flags << 16) | ((uint32_t)u.a_blk << 24);
+        r.w = u.d_col;
+        s_units[i] = r;
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -462,25 +486,35 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
         }
     } else if (warp == 13) {
         // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        // The whole warp walks the job / unit lists in lock-step (uniform control flow, waits included); the tcgen05
+        // instructions are issued by one elected lane.  Everything per unit comes from one prefetched LDS.128: a single
+        // thread retires a dependent instruction every ~4-5 cycles, so ~40 instructions between two MMAs already cost
+        // more than the 138 cycles the tensor pipe needs for an M128 x N256 x K16 step (tools/microbench7.cu).
+        {
             int stage = 0;
             uint32_t ph = 0, hpar = 0, in_par = 0, dpar = 3u;       // dpar bit d: parity to wait for on d_empty[d]
             uint32_t jc = 0;                                           // running job counter -> accumulator buffer
+            const uint64_t desc_hi = tc::smem_desc(0) & 0xffffffff00000000ull;        // layout / stride bits of every operand
+            const uint32_t bd0 = (uint32_t)tc::smem_desc(sB);                          // low word of stage 0's B descriptor
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 bool in_ok = false;
                 for (int j = 0; j < P.n_jobs; ++j, ++jc) {
-                    const TcJob job = P.jobs[j];
+                    const uint32_t first_unit = P.jobs[j].first_unit, n_units = P.jobs[j].n_units, jflags = P.jobs[j].flags;
                     const uint32_t d = jc & 1u;
+                    uint4 ur = s_units[first_unit];
                     if (!(dbg & 8)) tc::mbar_wait(d_empty + 8 * d, (dpar >> d) & 1u);
                     dpar ^= 1u << d;
                     const uint32_t a_region = tmem + (d ^ 1u) * 256u;             // the previous job's region holds this job's A
-                    for (int uu = 0; uu < job.n_units; ++uu) {
-                        const TcUnit u = P.units[job.first_unit + uu];
-                        const bool from_tmem = u.a_blk < 4;
+                    const uint32_t d_region = tmem + d * 256u;
+                    for (uint32_t uu = 0; uu < n_units; ++uu) {
+                        const uint4 u = ur;
+                        if (uu + 1 < n_units) ur = s_units[first_unit + uu + 1];  // next record in flight during the waits
+                        const uint32_t a_blk = u.z >> 24, uflags = (u.z >> 16) & 0xffu, nk = (u.z >> 8) & 0xffu;
+                        const bool from_tmem = a_blk < 4;
                         if (from_tmem) {
-                            if ((u.flags & 1) && !(dbg & 8)) {
-                                tc::mbar_wait(h_ready + 8 * u.a_blk, (hpar >> u.a_blk) & 1u);
-                                hpar ^= 1u << u.a_blk;
+                            if ((uflags & 1u) && !(dbg & 8)) {
+                                tc::mbar_wait(h_ready + 8 * a_blk, (hpar >> a_blk) & 1u);
+                                hpar ^= 1u << a_blk;
                             }
                         } else if (!in_ok && !(dbg & 16)) {
                             tc::mbar_wait(in_ready, in_par);
@@ -489,28 +523,34 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                         }
                         if (!(dbg & 16)) tc::mbar_wait(b_full + 8 * stage, ph);
                         tc::tc_fence_after();
-                        const uint32_t idesc = tc::instr_desc(u.n);
-                        const uint64_t bd = tc::smem_desc(sB + stage * kTcStageBytes);
-                        const uint32_t d_tmem = tmem + d * 256u + u.d_col;
-                        if (dbg & 2) {
-                        } else if (from_tmem) {
-                            // K step s of chunk c: 8 packed columns at column 64 c + 16 s of the previous region
-                            const uint32_t a_tmem = a_region + (uint32_t)u.a_blk * 64u;
-                            for (int s = 0; s < u.nk; ++s)
-                                tc::umma_bf16_ts(d_tmem, a_tmem + 16u * (uint32_t)(u.k0 + s), bd + (uint64_t)(2 * (u.k0 + s)), idesc,
-                                                 ((u.flags & 2) && s == 0) ? 0u : 1u);
-                        } else {
-                            const uint64_t ad = tc::smem_desc(sIN + (u.a_blk - 4) * kTcBlockBytes);
-                            for (int s = 0; s < u.nk; ++s) {
-                                const uint64_t ko = (uint64_t)(2 * (u.k0 + s));    // 32 B per K step, in 16-byte units
-                                tc::umma_bf16(d_tmem, ad + ko, bd + ko, idesc, ((u.flags & 2) && s == 0) ? 0u : 1u);
+                        const uint64_t bd = desc_hi | (uint64_t)(bd0 + (uint32_t)stage * (kTcStageBytes >> 4) + (u.z & 0xffu));
+                        const uint32_t d_tmem = d_region + u.w;
+                        const uint32_t acc0 = (uflags & 2u) ? 0u : 1u;             // first K block of the job overwrites D
+                        if (tc::elect_one()) {
+                            if (dbg & 2) {
+                            } else if (from_tmem) {
+                                // K step s of chunk c: 8 packed columns at column 64 c + 16 s of the previous region
+                                const uint32_t a_tmem = a_region + u.x;
+                                tc::umma_bf16_ts(d_tmem, a_tmem, bd, u.y, acc0);
+                                if (nk > 1) tc::umma_bf16_ts(d_tmem, a_tmem + 16u, bd + 2u, u.y, 1u);
+                                if (nk > 2) tc::umma_bf16_ts(d_tmem, a_tmem + 32u, bd + 4u, u.y, 1u);
+                                if (nk > 3) tc::umma_bf16_ts(d_tmem, a_tmem + 48u, bd + 6u, u.y, 1u);
+                            } else {
+                                const uint64_t ad = desc_hi | (uint64_t)u.x;           // 32 B per K step = 2 descriptor units
+                                tc::umma_bf16(d_tmem, ad, bd, u.y, acc0);
+                                if (nk > 1) tc::umma_bf16(d_tmem, ad + 2u, bd + 2u, u.y, 1u);
+                                if (nk > 2) tc::umma_bf16(d_tmem, ad + 4u, bd + 4u, u.y, 1u);
+                                if (nk > 3) tc::umma_bf16(d_tmem, ad + 6u, bd + 6u, u.y, 1u);
+                            }
+                            tc::umma_commit(b_empty + 8 * stage);                   // frees the B stage once these MMAs are done
+                            if (uu + 1 == n_units) {
+                                tc::umma_commit(d_full + 8 * d);
+                                if (jflags & kJobFreesIn) tc::umma_commit(in_free);
                             }
                         }
-                        tc::umma_commit(b_empty + 8 * stage);                       // frees the B stage once these MMAs are done
+                        __syncwarp();
                         if (++stage == kTcStages) { stage = 0; ph ^= 1u; }
                     }
-                    tc::umma_commit(d_full + 8 * d);
-                    if (job.flags & kJobFreesIn) tc::umma_commit(in_free);
                 }
             }
         }
