@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kOct)
 k_plane_index(const Tiling tiling, const float *__restrict__ points, const float *__restrict__ proj, int nv, int nvp,
               int n_octs, int64_t n_vox, int64_t n_pad, int height, int width, int elt, uint32_t zero_off,
               uint16_t *__restrict__ off16, uint8_t *__restrict__ cnt8, uint8_t *__restrict__ omask,
-              uint8_t *__restrict__ cost16) {
+              uint8_t *__restrict__ cost16, int view_w) {
     __shared__ float sp[kIdxViews * 12];
     __shared__ unsigned smask;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the dependent kernels start their prologues
@@ -229,7 +229,12 @@ k_plane_index(const Tiling tiling, const float *__restrict__ points, const float
     __syncthreads();
     const unsigned sm = smask;
     if (threadIdx.x < kIdxViews) omask[(int64_t)blockIdx.x * nvp + v0 + threadIdx.x] = (uint8_t)((sm >> (2 * threadIdx.x)) & 3u);
-    if (threadIdx.x == 32) cost16[(int64_t)blockIdx.y * n_octs + blockIdx.x] = (uint8_t)__popc(sm);
+    // cost of the oct in this view group: active quad-views plus `view_w` per view that sees the oct at all (a tile-view
+    // costs its warp a fixed ~400 cycles of list / offset-row handling besides the gathers of its quads)
+    if (threadIdx.x == 32) {
+        const unsigned any = (sm | (sm >> 1)) & 0x55555555u;
+        cost16[(int64_t)blockIdx.y * n_octs + blockIdx.x] = (uint8_t)(__popc(sm) + view_w * __popc(any));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -915,11 +920,12 @@ nd_status run_lift_planes(const nd_maps *f, const float *points, const float *pr
     uint16_t *pairs = reinterpret_cast<uint16_t *>(wsb);            wsb += g.pairs_bytes;
     uint32_t *gstart = reinterpret_cast<uint32_t *>(wsb);
 
-    int debug = 0;
+    int debug = 0, view_w = 2;
     if (const char *e = getenv("ND_LIFT_DEBUG")) debug = atoi(e);
+    if (const char *e = getenv("ND_LIFT_VIEW_W")) view_w = atoi(e);
     k_plane_index<<<dim3((unsigned)g.n_octs, (unsigned)g.nw16), kOct, 0, st>>>(
         g.tiling, points, proj, f->n_views, g.nvp, g.n_octs, n_vox, g.n_pad, f->height, f->width, g.elt, g.plane_bytes,
-        off16, cnt8, omask, cost16);
+        off16, cnt8, omask, cost16, view_w);
     ND_CUDA_LAUNCH_CHECK("k_plane_index");
     const int balanced = (g.n_octs <= kPMaxOcts && !(debug & 32)) ? 1 : 0;
     const size_t pack_smem = (((size_t)2 * g.warps * g.nvp + 15) & ~(size_t)15) + (size_t)g.nvp * sizeof(uint16_t);
