@@ -135,6 +135,7 @@ static bool tc_layout(const nd_mlp_weights *w, TcLayout &L, bool report) {
         const bool first_kb = j.n_units == 0;
         const int un = j.n < kTcUnitN ? j.n : kTcUnitN;
         for (int nh = 0; nh < j.n / un; ++nh) {
+            if (P.n_units >= kTcMaxUnits) { ++P.n_units; continue; }             // counted, rejected below
             TcUnit &u = P.units[P.n_units];
             TcPackUnit &pu = L.pack[P.n_units];
             ++P.n_units;
@@ -211,6 +212,13 @@ static bool tc_layout(const nd_mlp_weights *w, TcLayout &L, bool report) {
     L.off_bo = par;    par += 4;
     L.n_par = par;
     L.total_bytes = align_up(L.image_bytes, 256) + (size_t)par * sizeof(float);
+    if (P.n_units > kTcMaxUnits || 1024 + kOffTail + kTailPar + (size_t)par * sizeof(float) > 227 * 1024) {
+        if (report)
+            set_error("nerf_mlp (tensor-core path): net_depth %d with this skip pattern needs %d weight blocks / %zu bytes of shared "
+                      "memory per CTA (limits: %d, %d); use the fp32 path", depth, P.n_units,
+                      1024 + kOffTail + kTailPar + (size_t)par * sizeof(float), kTcMaxUnits, 227 * 1024);
+        return false;
+    }
     (void)head_ref;
     return true;
 }

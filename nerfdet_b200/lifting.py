@@ -27,7 +27,14 @@ def compute_projection(img_meta, stride: int, angles=None) -> torch.Tensor:
     intrinsic = torch.tensor(img_meta['lidar2img']['intrinsic'][:3, :3])
     ratio = img_meta['ori_shape'][0] / (img_meta['img_shape'][0] / stride)
     intrinsic[:2] /= ratio
-    return torch.stack([intrinsic @ torch.tensor(e)[:3] for e in img_meta['lidar2img']['extrinsic']])
+    # one host copy of all extrinsics, then the reference's own per-view 3x3 @ 3x4 product (the very same mm on the very
+    # same values: the projection matrices, and with them the pixel indices, stay bit-identical to the reference's)
+    import numpy as np
+    extr = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(e) for e in img_meta['lidar2img']['extrinsic']])))
+    out = torch.empty((extr.shape[0], 3, 4), dtype=intrinsic.dtype)
+    for i in range(extr.shape[0]):
+        torch.mm(intrinsic, extr[i, :3], out=out[i])
+    return out
 
 
 @torch.no_grad()
@@ -39,6 +46,29 @@ def get_points(n_voxels, voxel_size, origin) -> torch.Tensor:
     lattice = torch.stack(torch.meshgrid([torch.arange(int(k)) for k in n_voxels], indexing='ij'))
     new_origin = origin - n_voxels / 2. * voxel_size
     return lattice * voxel_size.view(3, 1, 1, 1) + new_origin.view(3, 1, 1, 1)
+
+
+_LATTICE_CACHE = {}
+
+
+@torch.no_grad()
+def get_points_device(n_voxels, voxel_size, origin, device) -> torch.Tensor:
+    """``get_points`` evaluated on ``device`` with the lattice term ``idx * voxel_size`` cached per (grid, voxel size,
+    device): the same two fp32 roundings as the reference (multiply, then add the shifted origin), so the result is
+    bit-identical to ``get_points(...).to(device)`` without the per-scene meshgrid on the host and its 300 KB copy."""
+    key = (tuple(int(k) for k in n_voxels), tuple(float(v) for v in voxel_size), str(device))
+    ent = _LATTICE_CACHE.get(key)
+    if ent is None:
+        nv = torch.as_tensor(n_voxels)
+        vs = torch.as_tensor(voxel_size, dtype=torch.float32)
+        lattice = torch.stack(torch.meshgrid([torch.arange(int(k)) for k in nv], indexing='ij'))
+        ent = ((lattice * vs.view(3, 1, 1, 1)).to(device), nv / 2. * vs)
+        if len(_LATTICE_CACHE) > 8:
+            _LATTICE_CACHE.clear()
+        _LATTICE_CACHE[key] = ent
+    scaled, half_extent = ent
+    new_origin = torch.as_tensor(origin, dtype=torch.float32) - half_extent
+    return scaled + new_origin.to(device).view(3, 1, 1, 1)
 
 
 def project_voxels(points: torch.Tensor, projection: torch.Tensor, height: int, width: int):

@@ -72,7 +72,7 @@ def lift_scene(feature: torch.Tensor, img_meta: Dict, n_voxels, voxel_size, mapp
     feature_2d [nv,32,h,w], global_volume [N,70], alpha [N]."""
     dev = feature.device
     projection = lifting.compute_projection(img_meta, stride).to(dev)
-    points = lifting.get_points(n_voxels, voxel_size, img_meta['lidar2img']['origin']).to(dev)
+    points = lifting.get_points_device(n_voxels, voxel_size, img_meta['lidar2img']['origin'], dev)
     height = img_meta['img_shape'][0] // stride
     width = img_meta['img_shape'][1] // stride
     sliced = feature[:, :, :height, :width]
