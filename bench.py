@@ -170,14 +170,21 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, exchange='peer'):
+    if n_gpus == 1:
+        part = 'single GPU'
+    elif exchange == 'peer':
+        part = (f'views sharded over {n_gpus} GPUs; (S1,S2,count) reduced and finalised by one kernel per rank over '
+                'NVLink peer memory (nd_lift_finalize_peers: P2P loads of the channel slice, P2P stores of the rows)')
+    else:
+        part = f'views sharded over {n_gpus} GPUs, 1 NCCL all-reduce of (S1,S2,count)'
     return {
         'workload': 'nerfdet_res50_2x_low_res lift: fused backproject + mean/var/count (nerfdet.py:164-181)',
         'views_per_gpu': NV_PER_GPU, 'views_total': NV_PER_GPU * n_gpus, 'channels': CHANNELS,
         'feature_hw': list(FEAT_HW), 'feature_hw_padded': list(FEAT_HW_PAD), 'n_voxels': list(N_VOXELS),
         'feature_layout': 'NCHW fp32, non-contiguous [:, :, :59, :80] slice (reference layout)',
         'l2_policy': f'inputs (241.7 MB/step) exceed the 126 MB L2 and {N_INPUT_SETS} input sets are rotated',
-        'partitioning': 'single GPU' if n_gpus == 1 else f'views sharded over {n_gpus} GPUs, 1 NCCL all-reduce of (S1,S2,count)',
+        'partitioning': part,
     }
 
 
@@ -190,6 +197,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'],
+                    help='N > 1: how the per-rank accumulators meet (peer-memory kernel, or NCCL all-reduce + finalise)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -221,10 +230,16 @@ def main():
     dev_sets = [h.to(dev) for h in host_sets]
     views_total = NV_PER_GPU * n_gpus
 
-    def step(feats):
+    # N > 1: one peer-mapped segment for the device-resident loop and one per end-to-end lane (their results are views of it)
+    use_peer = n_gpus > 1 and args.exchange == 'peer'
+    peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev) for _ in range(3)] if use_peer else None
+
+    def step(feats, lane=0):
         f = feats[:, :, :FEAT_HW[0], :FEAT_HW[1]]
         if n_gpus == 1:
             return lifting.lift_mean_var(f, pts_d, proj_d)
+        if use_peer:
+            return peers[lane](f, pts_d, proj_d, views_total)
         return nd_dist.lift_mean_var_view_sharded(f, pts_d, proj_d, n_views_total=views_total)
 
     def barrier():
@@ -272,7 +287,7 @@ def main():
             ln = lanes[i % 2]
             with torch.cuda.stream(ln['stream']):
                 ln['stage'].copy_(host_sets[i % N_INPUT_SETS], non_blocking=True)
-                mean, cov, cnt = step(ln['stage'])
+                mean, cov, cnt = step(ln['stage'], 1 + i % 2)
                 ln['host_out'][0].copy_(mean.view(CHANNELS, -1), non_blocking=True)
                 ln['host_out'][1].copy_(cov.view(CHANNELS, -1), non_blocking=True)
                 ln['host_cnt'].copy_(cnt.view(-1), non_blocking=True)
@@ -311,6 +326,9 @@ def main():
                        'every step; two streams so that consecutive steps overlap copy and compute'}
 
     clocks = sampler.stop() if rank == 0 else None
+    if peers is not None:
+        for p in peers:
+            p.check()                                   # a peer that missed an exchange step invalidates the run
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu_baseline = None
@@ -326,12 +344,14 @@ def main():
         bytes_per_step = algorithmic_bytes(NV_PER_GPU, CHANNELS, FEAT_HW[0], FEAT_HW[1], n_vox)
         achieved = bytes_per_step / (ms_per_step * 1e-3) / 1e9
         # launches per step: 1 pixel-index pre-pass + (stage, gather) per channel chunk (+ finalize when sharded)
-        launches = ops.lift_launch_count(dev_sets[0][:, :, :FEAT_HW[0], :FEAT_HW[1]], n_vox) + (1 if n_gpus > 1 else 0)
+        # (+ when sharded: finalise-over-peers + wait kernel, or our finalise kernel after NCCL's all-reduce)
+        launches = ops.lift_launch_count(dev_sets[0][:, :, :FEAT_HW[0], :FEAT_HW[1]], n_vox) + \
+            (0 if n_gpus == 1 else 2 if use_peer else 1)
         line = {
             'metric': 'voxel_view_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': n_gpus,
             'steps': steps, 'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(n_gpus),
+            'config': workload_config(n_gpus, args.exchange),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': ncu_traffic(), 'peak_source': peak_src,
                          'algorithmic_bytes_per_step': bytes_per_step,
@@ -340,6 +360,9 @@ def main():
             'cpu_baseline': cpu_baseline, 'e2e': e2e, 'gpu_launches': launches * steps, 'clocks': clocks,
         }
         print(json.dumps(line), flush=True)
+    if peers is not None:
+        for p in peers:
+            p.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -134,6 +134,40 @@ int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_v
 
 
 /* ---------------------------------------------------------------------------------------
+ * Exchange step of the view-sharded lift over NVLink peer memory (no counterpart in the
+ * reference, which lifts one scene per GPU).  Replaces "all-reduce the accumulators, then nd_lift_finalize on every
+ * rank" with one kernel per rank that loads its channel slice of S1 / S2 / count from EVERY rank's accumulators
+ * (P2P reads), finalises it with the global view count (nerfdet.py:171-181) and stores the rows into EVERY rank's
+ * mean / cov (P2P writes); a one-block wait kernel then holds `stream` until all peers are done with this rank's
+ * buffers.  Ranks meet through epoch flags inside the segments, so no NCCL call is needed on the data path.
+ *
+ *   nd_peer_alloc   cudaMalloc + zero a segment on the current device and export its CUDA IPC handle (64 bytes, host).
+ *                   The one place where the library owns device memory: an IPC handle covers a whole allocation.
+ *   nd_peer_open    map another process's segment into the current device's address space (lazy peer access);
+ *   nd_peer_close / nd_peer_free   undo the two above.
+ *   nd_lift_finalize_peers
+ *     acc_host / mean_host / cov_host / flags_host: HOST arrays of `world` DEVICE pointers, entry g = rank g's
+ *       accumulators [S1 (C*N) | S2 (C*N) | count (N)] f32 as written by nd_lift_accumulate, its mean [C][N], its cov
+ *       [C][N] (cov_host NULL: not wanted) and its flag block (ND_PEER_FLAG_WORDS uint32, zero before the first epoch);
+ *       entry `rank` is the local segment.  world <= ND_MAX_PEERS.
+ *     epoch: 1, 2, 3, ... the same on every rank for the same step.
+ *     count: int64 [N] local, or NULL.  alpha: f32 [N] local or NULL (alpha * mean, nerfdet.py:259-261).
+ *   Outputs are complete on `stream` when the call's kernels have run; a peer that never arrives raises word
+ *   2 * ND_MAX_PEERS + 1 of the local flag block after ~4 s instead of hanging.
+ * ------------------------------------------------------------------------------------- */
+#define ND_MAX_PEERS 8
+#define ND_PEER_FLAG_WORDS 32
+
+int nd_peer_alloc(size_t bytes, void **ptr, unsigned char *handle64_host);
+int nd_peer_open(const unsigned char *handle64_host, void **ptr);
+int nd_peer_close(void *ptr);
+int nd_peer_free(void *ptr);
+int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
+                           void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
+                           int channels, int64_t n_voxels, const float *alpha, int64_t *count, void *stream);
+
+
+/* ---------------------------------------------------------------------------------------
  * B7  nerfdet.py:190-197  the per-pixel Linear(C -> 32) ("mapping") on the sliced 2-D features:
  *   mapped[v][y][x][j] = bias[j] + sum_c weight[j][c] * features[v][c][y][x]      (fp32 FMA, channels ascending)
  * features: NCHW planes read in place (contiguous planes, 16-byte aligned; f32 or bf16); weight f32 [32][C]

@@ -12,6 +12,7 @@ from . import build as _build
 
 ND_F32, ND_BF16 = 0, 1
 ND_LIFT_PATH_AUTO, ND_LIFT_PATH_STAGED = 0, 1
+ND_MAX_PEERS, ND_PEER_FLAG_WORDS = 8, 32
 
 
 class NdMaps(ctypes.Structure):
@@ -51,6 +52,13 @@ SIGNATURES = {
                                    c_void_p, c_size_t, POINTER(NdLiftOptions), c_void_p]),
     'nd_lift_finalize': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
+    'nd_peer_alloc': (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    'nd_peer_open': (c_int, [c_void_p, POINTER(c_void_p)]),
+    'nd_peer_close': (c_int, [c_void_p]),
+    'nd_peer_free': (c_int, [c_void_p]),
+    'nd_lift_finalize_peers': (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                       c_int, c_int, ctypes.c_uint32, c_int, c_int, c_int64, c_void_p, c_void_p,
+                                       c_void_p]),
     'nd_live_stats': (c_int, [POINTER(NdMaps), POINTER(NdMaps), c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'nd_map_features': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

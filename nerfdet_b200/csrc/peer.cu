@@ -1,0 +1,294 @@
+// View-sharded lift, exchange step: reduce + finalise in ONE kernel over NVLink peer memory.
+//
+// Every rank has run nd_lift_accumulate on its own views into a peer-mapped segment [S1 (C*N) | S2 (C*N) | count (N)].
+// Instead of an NCCL all-reduce of the 52.5 MB accumulators followed by a finalise pass on every rank, rank r
+//   * owns a slice of the channels,
+//   * LOADS the partial sums of its slice from every rank's segment (P2P reads over NVLink / NVSwitch),
+//   * adds them in rank order, turns them into mean / exp(-var) with the GLOBAL view count (nerfdet.py:171-181), and
+//   * STORES the result rows into every rank's output buffers (P2P writes),
+// so the accumulators cross the links once (reduce-scatter traffic), the results once (all-gather traffic), and no
+// reduced accumulator is ever written back to memory.  The hand-shake between the ranks is a pair of epoch flags per
+// peer inside the segments (st.release.sys / ld.acquire.sys): `ready` = my accumulators of this epoch are complete
+// (raised by the first CTA of the finalise kernel, i.e. after the accumulate kernels in stream order), `done` = all my
+// reads of your accumulators and all my writes into your outputs have been performed (raised by the last CTA).
+// A one-block wait kernel holds the stream until every peer is `done`.  All spins are bounded: a peer that never shows up
+// raises an error flag after ~4 s instead of hanging the GPU.
+//
+// The segments are plain cudaMalloc allocations shared with CUDA IPC handles (nd_peer_alloc / nd_peer_open): the only
+// place where the library owns device memory, because a handle must cover a whole allocation.
+#include <string.h>
+
+#include "nd_common.cuh"
+
+namespace nd {
+
+constexpr int kMaxPeers = ND_MAX_PEERS;
+constexpr int kPeerThreads = 128;
+
+struct PeerArgs {
+    const float *acc[kMaxPeers];
+    float *mean[kMaxPeers];
+    float *cov[kMaxPeers];           // all null: no covariance wanted
+    uint32_t *flags[kMaxPeers];      // [0, P): ready, [P, 2P): done, [2P]: CTA counter, [2P + 1]: error
+    int world, rank;
+    uint32_t epoch;
+    int n_views_total, channels, c_begin, c_end, ch_per_cta;
+    int64_t n_vox;
+    const float *alpha;
+    int64_t *count;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// waits until *p has reached `epoch` (wrap-safe); false after ~4 s
+__device__ __forceinline__ bool spin_until(const uint32_t *p, uint32_t epoch) {
+    const unsigned long long t0 = global_ns();
+    while ((int32_t)(ld_acquire_sys(p) - epoch) < 0) {
+        __nanosleep(64);
+        if (global_ns() - t0 > 4000000000ull) return false;
+    }
+    return true;
+}
+
+template <int V> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<1> { using type = float; };
+
+template <int V> __device__ __forceinline__ void ld_vec(const float *p, float (&r)[V]);
+template <> __device__ __forceinline__ void ld_vec<4>(const float *p, float (&r)[4]) {
+    const float4 t = __ldcg(reinterpret_cast<const float4 *>(p));
+    r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+}
+template <> __device__ __forceinline__ void ld_vec<1>(const float *p, float (&r)[1]) { r[0] = __ldcg(p); }
+template <int V> __device__ __forceinline__ void st_vec(float *p, const float (&r)[V]);
+template <> __device__ __forceinline__ void st_vec<4>(float *p, const float (&r)[4]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(r[0], r[1], r[2], r[3]);
+}
+template <> __device__ __forceinline__ void st_vec<1>(float *p, const float (&r)[1]) { *p = r[0]; }
+
+// grid = (voxel tiles of kPeerThreads * V, channel sub-slices of this rank's slice)
+template <int V>
+__global__ void __launch_bounds__(kPeerThreads)
+k_lift_finalize_peers(const PeerArgs a) {
+    const int P = kMaxPeers;
+    uint32_t *my_flags = a.flags[a.rank];
+    // ---- hand-shake: my accumulators are complete; wait for everybody else's ----
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < a.world)
+        st_release_sys(a.flags[threadIdx.x] + a.rank, a.epoch);
+    if (threadIdx.x < a.world && threadIdx.x != a.rank) {
+        if (!spin_until(my_flags + threadIdx.x, a.epoch)) atomicExch(my_flags + 2 * P + 1, 1u);
+    }
+    __syncthreads();
+
+    const int64_t n = ((int64_t)blockIdx.x * kPeerThreads + threadIdx.x) * V;
+    const int64_t cn = (int64_t)a.channels * a.n_vox;
+    if (n < a.n_vox) {
+        float cnt[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) cnt[j] = 0.f;
+#pragma unroll
+        for (int g = 0; g < kMaxPeers; ++g) {
+            if (g < a.world) {
+                float t[V];
+                ld_vec<V>(a.acc[g] + 2 * cn + n, t);
+#pragma unroll
+                for (int j = 0; j < V; ++j) cnt[j] += t[j];
+            }
+        }
+        float al[V], inv[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            al[j] = a.alpha != nullptr ? __ldg(a.alpha + n + j) : 1.0f;
+            inv[j] = (float)a.n_views_total - cnt[j];
+        }
+        if (blockIdx.y == 0 && a.count != nullptr) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) a.count[n + j] = (int64_t)cnt[j];
+        }
+        const int c0 = a.c_begin + (int)blockIdx.y * a.ch_per_cta;
+        const int c1 = min(a.c_end, c0 + a.ch_per_cta);
+        for (int c = c0; c < c1; ++c) {
+            const int64_t o = (int64_t)c * a.n_vox + n;
+            float s1[V], s2[V];
+            float p1[kMaxPeers][V], p2[kMaxPeers][V];
+#pragma unroll
+            for (int g = 0; g < kMaxPeers; ++g) {               // all loads of the channel in flight together
+                if (g < a.world) {
+                    ld_vec<V>(a.acc[g] + o, p1[g]);
+                    ld_vec<V>(a.acc[g] + cn + o, p2[g]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+#pragma unroll
+            for (int g = 0; g < kMaxPeers; ++g) {               // rank order: every rank would get the same bits
+                if (g < a.world) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) { s1[j] += p1[g][j]; s2[j] += p2[g][j]; }
+                }
+            }
+            float m[V], cv[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                m[j] = 0.f;
+                cv[j] = 0.f;
+                if (cnt[j] > 0.f) {                             // same formula as k_lift_finalize (lift.cu)
+                    const float mm = s1[j] / cnt[j];
+                    float ssd = fmaxf(fmaf(-mm, s1[j], s2[j]), 0.0f);
+                    ssd = fmaf(inv[j] * mm, mm, ssd);
+                    cv[j] = expf(-(ssd / cnt[j]));
+                    m[j] = mm * al[j];
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < kMaxPeers; ++g) {
+                if (g < a.world) {
+                    st_vec<V>(a.mean[g] + o, m);
+                    if (a.cov[g] != nullptr) st_vec<V>(a.cov[g] + o, cv);
+                }
+            }
+        }
+    }
+    // ---- completion: the last CTA tells every peer that this rank is done with their segments ----
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = gridDim.x * gridDim.y;
+        const uint32_t prev = atomicAdd(my_flags + 2 * P, 1u);
+        if (prev == total - 1) {
+            my_flags[2 * P] = 0u;                               // ready for the next epoch (next launch is stream-ordered)
+            __threadfence_system();
+            for (int g = 0; g < a.world; ++g) st_release_sys(a.flags[g] + P + a.rank, a.epoch);
+        }
+    }
+}
+
+__global__ void k_peer_wait_done(uint32_t *my_flags, int world, uint32_t epoch) {
+    if (threadIdx.x < world) {
+        if (!spin_until(my_flags + kMaxPeers + threadIdx.x, epoch)) atomicExch(my_flags + 2 * kMaxPeers + 1, 1u);
+    }
+}
+
+}  // namespace nd
+
+using namespace nd;
+
+extern "C" {
+
+int nd_peer_alloc(size_t bytes, void **ptr, unsigned char *handle64_host) {
+    ND_REQUIRE(ptr && handle64_host && bytes > 0, ND_ERR_BAD_ARG, "nd_peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        if (p) cudaFree(p);
+        set_error("nd_peer_alloc: %s", cudaGetErrorString(e));
+        return ND_ERR_CUDA;
+    }
+    memcpy(handle64_host, &h, 64);
+    *ptr = p;
+    return ND_OK;
+}
+
+int nd_peer_open(const unsigned char *handle64_host, void **ptr) {
+    ND_REQUIRE(ptr && handle64_host, ND_ERR_BAD_ARG, "nd_peer_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, 64);
+    void *p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        set_error("nd_peer_open: %s", cudaGetErrorString(e));
+        return ND_ERR_CUDA;
+    }
+    *ptr = p;
+    return ND_OK;
+}
+
+int nd_peer_close(void *ptr) {
+    if (ptr == nullptr) return ND_OK;
+    const cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    if (e != cudaSuccess) {
+        set_error("nd_peer_close: %s", cudaGetErrorString(e));
+        return ND_ERR_CUDA;
+    }
+    return ND_OK;
+}
+
+int nd_peer_free(void *ptr) {
+    if (ptr == nullptr) return ND_OK;
+    const cudaError_t e = cudaFree(ptr);
+    if (e != cudaSuccess) {
+        set_error("nd_peer_free: %s", cudaGetErrorString(e));
+        return ND_ERR_CUDA;
+    }
+    return ND_OK;
+}
+
+int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
+                           void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
+                           int channels, int64_t n_voxels, const float *alpha, int64_t *count, void *stream) {
+    ND_REQUIRE(acc_host && mean_host && flags_host, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: null pointer table");
+    ND_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, ND_ERR_BAD_ARG,
+               "nd_lift_finalize_peers: world %d / rank %d outside [1, %d]", world, rank, kMaxPeers);
+    ND_REQUIRE(channels > 0 && n_voxels >= 0 && n_views_total > 0, ND_ERR_BAD_SHAPE, "nd_lift_finalize_peers: bad shape");
+    ND_REQUIRE(epoch != 0u, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: epoch 0 is the initial state of the flags");
+    if (n_voxels == 0) return ND_OK;
+    PeerArgs a{};
+    bool vec = n_voxels % 4 == 0 && (alpha == nullptr || reinterpret_cast<uintptr_t>(alpha) % 16 == 0);
+    for (int g = 0; g < world; ++g) {
+        ND_REQUIRE(acc_host[g] && mean_host[g] && flags_host[g], ND_ERR_BAD_ARG, "nd_lift_finalize_peers: null segment of rank %d", g);
+        a.acc[g] = static_cast<const float *>(acc_host[g]);
+        a.mean[g] = static_cast<float *>(mean_host[g]);
+        a.cov[g] = cov_host != nullptr ? static_cast<float *>(cov_host[g]) : nullptr;
+        a.flags[g] = static_cast<uint32_t *>(flags_host[g]);
+        vec = vec && reinterpret_cast<uintptr_t>(a.acc[g]) % 16 == 0 && reinterpret_cast<uintptr_t>(a.mean[g]) % 16 == 0 &&
+              reinterpret_cast<uintptr_t>(a.cov[g]) % 16 == 0;
+    }
+    a.world = world;
+    a.rank = rank;
+    a.epoch = epoch;
+    a.n_views_total = n_views_total;
+    a.channels = channels;
+    // channel slice of this rank: contiguous, sizes differ by at most one (the split of distributed.view_shard)
+    const int base = channels / world, rem = channels % world;
+    a.c_begin = rank * base + (rank < rem ? rank : rem);
+    a.c_end = a.c_begin + base + (rank < rem ? 1 : 0);
+    a.n_vox = n_voxels;
+    a.alpha = alpha;
+    a.count = count;
+    const int v = vec ? 4 : 1;
+    const int64_t tiles = ceil_div(n_voxels, (int64_t)kPeerThreads * v);
+    const int slice = a.c_end - a.c_begin;
+    // ~4 CTAs per SM so that enough loads are in flight over the links; a CTA keeps its tile's counts for its channels
+    int64_t subs = ceil_div((int64_t)148 * 4, tiles);
+    if (subs > slice) subs = slice;
+    if (subs < 1) subs = 1;
+    a.ch_per_cta = slice > 0 ? (int)ceil_div(slice, subs) : 1;
+    const dim3 grid((unsigned)tiles, (unsigned)(slice > 0 ? ceil_div(slice, a.ch_per_cta) : 1));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec)
+        k_lift_finalize_peers<4><<<grid, kPeerThreads, 0, st>>>(a);
+    else
+        k_lift_finalize_peers<1><<<grid, kPeerThreads, 0, st>>>(a);
+    ND_CUDA_LAUNCH_CHECK("k_lift_finalize_peers");
+    k_peer_wait_done<<<1, 32, 0, st>>>(a.flags[rank], world, epoch);
+    ND_CUDA_LAUNCH_CHECK("k_peer_wait_done");
+    return ND_OK;
+}
+
+}  // extern "C"

@@ -66,3 +66,187 @@ def lift_mean_var_view_sharded(features_local: torch.Tensor, points: torch.Tenso
                                    alpha.reshape(-1) if alpha is not None else None, want_cov)
     return (mean.view(c, gx, gy, gz), cov.view(c, gx, gy, gz) if want_cov else None,
             count.view(1, gx, gy, gz))
+
+
+def channel_shard(channels: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """[begin, end) of the channels rank ``rank`` reduces and finalises in the peer-memory exchange
+    (same split as ``view_shard``; csrc/peer.cu computes it the same way)."""
+    return view_shard(channels, rank, world_size)
+
+
+class _DevicePtr:
+    """``__cuda_array_interface__`` shim: lets torch address a raw device allocation without owning it."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2}
+
+
+_last_exchange = {}      # device index -> event of the most recent exchange issued by this process
+
+
+class PeerLift:
+    """View-sharded lift whose exchange step runs over NVLink peer memory instead of NCCL (csrc/peer.cu).
+
+    Every rank owns one peer-mapped segment ``[flags | S1 S2 count | mean | cov]``.  A call accumulates this rank's
+    views into the local segment (``nd_lift_accumulate``) and then launches ``nd_lift_finalize_peers``: the kernel
+    loads this rank's channel slice of every rank's partial sums (P2P reads), finalises it with the global view count
+    and stores the rows into every rank's mean / cov (P2P writes).  Compared with ``lift_mean_var_view_sharded`` the
+    52.5 MB accumulators cross the links once instead of twice, no reduced accumulator is written back, the finalise
+    pass is split over the ranks, and no NCCL kernel is launched on the data path.
+
+    Exchange kernels wait inside the kernel for their peers.  When one process drives several PeerLift objects from
+    different streams, each exchange is therefore made to wait (event) for the previous one issued on the device, so
+    that exchanges EXECUTE in the order they were issued -- the same order on every rank -- and a waiting kernel can
+    never hold the SMs that the kernel it waits for needs (the rule NCCL imposes on concurrent collectives).
+
+    The returned tensors are views of the segment: they are valid until the next call on ANY rank reaches its
+    exchange step, i.e. consume (or copy) them on the same stream before calling again.
+    """
+
+    def __init__(self, channels: int, n_voxels: int, device=None, group=None, want_cov: bool = True,
+                 _local_group=None):
+        from . import _lib
+        import ctypes
+        self._lib = _lib
+        self._ct = ctypes
+        self.lib = _lib.load()
+        self.channels, self.n_voxels, self.want_cov = int(channels), int(n_voxels), bool(want_cov)
+        self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        self.group = group
+        if _local_group is not None:
+            self.rank, self.world = _local_group
+        elif dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        if self.world > _lib.ND_MAX_PEERS:
+            raise ValueError(f'PeerLift supports up to {_lib.ND_MAX_PEERS} ranks on one box, got {self.world}')
+        cn = self.channels * self.n_voxels
+        al = lambda b: (b + 255) // 256 * 256
+        self._off_acc = al(4 * _lib.ND_PEER_FLAG_WORDS)
+        self._off_mean = self._off_acc + al(4 * (2 * cn + self.n_voxels))
+        self._off_cov = self._off_mean + al(4 * cn)
+        self._bytes = self._off_cov + al(4 * cn)
+        self.epoch = 0
+        self._ordered = _local_group is None     # in-process test ranks must run concurrently, see local_group
+        self._peer_bases = None
+        self._opened = []
+        with torch.cuda.device(self.device):
+            base = ctypes.c_void_p()
+            handle = (ctypes.c_uint8 * 64)()
+            _lib.check(self.lib.nd_peer_alloc(self._bytes, ctypes.byref(base), handle), 'nd_peer_alloc')
+        self._base = int(base.value)
+        self._handle = bytes(handle)
+        seg = torch.as_tensor(_DevicePtr(self._base, self._bytes), device=self.device)
+        self._seg = seg
+        self.flags = seg[:4 * _lib.ND_PEER_FLAG_WORDS].view(torch.int32)
+        self.acc = seg[self._off_acc:self._off_acc + 4 * (2 * cn + self.n_voxels)].view(torch.float32)
+        self.mean = seg[self._off_mean:self._off_mean + 4 * cn].view(torch.float32).view(self.channels, self.n_voxels)
+        self.cov = seg[self._off_cov:self._off_cov + 4 * cn].view(torch.float32).view(self.channels, self.n_voxels)
+        self.count = torch.empty((self.n_voxels,), dtype=torch.int64, device=self.device)
+        if _local_group is None:
+            self._connect()
+
+    # -- wiring ---------------------------------------------------------------------------------
+    def _connect(self):
+        ctypes = self._ct
+        if self.world == 1:
+            self._set_peers([self._base])
+            return
+        infos = [None] * self.world
+        dist.all_gather_object(infos, (self._handle, self._bytes), group=self.group)
+        bases = []
+        with torch.cuda.device(self.device):
+            for g, (h, nbytes) in enumerate(infos):
+                if nbytes != self._bytes:
+                    raise RuntimeError(f'rank {g} built a segment of {nbytes} bytes, this rank {self._bytes}: shapes differ')
+                if g == self.rank:
+                    bases.append(self._base)
+                    continue
+                p = ctypes.c_void_p()
+                hb = (ctypes.c_uint8 * 64).from_buffer_copy(h)
+                self._lib.check(self.lib.nd_peer_open(hb, ctypes.byref(p)), f'nd_peer_open (segment of rank {g})')
+                self._opened.append(int(p.value))
+                bases.append(int(p.value))
+        self._set_peers(bases)
+        dist.barrier(group=self.group)          # every segment is zeroed and mapped before the first epoch
+
+    def _set_peers(self, bases):
+        ctypes = self._ct
+        arr = ctypes.c_void_p * len(bases)
+        self._peer_bases = list(bases)
+        self._p_flags = arr(*[b for b in bases])
+        self._p_acc = arr(*[b + self._off_acc for b in bases])
+        self._p_mean = arr(*[b + self._off_mean for b in bases])
+        self._p_cov = arr(*[b + self._off_cov for b in bases])
+
+    @classmethod
+    def local_group(cls, world: int, channels: int, n_voxels: int, device=None, want_cov: bool = True):
+        """``world`` ranks inside ONE process on one device (their segments are addressed directly, no IPC): the
+        single-GPU test of the multi-rank protocol -- run each rank's call on its own stream.  Small shapes only:
+        the waiting CTAs of all ranks must fit the device together."""
+        ranks = [cls(channels, n_voxels, device, want_cov=want_cov, _local_group=(r, world)) for r in range(world)]
+        bases = [r._base for r in ranks]
+        for r in ranks:
+            r._set_peers(bases)
+        return ranks
+
+    # -- the op ---------------------------------------------------------------------------------
+    def exchange(self, n_views_total: int, alpha: Optional[torch.Tensor] = None):
+        """Reduce + finalise the accumulators already in ``self.acc`` (epoch advances by one)."""
+        from . import ops
+        ctypes = self._ct
+        if alpha is not None:
+            alpha = alpha.reshape(-1).contiguous()
+        self.epoch += 1
+        stream = torch.cuda.current_stream(self.device)
+        prev = _last_exchange.get(self.device.index) if self._ordered else None
+        if prev is not None:
+            stream.wait_event(prev)
+        self._lib.check(self.lib.nd_lift_finalize_peers(
+            self._p_acc, self._p_mean, self._p_cov if self.want_cov else None, self._p_flags, self.world, self.rank,
+            self.epoch, int(n_views_total), self.channels, self.n_voxels,
+            ctypes.c_void_p(alpha.data_ptr()) if alpha is not None else None,
+            ctypes.c_void_p(self.count.data_ptr()), stream.cuda_stream), 'nd_lift_finalize_peers')
+        if self._ordered:
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            _last_exchange[self.device.index] = ev
+        return self.mean, (self.cov if self.want_cov else None), self.count
+
+    def __call__(self, features_local: torch.Tensor, points: torch.Tensor, projection_local: torch.Tensor,
+                 n_views_total: int, alpha: Optional[torch.Tensor] = None):
+        """Same results on every rank as ``lifting.lift_mean_var`` over all views (see class docstring for lifetime)."""
+        from . import ops
+        if features_local.shape[1] != self.channels or points[0].numel() != self.n_voxels:
+            raise ValueError('PeerLift was built for another shape')
+        ops.lift_accumulate_into(features_local, points, projection_local, self.acc)
+        mean, cov, count = self.exchange(n_views_total, alpha)
+        shape = tuple(points.shape[1:]) if points.dim() == 4 else (self.n_voxels,)
+        return (mean.view(self.channels, *shape), cov.view(self.channels, *shape) if cov is not None else None,
+                count.view(1, *shape))
+
+    def check(self):
+        """Host-synchronising health check: raises if a peer never arrived at some exchange step."""
+        torch.cuda.synchronize(self.device)
+        if int(self.flags[2 * self._lib.ND_MAX_PEERS + 1].item()) != 0:
+            raise RuntimeError('PeerLift: a peer did not reach the exchange step within the time-out')
+
+    def close(self):
+        """Unmaps the peers' segments and frees the local one (collective when world > 1)."""
+        if self._base is None:
+            return
+        multi = self.world > 1 and dist.is_initialized() and bool(self._opened)
+        torch.cuda.synchronize(self.device)
+        if multi:
+            dist.barrier(group=self.group)      # nobody unmaps while a peer may still be inside an exchange
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                self.lib.nd_peer_close(self._ct.c_void_p(p))
+            self._opened = []
+        if multi:
+            dist.barrier(group=self.group)      # nobody frees a segment a peer still has mapped
+        self.flags = self.acc = self.mean = self.cov = self._seg = None
+        with torch.cuda.device(self.device):
+            self.lib.nd_peer_free(self._ct.c_void_p(self._base))
+        self._base = None

@@ -196,6 +196,30 @@ def _(features, points, projection, scratch_budget_bytes):
     return features.new_empty(((2 * c + 1) * n,), dtype=torch.float32)
 
 
+@torch.library.custom_op(f'{_NS}::lift_accumulate_into', mutates_args=('acc',))
+def lift_accumulate_into(features: Tensor, points: Tensor, projection: Tensor, acc: Tensor) -> None:
+    """``lift_accumulate`` into a caller-owned buffer (the peer-mapped segment of ``distributed.PeerLift``)."""
+    _need_cuda(features, points, projection, acc)
+    m = _maps(features)
+    _check_geometry(points, projection, m.n_views)
+    points, grid = _flat_points(points)
+    projection = projection.contiguous()
+    n = points.shape[1]
+    c = m.channels
+    if acc.dtype != torch.float32 or acc.numel() != (2 * c + 1) * n or not acc.is_contiguous():
+        raise ValueError(f'acc must be a contiguous float32 buffer of (2 * {c} + 1) * {n} elements')
+    lib = _lib.load()
+    opt = _options(0, grid)
+    optp = ctypes.byref(opt)
+    ws_bytes = lib.nd_lift_workspace_bytes(ctypes.byref(m), n, optp)
+    ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=features.device)
+    base = acc.data_ptr()
+    _lib.check(lib.nd_lift_accumulate(ctypes.byref(m), _ptr(points), _ptr(projection), n,
+                                      ctypes.c_void_p(base), ctypes.c_void_p(base + 4 * c * n),
+                                      ctypes.c_void_p(base + 8 * c * n), _ptr(ws), ws_bytes, optp, _stream()),
+               'nd_lift_accumulate')
+
+
 @torch.library.custom_op(f'{_NS}::lift_finalize', mutates_args=())
 def lift_finalize(acc: Tensor, n_views_total: int, channels: int, n_voxels: int, alpha: Optional[Tensor],
                   want_cov: bool) -> Tuple[Tensor, Tensor, Tensor]:

@@ -106,3 +106,15 @@ def test_view_shard_partitions():
             assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
     with pytest.raises(ValueError):
         nd_dist.view_shard(4, 2, 2)
+
+
+def test_channel_shard_partitions_channels():
+    """The channel slices of the peer-memory exchange (csrc/peer.cu computes the same split) tile [0, C) exactly."""
+    for c in (1, 3, 32, 35, 256):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(world):
+                b, e = nd_dist.channel_shard(c, r, world)
+                assert b == prev and e >= b and e - b in (c // world, c // world + 1)
+                prev = e
+            assert prev == c

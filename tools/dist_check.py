@@ -47,6 +47,51 @@ def main():
               f'mean max abs err {e_mean:.3e} ({int(res[1])} outside 1e-4), cov max abs err {e_cov:.3e} ({int(res[2])} outside 1e-4)',
               flush=True)
     assert int(res[0]) == world and int(res[1]) == 0 and int(res[2]) == 0
+
+    # ---- the same exchange over NVLink peer memory (csrc/peer.cu): CUDA IPC segments, epoch flags, no NCCL on the data path ----
+    peer = nd_dist.PeerLift(256, pts[0].numel(), dev)
+    for _ in range(3):
+        pm, pc, pn = peer(feats[b:e], pts, proj[b:e], nv)
+    peer.check()
+    e_mean, bad_mean = err(pm, m1)
+    e_cov, bad_cov = err(pc, c1)
+    same = torch.equal(pm, mean) and torch.equal(pc, cov)          # identical to the all-reduce path? (not required)
+    res = torch.tensor([int(torch.equal(pn, n1)), bad_mean, bad_cov, int(same)], device=dev)
+    dist.all_reduce(res, op=dist.ReduceOp.SUM)
+    # every rank must hold the same bits: checksum of the outputs
+    chk = torch.stack([pm.double().sum(), pc.double().sum()])
+    lo_, hi_ = chk.clone(), chk.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+
+    def timed(fn, steps=50):
+        for _ in range(5):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps * 1e3], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+    us_peer = timed(lambda: peer(feats[b:e], pts, proj[b:e], nv))
+    us_xchg = timed(lambda: peer.exchange(nv))
+    us_nccl = timed(lambda: nd_dist.lift_mean_var_view_sharded(feats[b:e], pts, proj[b:e], n_views_total=nv))
+    us_local = timed(lambda: lifting.lift_mean_var(feats[b:e], pts, proj[b:e]))
+    peer.check()
+    if rank == 0:
+        print(f'peer-memory exchange on {world} GPUs: counts equal on {int(res[0])}/{world} ranks, mean max abs err {e_mean:.3e} '
+              f'({int(res[1])} outside 1e-4), cov max abs err {e_cov:.3e} ({int(res[2])} outside 1e-4), bit-identical to the '
+              f'all-reduce path on {int(res[3])}/{world} ranks, checksums equal across ranks: {bool(torch.equal(lo_, hi_))}', flush=True)
+        print(f'per step ({nv // world} views per GPU, max over ranks): lift + peer exchange {us_peer:.1f} us '
+              f'(exchange alone {us_xchg:.1f} us), lift + NCCL all-reduce + finalise {us_nccl:.1f} us, '
+              f'local fused lift alone {us_local:.1f} us', flush=True)
+    assert int(res[0]) == world and int(res[1]) == 0 and int(res[2]) == 0 and torch.equal(lo_, hi_)
+    peer.close()
     dist.destroy_process_group()
 
 
