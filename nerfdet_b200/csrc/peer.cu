@@ -16,6 +16,7 @@
 //
 // The segments are plain cudaMalloc allocations shared with CUDA IPC handles (nd_peer_alloc / nd_peer_open): the only
 // place where the library owns device memory, because a handle must cover a whole allocation.
+#include <stdlib.h>
 #include <string.h>
 
 #include "nd_common.cuh"
@@ -78,8 +79,11 @@ template <> __device__ __forceinline__ void st_vec<4>(float *p, const float (&r)
 template <> __device__ __forceinline__ void st_vec<1>(float *p, const float (&r)[1]) { *p = r[0]; }
 
 // grid = (voxel tiles of kPeerThreads * V, channel sub-slices of this rank's slice)
-template <int V>
-__global__ void __launch_bounds__(kPeerThreads)
+// G = compile-time bound of the world size (1, 2, 4, 8), U = channels per iteration: G * U * 2 vector loads are in flight
+// per thread before the first is consumed -- remote loads take ~2 us over NVLink, so the link rate is set by the bytes
+// in flight (CTAs per SM x loads per thread), not by the instruction count.
+template <int V, int G, int U>
+__global__ void __launch_bounds__(kPeerThreads, (G * U <= 4) ? 6 : 4)
 k_lift_finalize_peers(const PeerArgs a) {
     const int P = kMaxPeers;
     uint32_t *my_flags = a.flags[a.rank];
@@ -98,7 +102,7 @@ k_lift_finalize_peers(const PeerArgs a) {
 #pragma unroll
         for (int j = 0; j < V; ++j) cnt[j] = 0.f;
 #pragma unroll
-        for (int g = 0; g < kMaxPeers; ++g) {
+        for (int g = 0; g < G; ++g) {
             if (g < a.world) {
                 float t[V];
                 ld_vec<V>(a.acc[g] + 2 * cn + n, t);
@@ -118,44 +122,52 @@ k_lift_finalize_peers(const PeerArgs a) {
         }
         const int c0 = a.c_begin + (int)blockIdx.y * a.ch_per_cta;
         const int c1 = min(a.c_end, c0 + a.ch_per_cta);
-        for (int c = c0; c < c1; ++c) {
-            const int64_t o = (int64_t)c * a.n_vox + n;
-            float s1[V], s2[V];
-            float p1[kMaxPeers][V], p2[kMaxPeers][V];
+        for (int cb = c0; cb < c1; cb += U) {
+            float p1[U][G][V], p2[U][G][V];
 #pragma unroll
-            for (int g = 0; g < kMaxPeers; ++g) {               // all loads of the channel in flight together
-                if (g < a.world) {
-                    ld_vec<V>(a.acc[g] + o, p1[g]);
-                    ld_vec<V>(a.acc[g] + cn + o, p2[g]);
+            for (int u = 0; u < U; ++u) {                       // all loads of the U channels in flight together
+                const int64_t o = (int64_t)min(cb + u, c1 - 1) * a.n_vox + n;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    if (g < a.world) {
+                        ld_vec<V>(a.acc[g] + o, p1[u][g]);
+                        ld_vec<V>(a.acc[g] + cn + o, p2[u][g]);
+                    }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < V; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+            for (int u = 0; u < U; ++u) {
+                if (cb + u >= c1) break;
+                const int64_t o = (int64_t)(cb + u) * a.n_vox + n;
+                float s1[V], s2[V];
 #pragma unroll
-            for (int g = 0; g < kMaxPeers; ++g) {               // rank order: every rank would get the same bits
-                if (g < a.world) {
+                for (int j = 0; j < V; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
 #pragma unroll
-                    for (int j = 0; j < V; ++j) { s1[j] += p1[g][j]; s2[j] += p2[g][j]; }
+                for (int g = 0; g < G; ++g) {                   // rank order: every rank would get the same bits
+                    if (g < a.world) {
+#pragma unroll
+                        for (int j = 0; j < V; ++j) { s1[j] += p1[u][g][j]; s2[j] += p2[u][g][j]; }
+                    }
                 }
-            }
-            float m[V], cv[V];
+                float m[V], cv[V];
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                m[j] = 0.f;
-                cv[j] = 0.f;
-                if (cnt[j] > 0.f) {                             // same formula as k_lift_finalize (lift.cu)
-                    const float mm = s1[j] / cnt[j];
-                    float ssd = fmaxf(fmaf(-mm, s1[j], s2[j]), 0.0f);
-                    ssd = fmaf(inv[j] * mm, mm, ssd);
-                    cv[j] = expf(-(ssd / cnt[j]));
-                    m[j] = mm * al[j];
+                for (int j = 0; j < V; ++j) {
+                    m[j] = 0.f;
+                    cv[j] = 0.f;
+                    if (cnt[j] > 0.f) {                         // same formula as k_lift_finalize (lift.cu)
+                        const float mm = s1[j] / cnt[j];
+                        float ssd = fmaxf(fmaf(-mm, s1[j], s2[j]), 0.0f);
+                        ssd = fmaf(inv[j] * mm, mm, ssd);
+                        cv[j] = expf(-(ssd / cnt[j]));
+                        m[j] = mm * al[j];
+                    }
                 }
-            }
 #pragma unroll
-            for (int g = 0; g < kMaxPeers; ++g) {
-                if (g < a.world) {
-                    st_vec<V>(a.mean[g] + o, m);
-                    if (a.cov[g] != nullptr) st_vec<V>(a.cov[g] + o, cv);
+                for (int g = 0; g < G; ++g) {
+                    if (g < a.world) {
+                        st_vec<V>(a.mean[g] + o, m);
+                        if (a.cov[g] != nullptr) st_vec<V>(a.cov[g] + o, cv);
+                    }
                 }
             }
         }
@@ -274,17 +286,29 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     const int v = vec ? 4 : 1;
     const int64_t tiles = ceil_div(n_voxels, (int64_t)kPeerThreads * v);
     const int slice = a.c_end - a.c_begin;
-    // ~4 CTAs per SM so that enough loads are in flight over the links; a CTA keeps its tile's counts for its channels
-    int64_t subs = ceil_div((int64_t)148 * 4, tiles);
+    const int gb = world <= 1 ? 1 : world <= 2 ? 2 : world <= 4 ? 4 : 8;     // compile-time bound of the kernel instantiation
+    // enough CTAs to fill every SM at the instantiation's occupancy; a CTA keeps its tile's counts for its channels
+    // measured on B200s (tools/dist_check.py sweep): 2 GPUs 102.9 us at 6 CTAs per SM (104-112 for 2-12); 8 GPUs 176.7 us at 2
+    // (191 at 4, 237 at 12) -- the step is bound by the links (~520 GB/s inbound per GPU), more CTAs only add contention
+    int per_sm = gb <= 2 ? 6 : gb <= 4 ? 4 : 2;
+    if (const char *e = getenv("ND_PEER_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
+    int64_t subs = ceil_div((int64_t)148 * per_sm, tiles);
     if (subs > slice) subs = slice;
     if (subs < 1) subs = 1;
     a.ch_per_cta = slice > 0 ? (int)ceil_div(slice, subs) : 1;
     const dim3 grid((unsigned)tiles, (unsigned)(slice > 0 ? ceil_div(slice, a.ch_per_cta) : 1));
     cudaStream_t st = (cudaStream_t)stream;
-    if (vec)
-        k_lift_finalize_peers<4><<<grid, kPeerThreads, 0, st>>>(a);
-    else
-        k_lift_finalize_peers<1><<<grid, kPeerThreads, 0, st>>>(a);
+#define ND_PEER_LAUNCH(V_, G_, U_) k_lift_finalize_peers<V_, G_, U_><<<grid, kPeerThreads, 0, st>>>(a)
+    if (vec) {
+        if (gb == 1) ND_PEER_LAUNCH(4, 1, 4);
+        else if (gb == 2) ND_PEER_LAUNCH(4, 2, 2);
+        else if (gb == 4) ND_PEER_LAUNCH(4, 4, 1);
+        else ND_PEER_LAUNCH(4, 8, 1);
+    } else {
+        if (gb <= 2) ND_PEER_LAUNCH(1, 2, 2);
+        else ND_PEER_LAUNCH(1, 8, 1);
+    }
+#undef ND_PEER_LAUNCH
     ND_CUDA_LAUNCH_CHECK("k_lift_finalize_peers");
     k_peer_wait_done<<<1, 32, 0, st>>>(a.flags[rank], world, epoch);
     ND_CUDA_LAUNCH_CHECK("k_peer_wait_done");

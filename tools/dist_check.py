@@ -82,8 +82,14 @@ def main():
     us_xchg = timed(lambda: peer.exchange(nv))
     us_nccl = timed(lambda: nd_dist.lift_mean_var_view_sharded(feats[b:e], pts, proj[b:e], n_views_total=nv))
     us_local = timed(lambda: lifting.lift_mean_var(feats[b:e], pts, proj[b:e]))
+    sweep = {}
+    for per_sm in (2, 4, 6, 8, 12, 16):                        # grid of the exchange kernel (loads in flight over the links)
+        os.environ['ND_PEER_CTAS_PER_SM'] = str(per_sm)
+        sweep[per_sm] = round(timed(lambda: peer.exchange(nv)), 1)
+    os.environ.pop('ND_PEER_CTAS_PER_SM')
     peer.check()
     if rank == 0:
+        print(f'exchange alone vs CTAs per SM: {sweep}', flush=True)
         print(f'peer-memory exchange on {world} GPUs: counts equal on {int(res[0])}/{world} ranks, mean max abs err {e_mean:.3e} '
               f'({int(res[1])} outside 1e-4), cov max abs err {e_cov:.3e} ({int(res[2])} outside 1e-4), bit-identical to the '
               f'all-reduce path on {int(res[3])}/{world} ranks, checksums equal across ranks: {bool(torch.equal(lo_, hi_))}', flush=True)
