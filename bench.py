@@ -173,6 +173,9 @@ def run_reference(args, rank):
 def workload_config(n_gpus, exchange='peer'):
     if n_gpus == 1:
         part = 'single GPU'
+    elif exchange == 'multicast':
+        part = (f'views sharded over {n_gpus} GPUs; (S1,S2,count) reduced in the NVSwitch and finalised by one kernel per rank '
+                '(nd_lift_finalize_peers: multimem.ld_reduce of the channel slice, multimem.st of the rows)')
     elif exchange == 'peer':
         part = (f'views sharded over {n_gpus} GPUs; (S1,S2,count) reduced and finalised by one kernel per rank over '
                 'NVLink peer memory (nd_lift_finalize_peers: P2P loads of the channel slice, P2P stores of the rows)')
@@ -197,8 +200,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'],
-                    help='N > 1: how the per-rank accumulators meet (peer-memory kernel, or NCCL all-reduce + finalise)')
+    ap.add_argument('--exchange', default='peer', choices=['peer', 'multicast', 'auto', 'nccl'],
+                    help='N > 1: how the per-rank accumulators meet: our kernel over per-peer P2P loads / stores (default: the '
+                         'fastest at 2 and at 8 GPUs, profiles/r01_s6_multigpu_exchange.txt), our kernel over NVLS multicast '
+                         '(in-switch reduction; auto = multicast if the box supports it, else peer), or NCCL all-reduce + finalise')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -231,8 +236,28 @@ def main():
     views_total = NV_PER_GPU * n_gpus
 
     # N > 1: one peer-mapped segment for the device-resident loop and one per end-to-end lane (their results are views of it)
-    use_peer = n_gpus > 1 and args.exchange == 'peer'
-    peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev) for _ in range(3)] if use_peer else None
+    exchange = args.exchange if n_gpus > 1 else 'none'
+    peers = None
+    if exchange in ('auto', 'multicast'):
+        err = ''
+        try:
+            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, transport='multicast') for _ in range(3)]
+        except Exception as e:                                 # no NVLS on this box / symmetric memory unavailable
+            err = f'{type(e).__name__}: {e}'
+        ok = torch.tensor([1 if peers is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)              # all ranks take the same path
+        if int(ok.item()) == 1:
+            exchange = 'multicast'
+        else:
+            if args.exchange == 'multicast':
+                raise SystemExit(f'--exchange multicast is not available on this box ({err})')
+            if rank == 0:
+                print(f'[bench] multicast transport unavailable ({err}); using per-peer P2P', file=sys.stderr, flush=True)
+            peers = None
+            exchange = 'peer'
+    if exchange == 'peer':
+        peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev) for _ in range(3)]
+    use_peer = peers is not None
 
     def step(feats, lane=0):
         f = feats[:, :, :FEAT_HW[0], :FEAT_HW[1]]
@@ -351,7 +376,7 @@ def main():
             'metric': 'voxel_view_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': n_gpus,
             'steps': steps, 'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(n_gpus, args.exchange),
+            'config': workload_config(n_gpus, exchange),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': ncu_traffic(), 'peak_source': peak_src,
                          'algorithmic_bytes_per_step': bytes_per_step,

@@ -152,6 +152,10 @@ int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_v
  *       entry `rank` is the local segment.  world <= ND_MAX_PEERS.
  *     epoch: 1, 2, 3, ... the same on every rank for the same step.
  *     count: int64 [N] local, or NULL.  alpha: f32 [N] local or NULL (alpha * mean, nerfdet.py:259-261).
+ *     acc_mc / mean_mc / cov_mc: NVLS multicast addresses of the same three buffers (one address that reaches every
+ *       rank's copy through the NVSwitch), or all NULL.  When given, the sums are taken in the switch
+ *       (multimem.ld_reduce) and the rows leave with one multimem.st, which roughly halves the bytes a GPU receives;
+ *       the per-rank tables are then only used for the flag blocks.  Needs N % 4 == 0.
  *   Outputs are complete on `stream` when the call's kernels have run; a peer that never arrives raises word
  *   2 * ND_MAX_PEERS + 1 of the local flag block after ~4 s instead of hanging.
  * ------------------------------------------------------------------------------------- */
@@ -164,7 +168,8 @@ int nd_peer_close(void *ptr);
 int nd_peer_free(void *ptr);
 int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
                            void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
-                           int channels, int64_t n_voxels, const float *alpha, int64_t *count, void *stream);
+                           int channels, int64_t n_voxels, const float *alpha, int64_t *count, const void *acc_mc,
+                           void *mean_mc, void *cov_mc, void *stream);
 
 
 /* ---------------------------------------------------------------------------------------

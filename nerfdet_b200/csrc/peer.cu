@@ -37,7 +37,23 @@ struct PeerArgs {
     int64_t n_vox;
     const float *alpha;
     int64_t *count;
+    // NVLS: multicast addresses of the accumulators / outputs (one address reaches every rank's copy through the switch)
+    const float *acc_mc;
+    float *mean_mc, *cov_mc;
 };
+
+// in-switch reduction: one load returns the sum over all ranks' copies; one store lands in all of them (PTX ISA 8.1, sm_90+)
+__device__ __forceinline__ void ld_reduce_mc(const float *p, float (&r)[4]) {
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3])
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void st_mc(float *p, const float (&r)[4]) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]),
+                 "f"(r[3])
+                 : "memory");
+}
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -82,9 +98,12 @@ template <> __device__ __forceinline__ void st_vec<1>(float *p, const float (&r)
 // G = compile-time bound of the world size (1, 2, 4, 8), U = channels per iteration: G * U * 2 vector loads are in flight
 // per thread before the first is consumed -- remote loads take ~2 us over NVLink, so the link rate is set by the bytes
 // in flight (CTAs per SM x loads per thread), not by the instruction count.
-template <int V, int G, int U>
+// MC: the sums come from multimem.ld_reduce on the multicast address (the switch adds the ranks' copies: (G-1) x fewer
+// bytes arrive than with per-peer loads) and the rows leave with one multimem.st instead of G stores.
+template <int V, int G, int U, bool MC>
 __global__ void __launch_bounds__(kPeerThreads, (G * U <= 4) ? 6 : 4)
 k_lift_finalize_peers(const PeerArgs a) {
+    static_assert(!MC || (V == 4 && G == 1), "multicast instantiation: 16-byte vectors, one (reduced) load per row");
     const int P = kMaxPeers;
     uint32_t *my_flags = a.flags[a.rank];
     // ---- hand-shake: my accumulators are complete; wait for everybody else's ----
@@ -103,9 +122,10 @@ k_lift_finalize_peers(const PeerArgs a) {
         for (int j = 0; j < V; ++j) cnt[j] = 0.f;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            if (g < a.world) {
+            if (MC || g < a.world) {
                 float t[V];
-                ld_vec<V>(a.acc[g] + 2 * cn + n, t);
+                if constexpr (MC) ld_reduce_mc(a.acc_mc + 2 * cn + n, t);
+                else ld_vec<V>(a.acc[g] + 2 * cn + n, t);
 #pragma unroll
                 for (int j = 0; j < V; ++j) cnt[j] += t[j];
             }
@@ -129,7 +149,10 @@ k_lift_finalize_peers(const PeerArgs a) {
                 const int64_t o = (int64_t)min(cb + u, c1 - 1) * a.n_vox + n;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    if (g < a.world) {
+                    if constexpr (MC) {
+                        ld_reduce_mc(a.acc_mc + o, p1[u][g]);
+                        ld_reduce_mc(a.acc_mc + cn + o, p2[u][g]);
+                    } else if (g < a.world) {
                         ld_vec<V>(a.acc[g] + o, p1[u][g]);
                         ld_vec<V>(a.acc[g] + cn + o, p2[u][g]);
                     }
@@ -144,7 +167,7 @@ k_lift_finalize_peers(const PeerArgs a) {
                 for (int j = 0; j < V; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
 #pragma unroll
                 for (int g = 0; g < G; ++g) {                   // rank order: every rank would get the same bits
-                    if (g < a.world) {
+                    if (MC || g < a.world) {
 #pragma unroll
                         for (int j = 0; j < V; ++j) { s1[j] += p1[u][g][j]; s2[j] += p2[u][g][j]; }
                     }
@@ -163,10 +186,16 @@ k_lift_finalize_peers(const PeerArgs a) {
                     }
                 }
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    if (g < a.world) {
-                        st_vec<V>(a.mean[g] + o, m);
-                        if (a.cov[g] != nullptr) st_vec<V>(a.cov[g] + o, cv);
+                if constexpr (MC) {
+                    st_mc(a.mean_mc + o, m);
+                    if (a.cov_mc != nullptr) st_mc(a.cov_mc + o, cv);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        if (g < a.world) {
+                            st_vec<V>(a.mean[g] + o, m);
+                            if (a.cov[g] != nullptr) st_vec<V>(a.cov[g] + o, cv);
+                        }
                     }
                 }
             }
@@ -253,7 +282,8 @@ int nd_peer_free(void *ptr) {
 
 int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
                            void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
-                           int channels, int64_t n_voxels, const float *alpha, int64_t *count, void *stream) {
+                           int channels, int64_t n_voxels, const float *alpha, int64_t *count, const void *acc_mc,
+                           void *mean_mc, void *cov_mc, void *stream) {
     ND_REQUIRE(acc_host && mean_host && flags_host, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: null pointer table");
     ND_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, ND_ERR_BAD_ARG,
                "nd_lift_finalize_peers: world %d / rank %d outside [1, %d]", world, rank, kMaxPeers);
@@ -283,10 +313,21 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     a.n_vox = n_voxels;
     a.alpha = alpha;
     a.count = count;
+    const bool mc = acc_mc != nullptr;
+    if (mc) {
+        ND_REQUIRE(mean_mc != nullptr && (cov_mc != nullptr) == (cov_host != nullptr), ND_ERR_BAD_ARG,
+                   "nd_lift_finalize_peers: multicast needs the multicast address of every buffer in use");
+        ND_REQUIRE(vec && (reinterpret_cast<uintptr_t>(acc_mc) | reinterpret_cast<uintptr_t>(mean_mc) |
+                           reinterpret_cast<uintptr_t>(cov_mc)) % 16 == 0,
+                   ND_ERR_BAD_ALIGNMENT, "nd_lift_finalize_peers: multicast needs 16-byte aligned rows (N %% 4 == 0)");
+        a.acc_mc = static_cast<const float *>(acc_mc);
+        a.mean_mc = static_cast<float *>(mean_mc);
+        a.cov_mc = static_cast<float *>(cov_mc);
+    }
     const int v = vec ? 4 : 1;
     const int64_t tiles = ceil_div(n_voxels, (int64_t)kPeerThreads * v);
     const int slice = a.c_end - a.c_begin;
-    const int gb = world <= 1 ? 1 : world <= 2 ? 2 : world <= 4 ? 4 : 8;     // compile-time bound of the kernel instantiation
+    const int gb = (mc || world <= 1) ? 1 : world <= 2 ? 2 : world <= 4 ? 4 : 8;   // compile-time bound of the instantiation
     // enough CTAs to fill every SM at the instantiation's occupancy; a CTA keeps its tile's counts for its channels
     // measured on B200s (tools/dist_check.py sweep): 2 GPUs 102.9 us at 6 CTAs per SM (104-112 for 2-12); 8 GPUs 176.7 us at 2
     // (191 at 4, 237 at 12) -- the step is bound by the links (~520 GB/s inbound per GPU), more CTAs only add contention
@@ -298,8 +339,10 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     a.ch_per_cta = slice > 0 ? (int)ceil_div(slice, subs) : 1;
     const dim3 grid((unsigned)tiles, (unsigned)(slice > 0 ? ceil_div(slice, a.ch_per_cta) : 1));
     cudaStream_t st = (cudaStream_t)stream;
-#define ND_PEER_LAUNCH(V_, G_, U_) k_lift_finalize_peers<V_, G_, U_><<<grid, kPeerThreads, 0, st>>>(a)
-    if (vec) {
+#define ND_PEER_LAUNCH(V_, G_, U_) k_lift_finalize_peers<V_, G_, U_, false><<<grid, kPeerThreads, 0, st>>>(a)
+    if (mc) {
+        k_lift_finalize_peers<4, 1, 4, true><<<grid, kPeerThreads, 0, st>>>(a);
+    } else if (vec) {
         if (gb == 1) ND_PEER_LAUNCH(4, 1, 4);
         else if (gb == 2) ND_PEER_LAUNCH(4, 2, 2);
         else if (gb == 4) ND_PEER_LAUNCH(4, 4, 1);

@@ -104,7 +104,11 @@ class PeerLift:
     """
 
     def __init__(self, channels: int, n_voxels: int, device=None, group=None, want_cov: bool = True,
-                 _local_group=None):
+                 transport: str = 'ipc', _local_group=None):
+        """``transport='ipc'``: cudaMalloc segments shared with CUDA IPC handles, per-peer P2P loads / stores.
+        ``transport='multicast'``: symmetric-memory segments (``torch.distributed._symmetric_memory``, plumbing only)
+        bound to an NVLS multicast object; the kernel then reduces in the NVSwitch (``multimem.ld_reduce``) and
+        broadcasts its rows with ``multimem.st``.  Raises if the box has no multicast support."""
         from . import _lib
         import ctypes
         self._lib = _lib
@@ -131,20 +135,48 @@ class PeerLift:
         self._ordered = _local_group is None     # in-process test ranks must run concurrently, see local_group
         self._peer_bases = None
         self._opened = []
-        with torch.cuda.device(self.device):
-            base = ctypes.c_void_p()
-            handle = (ctypes.c_uint8 * 64)()
-            _lib.check(self.lib.nd_peer_alloc(self._bytes, ctypes.byref(base), handle), 'nd_peer_alloc')
-        self._base = int(base.value)
-        self._handle = bytes(handle)
-        seg = torch.as_tensor(_DevicePtr(self._base, self._bytes), device=self.device)
+        self._mc_base = 0
+        self._symm = None
+        if transport not in ('ipc', 'multicast'):
+            raise ValueError(f"transport must be 'ipc' or 'multicast', got {transport!r}")
+        self.transport = transport
+        if transport == 'multicast':
+            if _local_group is not None or not dist.is_initialized() or self.world < 2:
+                raise RuntimeError('the multicast transport needs an initialised process group with at least 2 ranks')
+            if self.n_voxels % 4 != 0:
+                raise RuntimeError('the multicast transport needs a voxel count that is a multiple of 4')
+            import torch.distributed._symmetric_memory as symm_mem
+            seg = symm_mem.empty(self._bytes, dtype=torch.uint8, device=self.device)
+            seg.zero_()
+            torch.cuda.synchronize(self.device)
+            hdl = symm_mem.rendezvous(seg, group if group is not None else dist.group.WORLD)
+            if not hdl.has_multicast_support or int(hdl.multicast_ptr) == 0:
+                raise RuntimeError('symmetric memory on this box has no NVLS multicast support')
+            self._symm = hdl
+            self._base = int(seg.data_ptr())
+            self._handle = None
+            bases = [int(p) for p in hdl.buffer_ptrs]
+            if bases[self.rank] != self._base:
+                raise RuntimeError('symmetric-memory rendezvous returned a local pointer that is not the segment')
+            self._mc_base = int(hdl.multicast_ptr)
+        else:
+            with torch.cuda.device(self.device):
+                base = ctypes.c_void_p()
+                handle = (ctypes.c_uint8 * 64)()
+                _lib.check(self.lib.nd_peer_alloc(self._bytes, ctypes.byref(base), handle), 'nd_peer_alloc')
+            self._base = int(base.value)
+            self._handle = bytes(handle)
+            seg = torch.as_tensor(_DevicePtr(self._base, self._bytes), device=self.device)
         self._seg = seg
         self.flags = seg[:4 * _lib.ND_PEER_FLAG_WORDS].view(torch.int32)
         self.acc = seg[self._off_acc:self._off_acc + 4 * (2 * cn + self.n_voxels)].view(torch.float32)
         self.mean = seg[self._off_mean:self._off_mean + 4 * cn].view(torch.float32).view(self.channels, self.n_voxels)
         self.cov = seg[self._off_cov:self._off_cov + 4 * cn].view(torch.float32).view(self.channels, self.n_voxels)
         self.count = torch.empty((self.n_voxels,), dtype=torch.int64, device=self.device)
-        if _local_group is None:
+        if transport == 'multicast':
+            self._set_peers(bases)
+            dist.barrier(group=self.group)
+        elif _local_group is None:
             self._connect()
 
     # -- wiring ---------------------------------------------------------------------------------
@@ -199,6 +231,7 @@ class PeerLift:
         if alpha is not None:
             alpha = alpha.reshape(-1).contiguous()
         self.epoch += 1
+        mc = self._mc_base
         stream = torch.cuda.current_stream(self.device)
         prev = _last_exchange.get(self.device.index) if self._ordered else None
         if prev is not None:
@@ -207,7 +240,10 @@ class PeerLift:
             self._p_acc, self._p_mean, self._p_cov if self.want_cov else None, self._p_flags, self.world, self.rank,
             self.epoch, int(n_views_total), self.channels, self.n_voxels,
             ctypes.c_void_p(alpha.data_ptr()) if alpha is not None else None,
-            ctypes.c_void_p(self.count.data_ptr()), stream.cuda_stream), 'nd_lift_finalize_peers')
+            ctypes.c_void_p(self.count.data_ptr()),
+            ctypes.c_void_p(mc + self._off_acc) if mc else None, ctypes.c_void_p(mc + self._off_mean) if mc else None,
+            ctypes.c_void_p(mc + self._off_cov) if mc and self.want_cov else None,
+            stream.cuda_stream), 'nd_lift_finalize_peers')
         if self._ordered:
             ev = torch.cuda.Event()
             ev.record(stream)
@@ -236,7 +272,7 @@ class PeerLift:
         """Unmaps the peers' segments and frees the local one (collective when world > 1)."""
         if self._base is None:
             return
-        multi = self.world > 1 and dist.is_initialized() and bool(self._opened)
+        multi = self.world > 1 and dist.is_initialized() and (bool(self._opened) or self._symm is not None)
         torch.cuda.synchronize(self.device)
         if multi:
             dist.barrier(group=self.group)      # nobody unmaps while a peer may still be inside an exchange
@@ -247,6 +283,9 @@ class PeerLift:
         if multi:
             dist.barrier(group=self.group)      # nobody frees a segment a peer still has mapped
         self.flags = self.acc = self.mean = self.cov = self._seg = None
-        with torch.cuda.device(self.device):
-            self.lib.nd_peer_free(self._ct.c_void_p(self._base))
+        if self._symm is not None:
+            self._symm = None                   # the symmetric-memory allocator owns that segment
+        else:
+            with torch.cuda.device(self.device):
+                self.lib.nd_peer_free(self._ct.c_void_p(self._base))
         self._base = None

@@ -83,10 +83,11 @@ def main():
     us_nccl = timed(lambda: nd_dist.lift_mean_var_view_sharded(feats[b:e], pts, proj[b:e], n_views_total=nv))
     us_local = timed(lambda: lifting.lift_mean_var(feats[b:e], pts, proj[b:e]))
     sweep = {}
-    for per_sm in (2, 4, 6, 8, 12, 16):                        # grid of the exchange kernel (loads in flight over the links)
+    fast = os.environ.get('DIST_CHECK_FAST') == '1'            # skip the grid sweeps (8-GPU runs are charged 8x)
+    for per_sm in (() if fast else (2, 4, 6, 8, 12, 16)):      # grid of the exchange kernel (loads in flight over the links)
         os.environ['ND_PEER_CTAS_PER_SM'] = str(per_sm)
         sweep[per_sm] = round(timed(lambda: peer.exchange(nv)), 1)
-    os.environ.pop('ND_PEER_CTAS_PER_SM')
+    os.environ.pop('ND_PEER_CTAS_PER_SM', None)
     peer.check()
     if rank == 0:
         print(f'exchange alone vs CTAs per SM: {sweep}', flush=True)
@@ -98,6 +99,45 @@ def main():
               f'local fused lift alone {us_local:.1f} us', flush=True)
     assert int(res[0]) == world and int(res[1]) == 0 and int(res[2]) == 0 and torch.equal(lo_, hi_)
     peer.close()
+
+    # ---- the same kernel over NVLS multicast: sums taken in the switch (multimem.ld_reduce), rows broadcast (multimem.st) ----
+    mcp, why = None, ''
+    try:
+        mcp = nd_dist.PeerLift(256, pts[0].numel(), dev, transport='multicast')
+    except Exception as ex:
+        why = f'{type(ex).__name__}: {ex}'
+    ok = torch.tensor([1 if mcp is not None else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok) == 0:
+        if rank == 0:
+            print(f'multicast transport unavailable on this box: {why}', flush=True)
+    else:
+        for _ in range(3):
+            qm, qc, qn = mcp(feats[b:e], pts, proj[b:e], nv)
+        mcp.check()
+        e_mean, bad_mean = err(qm, m1)
+        e_cov, bad_cov = err(qc, c1)
+        res = torch.tensor([int(torch.equal(qn, n1)), bad_mean, bad_cov], device=dev)
+        dist.all_reduce(res, op=dist.ReduceOp.SUM)
+        chk = torch.stack([qm.double().sum(), qc.double().sum()])
+        lo_, hi_ = chk.clone(), chk.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        us_mc = timed(lambda: mcp(feats[b:e], pts, proj[b:e], nv))
+        sweep = {}
+        for per_sm in ((0, 2, 4) if fast else (0, 2, 4, 6, 8, 12)):
+            if per_sm:
+                os.environ['ND_PEER_CTAS_PER_SM'] = str(per_sm)
+            sweep[per_sm] = round(timed(lambda: mcp.exchange(nv)), 1)
+        os.environ.pop('ND_PEER_CTAS_PER_SM', None)
+        mcp.check()
+        if rank == 0:
+            print(f'multicast exchange on {world} GPUs: counts equal on {int(res[0])}/{world} ranks, mean max abs err {e_mean:.3e} '
+                  f'({int(res[1])} outside 1e-4), cov max abs err {e_cov:.3e} ({int(res[2])} outside 1e-4), checksums equal '
+                  f'across ranks: {bool(torch.equal(lo_, hi_))}', flush=True)
+            print(f'per step: lift + multicast exchange {us_mc:.1f} us; exchange alone vs CTAs per SM (0 = default): {sweep}', flush=True)
+        assert int(res[0]) == world and int(res[1]) == 0 and int(res[2]) == 0 and torch.equal(lo_, hi_)
+        mcp.close()
     dist.destroy_process_group()
 
 
