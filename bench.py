@@ -38,6 +38,7 @@ VOXEL_SIZE = (0.16, 0.16, 0.2)
 CHANNELS = 256
 FEAT_HW_PAD = (60, 80)
 FEAT_HW = (59, 80)
+OVERLAP_SMS = 20           # N > 1, pipelined: SMs that carry the exchange kernel while the others accumulate the next scene
 N_INPUT_SETS = 3          # rotated so that no step finds its features in L2
 
 
@@ -170,7 +171,7 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, exchange='peer'):
+def workload_config(n_gpus, exchange='peer', pipeline=False):
     if n_gpus == 1:
         part = 'single GPU'
     elif exchange == 'multicast':
@@ -188,6 +189,7 @@ def workload_config(n_gpus, exchange='peer'):
         'feature_layout': 'NCHW fp32, non-contiguous [:, :, :59, :80] slice (reference layout)',
         'l2_policy': f'inputs (241.7 MB/step) exceed the 126 MB L2 and {N_INPUT_SETS} input sets are rotated',
         'partitioning': part,
+        'scenes_in_flight': 2 if pipeline else 1,
     }
 
 
@@ -200,6 +202,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-pipeline', action='store_true',
+                    help='N > 1: one scene at a time (default: two scenes in flight on two streams, the exchange of scene i '
+                         'on OVERLAP_SMS SMs beside the accumulate of scene i + 1 on the others)')
     ap.add_argument('--exchange', default='peer', choices=['peer', 'multicast', 'auto', 'nccl'],
                     help='N > 1: how the per-rank accumulators meet: our kernel over per-peer P2P loads / stores (default: the '
                          'fastest at 2 and at 8 GPUs, profiles/r01_s6_multigpu_exchange.txt), our kernel over NVLS multicast '
@@ -237,11 +242,13 @@ def main():
 
     # N > 1: one peer-mapped segment for the device-resident loop and one per end-to-end lane (their results are views of it)
     exchange = args.exchange if n_gpus > 1 else 'none'
+    pipeline = n_gpus > 1 and exchange != 'nccl' and not args.no_pipeline
+    overlap_sms = OVERLAP_SMS if pipeline else 0
     peers = None
     if exchange in ('auto', 'multicast'):
         err = ''
         try:
-            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, transport='multicast') for _ in range(3)]
+            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, transport='multicast', overlap_sms=overlap_sms) for _ in range(4)]
         except Exception as e:                                 # no NVLS on this box / symmetric memory unavailable
             err = f'{type(e).__name__}: {e}'
         ok = torch.tensor([1 if peers is not None else 0], device=dev)
@@ -256,7 +263,7 @@ def main():
             peers = None
             exchange = 'peer'
     if exchange == 'peer':
-        peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev) for _ in range(3)]
+        peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, overlap_sms=overlap_sms) for _ in range(4)]
     use_peer = peers is not None
 
     def step(feats, lane=0):
@@ -277,13 +284,30 @@ def main():
         sampler.start()
 
     # ---- device-resident timing ----
-    for i in range(warmup):
-        out = step(dev_sets[i % N_INPUT_SETS])
+    dev_lanes = [torch.cuda.Stream(device=dev) for _ in range(2)] if pipeline else None
+
+    def run_steps(count):
+        """`count` steps; pipelined: scene i on lane i % 2 (its own stream and peer segment), all joined at the end."""
+        out = None
+        if not pipeline:
+            for i in range(count):
+                out = step(dev_sets[i % N_INPUT_SETS])
+            return out
+        cur = torch.cuda.current_stream()
+        for st in dev_lanes:
+            st.wait_stream(cur)
+        for i in range(count):
+            with torch.cuda.stream(dev_lanes[i % 2]):
+                out = step(dev_sets[i % N_INPUT_SETS], i % 2)
+        for st in dev_lanes:
+            cur.wait_stream(st)
+        return out
+
+    out = run_steps(warmup)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(steps):
-        out = step(dev_sets[i % N_INPUT_SETS])
+    out = run_steps(steps)
     ev1.record()
     barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
@@ -312,7 +336,7 @@ def main():
             ln = lanes[i % 2]
             with torch.cuda.stream(ln['stream']):
                 ln['stage'].copy_(host_sets[i % N_INPUT_SETS], non_blocking=True)
-                mean, cov, cnt = step(ln['stage'], 1 + i % 2)
+                mean, cov, cnt = step(ln['stage'], 2 + i % 2)
                 ln['host_out'][0].copy_(mean.view(CHANNELS, -1), non_blocking=True)
                 ln['host_out'][1].copy_(cov.view(CHANNELS, -1), non_blocking=True)
                 ln['host_cnt'].copy_(cnt.view(-1), non_blocking=True)
@@ -376,7 +400,7 @@ def main():
             'metric': 'voxel_view_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': n_gpus,
             'steps': steps, 'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(n_gpus, exchange),
+            'config': workload_config(n_gpus, exchange, pipeline),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': ncu_traffic(), 'peak_source': peak_src,
                          'algorithmic_bytes_per_step': bytes_per_step,

@@ -71,7 +71,9 @@ typedef struct nd_lift_options {
     int32_t grid_x, grid_y, grid_z; /* optional: the voxel lattice behind `points` (Z fastest, X*Y*Z == n_voxels),
                                       as in get_points (nerfdet.py:381-390); lets the plane-resident kernel
                                       use spatially compact warp tiles.  0 = unknown (results are identical) */
-    int32_t reserved;
+    int32_t sm_limit;              /* plane-resident kernel: occupy at most this many SMs (0 = all); the kernel also never uses
+                                      more CTAs than it needs for its number of rounds (512 units on 148 SMs take 4 rounds,
+                                      which 128 CTAs do as well) */
 } nd_lift_options;
 
 int nd_version(void);
@@ -156,6 +158,9 @@ int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_v
  *       rank's copy through the NVSwitch), or all NULL.  When given, the sums are taken in the switch
  *       (multimem.ld_reduce) and the rows leave with one multimem.st, which roughly halves the bytes a GPU receives;
  *       the per-rank tables are then only used for the flag blocks.  Needs N % 4 == 0.
+ *     max_ctas: 0 = a grid that fills the GPU; > 0 = at most that many one-per-SM CTAs (512 / 1024 threads) looping over
+ *       the work, so that the exchange of one scene can run beside the accumulate of the next on the SMs that
+ *       nd_lift_options.sm_limit keeps free (the exchange is bound by the links, not by the SMs).
  *   Outputs are complete on `stream` when the call's kernels have run; a peer that never arrives raises word
  *   2 * ND_MAX_PEERS + 1 of the local flag block after ~4 s instead of hanging.
  * ------------------------------------------------------------------------------------- */
@@ -169,7 +174,7 @@ int nd_peer_free(void *ptr);
 int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
                            void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
                            int channels, int64_t n_voxels, const float *alpha, int64_t *count, const void *acc_mc,
-                           void *mean_mc, void *cov_mc, void *stream);
+                           void *mean_mc, void *cov_mc, int max_ctas, void *stream);
 
 
 /* ---------------------------------------------------------------------------------------

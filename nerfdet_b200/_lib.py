@@ -23,7 +23,7 @@ class NdMaps(ctypes.Structure):
 
 class NdLiftOptions(ctypes.Structure):
     _fields_ = [('scratch_budget_bytes', c_size_t), ('voxels_per_cta', c_int32), ('path', c_int32),
-                ('grid_x', c_int32), ('grid_y', c_int32), ('grid_z', c_int32), ('reserved', c_int32)]
+                ('grid_x', c_int32), ('grid_y', c_int32), ('grid_z', c_int32), ('sm_limit', c_int32)]
 
 
 class NdMlpWeights(ctypes.Structure):
@@ -58,7 +58,7 @@ SIGNATURES = {
     'nd_peer_free': (c_int, [c_void_p]),
     'nd_lift_finalize_peers': (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                        c_int, c_int, ctypes.c_uint32, c_int, c_int, c_int64, c_void_p, c_void_p,
-                                       c_void_p, c_void_p, c_void_p, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'nd_live_stats': (c_int, [POINTER(NdMaps), POINTER(NdMaps), c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'nd_map_features': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

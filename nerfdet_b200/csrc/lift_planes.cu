@@ -850,10 +850,20 @@ static bool plane_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *o
         int dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    if (opt != nullptr && opt->sm_limit > 0 && opt->sm_limit < sms) sms = opt->sm_limit;
+    if (const char *e = getenv("ND_LIFT_SMS")) { const int v = atoi(e); if (v > 0 && v < sms) sms = v; }
     const int64_t n_units = (int64_t)f->channels * g.n_parts;
     int64_t grid = n_units < sms ? n_units : sms;
     grid -= grid % g.n_parts;
     if (grid < g.n_parts) grid = g.n_parts;
+    // the CTAs walk their units in rounds; the smallest grid with the same number of rounds takes the same time and leaves
+    // SMs free for a concurrent kernel (512 units: 4 rounds on 148 CTAs, of which 80 idle in the last round -- or on 128)
+    if (getenv("ND_LIFT_NO_TRIM") == nullptr) {
+        const int64_t rounds = ceil_div(n_units, grid);
+        int64_t trimmed = ceil_div(n_units, rounds);
+        trimmed = ceil_div(trimmed, g.n_parts) * g.n_parts;
+        if (trimmed < grid) grid = trimmed;
+    }
     g.grid = (int)grid;
     g.off_bytes = align_up((size_t)f->n_views * g.n_pad * sizeof(uint16_t), 256);
     g.cnt_bytes = align_up((size_t)g.nw16 * g.n_pad, 256);

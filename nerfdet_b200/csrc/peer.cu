@@ -33,7 +33,7 @@ struct PeerArgs {
     uint32_t *flags[kMaxPeers];      // [0, P): ready, [P, 2P): done, [2P]: CTA counter, [2P + 1]: error
     int world, rank;
     uint32_t epoch;
-    int n_views_total, channels, c_begin, c_end, ch_per_cta;
+    int n_views_total, channels, c_begin, c_end, ch_per_cta, n_tiles, n_items;
     int64_t n_vox;
     const float *alpha;
     int64_t *count;
@@ -100,22 +100,29 @@ template <> __device__ __forceinline__ void st_vec<1>(float *p, const float (&r)
 // in flight (CTAs per SM x loads per thread), not by the instruction count.
 // MC: the sums come from multimem.ld_reduce on the multicast address (the switch adds the ranks' copies: (G-1) x fewer
 // bytes arrive than with per-peer loads) and the rows leave with one multimem.st instead of G stores.
-template <int V, int G, int U, bool MC>
-__global__ void __launch_bounds__(kPeerThreads, (G * U <= 4) ? 6 : 4)
+// T = threads per CTA: 128 (wide grid, one work item per CTA) or 512 / 1024 (NARROW grid: a few fat CTAs, one per SM, each
+// looping over work items -- the exchange is link-bound, so ~20 SMs carry it while the other SMs run the next scene's
+// accumulate; fat CTAs because the block scheduler spreads small CTAs over all SMs, where none would leave room for a
+// persistent lift CTA).
+template <int V, int G, int U, bool MC, int T>
+__global__ void __launch_bounds__(T, T > 128 ? 1 : ((G * U <= 4) ? 6 : 4))
 k_lift_finalize_peers(const PeerArgs a) {
     static_assert(!MC || (V == 4 && G == 1), "multicast instantiation: 16-byte vectors, one (reduced) load per row");
     const int P = kMaxPeers;
     uint32_t *my_flags = a.flags[a.rank];
     // ---- hand-shake: my accumulators are complete; wait for everybody else's ----
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < a.world)
+    if (blockIdx.x == 0 && threadIdx.x < a.world)
         st_release_sys(a.flags[threadIdx.x] + a.rank, a.epoch);
     if (threadIdx.x < a.world && threadIdx.x != a.rank) {
         if (!spin_until(my_flags + threadIdx.x, a.epoch)) atomicExch(my_flags + 2 * P + 1, 1u);
     }
     __syncthreads();
 
-    const int64_t n = ((int64_t)blockIdx.x * kPeerThreads + threadIdx.x) * V;
     const int64_t cn = (int64_t)a.channels * a.n_vox;
+    // work item = (voxel tile of T * V voxels, channel sub-slice); wide grid: exactly one item per CTA
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    const int tile = item % a.n_tiles, sub = item / a.n_tiles;
+    const int64_t n = ((int64_t)tile * T + threadIdx.x) * V;
     if (n < a.n_vox) {
         float cnt[V];
 #pragma unroll
@@ -136,11 +143,11 @@ k_lift_finalize_peers(const PeerArgs a) {
             al[j] = a.alpha != nullptr ? __ldg(a.alpha + n + j) : 1.0f;
             inv[j] = (float)a.n_views_total - cnt[j];
         }
-        if (blockIdx.y == 0 && a.count != nullptr) {
+        if (sub == 0 && a.count != nullptr) {
 #pragma unroll
             for (int j = 0; j < V; ++j) a.count[n + j] = (int64_t)cnt[j];
         }
-        const int c0 = a.c_begin + (int)blockIdx.y * a.ch_per_cta;
+        const int c0 = a.c_begin + sub * a.ch_per_cta;
         const int c1 = min(a.c_end, c0 + a.ch_per_cta);
         for (int cb = c0; cb < c1; cb += U) {
             float p1[U][G][V], p2[U][G][V];
@@ -201,11 +208,12 @@ k_lift_finalize_peers(const PeerArgs a) {
             }
         }
     }
+    }
     // ---- completion: the last CTA tells every peer that this rank is done with their segments ----
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t total = gridDim.x * gridDim.y;
+        const uint32_t total = gridDim.x;
         const uint32_t prev = atomicAdd(my_flags + 2 * P, 1u);
         if (prev == total - 1) {
             my_flags[2 * P] = 0u;                               // ready for the next epoch (next launch is stream-ordered)
@@ -283,7 +291,7 @@ int nd_peer_free(void *ptr) {
 int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
                            void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
                            int channels, int64_t n_voxels, const float *alpha, int64_t *count, const void *acc_mc,
-                           void *mean_mc, void *cov_mc, void *stream) {
+                           void *mean_mc, void *cov_mc, int max_ctas, void *stream) {
     ND_REQUIRE(acc_host && mean_host && flags_host, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: null pointer table");
     ND_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, ND_ERR_BAD_ARG,
                "nd_lift_finalize_peers: world %d / rank %d outside [1, %d]", world, rank, kMaxPeers);
@@ -325,31 +333,42 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
         a.cov_mc = static_cast<float *>(cov_mc);
     }
     const int v = vec ? 4 : 1;
-    const int64_t tiles = ceil_div(n_voxels, (int64_t)kPeerThreads * v);
     const int slice = a.c_end - a.c_begin;
     const int gb = (mc || world <= 1) ? 1 : world <= 2 ? 2 : world <= 4 ? 4 : 8;   // compile-time bound of the instantiation
-    // enough CTAs to fill every SM at the instantiation's occupancy; a CTA keeps its tile's counts for its channels
+    const bool narrow = max_ctas > 0 && vec;
+    const int threads = !narrow ? kPeerThreads : gb <= 2 ? 1024 : 512;
+    const int64_t tiles = ceil_div(n_voxels, (int64_t)threads * v);
+    // wide grid: enough CTAs to fill every SM at the instantiation's occupancy; a CTA keeps its tile's counts for its channels
     // measured on B200s (tools/dist_check.py sweep): 2 GPUs 102.9 us at 6 CTAs per SM (104-112 for 2-12); 8 GPUs 176.7 us at 2
     // (191 at 4, 237 at 12) -- the step is bound by the links (~520 GB/s inbound per GPU), more CTAs only add contention
     int per_sm = gb <= 2 ? 6 : gb <= 4 ? 4 : 2;
     if (const char *e = getenv("ND_PEER_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
-    int64_t subs = ceil_div((int64_t)148 * per_sm, tiles);
+    // narrow grid: ~4 work items per CTA so that the CTAs finish together
+    int64_t subs = ceil_div(narrow ? (int64_t)max_ctas * 4 : (int64_t)148 * per_sm, tiles);
     if (subs > slice) subs = slice;
     if (subs < 1) subs = 1;
     a.ch_per_cta = slice > 0 ? (int)ceil_div(slice, subs) : 1;
-    const dim3 grid((unsigned)tiles, (unsigned)(slice > 0 ? ceil_div(slice, a.ch_per_cta) : 1));
+    a.n_tiles = (int)tiles;
+    a.n_items = (int)(tiles * (slice > 0 ? ceil_div(slice, a.ch_per_cta) : 1));
+    const dim3 grid((unsigned)(narrow && max_ctas < a.n_items ? max_ctas : a.n_items));
     cudaStream_t st = (cudaStream_t)stream;
-#define ND_PEER_LAUNCH(V_, G_, U_) k_lift_finalize_peers<V_, G_, U_, false><<<grid, kPeerThreads, 0, st>>>(a)
+#define ND_PEER_LAUNCH(V_, G_, U_, T_) k_lift_finalize_peers<V_, G_, U_, false, T_><<<grid, T_, 0, st>>>(a)
     if (mc) {
-        k_lift_finalize_peers<4, 1, 4, true><<<grid, kPeerThreads, 0, st>>>(a);
+        if (narrow) k_lift_finalize_peers<4, 1, 2, true, 1024><<<grid, 1024, 0, st>>>(a);
+        else k_lift_finalize_peers<4, 1, 4, true, kPeerThreads><<<grid, kPeerThreads, 0, st>>>(a);
+    } else if (narrow) {
+        if (gb == 1) ND_PEER_LAUNCH(4, 1, 2, 1024);
+        else if (gb == 2) ND_PEER_LAUNCH(4, 2, 1, 1024);
+        else if (gb == 4) ND_PEER_LAUNCH(4, 4, 1, 512);
+        else ND_PEER_LAUNCH(4, 8, 1, 512);
     } else if (vec) {
-        if (gb == 1) ND_PEER_LAUNCH(4, 1, 4);
-        else if (gb == 2) ND_PEER_LAUNCH(4, 2, 2);
-        else if (gb == 4) ND_PEER_LAUNCH(4, 4, 1);
-        else ND_PEER_LAUNCH(4, 8, 1);
+        if (gb == 1) ND_PEER_LAUNCH(4, 1, 4, kPeerThreads);
+        else if (gb == 2) ND_PEER_LAUNCH(4, 2, 2, kPeerThreads);
+        else if (gb == 4) ND_PEER_LAUNCH(4, 4, 1, kPeerThreads);
+        else ND_PEER_LAUNCH(4, 8, 1, kPeerThreads);
     } else {
-        if (gb <= 2) ND_PEER_LAUNCH(1, 2, 2);
-        else ND_PEER_LAUNCH(1, 8, 1);
+        if (gb <= 2) ND_PEER_LAUNCH(1, 2, 2, kPeerThreads);
+        else ND_PEER_LAUNCH(1, 8, 1, kPeerThreads);
     }
 #undef ND_PEER_LAUNCH
     ND_CUDA_LAUNCH_CHECK("k_lift_finalize_peers");

@@ -104,17 +104,22 @@ class PeerLift:
     """
 
     def __init__(self, channels: int, n_voxels: int, device=None, group=None, want_cov: bool = True,
-                 transport: str = 'ipc', _local_group=None):
+                 transport: str = 'ipc', overlap_sms: int = 0, _local_group=None):
         """``transport='ipc'``: cudaMalloc segments shared with CUDA IPC handles, per-peer P2P loads / stores.
         ``transport='multicast'``: symmetric-memory segments (``torch.distributed._symmetric_memory``, plumbing only)
         bound to an NVLS multicast object; the kernel then reduces in the NVSwitch (``multimem.ld_reduce``) and
-        broadcasts its rows with ``multimem.st``.  Raises if the box has no multicast support."""
+        broadcasts its rows with ``multimem.st``.  Raises if the box has no multicast support.
+
+        ``overlap_sms`` > 0 (scenes in flight on two streams, one PeerLift each): the exchange kernel runs as that many
+        one-per-SM CTAs and the accumulate keeps off that many SMs, so that the exchange of scene i (bound by the links,
+        not by the SMs) runs beside the accumulate of scene i + 1."""
         from . import _lib
         import ctypes
         self._lib = _lib
         self._ct = ctypes
         self.lib = _lib.load()
         self.channels, self.n_voxels, self.want_cov = int(channels), int(n_voxels), bool(want_cov)
+        self.overlap_sms = max(int(overlap_sms), 0)
         self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
         self.group = group
         if _local_group is not None:
@@ -213,11 +218,13 @@ class PeerLift:
         self._p_cov = arr(*[b + self._off_cov for b in bases])
 
     @classmethod
-    def local_group(cls, world: int, channels: int, n_voxels: int, device=None, want_cov: bool = True):
+    def local_group(cls, world: int, channels: int, n_voxels: int, device=None, want_cov: bool = True,
+                    overlap_sms: int = 0):
         """``world`` ranks inside ONE process on one device (their segments are addressed directly, no IPC): the
         single-GPU test of the multi-rank protocol -- run each rank's call on its own stream.  Small shapes only:
         the waiting CTAs of all ranks must fit the device together."""
-        ranks = [cls(channels, n_voxels, device, want_cov=want_cov, _local_group=(r, world)) for r in range(world)]
+        ranks = [cls(channels, n_voxels, device, want_cov=want_cov, overlap_sms=overlap_sms, _local_group=(r, world))
+                 for r in range(world)]
         bases = [r._base for r in ranks]
         for r in ranks:
             r._set_peers(bases)
@@ -243,7 +250,7 @@ class PeerLift:
             ctypes.c_void_p(self.count.data_ptr()),
             ctypes.c_void_p(mc + self._off_acc) if mc else None, ctypes.c_void_p(mc + self._off_mean) if mc else None,
             ctypes.c_void_p(mc + self._off_cov) if mc and self.want_cov else None,
-            stream.cuda_stream), 'nd_lift_finalize_peers')
+            self.overlap_sms, stream.cuda_stream), 'nd_lift_finalize_peers')
         if self._ordered:
             ev = torch.cuda.Event()
             ev.record(stream)
@@ -256,7 +263,10 @@ class PeerLift:
         from . import ops
         if features_local.shape[1] != self.channels or points[0].numel() != self.n_voxels:
             raise ValueError('PeerLift was built for another shape')
-        ops.lift_accumulate_into(features_local, points, projection_local, self.acc)
+        sm_limit = 0
+        if self.overlap_sms:
+            sm_limit = max(torch.cuda.get_device_properties(self.device).multi_processor_count - self.overlap_sms, 1)
+        ops.lift_accumulate_into(features_local, points, projection_local, self.acc, sm_limit)
         mean, cov, count = self.exchange(n_views_total, alpha)
         shape = tuple(points.shape[1:]) if points.dim() == 4 else (self.n_voxels,)
         return (mean.view(self.channels, *shape), cov.view(self.channels, *shape) if cov is not None else None,

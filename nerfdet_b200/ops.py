@@ -60,11 +60,11 @@ def _flat_points(points: Tensor) -> Tuple[Tensor, Tuple[int, int, int]]:
     return points.reshape(3, -1).contiguous(), grid
 
 
-def _options(scratch_budget_bytes: int, grid=(0, 0, 0)) -> NdLiftOptions:
+def _options(scratch_budget_bytes: int, grid=(0, 0, 0), sm_limit: int = 0) -> NdLiftOptions:
     """``scratch_budget_bytes`` > 0 selects the generic staged path (any strides) with that much
     L2-resident staging; 0 = automatic (plane-resident kernel for contiguous NCHW planes)."""
     path = _lib.ND_LIFT_PATH_STAGED if scratch_budget_bytes > 0 else _lib.ND_LIFT_PATH_AUTO
-    return NdLiftOptions(max(scratch_budget_bytes, 0), 0, path, int(grid[0]), int(grid[1]), int(grid[2]), 0)
+    return NdLiftOptions(max(scratch_budget_bytes, 0), 0, path, int(grid[0]), int(grid[1]), int(grid[2]), int(sm_limit))
 
 
 # ------------------------------------------------------------------------------------------
@@ -197,8 +197,9 @@ def _(features, points, projection, scratch_budget_bytes):
 
 
 @torch.library.custom_op(f'{_NS}::lift_accumulate_into', mutates_args=('acc',))
-def lift_accumulate_into(features: Tensor, points: Tensor, projection: Tensor, acc: Tensor) -> None:
-    """``lift_accumulate`` into a caller-owned buffer (the peer-mapped segment of ``distributed.PeerLift``)."""
+def lift_accumulate_into(features: Tensor, points: Tensor, projection: Tensor, acc: Tensor, sm_limit: int = 0) -> None:
+    """``lift_accumulate`` into a caller-owned buffer (the peer-mapped segment of ``distributed.PeerLift``);
+    ``sm_limit`` > 0 keeps the lift off some SMs so that a concurrent exchange kernel finds room."""
     _need_cuda(features, points, projection, acc)
     m = _maps(features)
     _check_geometry(points, projection, m.n_views)
@@ -209,7 +210,7 @@ def lift_accumulate_into(features: Tensor, points: Tensor, projection: Tensor, a
     if acc.dtype != torch.float32 or acc.numel() != (2 * c + 1) * n or not acc.is_contiguous():
         raise ValueError(f'acc must be a contiguous float32 buffer of (2 * {c} + 1) * {n} elements')
     lib = _lib.load()
-    opt = _options(0, grid)
+    opt = _options(0, grid, sm_limit)
     optp = ctypes.byref(opt)
     ws_bytes = lib.nd_lift_workspace_bytes(ctypes.byref(m), n, optp)
     ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=features.device)

@@ -37,11 +37,13 @@ def _scene(nv, n_voxels, voxel_size, channels, seed):
     return sc.features.to(DEV)[:, :, :59, :80], pts.to(DEV), proj.to(DEV)
 
 
-@pytest.mark.parametrize('nv,grid,channels', [(50, (40, 40, 16), 256), (6, (7, 5, 3), 16)])
-def test_single_rank_equals_fused_lift(nv, grid, channels):
+@pytest.mark.parametrize('nv,grid,channels,overlap', [(50, (40, 40, 16), 256, 0), (50, (40, 40, 16), 256, 20),
+                                                      (6, (7, 5, 3), 16, 0), (6, (7, 5, 3), 16, 4)])
+def test_single_rank_equals_fused_lift(nv, grid, channels, overlap):
+    """overlap > 0: accumulate with an SM limit + the narrow (few fat CTAs) exchange grid."""
     f, pts, proj = _scene(nv, grid, (0.16, 0.16, 0.2), channels, 91)
     mean, cov, cnt = lifting.lift_mean_var(f, pts, proj)
-    peer = nd_dist.PeerLift(channels, int(np.prod(grid)), DEV)
+    peer = nd_dist.PeerLift(channels, int(np.prod(grid)), DEV, overlap_sms=overlap)
     try:
         for _ in range(2):                                  # two epochs through the same segment
             m2, c2, n2 = peer(f, pts, proj, nv)
@@ -53,8 +55,8 @@ def test_single_rank_equals_fused_lift(nv, grid, channels):
         peer.close()
 
 
-@pytest.mark.parametrize('world', [2, 3, 8])
-def test_in_process_ranks_match_all_views(world):
+@pytest.mark.parametrize('world,overlap', [(2, 0), (3, 0), (8, 0), (2, 3), (4, 2), (8, 2)])
+def test_in_process_ranks_match_all_views(world, overlap):
     nv, grid, channels = 19, (16, 16, 8), 20                # uneven view split, channel slices of unequal size
     n = int(np.prod(grid))
     f, pts, proj = _scene(nv, grid, (0.4, 0.4, 0.4), channels, 92)
@@ -67,7 +69,7 @@ def test_in_process_ranks_match_all_views(world):
         a = ops.lift_accumulate(f[b:e], pts, proj[b:e], 0)
         acc = a if acc is None else acc + a
     m_ref, c_ref, n_ref = ops.lift_finalize(acc, nv, channels, n, alpha, True)
-    ranks = nd_dist.PeerLift.local_group(world, channels, n, DEV)
+    ranks = nd_dist.PeerLift.local_group(world, channels, n, DEV, overlap_sms=overlap)
     streams = [torch.cuda.Stream() for _ in range(world)]
     try:
         torch.cuda.synchronize()
