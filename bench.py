@@ -189,7 +189,7 @@ def workload_config(n_gpus, exchange='peer', pipeline=False):
         'feature_layout': 'NCHW fp32, non-contiguous [:, :, :59, :80] slice (reference layout)',
         'l2_policy': f'inputs (241.7 MB/step) exceed the 126 MB L2 and {N_INPUT_SETS} input sets are rotated',
         'partitioning': part,
-        'scenes_in_flight': 2 if pipeline else 1,
+        'scenes_in_flight': pipeline if pipeline else 1,
     }
 
 
@@ -202,6 +202,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--lanes', type=int, default=2, help='N > 1, pipelined: scenes in flight (streams / peer segments)')
     ap.add_argument('--no-pipeline', action='store_true',
                     help='N > 1: one scene at a time (default: two scenes in flight on two streams, the exchange of scene i '
                          'on OVERLAP_SMS SMs beside the accumulate of scene i + 1 on the others)')
@@ -244,11 +245,12 @@ def main():
     exchange = args.exchange if n_gpus > 1 else 'none'
     pipeline = n_gpus > 1 and exchange != 'nccl' and not args.no_pipeline
     overlap_sms = OVERLAP_SMS if pipeline else 0
+    n_lanes = max(2, args.lanes) if pipeline else 1
     peers = None
     if exchange in ('auto', 'multicast'):
         err = ''
         try:
-            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, transport='multicast', overlap_sms=overlap_sms) for _ in range(4)]
+            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, transport='multicast', overlap_sms=overlap_sms) for _ in range(n_lanes + 2)]
         except Exception as e:                                 # no NVLS on this box / symmetric memory unavailable
             err = f'{type(e).__name__}: {e}'
         ok = torch.tensor([1 if peers is not None else 0], device=dev)
@@ -263,7 +265,7 @@ def main():
             peers = None
             exchange = 'peer'
     if exchange == 'peer':
-        peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, overlap_sms=overlap_sms) for _ in range(4)]
+        peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, overlap_sms=overlap_sms) for _ in range(n_lanes + 2)]
     use_peer = peers is not None
 
     def step(feats, lane=0):
@@ -284,7 +286,7 @@ def main():
         sampler.start()
 
     # ---- device-resident timing ----
-    dev_lanes = [torch.cuda.Stream(device=dev) for _ in range(2)] if pipeline else None
+    dev_lanes = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)] if pipeline else None
 
     def run_steps(count):
         """`count` steps; pipelined: scene i on lane i % 2 (its own stream and peer segment), all joined at the end."""
@@ -297,8 +299,8 @@ def main():
         for st in dev_lanes:
             st.wait_stream(cur)
         for i in range(count):
-            with torch.cuda.stream(dev_lanes[i % 2]):
-                out = step(dev_sets[i % N_INPUT_SETS], i % 2)
+            with torch.cuda.stream(dev_lanes[i % n_lanes]):
+                out = step(dev_sets[i % N_INPUT_SETS], i % n_lanes)
         for st in dev_lanes:
             cur.wait_stream(st)
         return out
@@ -336,7 +338,7 @@ def main():
             ln = lanes[i % 2]
             with torch.cuda.stream(ln['stream']):
                 ln['stage'].copy_(host_sets[i % N_INPUT_SETS], non_blocking=True)
-                mean, cov, cnt = step(ln['stage'], 2 + i % 2)
+                mean, cov, cnt = step(ln['stage'], n_lanes + i % 2)
                 ln['host_out'][0].copy_(mean.view(CHANNELS, -1), non_blocking=True)
                 ln['host_out'][1].copy_(cov.view(CHANNELS, -1), non_blocking=True)
                 ln['host_cnt'].copy_(cnt.view(-1), non_blocking=True)
@@ -400,7 +402,7 @@ def main():
             'metric': 'voxel_view_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': n_gpus,
             'steps': steps, 'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(n_gpus, exchange, pipeline),
+            'config': workload_config(n_gpus, exchange, n_lanes if pipeline else 0),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': ncu_traffic(), 'peak_source': peak_src,
                          'algorithmic_bytes_per_step': bytes_per_step,

@@ -100,7 +100,7 @@ template <> __device__ __forceinline__ void st_vec<1>(float *p, const float (&r)
 // in flight (CTAs per SM x loads per thread), not by the instruction count.
 // MC: the sums come from multimem.ld_reduce on the multicast address (the switch adds the ranks' copies: (G-1) x fewer
 // bytes arrive than with per-peer loads) and the rows leave with one multimem.st instead of G stores.
-// T = threads per CTA: 128 (wide grid, one work item per CTA) or 512 / 1024 (NARROW grid: a few fat CTAs, one per SM, each
+// T = threads per CTA: 128 (wide grid, one work item per CTA) or 512 (NARROW grid: a few fat CTAs, one per SM, each
 // looping over work items -- the exchange is link-bound, so ~20 SMs carry it while the other SMs run the next scene's
 // accumulate; fat CTAs because the block scheduler spreads small CTAs over all SMs, where none would leave room for a
 // persistent lift CTA).
@@ -336,15 +336,17 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     const int slice = a.c_end - a.c_begin;
     const int gb = (mc || world <= 1) ? 1 : world <= 2 ? 2 : world <= 4 ? 4 : 8;   // compile-time bound of the instantiation
     const bool narrow = max_ctas > 0 && vec;
-    const int threads = !narrow ? kPeerThreads : gb <= 2 ? 1024 : 512;
+    // narrow: 512 threads x 16 vector loads in flight per thread = 128 KB per SM (a remote load takes ~2 us; with 4 loads per
+    // thread 20 CTAs of 1024 threads took 164 us for what the wide grid does in 100 us: latency-bound at 32 GB/s per SM)
+    const int threads = !narrow ? kPeerThreads : 512;
     const int64_t tiles = ceil_div(n_voxels, (int64_t)threads * v);
     // wide grid: enough CTAs to fill every SM at the instantiation's occupancy; a CTA keeps its tile's counts for its channels
     // measured on B200s (tools/dist_check.py sweep): 2 GPUs 102.9 us at 6 CTAs per SM (104-112 for 2-12); 8 GPUs 176.7 us at 2
     // (191 at 4, 237 at 12) -- the step is bound by the links (~520 GB/s inbound per GPU), more CTAs only add contention
     int per_sm = gb <= 2 ? 6 : gb <= 4 ? 4 : 2;
     if (const char *e = getenv("ND_PEER_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
-    // narrow grid: ~4 work items per CTA so that the CTAs finish together
-    int64_t subs = ceil_div(narrow ? (int64_t)max_ctas * 4 : (int64_t)148 * per_sm, tiles);
+    // narrow grid: ~8 work items per CTA so that the CTAs finish together
+    int64_t subs = ceil_div(narrow ? (int64_t)max_ctas * 8 : (int64_t)148 * per_sm, tiles);
     if (subs > slice) subs = slice;
     if (subs < 1) subs = 1;
     a.ch_per_cta = slice > 0 ? (int)ceil_div(slice, subs) : 1;
@@ -354,12 +356,12 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     cudaStream_t st = (cudaStream_t)stream;
 #define ND_PEER_LAUNCH(V_, G_, U_, T_) k_lift_finalize_peers<V_, G_, U_, false, T_><<<grid, T_, 0, st>>>(a)
     if (mc) {
-        if (narrow) k_lift_finalize_peers<4, 1, 2, true, 1024><<<grid, 1024, 0, st>>>(a);
+        if (narrow) k_lift_finalize_peers<4, 1, 4, true, 512><<<grid, 512, 0, st>>>(a);
         else k_lift_finalize_peers<4, 1, 4, true, kPeerThreads><<<grid, kPeerThreads, 0, st>>>(a);
     } else if (narrow) {
-        if (gb == 1) ND_PEER_LAUNCH(4, 1, 2, 1024);
-        else if (gb == 2) ND_PEER_LAUNCH(4, 2, 1, 1024);
-        else if (gb == 4) ND_PEER_LAUNCH(4, 4, 1, 512);
+        if (gb == 1) ND_PEER_LAUNCH(4, 1, 4, 512);
+        else if (gb == 2) ND_PEER_LAUNCH(4, 2, 4, 512);
+        else if (gb == 4) ND_PEER_LAUNCH(4, 4, 2, 512);
         else ND_PEER_LAUNCH(4, 8, 1, 512);
     } else if (vec) {
         if (gb == 1) ND_PEER_LAUNCH(4, 1, 4, kPeerThreads);

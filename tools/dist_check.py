@@ -88,9 +88,15 @@ def main():
         os.environ['ND_PEER_CTAS_PER_SM'] = str(per_sm)
         sweep[per_sm] = round(timed(lambda: peer.exchange(nv)), 1)
     os.environ.pop('ND_PEER_CTAS_PER_SM', None)
+    narrow = {}
+    for ctas in (8, 12, 16, 20, 32, 48):                       # narrow grid: that many one-per-SM CTAs (PeerLift(overlap_sms=...))
+        peer.overlap_sms = ctas
+        narrow[ctas] = round(timed(lambda: peer.exchange(nv)), 1)
+    peer.overlap_sms = 0
     peer.check()
     if rank == 0:
         print(f'exchange alone vs CTAs per SM: {sweep}', flush=True)
+        print(f'exchange alone, narrow grid, vs number of fat CTAs: {narrow}', flush=True)
         print(f'peer-memory exchange on {world} GPUs: counts equal on {int(res[0])}/{world} ranks, mean max abs err {e_mean:.3e} '
               f'({int(res[1])} outside 1e-4), cov max abs err {e_cov:.3e} ({int(res[2])} outside 1e-4), bit-identical to the '
               f'all-reduce path on {int(res[3])}/{world} ranks, checksums equal across ranks: {bool(torch.equal(lo_, hi_))}', flush=True)
@@ -101,9 +107,10 @@ def main():
     peer.close()
 
     # ---- the same kernel over NVLS multicast: sums taken in the switch (multimem.ld_reduce), rows broadcast (multimem.st) ----
-    mcp, why = None, ''
+    mcp, why = None, 'skipped (DIST_CHECK_NO_MC=1)'
     try:
-        mcp = nd_dist.PeerLift(256, pts[0].numel(), dev, transport='multicast')
+        if os.environ.get('DIST_CHECK_NO_MC') != '1':
+            mcp = nd_dist.PeerLift(256, pts[0].numel(), dev, transport='multicast')
     except Exception as ex:
         why = f'{type(ex).__name__}: {ex}'
     ok = torch.tensor([1 if mcp is not None else 0], device=dev)
