@@ -69,7 +69,8 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50',
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms',
+                 os.environ.get('BENCH_SMI_MS', '200'),      # the recipe's period; every query perturbs the GPU for a few ms
                  '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -197,7 +198,7 @@ def workload_config(n_gpus, exchange='peer', pipeline=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=1000)   # 140 ms timed region: a clocks query landing in a 28 ms one costs 25 %
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
