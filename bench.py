@@ -266,7 +266,14 @@ def main():
             peers = None
             exchange = 'peer'
     if exchange == 'peer':
-        peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, overlap_sms=overlap_sms) for _ in range(n_lanes + 2)]
+        try:
+            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, overlap_sms=overlap_sms) for _ in range(n_lanes + 2)]
+        except RuntimeError as e:
+            # PeerLift fails on ALL ranks together (it reduces a success flag) when CUDA IPC / peer access is not available
+            # between these GPUs; the all-reduce form of the same exchange (NCCL + our finalise kernel) still runs
+            if rank == 0:
+                print(f'[bench] peer-memory exchange unavailable ({e}); using the NCCL all-reduce form', file=sys.stderr, flush=True)
+            peers, exchange, pipeline, n_lanes = None, 'nccl', False, 1
     use_peer = peers is not None
 
     def step(feats, lane=0):

@@ -165,13 +165,23 @@ class PeerLift:
                 raise RuntimeError('symmetric-memory rendezvous returned a local pointer that is not the segment')
             self._mc_base = int(hdl.multicast_ptr)
         else:
-            with torch.cuda.device(self.device):
-                base = ctypes.c_void_p()
-                handle = (ctypes.c_uint8 * 64)()
-                _lib.check(self.lib.nd_peer_alloc(self._bytes, ctypes.byref(base), handle), 'nd_peer_alloc')
-            self._base = int(base.value)
-            self._handle = bytes(handle)
-            seg = torch.as_tensor(_DevicePtr(self._base, self._bytes), device=self.device)
+            try:
+                with torch.cuda.device(self.device):
+                    base = ctypes.c_void_p()
+                    handle = (ctypes.c_uint8 * 64)()
+                    _lib.check(self.lib.nd_peer_alloc(self._bytes, ctypes.byref(base), handle), 'nd_peer_alloc')
+                self._base = int(base.value)
+                self._handle = bytes(handle)
+                seg = torch.as_tensor(_DevicePtr(self._base, self._bytes), device=self.device)
+            except Exception as e:
+                if self.world == 1 or _local_group is not None or not dist.is_initialized():
+                    raise
+                # a rank that cannot allocate / export still joins the collectives of _connect, which then fails on
+                # every rank together (its handle is None)
+                self._base, self._handle = None, None
+                self._alloc_error = e
+                self._connect()
+                raise AssertionError('unreachable: _connect raises when a handle is missing')
         self._seg = seg
         self.flags = seg[:4 * _lib.ND_PEER_FLAG_WORDS].view(torch.int32)
         self.acc = seg[self._off_acc:self._off_acc + 4 * (2 * cn + self.n_voxels)].view(torch.float32)
@@ -192,21 +202,43 @@ class PeerLift:
             return
         infos = [None] * self.world
         dist.all_gather_object(infos, (self._handle, self._bytes), group=self.group)
-        bases = []
-        with torch.cuda.device(self.device):
-            for g, (h, nbytes) in enumerate(infos):
-                if nbytes != self._bytes:
-                    raise RuntimeError(f'rank {g} built a segment of {nbytes} bytes, this rank {self._bytes}: shapes differ')
-                if g == self.rank:
-                    bases.append(self._base)
-                    continue
-                p = ctypes.c_void_p()
-                hb = (ctypes.c_uint8 * 64).from_buffer_copy(h)
-                self._lib.check(self.lib.nd_peer_open(hb, ctypes.byref(p)), f'nd_peer_open (segment of rank {g})')
-                self._opened.append(int(p.value))
-                bases.append(int(p.value))
+        bases, failure = [], None
+        try:
+            missing = [g for g, (h, _) in enumerate(infos) if h is None]
+            if missing:
+                raise RuntimeError(f'ranks {missing} could not allocate or export their segment'
+                                   + (f' ({self._alloc_error})' if self._handle is None else ''))
+            with torch.cuda.device(self.device):
+                for g, (h, nbytes) in enumerate(infos):
+                    if nbytes != self._bytes:
+                        raise RuntimeError(f'rank {g} built a segment of {nbytes} bytes, this rank {self._bytes}: shapes differ')
+                    if g == self.rank:
+                        bases.append(self._base)
+                        continue
+                    p = ctypes.c_void_p()
+                    hb = (ctypes.c_uint8 * 64).from_buffer_copy(h)
+                    self._lib.check(self.lib.nd_peer_open(hb, ctypes.byref(p)), f'nd_peer_open (segment of rank {g})')
+                    self._opened.append(int(p.value))
+                    bases.append(int(p.value))
+        except Exception as e:                  # keep the ranks in step: everybody learns about it in the reduction below
+            failure = e
+        # every rank reaches this collective whether or not its mappings succeeded; it is also the barrier that
+        # guarantees every segment is zeroed and mapped before the first epoch
+        ok = torch.tensor([0 if failure is not None else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            with torch.cuda.device(self.device):
+                for p in self._opened:
+                    self.lib.nd_peer_close(ctypes.c_void_p(p))
+                self._opened = []
+                dist.barrier(group=self.group)  # nobody frees a segment a peer still has mapped
+                self.flags = self.acc = self.mean = self.cov = self._seg = None
+                if self._base is not None:
+                    self.lib.nd_peer_free(ctypes.c_void_p(self._base))
+            self._base = None
+            raise RuntimeError('PeerLift: peer-memory segments could not be mapped on every rank'
+                               + (f' (this rank: {failure})' if failure is not None else ' (another rank failed)'))
         self._set_peers(bases)
-        dist.barrier(group=self.group)          # every segment is zeroed and mapped before the first epoch
 
     def _set_peers(self, bases):
         ctypes = self._ct
