@@ -118,3 +118,65 @@ def test_channel_shard_partitions_channels():
                 assert b == prev and e >= b and e - b in (c // world, c // world + 1)
                 prev = e
             assert prev == c
+
+
+# ---- the peer-memory exchange (csrc/peer.cu) as data movement: "segments every rank can read" = all_gather of the flat
+# accumulators, rank r reduces + finalises ONLY its channel slice in rank order, "stores into every rank" = all_gather of the
+# finished slices.  The CUDA kernel itself is tested on the GPU (tests/test_peer_gpu.py, tools/dist_check.py); this checks
+# that slice ownership + per-slice finalisation reproduces the lift over all views and leaves identical bits on every rank.
+def _peer_worker(rank, world, port, nv, channels, queue):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        cfg = SceneConfig(n_views=nv, n_voxels=(8, 8, 4), voxel_size=(0.8, 0.8, 0.8), channels=channels)
+        sc = make_scene(cfg, seed=23, with_images=False)
+        proj = lifting.compute_projection(sc.img_meta, 4)
+        pts = lifting.get_points(cfg.n_voxels, cfg.voxel_size, sc.img_meta['lidar2img']['origin'])
+        feats = sc.features[:, :, :59, :80]
+        n = 8 * 8 * 4
+        b, e = nd_dist.view_shard(nv, rank, world)
+        acc = oracle_accumulate(feats[b:e], pts, proj[b:e])
+        segments = [torch.empty_like(acc) for _ in range(world)]
+        dist.all_gather(segments, acc)                                            # peer-readable segments
+        c0, c1 = nd_dist.channel_shard(channels, rank, world)
+        s1 = sum(s[:channels * n].view(channels, n)[c0:c1] for s in segments)     # rank order, like the kernel
+        s2 = sum(s[channels * n:2 * channels * n].view(channels, n)[c0:c1] for s in segments)
+        cnt = sum(s[2 * channels * n:] for s in segments)
+        m_slice, c_slice, count = oracle_finalize(torch.cat([s1.reshape(-1), s2.reshape(-1), cnt]), nv, c1 - c0, n, None, True)
+        # rows stored into every rank's outputs: slices may have different sizes -> pad to the largest
+        width = -(-channels // world)
+        send = torch.zeros(2, width, n)
+        send[0, :c1 - c0], send[1, :c1 - c0] = m_slice, c_slice
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(recv, send)
+        mean = torch.cat([recv[r][0, :nd_dist.channel_shard(channels, r, world)[1] - nd_dist.channel_shard(channels, r, world)[0]]
+                          for r in range(world)])
+        cov = torch.cat([recv[r][1, :nd_dist.channel_shard(channels, r, world)[1] - nd_dist.channel_shard(channels, r, world)[0]]
+                         for r in range(world)])
+        m_ref, c_ref, n_ref = lo.lift_mean_var(feats, pts, proj)
+        chk = torch.stack([mean.double().sum(), cov.double().sum()])
+        lo_, hi_ = chk.clone(), chk.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        queue.put((rank, bool(torch.equal(count, n_ref.view(-1))), float((mean - m_ref.view(channels, n)).abs().max()),
+                   float((cov - c_ref.view(channels, n)).abs().max()), float(m_ref.abs().max()), bool(torch.equal(lo_, hi_))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('nv,channels', [(6, 6), (5, 7)])
+def test_peer_exchange_data_movement_two_gloo_ranks(nv, channels):
+    ctx = mp.get_context('spawn')
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, nv, channels, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [queue.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_cnt, e_mean, e_cov, scale, same in results:
+        assert ok_cnt and same, f'rank {rank}: counts differ or ranks hold different results'
+        assert e_mean <= 1e-5 * max(scale, 1.0) and e_cov <= 1e-5, (rank, e_mean, e_cov)
