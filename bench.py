@@ -164,7 +164,9 @@ def run_reference(args, rank):
         'impl': 'reference', 'metric': 'voxel_view_samples_per_sec', 'value': value, 'unit': 'samples/s',
         'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': dt * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(args.gpus),
+        # the same `config` as our arm prints for these flags (the CPU port itself lifts one scene of views_per_gpu views)
+        'config': workload_config(args.gpus, args.exchange if args.exchange != 'auto' else 'peer',
+                                  max(2, args.lanes) if args.gpus > 1 and args.exchange != 'nccl' and not args.no_pipeline else 0),
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
