@@ -407,7 +407,9 @@ __device__ __forceinline__ int ring_pad(int total_rows, int R, int nv, int v) {
 // entry of the active-view list: view | quad mask << 8 | ring row of oct A << 12 | ring row of oct B << 22
 constexpr int kPMaxRingRows = 1023;
 
-template <typename T, bool kRaw, bool kDiag, int kG>
+// kPf (experimental, ND_LIFT_PREFETCH=1, not the default): the consumers walk their list of ENTRIES instead of the stages
+// and fetch the offset rows of the next entry before they gather the current one, see the consumer loop.
+template <typename T, bool kRaw, bool kDiag, int kG, bool kPf = false>
 __global__ void __launch_bounds__((kPMaxWarps + 3) * 32, 1)
 k_lift_planes(const PlaneArgs a) {
     const int S = a.stages;                                        // stages of kG consecutive views each
@@ -655,6 +657,62 @@ k_lift_planes(const PlaneArgs a) {
         const uint32_t *ap = act;
         uint32_t ent = *ap;
 
+        if constexpr (kPf) {
+            // Entry-driven walk.  In the stage-driven loop below every view that sees the warp costs two dependent
+            // shared-memory round trips before its first gather (list entry -> offset rows -> plane), ~245 cycles per
+            // view on the busiest warp (half of its time, tools/sim_lift_smem.py).  Here the offset rows of the NEXT
+            // entry are requested before the gathers of the current one are issued (they are in the row ring as soon as
+            // their stage has landed, which is certain when it is the current stage and otherwise checked against the
+            // forwarder's counter), and stages the warp does not appear in are skipped with one progress update.
+            const int spu = (a.nv + kG - 1) / kG;
+            const uint32_t g0 = gi;                                 // global index of this unit's first stage
+            int cur_j = 0;                                          // stage of the unit the warp stands at: gi == g0 + cur_j
+            uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = make_uint4(0u, 0u, 0u, 0u);
+            bool have = false;                                      // c0 / c1 already hold the rows of `ent`
+            while ((ent & 0xffu) != 0xffu) {
+                const int v = (int)(ent & 0xffu), j = v / kG, g = v % kG;
+                if (j != cur_j) {                                   // every stage before j is done for this warp
+                    s = (s + (j - cur_j)) % S;
+                    sb = sm_base + (uint32_t)s * stage_pitch;
+                    cur_j = j;
+                    gi = g0 + (uint32_t)j;
+                    __syncwarp();
+                    if (lane == 0) st_release(my_progress, gi);
+                }
+                if (!have) {
+                    while (ready <= gi) ready = ld_acquire(f_ready);
+                    if (ent & 0x300u) c0 = lds_u4(lane_row + ((ent >> 12) & 0x3ffu) * kRowBytes);
+                    if (ent & 0xc00u) c1 = lds_u4(lane_row + (ent >> 22) * kRowBytes);
+                }
+                const uint32_t pb = sb + (uint32_t)g * a.plane_pitch;
+                const uint32_t nxt = *++ap;
+                uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = make_uint4(0u, 0u, 0u, 0u);
+                bool nhave = false;
+                if ((nxt & 0xffu) != 0xffu) {
+                    const uint32_t gn = g0 + (nxt & 0xffu) / kG;
+                    if (gn != gi && ready <= gn) ready = ld_acquire(f_ready);      // one look, no spinning
+                    if (gn == gi || ready > gn) {
+                        if (nxt & 0x300u) n0 = lds_u4(lane_row + ((nxt >> 12) & 0x3ffu) * kRowBytes);
+                        if (nxt & 0xc00u) n1 = lds_u4(lane_row + (nxt >> 22) * kRowBytes);
+                        nhave = true;
+                    }
+                }
+                if (ent & 0x100u) gather_quad<T>(pb, c0.x, c0.y, s1[0], s2[0], s1[1], s2[1]);
+                if (ent & 0x200u) gather_quad<T>(pb, c0.z, c0.w, s1[2], s2[2], s1[3], s2[3]);
+                if (ent & 0x400u) gather_quad<T>(pb, c1.x, c1.y, s1[4], s2[4], s1[5], s2[5]);
+                if (ent & 0x800u) gather_quad<T>(pb, c1.z, c1.w, s1[6], s2[6], s1[7], s2[7]);
+                c0 = n0;
+                c1 = n1;
+                have = nhave;
+                ent = nxt;
+            }
+            // the rest of the unit's stages hold nothing for this warp
+            s = (s + (spu - cur_j)) % S;
+            sb = sm_base + (uint32_t)s * stage_pitch;
+            gi = g0 + (uint32_t)spu;
+            __syncwarp();
+            if (lane == 0) st_release(my_progress, gi);
+        } else
         for (int v0 = 0; v0 < a.nv; v0 += kG) {
             const long long tc0 = kDiag && a.trace != nullptr ? clock64() : 0;
             while (ready <= gi) ready = ld_acquire(f_ready);       // the forwarder publishes the number of landed stages
@@ -990,6 +1048,9 @@ nd_status run_lift_planes(const nd_maps *f, const float *points, const float *pr
         case 2: kern = diag ? k_lift_planes<T, kRaw, true, 2> : k_lift_planes<T, kRaw, false, 2>; break;
         default: kern = diag ? k_lift_planes<T, kRaw, true, 4> : k_lift_planes<T, kRaw, false, 4>; break;
     }
+    // experimental consumer loop (not validated on a GPU yet; opt-in for the next round's A/B, bench shape only: kG = 2)
+    if (!diag && g.group == 2 && getenv("ND_LIFT_PREFETCH") != nullptr && atoi(getenv("ND_LIFT_PREFETCH")) == 1)
+        kern = k_lift_planes<T, kRaw, false, 2, true>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
     if (e != cudaSuccess) {
         set_error("k_lift_planes: cannot reserve %zu bytes of shared memory: %s", g.smem_bytes, cudaGetErrorString(e));
