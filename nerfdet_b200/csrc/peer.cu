@@ -78,10 +78,6 @@ __device__ __forceinline__ bool spin_until(const uint32_t *p, uint32_t epoch) {
     return true;
 }
 
-template <int V> struct VecT;
-template <> struct VecT<4> { using type = float4; };
-template <> struct VecT<1> { using type = float; };
-
 template <int V> __device__ __forceinline__ void ld_vec(const float *p, float (&r)[V]);
 template <> __device__ __forceinline__ void ld_vec<4>(const float *p, float (&r)[4]) {
     const float4 t = __ldcg(reinterpret_cast<const float4 *>(p));
