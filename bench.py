@@ -253,7 +253,8 @@ def main():
     if exchange in ('auto', 'multicast'):
         err = ''
         try:
-            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, transport='multicast', overlap_sms=overlap_sms) for _ in range(n_lanes + 2)]
+            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, transport='multicast', overlap_sms=overlap_sms if i < n_lanes else 0)
+                     for i in range(n_lanes + 2)]
         except Exception as e:                                 # no NVLS on this box / symmetric memory unavailable
             err = f'{type(e).__name__}: {e}'
         ok = torch.tensor([1 if peers is not None else 0], device=dev)
@@ -269,7 +270,9 @@ def main():
             exchange = 'peer'
     if exchange == 'peer':
         try:
-            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, overlap_sms=overlap_sms) for _ in range(n_lanes + 2)]
+            # the last two segments serve the end-to-end lanes: host-link bound, exchange on the whole GPU (4.71 vs 5.43 ms/step at 2 GPUs)
+            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, overlap_sms=overlap_sms if i < n_lanes else 0)
+                     for i in range(n_lanes + 2)]
         except RuntimeError as e:
             # PeerLift fails on ALL ranks together (it reduces a success flag) when CUDA IPC / peer access is not available
             # between these GPUs; the all-reduce form of the same exchange (NCCL + our finalise kernel) still runs
