@@ -19,7 +19,8 @@ def _declared():
 def test_header_declares_entry_points():
     names = _declared()
     for must in ('nd_version', 'nd_last_error_string', 'nd_project_voxels', 'nd_backproject',
-                 'nd_lift_mean_var', 'nd_lift_accumulate', 'nd_lift_finalize'):
+                 'nd_lift_mean_var', 'nd_lift_accumulate', 'nd_lift_finalize', 'nd_lift_finalize_peers',
+                 'nd_peer_alloc', 'nd_peer_open', 'nd_peer_close', 'nd_peer_free'):
         assert must in names
 
 
@@ -55,3 +56,20 @@ def test_host_geometry_matches_golden():
         pts = lifting.get_points(inp['n_voxels'], inp['voxel_size'], inp['img_meta']['lidar2img']['origin'])
         assert np.array_equal(proj.numpy(), g['projection'])
         assert np.array_equal(pts.numpy(), g['points'])
+
+
+def test_peer_entry_points_validate_arguments_without_a_gpu():
+    """Argument checks of the multi-GPU exchange entry run before any CUDA call: they must answer with status codes
+    (and a message) on a machine without a GPU, never crash."""
+    from nerfdet_b200 import _lib
+    lib = _lib.load()
+    null = ctypes.POINTER(ctypes.c_void_p)()
+    args = (1, 0, 1, 4, 2, 8, None, None, None, None, None, 0, None)
+    assert lib.nd_lift_finalize_peers(null, null, null, null, *args) == 1                 # ND_ERR_BAD_ARG: no tables
+    assert b'null' in lib.nd_last_error_string()
+    one = (ctypes.c_void_p * 1)(ctypes.c_void_p(256))
+    assert lib.nd_lift_finalize_peers(one, one, None, one, 9, 0, 1, 4, 2, 8, None, None, None, None, None, 0, None) == 1
+    assert b'world' in lib.nd_last_error_string()                                         # more ranks than ND_MAX_PEERS
+    assert lib.nd_lift_finalize_peers(one, one, None, one, 1, 0, 0, 4, 2, 8, None, None, None, None, None, 0, None) == 1
+    assert b'epoch' in lib.nd_last_error_string()                                         # epoch 0 = initial flag state
+    assert lib.nd_peer_close(None) == 0 and lib.nd_peer_free(None) == 0
