@@ -71,9 +71,10 @@ typedef struct nd_lift_options {
     int32_t grid_x, grid_y, grid_z; /* optional: the voxel lattice behind `points` (Z fastest, X*Y*Z == n_voxels),
                                       as in get_points (nerfdet.py:381-390); lets the plane-resident kernel
                                       use spatially compact warp tiles.  0 = unknown (results are identical) */
-    int32_t sm_limit;              /* plane-resident kernel: occupy at most this many SMs (0 = all); the kernel also never uses
-                                      more CTAs than it needs for its number of rounds (512 units on 148 SMs take 4 rounds,
-                                      which 128 CTAs do as well) */
+    int32_t sm_limit;              /* plane-resident kernel: occupy at most this many SMs (0 = all), e.g. to leave room
+                                      for a concurrent exchange kernel */
+    int32_t views_per_stage;       /* plane-resident kernel: views per pipeline stage, 1 / 2 / 4 (0 = default 2) */
+    int32_t stages;                /* plane-resident kernel: pipeline stages, 2..8 (0 = as many as fit) */
 } nd_lift_options;
 
 int nd_version(void);
@@ -118,6 +119,36 @@ int nd_lift_launch_count(const nd_maps *features, int64_t n_voxels, const nd_lif
 int nd_lift_mean_var(const nd_maps *features, const float *points, const float *projection,
                      int64_t n_voxels, const float *alpha, float *mean, float *cov, int64_t *count,
                      void *workspace, size_t workspace_bytes, const nd_lift_options *opt, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The same in two steps: the GEOMETRY PLAN (everything that depends on points / projection / depth only: pixel
+ * offsets, view counts, frustum culling, work distribution) is built once and reused for every feature stack lifted
+ * with the same cameras and lattice -- nerfdet.py:155-160 recomputes projection and points per scene, so one plan per
+ * scene; several lifts of one scene (features + any further stack, both GPUs' halves of a sharded lift, a fixed camera
+ * rig) share it.
+ *   nd_lift_plan_bytes   size of the caller-owned plan buffer (256-byte aligned); 0 = these maps are not eligible for
+ *                        the plane-resident kernel (non-contiguous planes, planes > 64 KB, > 254 views, > 524288 voxels):
+ *                        use nd_lift_mean_var, which then takes the staged path.  Only dtype / shape / strides of
+ *                        `features` are read.
+ *   nd_lift_plan_build   depth_resized f32 [nv][height][width] or NULL and voxel_z: the depth gate of nerfdet.py:405-411.
+ *   nd_lift_plan_mean_var / nd_lift_plan_accumulate   outputs as nd_lift_mean_var / nd_lift_accumulate.
+ *     launch_index: number of nd_lift_plan_* launches already issued on this plan buffer since nd_lift_plan_build,
+ *       counted by the caller (0, 1, 2, ...; the library keeps no state).  All launches on one plan must use the same
+ *       channel count and options, and be issued on one stream (or otherwise ordered).
+ *     n_views_total: divisor-side view count of the all-view variance (0 = the plan's own view count).
+ * Consecutive launches overlap through programmatic dependent launch: a launch reads its inputs as soon as SMs are
+ * free and waits for its predecessor only before its first write.
+ * ------------------------------------------------------------------------------------- */
+size_t nd_lift_plan_bytes(const nd_maps *features, int64_t n_voxels, const nd_lift_options *opt);
+int nd_lift_plan_build(const nd_maps *features, const float *points, const float *projection, int64_t n_voxels,
+                       const float *depth_resized, float voxel_z, void *plan, size_t plan_bytes,
+                       const nd_lift_options *opt, void *stream);
+int nd_lift_plan_mean_var(const nd_maps *features, const void *plan, size_t plan_bytes, int64_t n_voxels,
+                          uint32_t launch_index, int n_views_total, const float *alpha, float *mean, float *cov,
+                          int64_t *count, const nd_lift_options *opt, void *stream);
+int nd_lift_plan_accumulate(const nd_maps *features, const void *plan, size_t plan_bytes, int64_t n_voxels,
+                            uint32_t launch_index, float *s1, float *s2, float *cnt, const nd_lift_options *opt,
+                            void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * View-sharded form of the same: each rank runs nd_lift_accumulate on

@@ -23,7 +23,8 @@ class NdMaps(ctypes.Structure):
 
 class NdLiftOptions(ctypes.Structure):
     _fields_ = [('scratch_budget_bytes', c_size_t), ('voxels_per_cta', c_int32), ('path', c_int32),
-                ('grid_x', c_int32), ('grid_y', c_int32), ('grid_z', c_int32), ('sm_limit', c_int32)]
+                ('grid_x', c_int32), ('grid_y', c_int32), ('grid_z', c_int32), ('sm_limit', c_int32),
+                ('views_per_stage', c_int32), ('stages', c_int32)]
 
 
 class NdMlpWeights(ctypes.Structure):
@@ -50,6 +51,13 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_size_t, POINTER(NdLiftOptions), c_void_p]),
     'nd_lift_accumulate': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_size_t, POINTER(NdLiftOptions), c_void_p]),
+    'nd_lift_plan_bytes': (c_size_t, [POINTER(NdMaps), c_int64, POINTER(NdLiftOptions)]),
+    'nd_lift_plan_build': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int64, c_void_p, c_float, c_void_p, c_size_t,
+                                   POINTER(NdLiftOptions), c_void_p]),
+    'nd_lift_plan_mean_var': (c_int, [POINTER(NdMaps), c_void_p, c_size_t, c_int64, ctypes.c_uint32, c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, POINTER(NdLiftOptions), c_void_p]),
+    'nd_lift_plan_accumulate': (c_int, [POINTER(NdMaps), c_void_p, c_size_t, c_int64, ctypes.c_uint32, c_void_p, c_void_p,
+                                        c_void_p, POINTER(NdLiftOptions), c_void_p]),
     'nd_lift_finalize': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
     'nd_peer_alloc': (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),

@@ -405,7 +405,16 @@ __global__ void k_backproject(const T *__restrict__ in, int64_t sv, int64_t sc, 
 // ======================================================================================
 // Host side
 // ======================================================================================
-// plane-resident path (lift_planes.cu)
+// plane-resident path (lift_quads.cu)
+bool lift_quads_eligible(const nd_maps *f, int64_t n_vox, const nd_lift_options *opt);
+size_t lift_quads_plan_bytes(const nd_maps *f, int64_t n_vox, const nd_lift_options *opt);
+nd_status lift_quads_plan_build(const nd_maps *f, const float *points, const float *proj, int64_t n_vox, const float *depth,
+                                float voxel_z, void *plan, size_t plan_bytes, const nd_lift_options *opt, cudaStream_t st);
+template <typename T, bool kRaw>
+nd_status lift_quads_run(const nd_maps *f, const void *plan, size_t plan_bytes, int64_t n_vox, uint32_t launch_index,
+                         int n_views_total, const float *alpha, float *out_a, float *out_b, int64_t *count_i64,
+                         float *count_f32, const nd_lift_options *opt, cudaStream_t st);
+// round-1 plane-resident kernel (lift_planes.cu), path == 2: kept for one A/B run, then removed
 bool lift_planes_eligible(const nd_maps *f, int64_t n_vox, const nd_lift_options *opt);
 size_t lift_planes_workspace_bytes(const nd_maps *f, int64_t n_vox, const nd_lift_options *opt);
 template <typename T, bool kRaw>
@@ -418,7 +427,8 @@ static size_t scratch_budget(const nd_lift_options *opt) {
 }
 
 struct LiftPlan {
-    bool planes;            // plane-resident path (lift_planes.cu): contiguous NCHW planes in shared memory
+    bool quads;             // plane-resident path (lift_quads.cu): contiguous NCHW planes in shared memory
+    bool planes;            // round-1 kernel (A/B only)
     int nv, nvp, c, h, w, n_pix;
     int elt;                // bytes per feature element
     bool direct;            // features already pixel-major (channels-last): no staging
@@ -457,7 +467,13 @@ static LiftPlan make_plan(const nd_maps *f, int64_t n_vox, const nd_lift_options
                (f->stride_y / f->stride_x) * (int64_t)p.h < (1ll << 30) && p.c % 32 == 0 && p.c <= 256 &&
                (p.c == 32 || p.c == 64 || p.c == 128 || p.c == 256);
     const bool force_staged = opt != nullptr && opt->path == ND_LIFT_PATH_STAGED;
-    p.planes = !p.direct && !force_staged && lift_planes_eligible(f, n_vox, opt);
+    const bool v1 = opt != nullptr && opt->path == 2;
+    p.quads = !p.direct && !force_staged && !v1 && lift_quads_eligible(f, n_vox, opt);
+    if (p.quads) {
+        p.total_bytes = lift_quads_plan_bytes(f, n_vox, opt);
+        return p;
+    }
+    p.planes = !p.direct && !force_staged && v1 && lift_planes_eligible(f, n_vox, opt);
     if (p.planes) {
         p.total_bytes = lift_planes_workspace_bytes(f, n_vox, opt);
         return p;
@@ -489,13 +505,8 @@ static nd_status launch_gather(const GatherArgs &ga, cudaStream_t st) {
     constexpr int kChunk = 32 * CPL;
     const size_t smem = (size_t)2 * kChunk * (kTileVox + 1) * sizeof(float);
     auto kern = k_lift_gather<T, CPL, kRaw>;
-    if (smem > 48 * 1024) {
-        static bool done = false;      // idempotent attribute; benign if set twice
-        if (!done) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            done = true;
-        }
-    }
+    if (smem > 48 * 1024)              // per device and idempotent: set on every call (no process-wide state)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned grid = (unsigned)ceil_div(ga.n_vox, kTileVox);
     kern<<<grid, kGatherThreads, smem, st>>>(ga);
     ND_CUDA_LAUNCH_CHECK("k_lift_gather");
@@ -535,6 +546,15 @@ static nd_status run_lift(const nd_maps *f, const float *points, const float *pr
                           const float *alpha, float *out_a, float *out_b, int64_t *count_i64, float *count_f32,
                           void *ws, size_t ws_bytes, const nd_lift_options *opt, cudaStream_t st) {
     const LiftPlan p = make_plan(f, n_vox, opt);
+    if (p.quads) {
+        // one-shot form: the caller's workspace holds the geometry plan of this call
+        ND_REQUIRE(ws != nullptr && ws_bytes >= p.total_bytes, ND_ERR_WORKSPACE,
+                   "lift: workspace too small (%zu < %zu bytes)", ws_bytes, p.total_bytes);
+        nd_status s = lift_quads_plan_build(f, points, proj, n_vox, nullptr, 0.0f, ws, ws_bytes, opt, st);
+        if (s != ND_OK) return s;
+        return lift_quads_run<T, kRaw>(f, ws, ws_bytes, n_vox, 0u, f->n_views, alpha, out_a, out_b, count_i64, count_f32,
+                                       opt, st);
+    }
     if (p.planes)
         return run_lift_planes<T, kRaw>(f, points, proj, n_vox, alpha, out_a, out_b, count_i64, count_f32, ws, ws_bytes, opt,
                                         st);
@@ -632,7 +652,7 @@ size_t nd_lift_workspace_bytes(const nd_maps *f, int64_t n_voxels, const nd_lift
 int nd_lift_launch_count(const nd_maps *f, int64_t n_voxels, const nd_lift_options *opt) {
     if (validate_maps(f, "nd_lift_launch_count") != ND_OK || n_voxels < 0) return -1;
     const LiftPlan p = make_plan(f, n_voxels, opt);
-    if (p.planes) return 3;   // k_plane_index, k_plane_pack, k_lift_planes
+    if (p.quads || p.planes) return 3;   // k_q_index, k_q_pack, k_lift_quads
     if (p.direct) return 2;
     return 1 + 2 * p.n_chunks;
 }
@@ -667,6 +687,53 @@ int nd_lift_accumulate(const nd_maps *f, const float *points, const float *proje
                                      workspace_bytes, opt, st);
     return run_lift<__nv_bfloat16, true>(f, points, projection, n_voxels, nullptr, s1, s2, nullptr, cnt, workspace,
                                          workspace_bytes, opt, st);
+}
+
+size_t nd_lift_plan_bytes(const nd_maps *f, int64_t n_voxels, const nd_lift_options *opt) {
+    if (f == nullptr || n_voxels <= 0 || f->n_views <= 0 || f->channels <= 0 || f->height <= 0 || f->width <= 0) return 0;
+    if (f->dtype != ND_F32 && f->dtype != ND_BF16) return 0;
+    if (opt != nullptr && opt->path == ND_LIFT_PATH_STAGED) return 0;
+    return lift_quads_plan_bytes(f, n_voxels, opt);
+}
+
+int nd_lift_plan_build(const nd_maps *f, const float *points, const float *projection, int64_t n_voxels,
+                       const float *depth_resized, float voxel_z, void *plan, size_t plan_bytes,
+                       const nd_lift_options *opt, void *stream) {
+    ND_REQUIRE(f != nullptr && points && projection && plan, ND_ERR_BAD_ARG, "nd_lift_plan_build: null pointer");
+    ND_REQUIRE(f->dtype == ND_F32 || f->dtype == ND_BF16, ND_ERR_BAD_ARG, "nd_lift_plan_build: unsupported dtype %d", f->dtype);
+    ND_REQUIRE(f->n_views > 0 && f->channels > 0 && f->height > 0 && f->width > 0 && n_voxels > 0, ND_ERR_BAD_SHAPE,
+               "nd_lift_plan_build: empty input");
+    return lift_quads_plan_build(f, points, projection, n_voxels, depth_resized, voxel_z, plan, plan_bytes, opt,
+                                 (cudaStream_t)stream);
+}
+
+int nd_lift_plan_mean_var(const nd_maps *f, const void *plan, size_t plan_bytes, int64_t n_voxels, uint32_t launch_index,
+                          int n_views_total, const float *alpha, float *mean, float *cov, int64_t *count,
+                          const nd_lift_options *opt, void *stream) {
+    nd_status s = validate_maps(f, "nd_lift_plan_mean_var");
+    if (s != ND_OK) return s;
+    ND_REQUIRE(plan && mean && count, ND_ERR_BAD_ARG, "nd_lift_plan_mean_var: null pointer");
+    ND_REQUIRE(n_voxels > 0 && n_views_total >= 0, ND_ERR_BAD_SHAPE, "nd_lift_plan_mean_var: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f->dtype == ND_F32)
+        return lift_quads_run<float, false>(f, plan, plan_bytes, n_voxels, launch_index, n_views_total, alpha, mean, cov,
+                                            count, nullptr, opt, st);
+    return lift_quads_run<__nv_bfloat16, false>(f, plan, plan_bytes, n_voxels, launch_index, n_views_total, alpha, mean,
+                                                cov, count, nullptr, opt, st);
+}
+
+int nd_lift_plan_accumulate(const nd_maps *f, const void *plan, size_t plan_bytes, int64_t n_voxels, uint32_t launch_index,
+                            float *s1, float *s2, float *cnt, const nd_lift_options *opt, void *stream) {
+    nd_status s = validate_maps(f, "nd_lift_plan_accumulate");
+    if (s != ND_OK) return s;
+    ND_REQUIRE(plan && s1 && s2 && cnt, ND_ERR_BAD_ARG, "nd_lift_plan_accumulate: null pointer");
+    ND_REQUIRE(n_voxels > 0, ND_ERR_BAD_SHAPE, "nd_lift_plan_accumulate: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f->dtype == ND_F32)
+        return lift_quads_run<float, true>(f, plan, plan_bytes, n_voxels, launch_index, 0, nullptr, s1, s2, nullptr, cnt,
+                                           opt, st);
+    return lift_quads_run<__nv_bfloat16, true>(f, plan, plan_bytes, n_voxels, launch_index, 0, nullptr, s1, s2, nullptr,
+                                               cnt, opt, st);
 }
 
 int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_views_total, int channels,

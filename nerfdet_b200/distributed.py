@@ -31,7 +31,7 @@ def view_shard(n_views: int, rank: int, world_size: int) -> Tuple[int, int]:
 
 def _cuda_accumulate(features, points, projection):
     from . import ops
-    return ops.lift_accumulate(features, points, projection, 0)
+    return ops.lift_accumulate_planned(features, points, projection)
 
 
 def _cuda_finalize(acc, n_views_total, channels, n_voxels, alpha, want_cov):
@@ -298,7 +298,7 @@ class PeerLift:
         sm_limit = 0
         if self.overlap_sms:
             sm_limit = max(torch.cuda.get_device_properties(self.device).multi_processor_count - self.overlap_sms, 1)
-        ops.lift_accumulate_into(features_local, points, projection_local, self.acc, sm_limit)
+        ops.lift_accumulate_planned(features_local, points, projection_local, self.acc, sm_limit)
         mean, cov, count = self.exchange(n_views_total, alpha)
         shape = tuple(points.shape[1:]) if points.dim() == 4 else (self.n_voxels,)
         return (mean.view(self.channels, *shape), cov.view(self.channels, *shape) if cov is not None else None,

@@ -11,6 +11,7 @@
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -92,15 +93,45 @@ def backproject(features, points, projection, depth, voxel_size):
 
 
 def lift_mean_var(features, points, projection, alpha: Optional[torch.Tensor] = None,
-                  want_cov: bool = True, scratch_budget_bytes: int = 0):
+                  want_cov: bool = True, scratch_budget_bytes: int = 0, depth: Optional[torch.Tensor] = None,
+                  voxel_size: Optional[Sequence[float]] = None):
     """Fused nerfdet.py:164-181.  Returns
     ``volume_mean [C,X,Y,Z]`` (times ``alpha`` per voxel when given, nerfdet.py:259-261),
     ``volume_cov [C,X,Y,Z]`` = exp(-var) (None when ``want_cov`` is False) and
-    ``valid [1,X,Y,Z]`` int64 view counts."""
+    ``valid [1,X,Y,Z]`` int64 view counts.
+
+    ``depth [nv, H, W]`` with ``voxel_size`` applies the depth gate of ``backproject`` (nerfdet.py:405-411): the
+    bilinear resize to the feature resolution stays ``F.interpolate`` like the reference, the gate itself runs in
+    the geometry pass.  The geometry (pixel offsets, counts, work distribution) is planned once per
+    (points, projection, depth) tensor identity and reused (``ops.cached_lift_plan``); ``scratch_budget_bytes`` > 0
+    forces the generic staged path instead."""
+    if any(t is not None and t.requires_grad for t in (features, alpha)):
+        raise RuntimeError('lift_mean_var is forward-only: detach() the inputs (the backward of the lift is not built)')
     c = features.shape[1]
     gx, gy, gz = points.shape[-3:]
-    mean, cov, count = ops.lift_mean_var(features, points, projection,
-                                         alpha.reshape(-1) if alpha is not None else None,
-                                         want_cov, scratch_budget_bytes)
+    al = alpha.reshape(-1) if alpha is not None else None
+    if scratch_budget_bytes > 0:
+        if depth is not None:
+            raise NotImplementedError('the depth gate is not available on the staged path')
+        mean, cov, count = ops.lift_mean_var(features, points, projection, al, want_cov, scratch_budget_bytes)
+    else:
+        depth_resized, voxel_z = None, 0.0
+        if depth is not None:
+            if voxel_size is None:
+                raise ValueError('depth needs voxel_size (the gate is |z - depth| < voxel_size[-1])')
+            key = id(depth)
+            ent = _DEPTH_CACHE.get(key)
+            if ent is None or ent[0]() is not depth or ent[1] != depth._version or ent[3] != tuple(features.shape[-2:]):
+                resized = F.interpolate(depth.unsqueeze(1), size=tuple(features.shape[-2:]), mode='bilinear').squeeze(1)
+                if len(_DEPTH_CACHE) > 8:
+                    _DEPTH_CACHE.clear()
+                ent = (weakref.ref(depth), depth._version, resized, tuple(features.shape[-2:]))
+                _DEPTH_CACHE[key] = ent
+            depth_resized, voxel_z = ent[2], float(voxel_size[-1])
+        mean, cov, count = ops.lift_mean_var_planned(features, points, projection, al, want_cov, depth_resized, voxel_z)
     return (mean.view(c, gx, gy, gz), cov.view(c, gx, gy, gz) if want_cov else None,
             count.view(1, gx, gy, gz))
+
+
+# resized depth maps, kept per depth tensor so that the geometry plan (keyed on tensor identity) is found again
+_DEPTH_CACHE = {}

@@ -5,7 +5,11 @@ Each op validates shapes / dtypes / devices in Python (the reference itself only
 on ``torch.cuda.current_stream()``.  CUDA tensors only -- there is no CPU path."""
 from __future__ import annotations
 
+import contextlib
 import ctypes
+import functools
+import weakref
+from collections import OrderedDict
 from typing import List, Optional, Tuple
 
 import torch
@@ -17,14 +21,43 @@ from ._lib import ND_BF16, ND_F32, NdLiftOptions, NdMaps
 _NS = 'nerfdet_b200'
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None) -> int:
+    """The current stream OF THE TENSORS' DEVICE (not of the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def _need_cuda(*tensors: Optional[Tensor]):
+    """All given tensors live on ONE CUDA device; returns it."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError('nerfdet_b200 ops run on CUDA tensors only (no CPU fallback)')
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f'nerfdet_b200 ops need all tensors on one device, got {dev} and {t.device}')
+    return dev
+
+
+def _guarded(fn):
+    """Runs an op with its tensors' device current (grids, function attributes and the stream are per device)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = next((a.device for a in args if isinstance(a, Tensor) and a.is_cuda), None)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+def _on(device):
+    """Makes ``device`` current for the body: the C side sizes grids and sets function attributes per current device."""
+    if device is None or device.index == torch.cuda.current_device():
+        return contextlib.nullcontext()
+    return torch.cuda.device(device)
 
 
 def _ptr(t: Optional[Tensor]):
@@ -60,15 +93,165 @@ def _flat_points(points: Tensor) -> Tuple[Tensor, Tuple[int, int, int]]:
     return points.reshape(3, -1).contiguous(), grid
 
 
-def _options(scratch_budget_bytes: int, grid=(0, 0, 0), sm_limit: int = 0) -> NdLiftOptions:
+def _options(scratch_budget_bytes: int, grid=(0, 0, 0), sm_limit: int = 0, views_per_stage: int = 0,
+             stages: int = 0, path: Optional[int] = None) -> NdLiftOptions:
     """``scratch_budget_bytes`` > 0 selects the generic staged path (any strides) with that much
     L2-resident staging; 0 = automatic (plane-resident kernel for contiguous NCHW planes)."""
-    path = _lib.ND_LIFT_PATH_STAGED if scratch_budget_bytes > 0 else _lib.ND_LIFT_PATH_AUTO
-    return NdLiftOptions(max(scratch_budget_bytes, 0), 0, path, int(grid[0]), int(grid[1]), int(grid[2]), int(sm_limit))
+    if path is None:
+        path = _lib.ND_LIFT_PATH_STAGED if scratch_budget_bytes > 0 else _lib.ND_LIFT_PATH_AUTO
+    return NdLiftOptions(max(scratch_budget_bytes, 0), 0, path, int(grid[0]), int(grid[1]), int(grid[2]), int(sm_limit),
+                         int(views_per_stage), int(stages))
+
+
+# ------------------------------------------------------------------------------------------
+# Geometry plan of the fused lift (nd_lift_plan_*): everything that depends on points / projection / depth only.
+# ------------------------------------------------------------------------------------------
+class LiftPlan:
+    """Pixel offsets, view counts, frustum culling and work distribution of one (points, projection[, depth]) geometry
+    for one feature layout, built once on the GPU (``nd_lift_plan_build``) and reused by every lift with these
+    cameras.  ``LiftPlan.eligible`` is False when the maps cannot take the plane-resident kernel (then use
+    ``lift_mean_var``, which falls back to the staged path).
+
+    A plan belongs to ONE stream: its launches hand out work through a running ticket counter inside the plan
+    buffer and overlap back to back (programmatic dependent launch), so they must be issued in order."""
+
+    def __init__(self, features: Tensor, points: Tensor, projection: Tensor, depth_resized: Optional[Tensor] = None,
+                 voxel_z: float = 0.0, sm_limit: int = 0, views_per_stage: int = 0, stages: int = 0):
+        self.device = _need_cuda(features, points, projection, depth_resized)
+        m = _maps(features)
+        _check_geometry(points, projection, m.n_views)
+        pts, grid = _flat_points(points)
+        self.n_voxels = pts.shape[1]
+        self.layout = _layout_key(features)
+        self.opt = _options(0, grid, sm_limit, views_per_stage, stages)
+        self.launches = 0
+        self.stream = None
+        lib = _lib.load()
+        with _on(self.device):
+            self.bytes = int(lib.nd_lift_plan_bytes(ctypes.byref(m), self.n_voxels, ctypes.byref(self.opt)))
+            self.eligible = self.bytes > 0
+            if not self.eligible:
+                return
+            if depth_resized is not None:
+                if depth_resized.dtype != torch.float32 or tuple(depth_resized.shape) != (m.n_views, m.height, m.width):
+                    raise ValueError('depth_resized must be float32 [n_views, H, W] at the feature resolution')
+                depth_resized = depth_resized.contiguous()
+            self.buf = torch.empty((self.bytes,), dtype=torch.uint8, device=self.device)
+            self.stream = _stream(self.device)
+            _lib.check(lib.nd_lift_plan_build(ctypes.byref(m), _ptr(pts), _ptr(projection.contiguous()), self.n_voxels,
+                                              _ptr(depth_resized), float(voxel_z), _ptr(self.buf), self.bytes,
+                                              ctypes.byref(self.opt), self.stream), 'nd_lift_plan_build')
+
+    def _launch_index(self, features: Tensor) -> int:
+        if _layout_key(features) != self.layout:
+            raise ValueError('LiftPlan: feature layout (shape / strides / dtype) differs from the one the plan was built for')
+        if _stream(self.device) != self.stream:
+            raise RuntimeError('LiftPlan: a plan must be used on the stream it was built on (one plan per stream)')
+        i = self.launches
+        self.launches = (i + 1) & 0xffffffff
+        return i
+
+    def mean_var(self, features: Tensor, alpha: Optional[Tensor] = None, want_cov: bool = True,
+                 n_views_total: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
+        """mean f32 [C, N] (times alpha), exp(-var) f32 [C, N] (empty unless ``want_cov``), count int64 [N]."""
+        m = _maps(features)
+        n, dev = self.n_voxels, self.device
+        if alpha is not None:
+            if alpha.dtype != torch.float32 or alpha.numel() != n or alpha.device != dev:
+                raise ValueError('alpha must be float32 with one value per voxel')
+            alpha = alpha.contiguous()
+        with _on(dev):
+            mean = torch.empty((m.channels, n), dtype=torch.float32, device=dev)
+            cov = torch.empty((m.channels, n) if want_cov else (0,), dtype=torch.float32, device=dev)
+            count = torch.empty((n,), dtype=torch.int64, device=dev)
+            _lib.check(_lib.load().nd_lift_plan_mean_var(
+                ctypes.byref(m), _ptr(self.buf), self.bytes, n, self._launch_index(features), int(n_views_total),
+                _ptr(alpha), _ptr(mean), _ptr(cov) if want_cov else None, _ptr(count), ctypes.byref(self.opt),
+                self.stream), 'nd_lift_plan_mean_var')
+        return mean, cov, count
+
+    def accumulate_into(self, features: Tensor, acc: Tensor) -> None:
+        """[S1 (C*N) | S2 (C*N) | count (N)] of this rank's views into the caller-owned flat f32 buffer ``acc``."""
+        m = _maps(features)
+        c, n = m.channels, self.n_voxels
+        if acc.dtype != torch.float32 or acc.numel() != (2 * c + 1) * n or not acc.is_contiguous() or acc.device != self.device:
+            raise ValueError(f'acc must be a contiguous float32 buffer of (2 * {c} + 1) * {n} elements')
+        base = acc.data_ptr()
+        with _on(self.device):
+            _lib.check(_lib.load().nd_lift_plan_accumulate(
+                ctypes.byref(m), _ptr(self.buf), self.bytes, n, self._launch_index(features), ctypes.c_void_p(base),
+                ctypes.c_void_p(base + 4 * c * n), ctypes.c_void_p(base + 8 * c * n), ctypes.byref(self.opt),
+                self.stream), 'nd_lift_plan_accumulate')
+
+
+def _layout_key(features: Tensor):
+    return (tuple(features.shape), tuple(features.stride()), features.dtype, features.data_ptr() % 16)
+
+
+_PLAN_CACHE: 'OrderedDict[tuple, tuple]' = OrderedDict()
+_PLAN_CACHE_SIZE = 16
+
+
+def cached_lift_plan(features: Tensor, points: Tensor, projection: Tensor, depth_resized: Optional[Tensor] = None,
+                     voxel_z: float = 0.0, sm_limit: int = 0) -> LiftPlan:
+    """The plan of this geometry, built on first use.  The key is the IDENTITY (and in-place version) of the
+    ``points`` / ``projection`` / depth tensor objects plus the feature layout and the current stream: a caller that
+    keeps its geometry tensors (a fixed rig, several lifts per scene, a benchmark loop) pays the geometry pass once;
+    new tensor objects -- the reference rebuilds projection and points for every scene (nerfdet.py:155-160) -- never
+    hit a stale plan.  Entries die with their tensors."""
+    dev = _need_cuda(features, points, projection, depth_resized)
+    key = (id(points), points._version, id(projection), projection._version,
+           id(depth_resized) if depth_resized is not None else 0, float(voxel_z), _layout_key(features),
+           _stream(dev), int(sm_limit))
+    ent = _PLAN_CACHE.get(key)
+    if ent is not None:
+        _PLAN_CACHE.move_to_end(key)
+        return ent[0]
+    plan = LiftPlan(features, points, projection, depth_resized, voxel_z, sm_limit)
+
+    def drop(_ref, key=key):
+        _PLAN_CACHE.pop(key, None)
+
+    refs = tuple(weakref.ref(t, drop) for t in (points, projection, depth_resized) if t is not None)
+    _PLAN_CACHE[key] = (plan, refs)
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def lift_mean_var_planned(features: Tensor, points: Tensor, projection: Tensor, alpha: Optional[Tensor], want_cov: bool,
+                          depth_resized: Optional[Tensor] = None, voxel_z: float = 0.0):
+    """Fused lift through the cached geometry plan; falls back to the one-shot op (staged path) for layouts the
+    plane-resident kernel does not take.  The call the Python API (``lifting.lift_mean_var``) makes: no dispatcher
+    round trip, one C call per lift."""
+    plan = cached_lift_plan(features, points, projection, depth_resized, voxel_z)
+    if plan.eligible:
+        return plan.mean_var(features, alpha, want_cov)
+    if depth_resized is not None:
+        raise NotImplementedError('the depth gate needs the plane-resident kernel (contiguous NCHW planes <= 64 KB); '
+                                  'use backproject() for other layouts')
+    return lift_mean_var(features, points, projection, alpha, want_cov, 0)
+
+
+def lift_accumulate_planned(features: Tensor, points: Tensor, projection: Tensor, acc: Optional[Tensor] = None,
+                            sm_limit: int = 0) -> Tensor:
+    """``[S1 | S2 | count]`` of these views (view-sharded lift) through the cached geometry plan,
+    into ``acc`` when given (the peer-mapped segment of ``distributed.PeerLift``) or a fresh buffer."""
+    plan = cached_lift_plan(features, points, projection, sm_limit=sm_limit)
+    if not plan.eligible:
+        if acc is None:
+            return lift_accumulate(features, points, projection, 0)
+        lift_accumulate_into(features, points, projection, acc, sm_limit)
+        return acc
+    if acc is None:
+        acc = torch.empty(((2 * features.shape[1] + 1) * plan.n_voxels,), dtype=torch.float32, device=features.device)
+    plan.accumulate_into(features, acc)
+    return acc
 
 
 # ------------------------------------------------------------------------------------------
 @torch.library.custom_op(f'{_NS}::project_voxels', mutates_args=())
+@_guarded
 def project_voxels(points: Tensor, projection: Tensor, height: int, width: int) -> Tuple[Tensor, Tensor, Tensor]:
     """x, y int64 [nv, N]; valid bool [nv, N]  (reference nerfdet.py:396-403)."""
     _need_cuda(points, projection)
@@ -95,6 +278,7 @@ def _(points, projection, height, width):
 
 # ------------------------------------------------------------------------------------------
 @torch.library.custom_op(f'{_NS}::backproject', mutates_args=())
+@_guarded
 def backproject(features: Tensor, points: Tensor, projection: Tensor, depth_resized: Optional[Tensor],
                 voxel_z: float) -> Tuple[Tensor, Tensor]:
     """Materialised volume f32 [nv, C, N] and valid bool [nv, N]  (reference nerfdet.py:393-420)."""
@@ -125,6 +309,7 @@ def _(features, points, projection, depth_resized, voxel_z):
 
 # ------------------------------------------------------------------------------------------
 @torch.library.custom_op(f'{_NS}::lift_mean_var', mutates_args=())
+@_guarded
 def lift_mean_var(features: Tensor, points: Tensor, projection: Tensor, alpha: Optional[Tensor],
                   want_cov: bool, scratch_budget_bytes: int) -> Tuple[Tensor, Tensor, Tensor]:
     """Fused project + gather + mean / all-view variance / count (reference nerfdet.py:164-181).
@@ -165,6 +350,7 @@ def _(features, points, projection, alpha, want_cov, scratch_budget_bytes):
 
 # ------------------------------------------------------------------------------------------
 @torch.library.custom_op(f'{_NS}::lift_accumulate', mutates_args=())
+@_guarded
 def lift_accumulate(features: Tensor, points: Tensor, projection: Tensor, scratch_budget_bytes: int) -> Tensor:
     """Per-rank accumulators of the view-sharded lift, one flat f32 buffer
     ``[S1 (C*N) | S2 (C*N) | count (N)]`` ready for a single all-reduce."""
@@ -197,6 +383,7 @@ def _(features, points, projection, scratch_budget_bytes):
 
 
 @torch.library.custom_op(f'{_NS}::lift_accumulate_into', mutates_args=('acc',))
+@_guarded
 def lift_accumulate_into(features: Tensor, points: Tensor, projection: Tensor, acc: Tensor, sm_limit: int = 0) -> None:
     """``lift_accumulate`` into a caller-owned buffer (the peer-mapped segment of ``distributed.PeerLift``);
     ``sm_limit`` > 0 keeps the lift off some SMs so that a concurrent exchange kernel finds room."""
@@ -222,6 +409,7 @@ def lift_accumulate_into(features: Tensor, points: Tensor, projection: Tensor, a
 
 
 @torch.library.custom_op(f'{_NS}::lift_finalize', mutates_args=())
+@_guarded
 def lift_finalize(acc: Tensor, n_views_total: int, channels: int, n_voxels: int, alpha: Optional[Tensor],
                   want_cov: bool) -> Tuple[Tensor, Tensor, Tensor]:
     """mean / exp(-var) / count from (all-reduced) accumulators and the GLOBAL view count."""
@@ -269,6 +457,7 @@ def _maps_contig(t: Tensor, what: str, allow_bf16: bool = True) -> NdMaps:
 
 
 @torch.library.custom_op(f'{_NS}::map_features', mutates_args=())
+@_guarded
 def map_features(features: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
     """B7 (reference nerfdet.py:190-197): per-pixel ``Linear(C -> 32)`` of NCHW ``features [nv, C, h, w]`` read in
     place; returns the mapped maps as a contiguous channels-last buffer ``[nv, h, w, 32]`` float32."""
@@ -294,6 +483,7 @@ def _(features, weight, bias):
 
 
 @torch.library.custom_op(f'{_NS}::live_stats', mutates_args=())
+@_guarded
 def live_stats(mapped: Tensor, rgb: Tensor, points: Tensor, projection: Tensor, rgb_projection: Tensor,
                map_bias: Tensor, want_planes: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """B8 + B9 (reference nerfdet.py:200-210, 232-253).  Returns ``global_volume [N, 2*(3+Cm)]``
@@ -382,6 +572,7 @@ def _mlp_entry(lib, precision: str):
 
 
 @torch.library.custom_op(f'{_NS}::nerf_mlp_fwd', mutates_args=())
+@_guarded
 def nerf_mlp_fwd(packed: Tensor, dims: List[int], x: Tensor, features: Tensor, cond: Optional[Tensor],
                  samples_per_ray: int, want_rgb: bool, want_alpha: bool,
                  precision: str = 'fp32') -> Tuple[Tensor, Tensor, Tensor]:
@@ -422,6 +613,7 @@ def _(packed, dims, x, features, cond, samples_per_ray, want_rgb, want_alpha, pr
 
 
 @torch.library.custom_op(f'{_NS}::sample_rays', mutates_args=())
+@_guarded
 def sample_rays(ray_o: Tensor, ray_d: Tensor, near: float, far: float, n_samples: int,
                 t_rand: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
     """pts [R, S, 3], z_vals [R, S] (reference render_ray.py:145-189; ``t_rand`` None = deterministic)."""
@@ -450,6 +642,7 @@ def _(ray_o, ray_d, near, far, n_samples, t_rand):
 
 
 @torch.library.custom_op(f'{_NS}::render_gather_stats', mutates_args=())
+@_guarded
 def render_gather_stats(pts: Tensor, cameras: Tensor, images: Tensor, featmaps: Tensor, want_pixels: bool,
                         want_view_features: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """R4 + R5 + R6 for P points: ``globalfeat [P, 2*(3+D)]``, ``view_mask bool [P, nv]``,
@@ -503,6 +696,7 @@ def _(pts, cameras, images, featmaps, want_pixels, want_view_features):
 
 
 @torch.library.custom_op(f'{_NS}::composite', mutates_args=())
+@_guarded
 def composite(rgb: Tensor, sigma: Tensor, z_vals: Tensor, pixel_mask: Optional[Tensor], z_bounds: Tensor,
               white_bkgd: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """raw2outputs (reference render_ray.py:196-247): rgb [R,3], depth [R], weights, alpha, transparency [R,S],
@@ -542,6 +736,7 @@ def _(rgb, sigma, z_vals, pixel_mask, z_bounds, white_bkgd):
 
 
 @torch.library.custom_op(f'{_NS}::volume_sample', mutates_args=())
+@_guarded
 def volume_sample(volume: Tensor, pts: Tensor, aabb_min: List[float], aabb_max: List[float]) -> Tuple[Tensor, Tensor]:
     """Trilinear lookup (reference render_ray.py:26-46): features [P, C], inside bool [P]."""
     _need_cuda(volume, pts)
