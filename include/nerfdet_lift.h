@@ -73,8 +73,9 @@ typedef struct nd_lift_options {
                                       use spatially compact warp tiles.  0 = unknown (results are identical) */
     int32_t sm_limit;              /* plane-resident kernel: occupy at most this many SMs (0 = all), e.g. to leave room
                                       for a concurrent exchange kernel */
-    int32_t views_per_stage;       /* plane-resident kernel: views per pipeline stage, 1 / 2 / 4 (0 = default 2) */
+    int32_t views_per_stage;       /* plane-resident kernel: views per pipeline stage, 1 or 2 (0 = default 2) */
     int32_t stages;                /* plane-resident kernel: pipeline stages, 2..8 (0 = as many as fit) */
+    int32_t prefetch_stages;       /* plane-resident kernel: L2 prefetch distance in stages (0 = off) */
 } nd_lift_options;
 
 int nd_version(void);

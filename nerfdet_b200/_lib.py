@@ -24,7 +24,7 @@ class NdMaps(ctypes.Structure):
 class NdLiftOptions(ctypes.Structure):
     _fields_ = [('scratch_budget_bytes', c_size_t), ('voxels_per_cta', c_int32), ('path', c_int32),
                 ('grid_x', c_int32), ('grid_y', c_int32), ('grid_z', c_int32), ('sm_limit', c_int32),
-                ('views_per_stage', c_int32), ('stages', c_int32)]
+                ('views_per_stage', c_int32), ('stages', c_int32), ('prefetch_stages', c_int32)]
 
 
 class NdMlpWeights(ctypes.Structure):

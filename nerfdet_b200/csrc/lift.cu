@@ -414,13 +414,6 @@ template <typename T, bool kRaw>
 nd_status lift_quads_run(const nd_maps *f, const void *plan, size_t plan_bytes, int64_t n_vox, uint32_t launch_index,
                          int n_views_total, const float *alpha, float *out_a, float *out_b, int64_t *count_i64,
                          float *count_f32, const nd_lift_options *opt, cudaStream_t st);
-// round-1 plane-resident kernel (lift_planes.cu), path == 2: kept for one A/B run, then removed
-bool lift_planes_eligible(const nd_maps *f, int64_t n_vox, const nd_lift_options *opt);
-size_t lift_planes_workspace_bytes(const nd_maps *f, int64_t n_vox, const nd_lift_options *opt);
-template <typename T, bool kRaw>
-nd_status run_lift_planes(const nd_maps *f, const float *points, const float *proj, int64_t n_vox, const float *alpha,
-                          float *out_a, float *out_b, int64_t *count_i64, float *count_f32, void *ws, size_t ws_bytes,
-                          const nd_lift_options *opt, cudaStream_t st);
 
 static size_t scratch_budget(const nd_lift_options *opt) {
     return (opt && opt->scratch_budget_bytes) ? opt->scratch_budget_bytes : ((size_t)64 << 20);
@@ -428,7 +421,6 @@ static size_t scratch_budget(const nd_lift_options *opt) {
 
 struct LiftPlan {
     bool quads;             // plane-resident path (lift_quads.cu): contiguous NCHW planes in shared memory
-    bool planes;            // round-1 kernel (A/B only)
     int nv, nvp, c, h, w, n_pix;
     int elt;                // bytes per feature element
     bool direct;            // features already pixel-major (channels-last): no staging
@@ -467,15 +459,9 @@ static LiftPlan make_plan(const nd_maps *f, int64_t n_vox, const nd_lift_options
                (f->stride_y / f->stride_x) * (int64_t)p.h < (1ll << 30) && p.c % 32 == 0 && p.c <= 256 &&
                (p.c == 32 || p.c == 64 || p.c == 128 || p.c == 256);
     const bool force_staged = opt != nullptr && opt->path == ND_LIFT_PATH_STAGED;
-    const bool v1 = opt != nullptr && opt->path == 2;
-    p.quads = !p.direct && !force_staged && !v1 && lift_quads_eligible(f, n_vox, opt);
+    p.quads = !p.direct && !force_staged && lift_quads_eligible(f, n_vox, opt);
     if (p.quads) {
         p.total_bytes = lift_quads_plan_bytes(f, n_vox, opt);
-        return p;
-    }
-    p.planes = !p.direct && !force_staged && v1 && lift_planes_eligible(f, n_vox, opt);
-    if (p.planes) {
-        p.total_bytes = lift_planes_workspace_bytes(f, n_vox, opt);
         return p;
     }
     if (p.direct) {
@@ -555,9 +541,6 @@ static nd_status run_lift(const nd_maps *f, const float *points, const float *pr
         return lift_quads_run<T, kRaw>(f, ws, ws_bytes, n_vox, 0u, f->n_views, alpha, out_a, out_b, count_i64, count_f32,
                                        opt, st);
     }
-    if (p.planes)
-        return run_lift_planes<T, kRaw>(f, points, proj, n_vox, alpha, out_a, out_b, count_i64, count_f32, ws, ws_bytes, opt,
-                                        st);
     ND_REQUIRE(ws != nullptr && ws_bytes >= p.total_bytes, ND_ERR_WORKSPACE,
                "lift: workspace too small (%zu < %zu bytes)", ws_bytes, p.total_bytes);
     ND_REQUIRE((reinterpret_cast<uintptr_t>(ws) % 256) == 0, ND_ERR_BAD_ALIGNMENT, "lift: workspace not 256-byte aligned");
@@ -652,7 +635,7 @@ size_t nd_lift_workspace_bytes(const nd_maps *f, int64_t n_voxels, const nd_lift
 int nd_lift_launch_count(const nd_maps *f, int64_t n_voxels, const nd_lift_options *opt) {
     if (validate_maps(f, "nd_lift_launch_count") != ND_OK || n_voxels < 0) return -1;
     const LiftPlan p = make_plan(f, n_voxels, opt);
-    if (p.quads || p.planes) return 3;   // k_q_index, k_q_pack, k_lift_quads
+    if (p.quads) return 3;   // k_q_index, k_q_pack, k_lift_quads (1 when the geometry plan is reused: nd_lift_plan_*)
     if (p.direct) return 2;
     return 1 + 2 * p.n_chunks;
 }

@@ -30,6 +30,7 @@
 //   on the SMs that step i's last round leaves idle (256 channels x 2 parts on 148 SMs: 3.46 rounds) -- back-to-back
 //   lifts pack without the 13 % quantisation loss.
 #include <algorithm>
+#include <atomic>
 
 #include "nd_common.cuh"
 
@@ -97,6 +98,9 @@ __device__ __forceinline__ void q_bulk_g2s(uint32_t dst, const void *src, uint32
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ void q_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ float q_lds_f32(uint32_t addr) {
     float v;
@@ -188,7 +192,7 @@ k_q_index(const QTiling tiling, const float *__restrict__ points, const float *_
             w.y = off[2] | (off[3] << 16);
             *reinterpret_cast<uint2 *>(off16 + ((int64_t)(v0 + i) * n_quads + q) * kQuad + lane * kQV) = w;
         }
-        if (lane == 0) act[(int64_t)q * nvp + v0 + i] = any ? 1 : 0;
+        if (lane == 0) act[(int64_t)(v0 + i) * n_quads + q] = any ? 1 : 0;
     }
     cntp[((int64_t)blockIdx.y * n_quads + q) * 32 + lane] = cnt;
 }
@@ -224,14 +228,14 @@ k_q_pack(const QPackArgs a) {
     __shared__ uint16_t s_quad[kQMaxWarps * kSlots];
     const int j = blockIdx.x, part = blockIdx.y, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    const int zi = blockIdx.z, zn = gridDim.z;                 // the copy work of a (stage, part) is split over zn blocks
 
     // 1. cost of every quad = number of views that see it; key sorts by descending cost, then by index
     for (int q = tid; q < a.n_quads_pad; q += blockDim.x) {
         uint32_t key = 0xffffffffu;
         if (q < a.n_quads) {
             int c = 0;
-            const uint8_t *row = a.act + (int64_t)q * a.nvp;
-            for (int v = 0; v < a.nv; ++v) c += (int)__ldg(row + v);
+            for (int v = 0; v < a.nv; ++v) c += (int)__ldg(a.act + (int64_t)v * a.n_quads + q);    // coalesced over q
             key = ((uint32_t)(255 - min(c, 255)) << 16) | (uint32_t)q;
         }
         s_key[q] = key;
@@ -269,7 +273,7 @@ k_q_pack(const QPackArgs a) {
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) {
                 const uint16_t q = s_quad[w * kSlots + s];
-                if (q != 0xffffu && __ldg(a.act + (int64_t)q * a.nvp + v)) m |= 1u << (4 * g + s);
+                if (q != 0xffffu && __ldg(a.act + (int64_t)v * a.n_quads + q)) m |= 1u << (4 * g + s);
             }
         }
         s_mask[i] = (uint16_t)m;
@@ -302,17 +306,17 @@ k_q_pack(const QPackArgs a) {
     }
     __syncthreads();
     // 5. this block's column of the tables
-    if (tid < a.W)
+    if (zi == 0 && tid < a.W)
         a.hdr[((int64_t)part * a.W + tid) * a.spu + j] = (uint32_t)s_mask[tid * a.spu + j] | ((uint32_t)s_start[tid * a.spu + j] << 16);
-    if (tid == 0) {
+    if (zi == 0 && tid == 0) {
         a.nrows[(int64_t)part * a.spu + j] = s_tot[j];
         a.grow[(int64_t)part * a.spu + j] = s_grow[j];
     }
     if (j == 0) {
-        if (tid < a.W * kSlots) a.quadmap[(int64_t)part * a.W * kSlots + tid] = s_quad[tid];
-        if (tid == 0) a.tickets[part] = 0u;
+        if (zi == 0 && tid < a.W * kSlots) a.quadmap[(int64_t)part * a.W * kSlots + tid] = s_quad[tid];
+        if (zi == 0 && tid == 0) a.tickets[part] = 0u;
         // view counts of the part's voxels in slot order (sum of the per-group partials; <= 254 per byte, no carries)
-        for (int i = tid; i < a.W * kSlots * 32; i += blockDim.x) {
+        for (int i = zi * (int)blockDim.x + tid; i < a.W * kSlots * 32; i += zn * (int)blockDim.x) {
             const uint16_t q = s_quad[i >> 5];
             uint32_t c = 0u;
             if (q != 0xffffu)
@@ -322,7 +326,7 @@ k_q_pack(const QPackArgs a) {
     }
     // 6. offset rows of stage j: warp -> view -> slot, one block warp per row, 8 B per lane
     const int n_bw = (int)(blockDim.x >> 5);
-    for (int w = warp; w < a.W; w += n_bw) {
+    for (int w = zi * n_bw + warp; w < a.W; w += zn * n_bw) {
         const uint32_t m = (uint32_t)s_mask[w * a.spu + j];
         if (!m) continue;
         int64_t row = (int64_t)part * a.part_rows + s_grow[j] + s_start[w * a.spu + j];
@@ -358,12 +362,24 @@ struct QArgs {
     int64_t sv, sc;            // elements
     uint32_t plane_bytes, pitch;   // smem slot = plane + zero word, padded to `pitch`
     int S, R;                  // plane ring: S stages of kG slots; offset-row ring: R rows of 256 B
+    int pf;                    // planes are prefetched into L2 this many stages ahead of their copy (0 = off)
     int n_views_total;
     const float *alpha;
     float *out_a, *out_b;
     int64_t *count_i64;
     float *count_f32;
 };
+
+// accumulate one quad (4 voxels per lane) into the registers of slot `slot` (warp-uniform)
+__device__ __forceinline__ void q_acc_slot(int slot, unsigned long long (&s1)[kSlots * 2], unsigned long long (&s2)[kSlots * 2],
+                                           const float *f) {
+    switch (slot) {
+        case 0: q_acc2(s1[0], s2[0], f[0], f[1]); q_acc2(s1[1], s2[1], f[2], f[3]); break;
+        case 1: q_acc2(s1[2], s2[2], f[0], f[1]); q_acc2(s1[3], s2[3], f[2], f[3]); break;
+        case 2: q_acc2(s1[4], s2[4], f[0], f[1]); q_acc2(s1[5], s2[5], f[2], f[3]); break;
+        default: q_acc2(s1[6], s2[6], f[0], f[1]); q_acc2(s1[7], s2[7], f[2], f[3]); break;
+    }
+}
 
 template <typename T>
 __device__ __forceinline__ void q_gather4(uint32_t pb, const uint2 o, float *f) {
@@ -398,7 +414,7 @@ k_lift_quads(const QArgs a) {
     const int part = blockIdx.x % a.n_parts;
 
     // planes [S][kG][pitch] | offset rows [R][256] | barriers [S] | progress flags [32] | unit queue [16] |
-    // producer's row intervals [8][2] | stage tables
+    // stage tables
     const uint32_t sm_base = q_smem_u32(smem);
     const uint32_t stage_pitch = (uint32_t)kG * a.pitch;
     const uint32_t row_base = sm_base + (uint32_t)S * stage_pitch;
@@ -406,11 +422,12 @@ k_lift_quads(const QArgs a) {
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(p_tab);
     uint32_t *s_flags = reinterpret_cast<uint32_t *>(bars + kQMaxStages);      // [32] stages done per warp
     uint32_t *s_units = s_flags + 32;                                           // [16] (ordinal + 1) << 16 | channel + 1 (0: end)
-    uint32_t *s_iv = s_units + 16;                                              // [8][2] first ring row, rows
-    uint32_t *s_nrows = s_iv + 16;                                              // [spu]
+    uint32_t *s_nrows = s_units + 16;                                           // [spu]
     uint32_t *s_grow = s_nrows + spu;                                           // [spu]
-    uint32_t *s_hdr = s_grow + spu;                                             // [W][spu]
-    float *s_rcp = reinterpret_cast<float *>(s_hdr + W * spu);                  // [256] RN(1 / count), [0] = 0
+    uint32_t *s_pos = s_grow + spu;                                             // [spu] first ring row of the stage (restarts at 0 every unit)
+    uint2 *s_tab = reinterpret_cast<uint2 *>(s_pos + spu + (spu & 1));            // [W][spu] item list (4-bit codes), smem address of the warp's first row | items << 24
+    uint4 *s_stage = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(s_tab + W * spu) + 15) & ~(uintptr_t)15);   // [spu] producer: rows, first ring row, lag, first row in the stream
+    float *s_rcp = reinterpret_cast<float *>(s_stage + spu);                    // [256] RN(1 / count), [0] = 0
     int32_t *s_qbase = reinterpret_cast<int32_t *>(s_rcp + 256);                // [W][4] first voxel of the quad (lane 0), -1: none
     const uint32_t bar_full = q_smem_u32(bars);
     const uint32_t f_progress = q_smem_u32(s_flags), f_units = q_smem_u32(s_units);
@@ -419,7 +436,7 @@ k_lift_quads(const QArgs a) {
         for (int s = 0; s < S; ++s) q_mbar_init(bar_full + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 32 + 16 + 16) s_flags[threadIdx.x] = 0u;
+    if (threadIdx.x < 32 + 16) s_flags[threadIdx.x] = 0u;
     for (int i = threadIdx.x; i < S * kG; i += blockDim.x)                      // the zero word behind every plane slot
         *reinterpret_cast<uint32_t *>(smem + (size_t)i * a.pitch + a.plane_bytes) = 0u;
     // the plan's tables are complete when this kernel starts (their producer does not trigger early, see the header)
@@ -427,7 +444,39 @@ k_lift_quads(const QArgs a) {
         s_nrows[i] = __ldg(a.nrows + (int64_t)part * spu + i);
         s_grow[i] = __ldg(a.grow + (int64_t)part * spu + i);
     }
-    for (int i = threadIdx.x; i < W * spu; i += blockDim.x) s_hdr[i] = __ldg(a.hdr + (int64_t)part * W * spu + i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // ring rows of the stages: a stage's rows never wrap around the ring, and every unit starts at row 0, so that
+        // the positions are the same for every unit (the producer checks overlaps with stages still in use)
+        uint32_t head = 0;
+        for (int j = 0; j < spu; ++j) {
+            const uint32_t n = s_nrows[j];
+            if (head + n > (uint32_t)R) head = 0;
+            s_pos[j] = head;
+            head += n;
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < spu; j += blockDim.x) {
+        // lag: how many of the preceding stages (cyclically: the positions repeat every unit) may still be in use
+        // when stage j is written -- at most S - 1 (plane slots), fewer when their ring rows would be overwritten
+        const uint32_t n = s_nrows[j], pos = s_pos[j];
+        uint32_t lag = (uint32_t)S - 1u;
+        for (int d = 1; d < S; ++d) {
+            int jj = (j - d) % spu;
+            if (jj < 0) jj += spu;
+            const uint32_t nn = s_nrows[jj], pp = s_pos[jj];
+            if (n != 0u && nn != 0u && pos < pp + nn && pp < pos + n) { lag = (uint32_t)d - 1u; break; }
+        }
+        s_stage[j] = make_uint4(n, pos, lag, s_grow[j]);
+    }
+    for (int i = threadIdx.x; i < W * spu; i += blockDim.x) {
+        const uint32_t h = __ldg(a.hdr + (int64_t)part * W * spu + i);
+        // the warp's items of the stage as a list of 4-bit codes (view g << 2 | slot s), in row order, and their number
+        uint32_t desc = 0u, n = 0u;
+        for (uint32_t m = h & 0xffffu; m != 0u; m &= m - 1u) desc |= (uint32_t)(__ffs((int)m) - 1) << (4 * n++);
+        s_tab[i] = make_uint2(desc, (row_base + (s_pos[i % spu] + (h >> 16)) * kQRowBytes) | (n << 24));
+    }
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_rcp[i] = i ? __frcp_rn((float)i) : 0.0f;
     for (int i = threadIdx.x; i < W * kSlots; i += blockDim.x) {
         const uint16_t q = __ldg(a.quadmap + (int64_t)part * W * kSlots + i);
@@ -452,49 +501,42 @@ k_lift_quads(const QArgs a) {
         int ch_next = ch >= 0 ? pull() : -1;
         const int64_t view_bytes = a.sv * (int64_t)sizeof(T), chan_bytes = a.sc * (int64_t)sizeof(T);
         const char *off_part = reinterpret_cast<const char *>(a.offc) + (int64_t)part * a.part_rows * kQRowBytes;
-        uint32_t i = 0, head = 0, released = 0;
+        uint32_t i = 0, released = 0;
         int slot = 0, k = 0;
         while (ch >= 0) {
             if (lane == 0) q_st_flag(f_units + 4 * (k & 15), ((uint32_t)(k + 1) << 16) | (uint32_t)(ch + 1));
-            const char *psrc = reinterpret_cast<const char *>(a.feat) + (int64_t)ch * chan_bytes;
+            const char *psrc = reinterpret_cast<const char *>(a.feat) + (int64_t)ch * chan_bytes + (int64_t)lane * view_bytes;
+            // The loop body is one table read, one compare and the copies: this warp runs ahead of 25 others on a
+            // serial chain of dependent instructions, and everything it does per stage delays the refill of a slot.
             for (int j = 0; j < spu; ++j) {
-                const uint32_t n = s_nrows[j];
-                uint32_t pos = head;
-                if (pos + n > (uint32_t)R) pos = 0;                             // a stage's rows never wrap around the ring
-                // the plane slot is free once stage i - S is released by every warp; the rows must not overlap the rows
-                // of a younger stage that is still in use
-                uint32_t need = i >= (uint32_t)S ? i - S + 1 : 0u;
-                for (uint32_t d = 1; d < (uint32_t)S && d <= i; ++d) {
-                    const uint32_t kk = i - d;
-                    const uint32_t st = s_iv[2 * (kk & 7)], nn = s_iv[2 * (kk & 7) + 1];
-                    if (n != 0u && nn != 0u && pos < st + nn && st < pos + n) {
-                        need = max(need, kk + 1);
-                        break;
-                    }
-                }
+                const uint4 st = s_stage[j];                                    // rows, first ring row, lag, first row in the stream
+                // stages i-1 .. i-lag may still be in use (lag < S: the plane slot of stage i - S is reused, and the
+                // ring rows of stage i overlap those of stage i - lag - 1 at the earliest)
+                const uint32_t need = i > st.z ? i - st.z : 0u;
                 if (released < need) {
-                    for (;;) {                                                  // lane w reads the progress word of compute warp w
+                    do {                                                        // lane w reads the progress word of compute warp w
                         const uint32_t pr = lane < W ? q_ld_flag(f_progress + 4 * lane) : 0xffffffffu;
                         released = __reduce_min_sync(0xffffffffu, pr);
-                        if (released >= need) break;
-                        __nanosleep(64);
-                    }
+                    } while (released < need);                                  // busy poll: one LDS per look
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // their reads before our async-proxy writes
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // their reads before our async-proxy writes
                 const int nvs = min(kG, a.nv - j * kG);
                 const uint32_t fb = bar_full + 8 * slot;
-                if (lane == 0) {
-                    q_mbar_expect_tx(fb, (uint32_t)nvs * a.plane_bytes + n * kQRowBytes);
-                    s_iv[2 * (i & 7)] = pos;
-                    s_iv[2 * (i & 7) + 1] = n;
-                }
-                __syncwarp();
+                if (lane == 0) q_mbar_expect_tx(fb, (uint32_t)nvs * a.plane_bytes + st.x * kQRowBytes);
                 if (lane < nvs)
-                    q_bulk_g2s(sm_base + (uint32_t)(slot * kG + lane) * a.pitch, psrc + (int64_t)(j * kG + lane) * view_bytes,
-                               a.plane_bytes, fb);
-                else if (lane == kG && n != 0u)
-                    q_bulk_g2s(row_base + pos * kQRowBytes, off_part + (size_t)s_grow[j] * kQRowBytes, n * kQRowBytes, fb);
-                head = pos + n;
+                    q_bulk_g2s(sm_base + (uint32_t)(slot * kG + lane) * a.pitch, psrc, a.plane_bytes, fb);
+                else if (lane == kG && st.x != 0u)
+                    q_bulk_g2s(row_base + st.y * kQRowBytes, off_part + (size_t)st.w * kQRowBytes, st.x * kQRowBytes, fb);
+                else if (a.pf > 0 && lane >= 16 && lane < 16 + kG) {
+                    // optional: HBM -> L2 ahead of the ring, so that the copy into shared memory sees L2 latency
+                    int jp = j + a.pf, cp = ch;
+                    if (jp >= spu) { jp -= spu; cp = ch_next; }
+                    const int vp = jp * kG + (lane - 16);
+                    if (cp >= 0 && jp < spu && vp < a.nv)
+                        q_prefetch_l2(reinterpret_cast<const char *>(a.feat) + (int64_t)cp * chan_bytes + (int64_t)vp * view_bytes,
+                                      a.plane_bytes);
+                }
+                psrc += (int64_t)kG * view_bytes;
                 ++i;
                 if (++slot == S) slot = 0;
             }
@@ -507,13 +549,15 @@ k_lift_quads(const QArgs a) {
     }
 
     // ---------------- compute warps ----------------
-    uint32_t gi = 0, head = 0, par = 0;
+    uint32_t gi = 0, par = 0;
     int slot = 0;
     bool landed = false;                                                        // stage gi is known to have landed
     bool waited = false;                                                        // griddepcontrol.wait done
-    const uint32_t my_progress = f_progress + 4 * warp;
-    const uint32_t *my_hdr = s_hdr + warp * spu;
     const int lane_off = (int)(a.tiling.voxel(0, lane) - a.tiling.voxel(0, 0));
+    // loop constants the compiler must keep in registers instead of re-deriving them from the thread index every stage
+    uint32_t my_progress = f_progress + 4 * warp, tab_addr = q_smem_u32(s_tab + warp * spu), lane8 = (uint32_t)lane * 8u;
+    uint32_t pitch = a.pitch;
+    asm volatile("" : "+r"(my_progress), "+r"(tab_addr), "+r"(lane8), "+r"(pitch));
     for (int k = 0;; ++k) {
         uint32_t e;
         do { e = q_ld_flag(f_units + 4 * (k & 15)); } while ((e >> 16) != (uint32_t)(k + 1));
@@ -523,39 +567,41 @@ k_lift_quads(const QArgs a) {
 #pragma unroll
         for (int i = 0; i < kSlots * 2; ++i) { s1[i] = 0ull; s2[i] = 0ull; }
 
-        for (int j = 0; j < spu; ++j) {
-            const uint32_t h = my_hdr[j], n = s_nrows[j];
-            uint32_t pos = head;
-            if (pos + n > (uint32_t)R) pos = 0;
-            head = pos + n;
-            const uint32_t fb = bar_full + 8 * slot;
-            if (!landed) q_mbar_wait(fb, par);
-            uint32_t raddr = row_base + (pos + (h >> 16)) * kQRowBytes + lane * 8;
-            const uint32_t sb = sm_base + (uint32_t)slot * stage_pitch;
+        // view counts of this lane's 16 voxels: requested now, needed in the epilogue
+        uint32_t cw[kSlots];
 #pragma unroll
-            for (int g = 0; g < kG; ++g) {
-                const uint32_t m = (h >> (4 * g)) & 15u;
-                if (m == 0u) continue;                                          // warp-uniform
-                const uint32_t pb = sb + (uint32_t)g * a.pitch;
-                uint2 o[kSlots];
-                float f[kSlots * 4];
-                // all offset rows of the view, then all its gathers, then the arithmetic: up to 16 gathers in flight
-#pragma unroll
-                for (int s = 0; s < kSlots; ++s)
-                    if (m & (1u << s)) { o[s] = q_lds_u2(raddr); raddr += kQRowBytes; }
-#pragma unroll
-                for (int s = 0; s < kSlots; ++s) {
-                    if (m & (1u << s)) {
-                        q_gather4<T>(pb, o[s], f + 4 * s);
-                    } else {
-                        f[4 * s] = 0.0f; f[4 * s + 1] = 0.0f; f[4 * s + 2] = 0.0f; f[4 * s + 3] = 0.0f;
+        for (int s = 0; s < kSlots; ++s) cw[s] = __ldg(a.cntc + (((int64_t)part * W + warp) * kSlots + s) * 32 + lane);
+
+        uint32_t ta = tab_addr;
+        for (int j = 0; j < spu; ++j, ta += 8) {
+            const uint2 t = q_lds_u2(ta);
+            if (!landed) q_mbar_wait(bar_full + 8 * slot, par);
+            int n = (int)(t.y >> 24);                                           // items of this warp in the stage
+            if (n != 0) {                                                       // warp-uniform
+                // Two items at a time, software-pipelined: the offset rows of the NEXT pair are requested while the 8
+                // gathers of the current pair are in flight.  The cost is proportional to the number of active
+                // (view, quad) pairs; nothing is paid for the inactive ones.
+                uint32_t desc = t.x;
+                const uint32_t sb = sm_base + (uint32_t)slot * stage_pitch;
+                uint32_t raddr = (t.y & 0xffffffu) + lane8;
+                uint2 o0 = q_lds_u2(raddr), o1 = make_uint2(0u, 0u);
+                if (n > 1) o1 = q_lds_u2(raddr + kQRowBytes);
+                for (;;) {
+                    const uint32_t d0 = desc & 15u, d1 = (desc >> 4) & 15u;
+                    desc >>= 8;
+                    const bool two = n > 1;
+                    float f[8];
+                    q_gather4<T>(sb + (d0 >> 2) * pitch, o0, f);
+                    if (two) q_gather4<T>(sb + (d1 >> 2) * pitch, o1, f + 4);
+                    n -= 2;
+                    raddr += 2 * kQRowBytes;
+                    if (n > 0) {
+                        o0 = q_lds_u2(raddr);
+                        if (n > 1) o1 = q_lds_u2(raddr + kQRowBytes);
                     }
-                }
-                // unconditional: a quad the view does not see adds zeros (a predicated packed op costs three issue slots)
-#pragma unroll
-                for (int s = 0; s < kSlots; ++s) {
-                    q_acc2(s1[2 * s], s2[2 * s], f[4 * s], f[4 * s + 1]);
-                    q_acc2(s1[2 * s + 1], s2[2 * s + 1], f[4 * s + 2], f[4 * s + 3]);
+                    q_acc_slot((int)(d0 & 3u), s1, s2, f);
+                    if (two) q_acc_slot((int)(d1 & 3u), s1, s2, f + 4);
+                    if (n <= 0) break;
                 }
             }
             // next stage: look now, use the answer in the next iteration (a completed test costs ~90 cycles)
@@ -580,7 +626,6 @@ k_lift_quads(const QArgs a) {
             const int32_t qb = s_qbase[warp * kSlots + s];
             const int64_t nb = (int64_t)qb + lane_off;                          // first of this lane's 4 voxels of the quad
             if (qb < 0 || nb >= a.n_vox) continue;
-            const uint32_t cw = __ldg(a.cntc + (((int64_t)part * W + warp) * kSlots + s) * 32 + lane);
             const bool full = vec_ok && nb + 4 <= a.n_vox && nb % 4 == 0;
             float4 al = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
             if (!kRaw && a.alpha != nullptr) {
@@ -605,7 +650,7 @@ k_lift_quads(const QArgs a) {
                     oa[t] = v1[t];
                     ob[t] = v2[t];
                 } else {
-                    const uint32_t cn = (cw >> (8 * t)) & 0xffu;
+                    const uint32_t cn = (cw[s] >> (8 * t)) & 0xffu;
                     const float cf = (float)cn;                                 // count + 1e-8 == count in fp32
                     const float rc = s_rcp[cn];                                 // RN(1 / count); 0 for count 0
                     // correctly rounded S1 / count from the reciprocal (one Newton step on the quotient): the mean is
@@ -628,7 +673,7 @@ k_lift_quads(const QArgs a) {
                 q_store_partial(a.out_a, a.out_b, o, a.n_vox - nb, make_float4(oa[0], oa[1], oa[2], oa[3]),
                                 make_float4(ob[0], ob[1], ob[2], ob[3]));
             }
-            if (c == 0) q_store_counts(a.count_i64, a.count_f32, nb, a.n_vox - nb, cw);
+            if (c == 0) q_store_counts(a.count_i64, a.count_f32, nb, a.n_vox - nb, cw[s]);
         }
     }
 }
@@ -646,14 +691,37 @@ struct QGeom {
     size_t smem_bytes, pack_smem;
 };
 
+// Per-device facts, looked up once (idempotent caches of immutable values, not mutable state): the SM count and whether
+// a kernel instantiation already carries its dynamic shared-memory attribute on the device.
+constexpr int kQMaxDevices = 64;
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kQMaxDevices ? dev : 0;
+}
 static int device_sm_count() {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static std::atomic<int> cache[kQMaxDevices];
+    const int dev = current_device();
+    int sms = cache[dev].load(std::memory_order_relaxed);
+    if (sms == 0) {
+        sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev].store(sms, std::memory_order_relaxed);
+    }
     return sms;
+}
+// dynamic shared memory attribute of kernel variant `slot` (0..15): set when the size grows on this device
+static cudaError_t ensure_smem(const void *kern, int slot, size_t bytes) {
+    static std::atomic<unsigned> have[kQMaxDevices][16];
+    const int dev = current_device();
+    if (have[dev][slot].load(std::memory_order_relaxed) >= bytes) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have[dev][slot].store((unsigned)bytes, std::memory_order_relaxed);
+    return e;
 }
 
 static size_t q_fixed_smem(int W, int spu) {
-    return (size_t)kQMaxStages * 8 + (32 + 16 + 16) * 4 + (size_t)2 * spu * 4 + (size_t)W * spu * 4 + 256 * 4 + (size_t)W * kSlots * 4 + 16;
+    return (size_t)kQMaxStages * 8 + (32 + 16) * 4 + (size_t)spu * 16 + 16 + (size_t)4 * spu * 4 + (size_t)W * spu * 8 + 256 * 4 + (size_t)W * kSlots * 4 + 16;
 }
 
 static bool quad_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *opt, QGeom &g) {
@@ -692,7 +760,7 @@ static bool quad_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *op
     // views per stage and ring depth: as many plane slots as fit beside an offset-row ring that holds the worst case of
     // one stage (every quad of the part active in every view of the stage) and about half of that per further stage
     int G = 2, S = 0;
-    if (opt != nullptr && (opt->views_per_stage == 1 || opt->views_per_stage == 2 || opt->views_per_stage == 4)) G = opt->views_per_stage;
+    if (opt != nullptr && (opt->views_per_stage == 1 || opt->views_per_stage == 2)) G = opt->views_per_stage;
     if (opt != nullptr && opt->stages >= 2 && opt->stages <= kQMaxStages) S = opt->stages;
     const size_t cap = (size_t)227 * 1024;
     for (;; G >>= 1) {
@@ -733,7 +801,7 @@ static bool quad_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *op
     g.o_tickets = take((size_t)g.n_parts * 4);
     g.o_offc = take((size_t)g.n_parts * (size_t)g.part_rows * kQRowBytes);
     g.o_off16 = take((size_t)g.nv * g.n_quads * kQRowBytes);
-    g.o_act = take((size_t)g.n_quads * g.nvp);
+    g.o_act = take((size_t)g.n_quads * g.nvp);                        // [nv][n_quads]
     g.o_cntp = take((size_t)g.nvg * g.n_quads * 32 * 4);
     g.total_bytes = o;
     g.pack_smem = (size_t)g.n_quads_pad * 4 + (size_t)2 * ((g.W * g.spu + 1) & ~1) * 2 + (size_t)2 * g.spu * 4;
@@ -800,7 +868,7 @@ nd_status lift_quads_plan_build(const nd_maps *f, const float *points, const flo
             return ND_ERR_CUDA;
         }
     }
-    k_q_pack<<<dim3((unsigned)g.spu, (unsigned)g.n_parts), 256, g.pack_smem, st>>>(pa);
+    k_q_pack<<<dim3((unsigned)g.spu, (unsigned)g.n_parts, 4u), 256, g.pack_smem, st>>>(pa);
     ND_CUDA_LAUNCH_CHECK("k_q_pack");
     return ND_OK;
 }
@@ -833,15 +901,16 @@ nd_status lift_quads_run(const nd_maps *f, const void *plan, size_t plan_bytes, 
     a.n_vox = n_vox;
     a.feat = f->data; a.sv = f->stride_v; a.sc = f->stride_c;
     a.plane_bytes = g.plane_bytes; a.pitch = g.pitch; a.S = g.S; a.R = g.R;
+    a.pf = opt != nullptr && opt->prefetch_stages != 0 ? (opt->prefetch_stages > 0 ? std::min(opt->prefetch_stages, g.spu) : 0) : 0;
     a.n_views_total = n_views_total > 0 ? n_views_total : g.nv;
     a.alpha = alpha; a.out_a = out_a; a.out_b = out_b; a.count_i64 = count_i64; a.count_f32 = count_f32;
     void (*kern)(const QArgs) = nullptr;
     switch (g.G) {
         case 1: kern = k_lift_quads<T, kRaw, 1>; break;
-        case 2: kern = k_lift_quads<T, kRaw, 2>; break;
-        default: kern = k_lift_quads<T, kRaw, 4>; break;
+        default: kern = k_lift_quads<T, kRaw, 2>; break;
     }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes);
+    const int variant = (sizeof(T) == 4 ? 0 : 1) * 4 + (kRaw ? 2 : 0) + (g.G == 1 ? 0 : 1);
+    cudaError_t e = ensure_smem(reinterpret_cast<const void *>(kern), variant, g.smem_bytes);
     if (e != cudaSuccess) {
         set_error("k_lift_quads: cannot reserve %zu bytes of shared memory: %s", g.smem_bytes, cudaGetErrorString(e));
         return ND_ERR_CUDA;

@@ -94,13 +94,13 @@ def _flat_points(points: Tensor) -> Tuple[Tensor, Tuple[int, int, int]]:
 
 
 def _options(scratch_budget_bytes: int, grid=(0, 0, 0), sm_limit: int = 0, views_per_stage: int = 0,
-             stages: int = 0, path: Optional[int] = None) -> NdLiftOptions:
+             stages: int = 0, path: Optional[int] = None, prefetch_stages: int = 0) -> NdLiftOptions:
     """``scratch_budget_bytes`` > 0 selects the generic staged path (any strides) with that much
     L2-resident staging; 0 = automatic (plane-resident kernel for contiguous NCHW planes)."""
     if path is None:
         path = _lib.ND_LIFT_PATH_STAGED if scratch_budget_bytes > 0 else _lib.ND_LIFT_PATH_AUTO
     return NdLiftOptions(max(scratch_budget_bytes, 0), 0, path, int(grid[0]), int(grid[1]), int(grid[2]), int(sm_limit),
-                         int(views_per_stage), int(stages))
+                         int(views_per_stage), int(stages), int(prefetch_stages))
 
 
 # ------------------------------------------------------------------------------------------
@@ -116,14 +116,15 @@ class LiftPlan:
     buffer and overlap back to back (programmatic dependent launch), so they must be issued in order."""
 
     def __init__(self, features: Tensor, points: Tensor, projection: Tensor, depth_resized: Optional[Tensor] = None,
-                 voxel_z: float = 0.0, sm_limit: int = 0, views_per_stage: int = 0, stages: int = 0):
+                 voxel_z: float = 0.0, sm_limit: int = 0, views_per_stage: int = 0, stages: int = 0,
+                 prefetch_stages: int = 0):
         self.device = _need_cuda(features, points, projection, depth_resized)
         m = _maps(features)
         _check_geometry(points, projection, m.n_views)
         pts, grid = _flat_points(points)
         self.n_voxels = pts.shape[1]
         self.layout = _layout_key(features)
-        self.opt = _options(0, grid, sm_limit, views_per_stage, stages)
+        self.opt = _options(0, grid, sm_limit, views_per_stage, stages, prefetch_stages=prefetch_stages)
         self.launches = 0
         self.stream = None
         lib = _lib.load()

@@ -108,3 +108,20 @@ def test_mlp_packed_size_and_unsupported_architectures():
     assert lib.nd_mlp_packed_bytes(ctypes.byref(ops.mlp_arch({}, [4, 128, 3, 70, 128, 10, 4]))) == 0
     with pytest.raises(NotImplementedError):
         nerf_mlp.VanillaNeRFRadianceField(4, 256, 3, 70, net_depth_condition=2)
+
+
+def test_reciprocal_quotient_is_correctly_rounded():
+    """The lift epilogue (csrc/lift_quads.cu) computes the mean S1 / count as q0 = S1 * rc,
+    q = fma(fma(-q0, count, S1), rc, q0) with rc = RN(1 / count).  For the integer divisors 1..254 (uint8 view counts)
+    that is the correctly rounded quotient, i.e. bit-equal to the reference's IEEE divide (nerfdet.py:175).  The fma is
+    emulated exactly in float64 (a 24-bit by 8-bit product is exact there)."""
+    import numpy as np
+    rs = np.random.RandomState(0)
+    a = (rs.randn(1 << 18) * np.logspace(-6, 6, 1 << 18)).astype(np.float32)
+    for n in range(1, 255):
+        cf = np.float32(n)
+        rc = np.float32(1.0) / cf
+        q0 = (a * rc).astype(np.float32)
+        r = (a.astype(np.float64) - q0.astype(np.float64) * float(n)).astype(np.float32)
+        q = (q0.astype(np.float64) + r.astype(np.float64) * float(rc)).astype(np.float32)
+        assert np.array_equal(q, (a / cf).astype(np.float32)), n

@@ -2,7 +2,7 @@
 """Development harness of the fused lift (csrc/lift_quads.cu): parity against the C oracle, then timings of the
 plan-based kernel under its tuning knobs (views per stage, stages) and of the geometry pass.
 
-  python tools/lift_dev.py [--quick] [--old]      (GPU box; prints one line per measurement)
+  python tools/lift_dev.py [--quick]      (GPU box; prints one line per measurement)
 """
 import argparse
 import os
@@ -89,7 +89,6 @@ def per_step(fn, steps, warmup=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--quick', action='store_true')
-    ap.add_argument('--old', action='store_true', help='also time the round-1 kernel (path 2)')
     ap.add_argument('--steps', type=int, default=300)
     args = ap.parse_args()
     torch.cuda.set_device(0)
@@ -99,7 +98,7 @@ def main():
     ok &= parity(50, 32, (40, 40, 16), (0.16, 0.16, 0.2), 12)
     ok &= parity(100, 16, (40, 40, 16), (0.16, 0.16, 0.2), 14)
     ok &= parity(50, 16, (40, 40, 16), (0.16, 0.16, 0.2), 12, views_per_stage=1)
-    ok &= parity(50, 16, (40, 40, 16), (0.16, 0.16, 0.2), 12, views_per_stage=4, stages=2)
+    ok &= parity(50, 16, (40, 40, 16), (0.16, 0.16, 0.2), 12, stages=2)
     ok &= parity(20, 16, (56, 56, 16), (0.16, 0.16, 0.2), 15)
     ok &= parity(7, 8, (13, 11, 7), (0.4, 0.4, 0.4), 16)            # linear tiling, ragged quads
     print('PARITY', 'OK' if ok else 'FAILED', flush=True)
@@ -112,8 +111,7 @@ def main():
     views = [s[:, :, :59, :80] for s in sets]
     n_vox = int(np.prod(grid))
     bytes_step = nv * c * 59 * 80 * 4 + 2 * c * n_vox * 4 + n_vox * 8 + nv * 48
-    variants = [dict(), dict(stages=3), dict(stages=4), dict(stages=5), dict(views_per_stage=1), dict(views_per_stage=1, stages=6),
-                dict(views_per_stage=4, stages=2)]
+    variants = [dict(), dict(prefetch_stages=6), dict(stages=4), dict(views_per_stage=1)]
     if args.quick:
         variants = variants[:1]
     for kw in variants:
@@ -149,25 +147,6 @@ def main():
     host_us = (time.perf_counter() - t0) / 2000 * 1e6
     torch.cuda.synchronize()
     print(f'host time per lifting.lift_mean_var call (enqueue only): {host_us:.1f} us', flush=True)
-    if args.old:
-        opt = ops._options(0, grid, path=2)
-        import ctypes
-        m = ops._maps(views[0])
-        lib = _lib.load()
-        wsb = lib.nd_lift_workspace_bytes(ctypes.byref(m), n_vox, ctypes.byref(opt))
-        ws = torch.empty((wsb,), dtype=torch.uint8, device=DEV)
-        mean = torch.empty((c, n_vox), device=DEV)
-        cov = torch.empty((c, n_vox), device=DEV)
-        cnt = torch.empty((n_vox,), dtype=torch.int64, device=DEV)
-        p3 = pd.reshape(3, -1).contiguous()
-
-        def old():
-            it[0] += 1
-            mm = ops._maps(views[it[0] % 3])
-            _lib.check(lib.nd_lift_mean_var(ctypes.byref(mm), ops._ptr(p3), ops._ptr(qd), n_vox, None, ops._ptr(mean),
-                                            ops._ptr(cov), ops._ptr(cnt), ops._ptr(ws), wsb, ctypes.byref(opt),
-                                            ops._stream()), 'old')
-        print(f'round-1 kernel (3 launches, direct C call): {timed(old, args.steps):.1f} us/step', flush=True)
 
 
 if __name__ == '__main__':
