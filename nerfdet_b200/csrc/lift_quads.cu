@@ -550,39 +550,34 @@ k_lift_quads(const QArgs a) {
 
     // ---------------- compute warps ----------------
     uint32_t gi = 0, par = 0;
-    int slot = 0;
     bool landed = false;                                                        // stage gi is known to have landed
     bool waited = false;                                                        // griddepcontrol.wait done
     const int lane_off = (int)(a.tiling.voxel(0, lane) - a.tiling.voxel(0, 0));
-    // loop constants the compiler must keep in registers instead of re-deriving them from the thread index every stage
+    // Loop state kept in registers (made opaque so that the compiler does not re-derive it from the thread index, the
+    // shared-memory window or the constant bank inside the item loop): this warp's table row, progress word and lane
+    // offset; barrier and plane base of the current slot, advanced incrementally.
     uint32_t my_progress = f_progress + 4 * warp, tab_addr = q_smem_u32(s_tab + warp * spu), lane8 = (uint32_t)lane * 8u;
-    uint32_t pitch = a.pitch;
-    asm volatile("" : "+r"(my_progress), "+r"(tab_addr), "+r"(lane8), "+r"(pitch));
+    uint32_t pitch = a.pitch, bar = bar_full, sb = sm_base;
+    const uint32_t bar_end = bar_full + 8u * (uint32_t)S, ring_bytes = (uint32_t)S * stage_pitch;
+    asm volatile("" : "+r"(my_progress), "+r"(tab_addr), "+r"(lane8), "+r"(pitch), "+r"(bar), "+r"(sb));
     for (int k = 0;; ++k) {
         uint32_t e;
         do { e = q_ld_flag(f_units + 4 * (k & 15)); } while ((e >> 16) != (uint32_t)(k + 1));
-        const int c = (int)(e & 0xffffu) - 1;
-        if (c < 0) break;
+        if ((e & 0xffffu) == 0u) break;
         unsigned long long s1[kSlots * 2], s2[kSlots * 2];
 #pragma unroll
         for (int i = 0; i < kSlots * 2; ++i) { s1[i] = 0ull; s2[i] = 0ull; }
 
-        // view counts of this lane's 16 voxels: requested now, needed in the epilogue
-        uint32_t cw[kSlots];
-#pragma unroll
-        for (int s = 0; s < kSlots; ++s) cw[s] = __ldg(a.cntc + (((int64_t)part * W + warp) * kSlots + s) * 32 + lane);
-
         uint32_t ta = tab_addr;
         for (int j = 0; j < spu; ++j, ta += 8) {
             const uint2 t = q_lds_u2(ta);
-            if (!landed) q_mbar_wait(bar_full + 8 * slot, par);
+            if (!landed) q_mbar_wait(bar, par);
             int n = (int)(t.y >> 24);                                           // items of this warp in the stage
             if (n != 0) {                                                       // warp-uniform
                 // Two items at a time, software-pipelined: the offset rows of the NEXT pair are requested while the 8
                 // gathers of the current pair are in flight.  The cost is proportional to the number of active
                 // (view, quad) pairs; nothing is paid for the inactive ones.
                 uint32_t desc = t.x;
-                const uint32_t sb = sm_base + (uint32_t)slot * stage_pitch;
                 uint32_t raddr = (t.y & 0xffffffu) + lane8;
                 uint2 o0 = q_lds_u2(raddr), o1 = make_uint2(0u, 0u);
                 if (n > 1) o1 = q_lds_u2(raddr + kQRowBytes);
@@ -605,12 +600,15 @@ k_lift_quads(const QArgs a) {
                 }
             }
             // next stage: look now, use the answer in the next iteration (a completed test costs ~90 cycles)
-            if (++slot == S) { slot = 0; par ^= 1u; }
-            landed = q_mbar_test(bar_full + 8 * slot, par);
+            bar += 8u;
+            sb += stage_pitch;
+            if (bar == bar_end) { bar = bar_full; sb -= ring_bytes; par ^= 1u; }
+            landed = q_mbar_test(bar, par);
             __syncwarp();
             ++gi;
             if (lane == 0) q_st_flag(my_progress, gi);
         }
+        const int c = (int)(q_ld_flag(f_units + 4 * (k & 15)) & 0xffffu) - 1;    // this unit's channel
 
         // ---------------- epilogue of unit (c, part); the producer is already streaming the next unit ----------------
         if (!waited) {                                                          // first global write of this launch
@@ -621,11 +619,15 @@ k_lift_quads(const QArgs a) {
         const bool vec_ok = (row % 4 == 0) &&
                             ((reinterpret_cast<uintptr_t>(a.out_a) | reinterpret_cast<uintptr_t>(a.out_b)) % 16 == 0);
         const float nvt = (float)a.n_views_total;
+        uint32_t cws[kSlots];                                                   // view counts of this lane's 16 voxels (4 loads in flight)
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) cws[s] = __ldg(a.cntc + (((int64_t)part * W + warp) * kSlots + s) * 32 + lane);
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) {
             const int32_t qb = s_qbase[warp * kSlots + s];
             const int64_t nb = (int64_t)qb + lane_off;                          // first of this lane's 4 voxels of the quad
             if (qb < 0 || nb >= a.n_vox) continue;
+            const uint32_t cw = cws[s];
             const bool full = vec_ok && nb + 4 <= a.n_vox && nb % 4 == 0;
             float4 al = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
             if (!kRaw && a.alpha != nullptr) {
@@ -650,7 +652,7 @@ k_lift_quads(const QArgs a) {
                     oa[t] = v1[t];
                     ob[t] = v2[t];
                 } else {
-                    const uint32_t cn = (cw[s] >> (8 * t)) & 0xffu;
+                    const uint32_t cn = (cw >> (8 * t)) & 0xffu;
                     const float cf = (float)cn;                                 // count + 1e-8 == count in fp32
                     const float rc = s_rcp[cn];                                 // RN(1 / count); 0 for count 0
                     // correctly rounded S1 / count from the reciprocal (one Newton step on the quotient): the mean is
@@ -673,7 +675,7 @@ k_lift_quads(const QArgs a) {
                 q_store_partial(a.out_a, a.out_b, o, a.n_vox - nb, make_float4(oa[0], oa[1], oa[2], oa[3]),
                                 make_float4(ob[0], ob[1], ob[2], ob[3]));
             }
-            if (c == 0) q_store_counts(a.count_i64, a.count_f32, nb, a.n_vox - nb, cw[s]);
+            if (c == 0) q_store_counts(a.count_i64, a.count_f32, nb, a.n_vox - nb, cw);
         }
     }
 }
@@ -758,7 +760,8 @@ static bool quad_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *op
     g.n_parts = (int)ceil_div(nwt, kQMaxWarps);
     g.W = (int)ceil_div(nwt, g.n_parts);
     // views per stage and ring depth: as many plane slots as fit beside an offset-row ring that holds the worst case of
-    // one stage (every quad of the part active in every view of the stage) and about half of that per further stage
+    // one stage (every quad of the part active in every view of the stage) and 40 % of that (the typical activity) per
+    // further stage
     int G = 2, S = 0;
     if (opt != nullptr && (opt->views_per_stage == 1 || opt->views_per_stage == 2)) G = opt->views_per_stage;
     if (opt != nullptr && opt->stages >= 2 && opt->stages <= kQMaxStages) S = opt->stages;
@@ -773,7 +776,7 @@ static bool quad_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *op
             const size_t planes = (size_t)s * G * g.pitch;
             if (planes + fixed + worst * kQRowBytes > cap) continue;
             const size_t rows = (cap - planes - fixed) / kQRowBytes;
-            if (S > 0 || rows >= worst + (size_t)(s - 1) * worst / 2 || s == 2) {
+            if (S > 0 || rows >= worst + (size_t)(s - 1) * worst * 2 / 5 || s == 2) {
                 g.S = s;
                 g.R = (int)std::min<size_t>(rows, 4095);
                 break;
