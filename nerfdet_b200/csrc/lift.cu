@@ -635,7 +635,7 @@ size_t nd_lift_workspace_bytes(const nd_maps *f, int64_t n_voxels, const nd_lift
 int nd_lift_launch_count(const nd_maps *f, int64_t n_voxels, const nd_lift_options *opt) {
     if (validate_maps(f, "nd_lift_launch_count") != ND_OK || n_voxels < 0) return -1;
     const LiftPlan p = make_plan(f, n_voxels, opt);
-    if (p.quads) return 3;   // k_q_index, k_q_pack, k_lift_quads (1 when the geometry plan is reused: nd_lift_plan_*)
+    if (p.quads) return 4;   // k_q_index, k_q_rank, k_q_pack, k_lift_quads (1 when the geometry plan is reused: nd_lift_plan_*)
     if (p.direct) return 2;
     return 1 + 2 * p.n_chunks;
 }

@@ -14,8 +14,9 @@
 //     k_q_index     bit-exact nearest-pixel projection of every voxel-view (nd_common.cuh:project_nearest), stored as a
 //                   uint16 BYTE offset into a plane (invalid -> offset of a zero word behind the plane), one 256 B row
 //                   per (view, quad); per (quad, view) "any voxel valid"; per-voxel view counts.
-//     k_q_pack      ranks the quads by the number of views that see them and deals them out to the compute warps in
-//                   snake order, 4 per warp (equal load per warp); a PART is the set of warps of one CTA.  Per part the
+//     k_q_rank      one block ranks the quads by the number of views that see them.
+//     k_q_pack      deals the ranked quads out to the compute warps in snake order, 4 per warp (equal load per warp);
+//                   a PART is the set of warps of one CTA.  Per part the
 //                   offset rows of the active (view, quad) pairs are compacted into ONE stream in exactly the order
 //                   the lift kernel consumes them: stage (kG views) -> warp -> view -> slot.
 //   k_lift_quads    persistent, one CTA per SM.  Work unit = (channel c, part p); units are handed out by a ticket
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(32)
 k_q_index(const QTiling tiling, const float *__restrict__ points, const float *__restrict__ proj,
           const float *__restrict__ depth, float voxel_z, int nv, int nvp, int n_quads, int64_t n_vox, int height,
           int width, int elt, uint32_t zero_off, uint16_t *__restrict__ off16, uint8_t *__restrict__ act,
-          uint32_t *__restrict__ cntp) {
+          uint32_t *__restrict__ cntp, uint8_t *__restrict__ costp) {
     __shared__ float sp[kVG * 12];
     const int q = blockIdx.x, lane = threadIdx.x;
     const int v0 = blockIdx.y * kVG;
@@ -169,6 +170,7 @@ k_q_index(const QTiling tiling, const float *__restrict__ points, const float *_
         Z[k] = __ldg(points + 2 * n_vox + n);
     }
     uint32_t cnt = 0u;                                          // 4 packed uint8 counts
+    int n_act = 0;                                              // views of this group that see the quad
     for (int i = 0; i < nvg; ++i) {
         uint32_t off[kQV];
         bool any = false;
@@ -186,6 +188,7 @@ k_q_index(const QTiling tiling, const float *__restrict__ points, const float *_
             any |= ok;
         }
         any = __any_sync(0xffffffffu, any);
+        n_act += any ? 1 : 0;
         if (any) {
             uint2 w;
             w.x = off[0] | (off[1] << 16);
@@ -195,11 +198,46 @@ k_q_index(const QTiling tiling, const float *__restrict__ points, const float *_
         if (lane == 0) act[(int64_t)(v0 + i) * n_quads + q] = any ? 1 : 0;
     }
     cntp[((int64_t)blockIdx.y * n_quads + q) * 32 + lane] = cnt;
+    if (lane == 0) costp[(int64_t)blockIdx.y * n_quads + q] = (uint8_t)n_act;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Ranking, ownership and compaction.  grid = (stages per unit, parts).  Every block repeats the (small) ranking and
-// the per-part stage table, then compacts the offset rows of ITS stage and writes its column of the tables.
+// Ranking: one block sorts the quads by the number of views that see them (descending, ties by index).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_q_rank(const uint8_t *__restrict__ costp, int nvg, int n_quads, int n_quads_pad, uint16_t *__restrict__ ranked) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    uint32_t *s_key = reinterpret_cast<uint32_t *>(s_dyn);                              // [n_quads_pad]
+    const int tid = threadIdx.x;
+    for (int q = tid; q < n_quads_pad; q += blockDim.x) {
+        uint32_t key = 0xffffffffu;
+        if (q < n_quads) {
+            int c = 0;
+            for (int g = 0; g < nvg; ++g) c += (int)__ldg(costp + (int64_t)g * n_quads + q);        // coalesced over q
+            key = ((uint32_t)(255 - min(c, 255)) << 16) | (uint32_t)q;
+        }
+        s_key[q] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n_quads_pad; k <<= 1) {                                        // bitonic sort, ascending
+        for (int s = k >> 1; s > 0; s >>= 1) {
+            for (int i = tid; i < n_quads_pad; i += blockDim.x) {
+                const int l = i ^ s;
+                if (l > i) {
+                    const uint32_t x = s_key[i], y = s_key[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { s_key[i] = y; s_key[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int q = tid; q < n_quads; q += blockDim.x) ranked[q] = (uint16_t)(s_key[q] & 0xffffu);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ownership and compaction.  grid = (stages per unit, parts, copy split).  Every block repeats the (small) per-part
+// stage table, then compacts the offset rows of ITS stage and writes its column of the tables.
 // ---------------------------------------------------------------------------------------------
 struct QPackArgs {
     int nv, nvp, nvg, n_quads, n_quads_pad, n_parts, W, G, spu;
@@ -207,6 +245,7 @@ struct QPackArgs {
     const uint16_t *off16;
     const uint8_t *act;
     const uint32_t *cntp;
+    const uint16_t *ranked;   // [n_quads] quad ids by descending cost (k_q_rank)
     uint16_t *quadmap;        // [n_parts][W][4]
     uint32_t *hdr;            // [n_parts][W][spu]  mask (4 bits per view of the stage: slot s of view g = bit 4 g + s) | first row << 16
     uint32_t *nrows;          // [n_parts][spu]
@@ -219,8 +258,7 @@ struct QPackArgs {
 __global__ void __launch_bounds__(256)
 k_q_pack(const QPackArgs a) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    uint32_t *s_key = reinterpret_cast<uint32_t *>(s_dyn);                              // [n_quads_pad]
-    uint16_t *s_mask = reinterpret_cast<uint16_t *>(s_key + a.n_quads_pad);             // [W][spu]
+    uint16_t *s_mask = reinterpret_cast<uint16_t *>(s_dyn);                             // [W][spu]
     const int n2 = (a.W * a.spu + 1) & ~1;
     uint16_t *s_start = s_mask + n2;                                                    // [W][spu]
     uint32_t *s_tot = reinterpret_cast<uint32_t *>(s_start + n2);                       // [spu]
@@ -230,37 +268,13 @@ k_q_pack(const QPackArgs a) {
     const int warp = tid >> 5, lane = tid & 31;
     const int zi = blockIdx.z, zn = gridDim.z;                 // the copy work of a (stage, part) is split over zn blocks
 
-    // 1. cost of every quad = number of views that see it; key sorts by descending cost, then by index
-    for (int q = tid; q < a.n_quads_pad; q += blockDim.x) {
-        uint32_t key = 0xffffffffu;
-        if (q < a.n_quads) {
-            int c = 0;
-            for (int v = 0; v < a.nv; ++v) c += (int)__ldg(a.act + (int64_t)v * a.n_quads + q);    // coalesced over q
-            key = ((uint32_t)(255 - min(c, 255)) << 16) | (uint32_t)q;
-        }
-        s_key[q] = key;
-    }
-    __syncthreads();
-    for (int k = 2; k <= a.n_quads_pad; k <<= 1) {                                      // bitonic sort, ascending
-        for (int s = k >> 1; s > 0; s >>= 1) {
-            for (int i = tid; i < a.n_quads_pad; i += blockDim.x) {
-                const int l = i ^ s;
-                if (l > i) {
-                    const uint32_t x = s_key[i], y = s_key[l];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) { s_key[i] = y; s_key[l] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
     // 2. ownership: rank r goes to warp snake(r) of all n_parts * W warps, slot r / (n_parts * W)
     const int nwt = a.n_parts * a.W;
     if (tid < a.W * kSlots) {
         const int w = tid / kSlots, s = tid % kSlots;
         const int gw = w * a.n_parts + part;
         const int r = s * nwt + ((s & 1) ? nwt - 1 - gw : gw);
-        s_quad[tid] = r < a.n_quads ? (uint16_t)(s_key[r] & 0xffffu) : (uint16_t)0xffffu;
+        s_quad[tid] = r < a.n_quads ? __ldg(a.ranked + r) : (uint16_t)0xffffu;
     }
     __syncthreads();
     // 3. masks of every (warp, stage) of the part
@@ -689,7 +703,7 @@ struct QGeom {
     int64_t part_rows;
     uint32_t plane_bytes, pitch;
     // plan layout (bytes from the start of the plan buffer): the tables the lift kernel reads, then build scratch
-    size_t o_hdr, o_nrows, o_grow, o_quadmap, o_cntc, o_tickets, o_offc, o_off16, o_act, o_cntp, total_bytes;
+    size_t o_hdr, o_nrows, o_grow, o_quadmap, o_cntc, o_tickets, o_offc, o_off16, o_act, o_cntp, o_ranked, o_costp, total_bytes;
     size_t smem_bytes, pack_smem;
 };
 
@@ -806,8 +820,10 @@ static bool quad_geom(const nd_maps *f, int64_t n_vox, const nd_lift_options *op
     g.o_off16 = take((size_t)g.nv * g.n_quads * kQRowBytes);
     g.o_act = take((size_t)g.n_quads * g.nvp);                        // [nv][n_quads]
     g.o_cntp = take((size_t)g.nvg * g.n_quads * 32 * 4);
+    g.o_ranked = take((size_t)g.n_quads * 2);
+    g.o_costp = take((size_t)g.nvg * g.n_quads);
     g.total_bytes = o;
-    g.pack_smem = (size_t)g.n_quads_pad * 4 + (size_t)2 * ((g.W * g.spu + 1) & ~1) * 2 + (size_t)2 * g.spu * 4;
+    g.pack_smem = (size_t)2 * ((g.W * g.spu + 1) & ~1) * 2 + (size_t)2 * g.spu * 4;
     return g.pack_smem <= 200 * 1024;
 }
 
@@ -849,14 +865,19 @@ nd_status lift_quads_plan_build(const nd_maps *f, const float *points, const flo
     uint16_t *off16 = reinterpret_cast<uint16_t *>(b + g.o_off16);
     uint8_t *act = reinterpret_cast<uint8_t *>(b + g.o_act);
     uint32_t *cntp = reinterpret_cast<uint32_t *>(b + g.o_cntp);
+    uint8_t *costp = reinterpret_cast<uint8_t *>(b + g.o_costp);
     k_q_index<<<dim3((unsigned)g.n_quads, (unsigned)g.nvg), 32, 0, st>>>(g.tiling, points, proj, depth, voxel_z, g.nv, g.nvp,
                                                                          g.n_quads, n_vox, f->height, f->width, g.elt,
-                                                                         g.plane_bytes, off16, act, cntp);
+                                                                         g.plane_bytes, off16, act, cntp, costp);
     ND_CUDA_LAUNCH_CHECK("k_q_index");
+    uint16_t *ranked = reinterpret_cast<uint16_t *>(b + g.o_ranked);
+    k_q_rank<<<1, g.n_quads_pad >= 1024 ? 1024 : std::max(g.n_quads_pad, 64), (size_t)g.n_quads_pad * 4, st>>>(
+        costp, g.nvg, g.n_quads, g.n_quads_pad, ranked);
+    ND_CUDA_LAUNCH_CHECK("k_q_rank");
     QPackArgs pa{};
     pa.nv = g.nv; pa.nvp = g.nvp; pa.nvg = g.nvg; pa.n_quads = g.n_quads; pa.n_quads_pad = g.n_quads_pad;
     pa.n_parts = g.n_parts; pa.W = g.W; pa.G = g.G; pa.spu = g.spu; pa.part_rows = g.part_rows;
-    pa.off16 = off16; pa.act = act; pa.cntp = cntp;
+    pa.off16 = off16; pa.act = act; pa.cntp = cntp; pa.ranked = ranked;
     pa.quadmap = reinterpret_cast<uint16_t *>(b + g.o_quadmap);
     pa.hdr = reinterpret_cast<uint32_t *>(b + g.o_hdr);
     pa.nrows = reinterpret_cast<uint32_t *>(b + g.o_nrows);

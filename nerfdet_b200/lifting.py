@@ -94,7 +94,7 @@ def backproject(features, points, projection, depth, voxel_size):
 
 def lift_mean_var(features, points, projection, alpha: Optional[torch.Tensor] = None,
                   want_cov: bool = True, scratch_budget_bytes: int = 0, depth: Optional[torch.Tensor] = None,
-                  voxel_size: Optional[Sequence[float]] = None):
+                  voxel_size: Optional[Sequence[float]] = None, out=None):
     """Fused nerfdet.py:164-181.  Returns
     ``volume_mean [C,X,Y,Z]`` (times ``alpha`` per voxel when given, nerfdet.py:259-261),
     ``volume_cov [C,X,Y,Z]`` = exp(-var) (None when ``want_cov`` is False) and
@@ -104,15 +104,16 @@ def lift_mean_var(features, points, projection, alpha: Optional[torch.Tensor] = 
     bilinear resize to the feature resolution stays ``F.interpolate`` like the reference, the gate itself runs in
     the geometry pass.  The geometry (pixel offsets, counts, work distribution) is planned once per
     (points, projection, depth) tensor identity and reused (``ops.cached_lift_plan``); ``scratch_budget_bytes`` > 0
-    forces the generic staged path instead."""
+    forces the generic staged path instead.  ``out`` = caller-owned contiguous ``(mean [C, N] f32, cov [C, N] f32,
+    count [N] int64)`` buffers to write into instead of allocating (the returned tensors are views of them)."""
     if any(t is not None and t.requires_grad for t in (features, alpha)):
         raise RuntimeError('lift_mean_var is forward-only: detach() the inputs (the backward of the lift is not built)')
     c = features.shape[1]
     gx, gy, gz = points.shape[-3:]
     al = alpha.reshape(-1) if alpha is not None else None
     if scratch_budget_bytes > 0:
-        if depth is not None:
-            raise NotImplementedError('the depth gate is not available on the staged path')
+        if depth is not None or out is not None:
+            raise NotImplementedError('the depth gate and caller-owned outputs are not available on the staged path')
         mean, cov, count = ops.lift_mean_var(features, points, projection, al, want_cov, scratch_budget_bytes)
     else:
         depth_resized, voxel_z = None, 0.0
@@ -128,7 +129,7 @@ def lift_mean_var(features, points, projection, alpha: Optional[torch.Tensor] = 
                 ent = (weakref.ref(depth), depth._version, resized, tuple(features.shape[-2:]))
                 _DEPTH_CACHE[key] = ent
             depth_resized, voxel_z = ent[2], float(voxel_size[-1])
-        mean, cov, count = ops.lift_mean_var_planned(features, points, projection, al, want_cov, depth_resized, voxel_z)
+        mean, cov, count = ops.lift_mean_var_planned(features, points, projection, al, want_cov, depth_resized, voxel_z, out)
     return (mean.view(c, gx, gy, gz), cov.view(c, gx, gy, gz) if want_cov else None,
             count.view(1, gx, gy, gz))
 

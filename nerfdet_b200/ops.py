@@ -153,8 +153,10 @@ class LiftPlan:
         return i
 
     def mean_var(self, features: Tensor, alpha: Optional[Tensor] = None, want_cov: bool = True,
-                 n_views_total: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
-        """mean f32 [C, N] (times alpha), exp(-var) f32 [C, N] (empty unless ``want_cov``), count int64 [N]."""
+                 n_views_total: int = 0, out: Optional[Tuple[Tensor, Tensor, Tensor]] = None) -> Tuple[Tensor, Tensor, Tensor]:
+        """mean f32 [C, N] (times alpha), exp(-var) f32 [C, N] (empty unless ``want_cov``), count int64 [N].
+        ``out`` = caller-owned (mean, cov, count) buffers of those shapes to write into (no allocation per call: at
+        80x80x32 the two volumes are 420 MB)."""
         m = _maps(features)
         n, dev = self.n_voxels, self.device
         if alpha is not None:
@@ -162,9 +164,18 @@ class LiftPlan:
                 raise ValueError('alpha must be float32 with one value per voxel')
             alpha = alpha.contiguous()
         with _on(dev):
-            mean = torch.empty((m.channels, n), dtype=torch.float32, device=dev)
-            cov = torch.empty((m.channels, n) if want_cov else (0,), dtype=torch.float32, device=dev)
-            count = torch.empty((n,), dtype=torch.int64, device=dev)
+            if out is not None:
+                mean, cov, count = out
+                ok = (mean.dtype == torch.float32 and mean.numel() == m.channels * n and mean.is_contiguous() and
+                      count.dtype == torch.int64 and count.numel() == n and count.is_contiguous() and
+                      (not want_cov or (cov.dtype == torch.float32 and cov.numel() == m.channels * n and cov.is_contiguous())) and
+                      all(t.device == dev for t in ((mean, cov, count) if want_cov else (mean, count))))
+                if not ok:
+                    raise ValueError('out must be contiguous (float32 [C, N], float32 [C, N], int64 [N]) buffers on the plan\'s device')
+            else:
+                mean = torch.empty((m.channels, n), dtype=torch.float32, device=dev)
+                cov = torch.empty((m.channels, n) if want_cov else (0,), dtype=torch.float32, device=dev)
+                count = torch.empty((n,), dtype=torch.int64, device=dev)
             _lib.check(_lib.load().nd_lift_plan_mean_var(
                 ctypes.byref(m), _ptr(self.buf), self.bytes, n, self._launch_index(features), int(n_views_total),
                 _ptr(alpha), _ptr(mean), _ptr(cov) if want_cov else None, _ptr(count), ctypes.byref(self.opt),
@@ -190,7 +201,8 @@ def _layout_key(features: Tensor):
 
 
 _PLAN_CACHE: 'OrderedDict[tuple, tuple]' = OrderedDict()
-_PLAN_CACHE_SIZE = 16
+plan_builds = 0            # geometry plans built through cached_lift_plan so far (cache misses); for tests and benchmarks
+_PLAN_CACHE_SIZE = 64
 
 
 def cached_lift_plan(features: Tensor, points: Tensor, projection: Tensor, depth_resized: Optional[Tensor] = None,
@@ -208,6 +220,8 @@ def cached_lift_plan(features: Tensor, points: Tensor, projection: Tensor, depth
     if ent is not None:
         _PLAN_CACHE.move_to_end(key)
         return ent[0]
+    global plan_builds
+    plan_builds += 1
     plan = LiftPlan(features, points, projection, depth_resized, voxel_z, sm_limit)
 
     def drop(_ref, key=key):
@@ -221,13 +235,15 @@ def cached_lift_plan(features: Tensor, points: Tensor, projection: Tensor, depth
 
 
 def lift_mean_var_planned(features: Tensor, points: Tensor, projection: Tensor, alpha: Optional[Tensor], want_cov: bool,
-                          depth_resized: Optional[Tensor] = None, voxel_z: float = 0.0):
+                          depth_resized: Optional[Tensor] = None, voxel_z: float = 0.0, out=None):
     """Fused lift through the cached geometry plan; falls back to the one-shot op (staged path) for layouts the
     plane-resident kernel does not take.  The call the Python API (``lifting.lift_mean_var``) makes: no dispatcher
     round trip, one C call per lift."""
     plan = cached_lift_plan(features, points, projection, depth_resized, voxel_z)
     if plan.eligible:
-        return plan.mean_var(features, alpha, want_cov)
+        return plan.mean_var(features, alpha, want_cov, out=out)
+    if out is not None:
+        raise NotImplementedError('caller-owned outputs need the plane-resident kernel (contiguous NCHW planes <= 64 KB)')
     if depth_resized is not None:
         raise NotImplementedError('the depth gate needs the plane-resident kernel (contiguous NCHW planes <= 64 KB); '
                                   'use backproject() for other layouts')

