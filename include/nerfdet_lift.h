@@ -193,8 +193,12 @@ int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_v
  *     max_ctas: 0 = a grid that fills the GPU; > 0 = at most that many one-per-SM CTAs (512 / 1024 threads) looping over
  *       the work, so that the exchange of one scene can run beside the accumulate of the next on the SMs that
  *       nd_lift_options.sm_limit keeps free (the exchange is bound by the links, not by the SMs).
- *   Outputs are complete on `stream` when the call's kernels have run; a peer that never arrives raises word
- *   2 * ND_MAX_PEERS + 1 of the local flag block after ~4 s instead of hanging.
+ *     timeout_ms: bound of every wait for a peer (0 = 4000).
+ *   Outputs are complete on `stream` when the call's kernels have run.  A peer that does not arrive within the
+ *   time-out raises word 2 * ND_MAX_PEERS + 1 (the error word) of EVERY rank's flag block instead of hanging; a rank
+ *   that finds its error word set performs no reduce and no peer store, fills the rows it owns with NaN in its own
+ *   mean / cov and still completes the hand-shake, so the step fails visibly on every rank (the caller polls the
+ *   error word, e.g. with an asynchronous copy to pinned host memory after each step).
  * ------------------------------------------------------------------------------------- */
 #define ND_MAX_PEERS 8
 #define ND_PEER_FLAG_WORDS 32
@@ -206,7 +210,7 @@ int nd_peer_free(void *ptr);
 int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
                            void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
                            int channels, int64_t n_voxels, const float *alpha, int64_t *count, const void *acc_mc,
-                           void *mean_mc, void *cov_mc, int max_ctas, void *stream);
+                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, void *stream);
 
 
 /* ---------------------------------------------------------------------------------------

@@ -817,10 +817,9 @@ int nd_nerf_mlp_fwd_tc(const nd_mlp_weights *arch, const void *packed, const flo
     a.feat_dim = L.feat;
     a.n_tiles = (int)ceil_div(n_points, kTcTile);
     a.sigma = sigma; a.alpha = alpha; a.rgb = want_rgb ? rgb : nullptr;
-    if (const char *e = getenv("ND_MLP_TC_DEBUG")) a.debug = atoi(e);
     const size_t smem = 1024 + kOffTail + kTailPar + (size_t)L.n_par * sizeof(float);
     ND_REQUIRE(smem <= 227 * 1024, ND_ERR_BAD_SHAPE, "nd_nerf_mlp_fwd_tc: %zu bytes of shared memory needed", smem);
-    void (*kern)(const TcArgs) = a.debug != 0 ? k_nerf_mlp_tc<true> : k_nerf_mlp_tc<false>;
+    void (*kern)(const TcArgs) = k_nerf_mlp_tc<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         set_error("k_nerf_mlp_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
@@ -828,10 +827,6 @@ int nd_nerf_mlp_fwd_tc(const nd_mlp_weights *arch, const void *packed, const flo
     }
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (const char *g = getenv("ND_MLP_TC_GRID")) {              // diagnostics: fewer CTAs (L2 contention probe)
-        const int v = atoi(g);
-        if (v >= 1 && v < sms) sms = v;
-    }
     const int grid = a.n_tiles < sms ? a.n_tiles : sms;
     kern<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(a);
     ND_CUDA_LAUNCH_CHECK("k_nerf_mlp_tc");

@@ -12,7 +12,8 @@
 // (raised by the first CTA of the finalise kernel, i.e. after the accumulate kernels in stream order), `done` = all my
 // reads of your accumulators and all my writes into your outputs have been performed (raised by the last CTA).
 // A one-block wait kernel holds the stream until every peer is `done`.  All spins are bounded: a peer that never shows up
-// raises an error flag after ~4 s instead of hanging the GPU.
+// raises the error word of EVERY rank's flag block after a bounded wait (default 4 s) instead of hanging the GPU; ranks
+// that see the error skip the reduce / store phase and fill the rows they own with NaN in their own outputs.
 //
 // The segments are plain cudaMalloc allocations shared with CUDA IPC handles (nd_peer_alloc / nd_peer_open): the only
 // place where the library owns device memory, because a handle must cover a whole allocation.
@@ -33,6 +34,7 @@ struct PeerArgs {
     uint32_t *flags[kMaxPeers];      // [0, P): ready, [P, 2P): done, [2P]: CTA counter, [2P + 1]: error
     int world, rank;
     uint32_t epoch;
+    unsigned long long timeout_ns;   // bound of every wait for a peer
     int n_views_total, channels, c_begin, c_end, ch_per_cta, n_tiles, n_items;
     int64_t n_vox;
     const float *alpha;
@@ -68,14 +70,20 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// waits until *p has reached `epoch` (wrap-safe); false after ~4 s
-__device__ __forceinline__ bool spin_until(const uint32_t *p, uint32_t epoch) {
+// waits until *p has reached `epoch` (wrap-safe); false after `timeout_ns`
+__device__ __forceinline__ bool spin_until(const uint32_t *p, uint32_t epoch, unsigned long long timeout_ns) {
     const unsigned long long t0 = global_ns();
     while ((int32_t)(ld_acquire_sys(p) - epoch) < 0) {
         __nanosleep(64);
-        if (global_ns() - t0 > 4000000000ull) return false;
+        if (global_ns() - t0 > timeout_ns) return false;
     }
     return true;
+}
+// A wait that timed out poisons the step on EVERY rank: the error word of every rank's flag block is raised (a rank
+// that sees it set skips its reduce / store phase as well), so that no rank hands out rows built from stale or
+// partial accumulators without an error it can see.
+__device__ __forceinline__ void raise_error_everywhere(uint32_t *const *flags, int world) {
+    for (int g = 0; g < world; ++g) atomicExch_system(flags[g] + 2 * kMaxPeers + 1, 1u);
 }
 
 template <int V> __device__ __forceinline__ void ld_vec(const float *p, float (&r)[V]);
@@ -106,19 +114,42 @@ k_lift_finalize_peers(const PeerArgs a) {
     static_assert(!MC || (V == 4 && G == 1), "multicast instantiation: 16-byte vectors, one (reduced) load per row");
     const int P = kMaxPeers;
     uint32_t *my_flags = a.flags[a.rank];
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
     // ---- hand-shake: my accumulators are complete; wait for everybody else's ----
     if (blockIdx.x == 0 && threadIdx.x < a.world)
         st_release_sys(a.flags[threadIdx.x] + a.rank, a.epoch);
     if (threadIdx.x < a.world && threadIdx.x != a.rank) {
-        if (!spin_until(my_flags + threadIdx.x, a.epoch)) atomicExch(my_flags + 2 * P + 1, 1u);
+        if (!spin_until(my_flags + threadIdx.x, a.epoch, a.timeout_ns)) {
+            s_bad = 1;
+            raise_error_everywhere(a.flags, a.world);
+        }
     }
+    if (threadIdx.x == 0 && ld_acquire_sys(my_flags + 2 * P + 1) != 0u) s_bad = 1;     // raised here or by a peer, now or earlier
     __syncthreads();
+    const bool bad = s_bad != 0;
 
     const int64_t cn = (int64_t)a.channels * a.n_vox;
     // work item = (voxel tile of T * V voxels, channel sub-slice); wide grid: exactly one item per CTA
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const int tile = item % a.n_tiles, sub = item / a.n_tiles;
     const int64_t n = ((int64_t)tile * T + threadIdx.x) * V;
+    if (bad) {
+        // no reduce, no peer traffic: the rows this CTA owns become NaN in the LOCAL outputs (the peers' copies are
+        // theirs to poison; their error words are raised), the error word makes the step a hard error on the host
+        if (n < a.n_vox) {
+            const int c0 = a.c_begin + sub * a.ch_per_cta, c1 = min(a.c_end, c0 + a.ch_per_cta);
+            float nanv[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) nanv[j] = __int_as_float(0x7fc00000);
+            for (int c = c0; c < c1; ++c) {
+                st_vec<V>(a.mean[a.rank] + (int64_t)c * a.n_vox + n, nanv);
+                if (a.cov[a.rank] != nullptr) st_vec<V>(a.cov[a.rank] + (int64_t)c * a.n_vox + n, nanv);
+            }
+        }
+        continue;
+    }
     if (n < a.n_vox) {
         float cnt[V];
 #pragma unroll
@@ -219,9 +250,10 @@ k_lift_finalize_peers(const PeerArgs a) {
     }
 }
 
-__global__ void k_peer_wait_done(uint32_t *my_flags, int world, uint32_t epoch) {
-    if (threadIdx.x < world) {
-        if (!spin_until(my_flags + kMaxPeers + threadIdx.x, epoch)) atomicExch(my_flags + 2 * kMaxPeers + 1, 1u);
+__global__ void k_peer_wait_done(const PeerArgs a) {
+    uint32_t *my_flags = a.flags[a.rank];
+    if (threadIdx.x < a.world) {
+        if (!spin_until(my_flags + kMaxPeers + threadIdx.x, a.epoch, a.timeout_ns)) raise_error_everywhere(a.flags, a.world);
     }
 }
 
@@ -287,7 +319,7 @@ int nd_peer_free(void *ptr) {
 int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
                            void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
                            int channels, int64_t n_voxels, const float *alpha, int64_t *count, const void *acc_mc,
-                           void *mean_mc, void *cov_mc, int max_ctas, void *stream) {
+                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, void *stream) {
     ND_REQUIRE(acc_host && mean_host && flags_host, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: null pointer table");
     ND_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, ND_ERR_BAD_ARG,
                "nd_lift_finalize_peers: world %d / rank %d outside [1, %d]", world, rank, kMaxPeers);
@@ -308,6 +340,7 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     a.world = world;
     a.rank = rank;
     a.epoch = epoch;
+    a.timeout_ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 4000) * 1000000ull;
     a.n_views_total = n_views_total;
     a.channels = channels;
     // channel slice of this rank: contiguous, sizes differ by at most one (the split of distributed.view_shard)
@@ -339,8 +372,7 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     // wide grid: enough CTAs to fill every SM at the instantiation's occupancy; a CTA keeps its tile's counts for its channels
     // measured on B200s (tools/dist_check.py sweep): 2 GPUs 102.9 us at 6 CTAs per SM (104-112 for 2-12); 8 GPUs 176.7 us at 2
     // (191 at 4, 237 at 12) -- the step is bound by the links (~520 GB/s inbound per GPU), more CTAs only add contention
-    int per_sm = gb <= 2 ? 6 : gb <= 4 ? 4 : 2;
-    if (const char *e = getenv("ND_PEER_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
+    const int per_sm = gb <= 2 ? 6 : gb <= 4 ? 4 : 2;
     // narrow grid: ~8 work items per CTA so that the CTAs finish together
     int64_t subs = ceil_div(narrow ? (int64_t)max_ctas * 8 : (int64_t)148 * per_sm, tiles);
     if (subs > slice) subs = slice;
@@ -370,7 +402,7 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     }
 #undef ND_PEER_LAUNCH
     ND_CUDA_LAUNCH_CHECK("k_lift_finalize_peers");
-    k_peer_wait_done<<<1, 32, 0, st>>>(a.flags[rank], world, epoch);
+    k_peer_wait_done<<<1, 32, 0, st>>>(a);
     ND_CUDA_LAUNCH_CHECK("k_peer_wait_done");
     return ND_OK;
 }

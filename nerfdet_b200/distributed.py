@@ -104,7 +104,7 @@ class PeerLift:
     """
 
     def __init__(self, channels: int, n_voxels: int, device=None, group=None, want_cov: bool = True,
-                 transport: str = 'ipc', overlap_sms: int = 0, _local_group=None):
+                 transport: str = 'ipc', overlap_sms: int = 0, timeout_ms: int = 0, _local_group=None):
         """``transport='ipc'``: cudaMalloc segments shared with CUDA IPC handles, per-peer P2P loads / stores.
         ``transport='multicast'``: symmetric-memory segments (``torch.distributed._symmetric_memory``, plumbing only)
         bound to an NVLS multicast object; the kernel then reduces in the NVSwitch (``multimem.ld_reduce``) and
@@ -120,6 +120,8 @@ class PeerLift:
         self.lib = _lib.load()
         self.channels, self.n_voxels, self.want_cov = int(channels), int(n_voxels), bool(want_cov)
         self.overlap_sms = max(int(overlap_sms), 0)
+        self.timeout_ms = max(int(timeout_ms), 0)                  # 0 = the library default (4 s)
+        self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory() if torch.cuda.is_available() else torch.zeros(1, dtype=torch.int32)
         self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
         self.group = group
         if _local_group is not None:
@@ -251,11 +253,12 @@ class PeerLift:
 
     @classmethod
     def local_group(cls, world: int, channels: int, n_voxels: int, device=None, want_cov: bool = True,
-                    overlap_sms: int = 0):
+                    overlap_sms: int = 0, timeout_ms: int = 0):
         """``world`` ranks inside ONE process on one device (their segments are addressed directly, no IPC): the
         single-GPU test of the multi-rank protocol -- run each rank's call on its own stream.  Small shapes only:
         the waiting CTAs of all ranks must fit the device together."""
-        ranks = [cls(channels, n_voxels, device, want_cov=want_cov, overlap_sms=overlap_sms, _local_group=(r, world))
+        ranks = [cls(channels, n_voxels, device, want_cov=want_cov, overlap_sms=overlap_sms, timeout_ms=timeout_ms,
+                     _local_group=(r, world))
                  for r in range(world)]
         bases = [r._base for r in ranks]
         for r in ranks:
@@ -269,6 +272,10 @@ class PeerLift:
         ctypes = self._ct
         if alpha is not None:
             alpha = alpha.reshape(-1).contiguous()
+        # the error word of the previous steps, copied to pinned memory behind each of them: no synchronisation here
+        if int(self._err_host[0]) != 0:
+            raise RuntimeError('PeerLift: a peer did not reach an earlier exchange step within the time-out; the results of '
+                               'that step are invalid (NaN rows) and the segments must be rebuilt')
         self.epoch += 1
         mc = self._mc_base
         stream = torch.cuda.current_stream(self.device)
@@ -282,7 +289,10 @@ class PeerLift:
             ctypes.c_void_p(self.count.data_ptr()),
             ctypes.c_void_p(mc + self._off_acc) if mc else None, ctypes.c_void_p(mc + self._off_mean) if mc else None,
             ctypes.c_void_p(mc + self._off_cov) if mc and self.want_cov else None,
-            self.overlap_sms, stream.cuda_stream), 'nd_lift_finalize_peers')
+            self.overlap_sms, self.timeout_ms, stream.cuda_stream), 'nd_lift_finalize_peers')
+        with torch.cuda.stream(stream):
+            w = 2 * self._lib.ND_MAX_PEERS + 1
+            self._err_host.copy_(self.flags[w:w + 1], non_blocking=True)
         if self._ordered:
             ev = torch.cuda.Event()
             ev.record(stream)

@@ -97,11 +97,22 @@ def test_in_process_ranks_match_all_views(world, overlap):
 
 
 def test_missing_peer_times_out_instead_of_hanging():
-    """A rank whose peer never reaches the exchange step raises the error flag after the bounded spin."""
-    ranks = nd_dist.PeerLift.local_group(2, 4, 64, DEV)
+    """A rank whose peer never reaches the exchange step: after the bounded wait the error word is raised on EVERY
+    rank, the rows the waiting rank owns are NaN (no stale or partial sums are handed out), the next call fails
+    without a synchronisation, and check() fails."""
+    ranks = nd_dist.PeerLift.local_group(2, 4, 64, DEV, timeout_ms=100)
     try:
-        ranks[0].acc.zero_()
-        ranks[0].exchange(3)
+        ranks[0].acc.fill_(1.0)
+        ranks[0].mean.fill_(7.0)
+        mean, cov, cnt = ranks[0].exchange(3)
+        torch.cuda.synchronize()
+        b, e = nd_dist.channel_shard(4, 0, 2)
+        assert torch.isnan(mean[b:e]).all() and torch.isnan(cov[b:e]).all()     # own slice poisoned
+        assert (mean[e:] == 7.0).all()                                          # the peer's slice was never written
+        w = 2 * ranks[0]._lib.ND_MAX_PEERS + 1
+        assert int(ranks[0].flags[w]) == 1 and int(ranks[1].flags[w]) == 1      # raised in both flag blocks
+        with pytest.raises(RuntimeError, match='time-out'):
+            ranks[0].exchange(3)                                                # hard error at the next call
         with pytest.raises(RuntimeError, match='peer'):
             ranks[0].check()
     finally:
