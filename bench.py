@@ -335,6 +335,7 @@ def bench_lift(args, rank, local_rank, world):
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     n_vox = int(np.prod(N_VOXELS))
     strong = args.scaling == 'strong'
+    want_cov = not args.no_cov
     if strong:
         views_total = args.views
         v0, v1 = nd_dist.view_shard(views_total, rank, world)
@@ -361,7 +362,7 @@ def bench_lift(args, rank, local_rank, world):
     if exchange in ('auto', 'multicast'):
         err = ''
         try:
-            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, transport='multicast', overlap_sms=overlap_sms if i < n_lanes else 0)
+            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, transport='multicast', want_cov=want_cov, overlap_sms=overlap_sms if i < n_lanes else 0)
                      for i in range(n_lanes + 2)]
         except Exception as e:                                 # no NVLS on this box / symmetric memory unavailable
             err = f'{type(e).__name__}: {e}'
@@ -375,7 +376,7 @@ def bench_lift(args, rank, local_rank, world):
             peers, exchange = None, 'peer'
     if exchange == 'peer':
         try:
-            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, overlap_sms=overlap_sms if i < n_lanes else 0)
+            peers = [nd_dist.PeerLift(CHANNELS, n_vox, dev, want_cov=want_cov, overlap_sms=overlap_sms if i < n_lanes else 0)
                      for i in range(n_lanes + 2)]
         except RuntimeError as e:
             # PeerLift fails on ALL ranks together when CUDA IPC / peer access is not available between these GPUs; the
@@ -388,10 +389,10 @@ def bench_lift(args, rank, local_rank, world):
     def step(feats, lane=0):
         f = feats[:, :, :FEAT_HW[0], :FEAT_HW[1]]
         if n_gpus == 1:
-            return lifting.lift_mean_var(f, pts_d, proj_d)
+            return lifting.lift_mean_var(f, pts_d, proj_d, want_cov=want_cov)
         if use_peer:
             return peers[lane](f, pts_d, proj_d, views_total)
-        return nd_dist.lift_mean_var_view_sharded(f, pts_d, proj_d, n_views_total=views_total)
+        return nd_dist.lift_mean_var_view_sharded(f, pts_d, proj_d, n_views_total=views_total, want_cov=want_cov)
 
     def barrier():
         if world > 1:
@@ -499,10 +500,12 @@ def bench_lift(args, rank, local_rank, world):
                 ln['stage'].copy_(host_sets[i % N_INPUT_SETS], non_blocking=True)
                 mean, cov, cnt = step(ln['stage'], n_lanes + i % 2)
                 ln['host_out'][0].copy_(mean.view(CHANNELS, -1), non_blocking=True)
-                ln['host_out'][1].copy_(cov.view(CHANNELS, -1), non_blocking=True)
+                if cov is not None:
+                    ln['host_out'][1].copy_(cov.view(CHANNELS, -1), non_blocking=True)
                 ln['host_cnt'].copy_(cnt.view(-1), non_blocking=True)
                 for t in (mean, cov, cnt):                  # allocated on this side stream: keep alive until it is done
-                    t.record_stream(ln['stream'])
+                    if t is not None:
+                        t.record_stream(ln['stream'])
 
         def e2e_join():
             for ln in lanes:
@@ -532,7 +535,7 @@ def bench_lift(args, rank, local_rank, world):
             dist.all_reduce(h2d)
         e2e = {'value': views_total * n_vox / (e2e_ms * 1e-3), 'unit': 'samples/s',
                'h2d_bytes_per_step': int(h2d.item()),
-               'd2h_bytes_per_step': int(2 * CHANNELS * n_vox * 4 + n_vox * 8) * n_gpus,
+               'd2h_bytes_per_step': int((2 if want_cov else 1) * CHANNELS * n_vox * 4 + n_vox * 8) * n_gpus,
                'ms_per_step': e2e_ms, 'steps': e2e_steps,
                'note': 'pinned host features -> device, fused lift through the Python API, mean / cov / count -> pinned host, '
                        'every step; two streams so that consecutive steps overlap copy and compute'}
@@ -552,7 +555,7 @@ def bench_lift(args, rank, local_rank, world):
             res = gpu_eager_reference(dev, dev_sets[0], pts_d, proj_d)
             if res is not None:
                 gpu_eager, ref_out = res
-                mean, cov, cnt = step(dev_sets[0])
+                mean, _, cnt = step(dev_sets[0])
                 torch.cuda.synchronize()
                 gpu_eager['count_equal_to_ours'] = bool(torch.equal(ref_out[2].view(-1), cnt.view(-1)))
                 gpu_eager['max_abs_mean_diff'] = float((ref_out[0] - mean).abs().max())
@@ -564,14 +567,14 @@ def bench_lift(args, rank, local_rank, world):
     if rank == 0:
         peaks, peak_src = measured_peaks()
         peak = float(peaks['hbm_gbs'])
-        bytes_per_step = algorithmic_bytes(nv_local, CHANNELS, FEAT_HW[0], FEAT_HW[1], n_vox)
+        bytes_per_step = algorithmic_bytes(nv_local, CHANNELS, FEAT_HW[0], FEAT_HW[1], n_vox) - (0 if want_cov else CHANNELS * n_vox * 4)
         achieved = bytes_per_step / (ms_per_step * 1e-3) / 1e9
         launches = 1 + (0 if n_gpus == 1 else 2 if use_peer else 1)        # cached plan: the lift kernel (+ exchange)
         line = {
             'metric': 'voxel_view_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': n_gpus,
             'steps': steps, 'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': lift_config(n_gpus, args.scaling, views_total, nv_local, exchange, n_lanes if pipeline else 0),
+            'config': lift_config(n_gpus, args.scaling, views_total, nv_local, exchange, n_lanes if pipeline else 0, want_cov),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': ncu_traffic(), 'peak_source': peak_src,
                          'algorithmic_bytes_per_step': bytes_per_step,
@@ -601,7 +604,9 @@ def multi_gpu_parity(dev, rank, world, step, feats_local, pts, proj_local, pts_d
     n_chk = 16
     mean, cov, cnt = step(feats_local)
     torch.cuda.synchronize()
-    mean, cov, cnt = mean.reshape(CHANNELS, -1)[:n_chk].clone(), cov.reshape(CHANNELS, -1)[:n_chk].clone(), cnt.reshape(-1).clone()
+    has_cov = cov is not None
+    mean, cnt = mean.reshape(CHANNELS, -1)[:n_chk].clone(), cnt.reshape(-1).clone()
+    cov = cov.reshape(CHANNELS, -1)[:n_chk].clone() if has_cov else torch.zeros_like(mean)
     f_chk = feats_local[:, :n_chk].contiguous()
     nv_max = torch.tensor([f_chk.shape[0]], device=dev)
     dist.all_reduce(nv_max, op=dist.ReduceOp.MAX)
@@ -642,15 +647,15 @@ def multi_gpu_parity(dev, rank, world, step, feats_local, pts, proj_local, pts_d
         m1, c1, n1 = ops.lift_mean_var(fs, pts_d, projs, None, True, 0)            # single GPU, all views
         torch.cuda.synchronize()
         bm, em = bad(mean, m1.cpu().numpy())
-        bc, ec = bad(cov, c1.cpu().numpy())
+        bc, ec = bad(cov, c1.cpu().numpy()) if has_cov else (0, 0.0)
         m2, c2, n2 = c_oracle.lift(fs[:, :2].cpu().numpy(), pts.numpy(), projs.cpu().numpy())
         bm2, em2 = bad(mean[:2], m2)
-        bc2, ec2 = bad(cov[:2], c2)
+        bc2, ec2 = bad(cov[:2], c2) if has_cov else (0, 0.0)
         cnt_ok = bool(np.array_equal(cnt.cpu().numpy(), n2)) and bool(torch.equal(cnt, n1))
         res = {'ok': bool(bm == 0 and bc == 0 and bm2 == 0 and bc2 == 0 and cnt_ok and int(same.item()) == 1),
                'vs_single_gpu_lift_16_channels': {'mean_outside_tol': bm, 'cov_outside_tol': bc, 'max_abs_err': [em, ec]},
                'vs_c_oracle_2_channels': {'mean_outside_tol': bm2, 'cov_outside_tol': bc2, 'max_abs_err': [em2, ec2]},
-               'counts_equal': cnt_ok, 'all_ranks_bit_identical': bool(int(same.item()) == 1),
+               'counts_equal': cnt_ok, 'all_ranks_bit_identical': bool(int(same.item()) == 1), 'cov_checked': has_cov,
                'tolerance': '|a-b| <= 1e-4 |ref| + 1e-5 max|ref|; counts exact', 'views_total': views_total}
     dist.barrier()
     return res
@@ -942,6 +947,9 @@ def main():
                     help='lift, N > 1: weak = 50 views per GPU (default), strong = --views in total, sharded')
     ap.add_argument('--views', type=int, default=100, help='--scaling strong: views of the scene (BASELINE.json configs[3]: ~100)')
     ap.add_argument('--mlp', default='bf16', choices=['fp32', 'bf16'], help='render: precision of the shared MLP kernel')
+    ap.add_argument('--no-cov', action='store_true',
+                    help='lift: mean and count only (the live path never reads the 256-channel volume_cov, SURVEY.md section 0.5); '
+                         'a labelled variant of the workload: half the bytes are written, and half cross the links at N > 1')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--lanes', type=int, default=2, help='N > 1, pipelined: scenes in flight (streams / peer segments)')

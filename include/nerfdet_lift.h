@@ -150,12 +150,21 @@ int nd_lift_plan_mean_var(const nd_maps *features, const void *plan, size_t plan
 int nd_lift_plan_accumulate(const nd_maps *features, const void *plan, size_t plan_bytes, int64_t n_voxels,
                             uint32_t launch_index, float *s1, float *s2, float *cnt, const nd_lift_options *opt,
                             void *stream);
+/* The view-sharded accumulate with the reduce-scatter fused into its epilogue (no counterpart in the reference; SURVEY.md
+ * section 8e): as soon as a CTA has finished the sums of channel c it stores the row into the segment of the rank that owns c
+ * (channels split contiguously over the ranks, sizes differing by at most one, first ranks larger).
+ *   part_host: HOST array of `world` DEVICE pointers (peer-mapped), entry g = the block inside rank g's segment that
+ *     receives THIS rank's partials: [S1: slice x N | S2: slice x N (absent when with_s2 == 0) | count: N] f32,
+ *     slice = ceil(channels / world).  Complete (system-wide visible) when the kernel has finished on `stream`. */
+int nd_lift_plan_accumulate_scatter(const nd_maps *features, const void *plan, size_t plan_bytes, int64_t n_voxels,
+                                    uint32_t launch_index, void *const *part_host, int world, int with_s2,
+                                    const nd_lift_options *opt, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * View-sharded form of the same: each rank runs nd_lift_accumulate on
  * its own views, the caller all-reduces (sum) the accumulators, then nd_lift_finalize with
  * the GLOBAL view count.
- *   s1, s2 f32 [C][N]  (sum and sum of squares over this rank's valid views)
+ *   s1, s2 f32 [C][N]  (sum and sum of squares over this rank's valid views; s2 may be NULL when no variance is wanted)
  *   cnt    f32 [N]     (valid views on this rank; exact in fp32 up to 2^24)
  * ------------------------------------------------------------------------------------- */
 int nd_lift_accumulate(const nd_maps *features, const float *points, const float *projection,
@@ -182,7 +191,9 @@ int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_v
  *   nd_lift_finalize_peers
  *     acc_host / mean_host / cov_host / flags_host: HOST arrays of `world` DEVICE pointers, entry g = rank g's
  *       accumulators [S1 (C*N) | S2 (C*N) | count (N)] f32 as written by nd_lift_accumulate, its mean [C][N], its cov
- *       [C][N] (cov_host NULL: not wanted) and its flag block (ND_PEER_FLAG_WORDS uint32, zero before the first epoch);
+ *       [C][N] and its flag block.  cov_host NULL: the variance is not wanted (the live path never reads the 256-channel
+ *       volume_cov, nerfdet.py:179-181 vs :232-261) -- the accumulators are then [S1 (C*N) | count (N)] (nd_lift_accumulate
+ *       with s2 == NULL) and half as many bytes cross the links.  Flag block: (ND_PEER_FLAG_WORDS uint32, zero before the first epoch);
  *       entry `rank` is the local segment.  world <= ND_MAX_PEERS.
  *     epoch: 1, 2, 3, ... the same on every rank for the same step.
  *     count: int64 [N] local, or NULL.  alpha: f32 [N] local or NULL (alpha * mean, nerfdet.py:259-261).
@@ -194,6 +205,11 @@ int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_v
  *       the work, so that the exchange of one scene can run beside the accumulate of the next on the SMs that
  *       nd_lift_options.sm_limit keeps free (the exchange is bound by the links, not by the SMs).
  *     timeout_ms: bound of every wait for a peer (0 = 4000).
+ *     scattered: 0 = acc_host[g] is rank g's own accumulator buffer (the kernel loads its channel slice of it over NVLink);
+ *       1 = acc_host[g] is the LOCAL block into which rank g has already stored its partial sums of THIS rank's channel
+ *       slice (nd_lift_plan_accumulate_scatter: the reduce-scatter half of the exchange is fused into the lift kernel's
+ *       epilogue as peer stores) -- [S1: slice x N | S2: slice x N (absent when cov_host is NULL) | count: N] f32 with
+ *       slice = ceil(channels / world); the kernel then reads local memory only and its NVLink traffic is the result rows.
  *   Outputs are complete on `stream` when the call's kernels have run.  A peer that does not arrive within the
  *   time-out raises word 2 * ND_MAX_PEERS + 1 (the error word) of EVERY rank's flag block instead of hanging; a rank
  *   that finds its error word set performs no reduce and no peer store, fills the rows it owns with NaN in its own
@@ -210,7 +226,7 @@ int nd_peer_free(void *ptr);
 int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
                            void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
                            int channels, int64_t n_voxels, const float *alpha, int64_t *count, const void *acc_mc,
-                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, void *stream);
+                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, int scattered, void *stream);
 
 
 /* ---------------------------------------------------------------------------------------

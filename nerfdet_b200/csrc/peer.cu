@@ -28,7 +28,10 @@ constexpr int kMaxPeers = ND_MAX_PEERS;
 constexpr int kPeerThreads = 128;
 
 struct PeerArgs {
-    const float *acc[kMaxPeers];
+    // per source rank g: S1 / S2 rows addressed [c * N + n] with the GLOBAL channel index c, counts [n].  Gathered layout:
+    // rank g's own accumulators (remote loads).  Scattered layout: the LOCAL block rank g stored its partials of this
+    // rank's channel slice into (nd_lift_plan_accumulate_scatter), pointers shifted by the slice start.
+    const float *s1[kMaxPeers], *s2[kMaxPeers], *cntp[kMaxPeers];
     float *mean[kMaxPeers];
     float *cov[kMaxPeers];           // all null: no covariance wanted
     uint32_t *flags[kMaxPeers];      // [0, P): ready, [P, 2P): done, [2P]: CTA counter, [2P + 1]: error
@@ -108,7 +111,7 @@ template <> __device__ __forceinline__ void st_vec<1>(float *p, const float (&r)
 // looping over work items -- the exchange is link-bound, so ~20 SMs carry it while the other SMs run the next scene's
 // accumulate; fat CTAs because the block scheduler spreads small CTAs over all SMs, where none would leave room for a
 // persistent lift CTA).
-template <int V, int G, int U, bool MC, int T>
+template <int V, int G, int U, bool MC, int T, bool COV>
 __global__ void __launch_bounds__(T, T > 128 ? 1 : ((G * U <= 4) ? 6 : 4))
 k_lift_finalize_peers(const PeerArgs a) {
     static_assert(!MC || (V == 4 && G == 1), "multicast instantiation: 16-byte vectors, one (reduced) load per row");
@@ -131,6 +134,7 @@ k_lift_finalize_peers(const PeerArgs a) {
     const bool bad = s_bad != 0;
 
     const int64_t cn = (int64_t)a.channels * a.n_vox;
+    const int64_t cnt_off = COV ? 2 * cn : cn;                  // accumulators: [S1 | S2 | count], or [S1 | count] without the variance
     // work item = (voxel tile of T * V voxels, channel sub-slice); wide grid: exactly one item per CTA
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const int tile = item % a.n_tiles, sub = item / a.n_tiles;
@@ -145,7 +149,7 @@ k_lift_finalize_peers(const PeerArgs a) {
             for (int j = 0; j < V; ++j) nanv[j] = __int_as_float(0x7fc00000);
             for (int c = c0; c < c1; ++c) {
                 st_vec<V>(a.mean[a.rank] + (int64_t)c * a.n_vox + n, nanv);
-                if (a.cov[a.rank] != nullptr) st_vec<V>(a.cov[a.rank] + (int64_t)c * a.n_vox + n, nanv);
+                if constexpr (COV) st_vec<V>(a.cov[a.rank] + (int64_t)c * a.n_vox + n, nanv);
             }
         }
         continue;
@@ -158,8 +162,8 @@ k_lift_finalize_peers(const PeerArgs a) {
         for (int g = 0; g < G; ++g) {
             if (MC || g < a.world) {
                 float t[V];
-                if constexpr (MC) ld_reduce_mc(a.acc_mc + 2 * cn + n, t);
-                else ld_vec<V>(a.acc[g] + 2 * cn + n, t);
+                if constexpr (MC) ld_reduce_mc(a.acc_mc + cnt_off + n, t);
+                else ld_vec<V>(a.cntp[g] + n, t);
 #pragma unroll
                 for (int j = 0; j < V; ++j) cnt[j] += t[j];
             }
@@ -177,7 +181,7 @@ k_lift_finalize_peers(const PeerArgs a) {
         const int c0 = a.c_begin + sub * a.ch_per_cta;
         const int c1 = min(a.c_end, c0 + a.ch_per_cta);
         for (int cb = c0; cb < c1; cb += U) {
-            float p1[U][G][V], p2[U][G][V];
+            float p1[U][G][V], p2[COV ? U : 1][COV ? G : 1][V];
 #pragma unroll
             for (int u = 0; u < U; ++u) {                       // all loads of the U channels in flight together
                 const int64_t o = (int64_t)min(cb + u, c1 - 1) * a.n_vox + n;
@@ -185,10 +189,10 @@ k_lift_finalize_peers(const PeerArgs a) {
                 for (int g = 0; g < G; ++g) {
                     if constexpr (MC) {
                         ld_reduce_mc(a.acc_mc + o, p1[u][g]);
-                        ld_reduce_mc(a.acc_mc + cn + o, p2[u][g]);
+                        if constexpr (COV) ld_reduce_mc(a.acc_mc + cn + o, p2[u][g]);
                     } else if (g < a.world) {
-                        ld_vec<V>(a.acc[g] + o, p1[u][g]);
-                        ld_vec<V>(a.acc[g] + cn + o, p2[u][g]);
+                        ld_vec<V>(a.s1[g] + o, p1[u][g]);
+                        if constexpr (COV) ld_vec<V>(a.s2[g] + o, p2[u][g]);
                     }
                 }
             }
@@ -203,7 +207,10 @@ k_lift_finalize_peers(const PeerArgs a) {
                 for (int g = 0; g < G; ++g) {                   // rank order: every rank would get the same bits
                     if (MC || g < a.world) {
 #pragma unroll
-                        for (int j = 0; j < V; ++j) { s1[j] += p1[u][g][j]; s2[j] += p2[u][g][j]; }
+                        for (int j = 0; j < V; ++j) {
+                            s1[j] += p1[u][g][j];
+                            if constexpr (COV) s2[j] += p2[u][g][j];
+                        }
                     }
                 }
                 float m[V], cv[V];
@@ -213,22 +220,24 @@ k_lift_finalize_peers(const PeerArgs a) {
                     cv[j] = 0.f;
                     if (cnt[j] > 0.f) {                         // same formula as k_lift_finalize (lift.cu)
                         const float mm = s1[j] / cnt[j];
-                        float ssd = fmaxf(fmaf(-mm, s1[j], s2[j]), 0.0f);
-                        ssd = fmaf(inv[j] * mm, mm, ssd);
-                        cv[j] = expf(-(ssd / cnt[j]));
+                        if constexpr (COV) {
+                            float ssd = fmaxf(fmaf(-mm, s1[j], s2[j]), 0.0f);
+                            ssd = fmaf(inv[j] * mm, mm, ssd);
+                            cv[j] = expf(-(ssd / cnt[j]));
+                        }
                         m[j] = mm * al[j];
                     }
                 }
 #pragma unroll
                 if constexpr (MC) {
                     st_mc(a.mean_mc + o, m);
-                    if (a.cov_mc != nullptr) st_mc(a.cov_mc + o, cv);
+                    if constexpr (COV) st_mc(a.cov_mc + o, cv);
                 } else {
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         if (g < a.world) {
                             st_vec<V>(a.mean[g] + o, m);
-                            if (a.cov[g] != nullptr) st_vec<V>(a.cov[g] + o, cv);
+                            if constexpr (COV) st_vec<V>(a.cov[g] + o, cv);
                         }
                     }
                 }
@@ -319,7 +328,7 @@ int nd_peer_free(void *ptr) {
 int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
                            void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
                            int channels, int64_t n_voxels, const float *alpha, int64_t *count, const void *acc_mc,
-                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, void *stream) {
+                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, int scattered, void *stream) {
     ND_REQUIRE(acc_host && mean_host && flags_host, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: null pointer table");
     ND_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, ND_ERR_BAD_ARG,
                "nd_lift_finalize_peers: world %d / rank %d outside [1, %d]", world, rank, kMaxPeers);
@@ -330,12 +339,12 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     bool vec = n_voxels % 4 == 0 && (alpha == nullptr || reinterpret_cast<uintptr_t>(alpha) % 16 == 0);
     for (int g = 0; g < world; ++g) {
         ND_REQUIRE(acc_host[g] && mean_host[g] && flags_host[g], ND_ERR_BAD_ARG, "nd_lift_finalize_peers: null segment of rank %d", g);
-        a.acc[g] = static_cast<const float *>(acc_host[g]);
+        a.s1[g] = static_cast<const float *>(acc_host[g]);
         a.mean[g] = static_cast<float *>(mean_host[g]);
         a.cov[g] = cov_host != nullptr ? static_cast<float *>(cov_host[g]) : nullptr;
         a.flags[g] = static_cast<uint32_t *>(flags_host[g]);
-        vec = vec && reinterpret_cast<uintptr_t>(a.acc[g]) % 16 == 0 && reinterpret_cast<uintptr_t>(a.mean[g]) % 16 == 0 &&
-              reinterpret_cast<uintptr_t>(a.cov[g]) % 16 == 0;
+        vec = vec && reinterpret_cast<uintptr_t>(a.s1[g]) % 16 == 0 && reinterpret_cast<uintptr_t>(a.mean[g]) % 16 == 0 &&
+              reinterpret_cast<uintptr_t>(a.cov[g]) % 16 == 0 && ((int64_t)channels * n_voxels) % 4 == 0;
     }
     a.world = world;
     a.rank = rank;
@@ -350,6 +359,24 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     a.n_vox = n_voxels;
     a.alpha = alpha;
     a.count = count;
+    {
+        const bool with_s2 = cov_host != nullptr;
+        const int64_t cn = (int64_t)channels * n_voxels;
+        const int64_t slice_n = (int64_t)((channels + world - 1) / world) * n_voxels;
+        for (int g = 0; g < world; ++g) {
+            const float *blk = a.s1[g];
+            if (scattered) {                                    // [S1: slice x N | S2: slice x N | count: N], local
+                a.s1[g] = blk - (int64_t)a.c_begin * n_voxels;
+                a.s2[g] = with_s2 ? blk + slice_n - (int64_t)a.c_begin * n_voxels : nullptr;
+                a.cntp[g] = blk + (with_s2 ? 2 : 1) * slice_n;
+            } else {                                            // [S1: C x N | S2: C x N | count: N], rank g's own
+                a.s2[g] = with_s2 ? blk + cn : nullptr;
+                a.cntp[g] = blk + (with_s2 ? 2 : 1) * cn;
+            }
+        }
+        ND_REQUIRE(!scattered || acc_mc == nullptr, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: scattered partials and multicast exclude each other");
+        if (scattered) vec = vec && slice_n % 4 == 0 && ((int64_t)a.c_begin * n_voxels) % 4 == 0;
+    }
     const bool mc = acc_mc != nullptr;
     if (mc) {
         ND_REQUIRE(mean_mc != nullptr && (cov_mc != nullptr) == (cov_host != nullptr), ND_ERR_BAD_ARG,
@@ -382,10 +409,16 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     a.n_items = (int)(tiles * (slice > 0 ? ceil_div(slice, a.ch_per_cta) : 1));
     const dim3 grid((unsigned)(narrow && max_ctas < a.n_items ? max_ctas : a.n_items));
     cudaStream_t st = (cudaStream_t)stream;
-#define ND_PEER_LAUNCH(V_, G_, U_, T_) k_lift_finalize_peers<V_, G_, U_, false, T_><<<grid, T_, 0, st>>>(a)
+    const bool with_cov = cov_host != nullptr;
+#define ND_PEER_LAUNCH(V_, G_, U_, T_)                                                       \
+    do {                                                                                     \
+        if (with_cov) k_lift_finalize_peers<V_, G_, U_, false, T_, true><<<grid, T_, 0, st>>>(a);  \
+        else k_lift_finalize_peers<V_, G_, U_, false, T_, false><<<grid, T_, 0, st>>>(a);    \
+    } while (0)
     if (mc) {
-        if (narrow) k_lift_finalize_peers<4, 1, 4, true, 512><<<grid, 512, 0, st>>>(a);
-        else k_lift_finalize_peers<4, 1, 4, true, kPeerThreads><<<grid, kPeerThreads, 0, st>>>(a);
+        ND_REQUIRE(with_cov, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: the multicast transport carries mean and cov");
+        if (narrow) k_lift_finalize_peers<4, 1, 4, true, 512, true><<<grid, 512, 0, st>>>(a);
+        else k_lift_finalize_peers<4, 1, 4, true, kPeerThreads, true><<<grid, kPeerThreads, 0, st>>>(a);
     } else if (narrow) {
         if (gb == 1) ND_PEER_LAUNCH(4, 1, 4, 512);
         else if (gb == 2) ND_PEER_LAUNCH(4, 2, 4, 512);

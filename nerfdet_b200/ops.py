@@ -182,18 +182,34 @@ class LiftPlan:
                 self.stream), 'nd_lift_plan_mean_var')
         return mean, cov, count
 
-    def accumulate_into(self, features: Tensor, acc: Tensor) -> None:
-        """[S1 (C*N) | S2 (C*N) | count (N)] of this rank's views into the caller-owned flat f32 buffer ``acc``."""
+    def accumulate_into(self, features: Tensor, acc: Tensor, with_s2: bool = True) -> None:
+        """[S1 (C*N) | S2 (C*N) | count (N)] of this rank's views into the caller-owned flat f32 buffer ``acc``;
+        ``with_s2=False``: [S1 (C*N) | count (N)] (no variance wanted downstream)."""
         m = _maps(features)
         c, n = m.channels, self.n_voxels
-        if acc.dtype != torch.float32 or acc.numel() != (2 * c + 1) * n or not acc.is_contiguous() or acc.device != self.device:
-            raise ValueError(f'acc must be a contiguous float32 buffer of (2 * {c} + 1) * {n} elements')
+        k = 2 if with_s2 else 1
+        if acc.dtype != torch.float32 or acc.numel() != (k * c + 1) * n or not acc.is_contiguous() or acc.device != self.device:
+            raise ValueError(f'acc must be a contiguous float32 buffer of ({k} * {c} + 1) * {n} elements')
         base = acc.data_ptr()
         with _on(self.device):
             _lib.check(_lib.load().nd_lift_plan_accumulate(
                 ctypes.byref(m), _ptr(self.buf), self.bytes, n, self._launch_index(features), ctypes.c_void_p(base),
-                ctypes.c_void_p(base + 4 * c * n), ctypes.c_void_p(base + 8 * c * n), ctypes.byref(self.opt),
-                self.stream), 'nd_lift_plan_accumulate')
+                ctypes.c_void_p(base + 4 * c * n) if with_s2 else None, ctypes.c_void_p(base + 4 * k * c * n),
+                ctypes.byref(self.opt), self.stream), 'nd_lift_plan_accumulate')
+
+
+def _plan_accumulate_scatter(self, features: Tensor, part_ptrs, world: int, with_s2: bool = True) -> None:
+    """The view-sharded accumulate with the reduce-scatter fused into its epilogue: the sums of every channel are stored
+    into the segment of the rank that owns the channel.  ``part_ptrs``: ctypes array of ``world`` peer-mapped device
+    pointers (``distributed.PeerLift`` keeps them)."""
+    m = _maps(features)
+    with _on(self.device):
+        _lib.check(_lib.load().nd_lift_plan_accumulate_scatter(
+            ctypes.byref(m), _ptr(self.buf), self.bytes, self.n_voxels, self._launch_index(features), part_ptrs, int(world),
+            1 if with_s2 else 0, ctypes.byref(self.opt), self.stream), 'nd_lift_plan_accumulate_scatter')
+
+
+LiftPlan.accumulate_scatter = _plan_accumulate_scatter
 
 
 def _layout_key(features: Tensor):
@@ -251,18 +267,22 @@ def lift_mean_var_planned(features: Tensor, points: Tensor, projection: Tensor, 
 
 
 def lift_accumulate_planned(features: Tensor, points: Tensor, projection: Tensor, acc: Optional[Tensor] = None,
-                            sm_limit: int = 0) -> Tensor:
+                            sm_limit: int = 0, with_s2: bool = True) -> Tensor:
     """``[S1 | S2 | count]`` of these views (view-sharded lift) through the cached geometry plan,
-    into ``acc`` when given (the peer-mapped segment of ``distributed.PeerLift``) or a fresh buffer."""
+    into ``acc`` when given (the peer-mapped segment of ``distributed.PeerLift``) or a fresh buffer;
+    ``with_s2=False``: ``[S1 | count]`` only."""
     plan = cached_lift_plan(features, points, projection, sm_limit=sm_limit)
     if not plan.eligible:
+        if not with_s2:
+            raise NotImplementedError('the S1-only accumulators need the plane-resident kernel')
         if acc is None:
             return lift_accumulate(features, points, projection, 0)
         lift_accumulate_into(features, points, projection, acc, sm_limit)
         return acc
     if acc is None:
-        acc = torch.empty(((2 * features.shape[1] + 1) * plan.n_voxels,), dtype=torch.float32, device=features.device)
-    plan.accumulate_into(features, acc)
+        acc = torch.empty((((2 if with_s2 else 1) * features.shape[1] + 1) * plan.n_voxels,), dtype=torch.float32,
+                          device=features.device)
+    plan.accumulate_into(features, acc, with_s2)
     return acc
 
 

@@ -55,8 +55,9 @@ def test_single_rank_equals_fused_lift(nv, grid, channels, overlap):
         peer.close()
 
 
+@pytest.mark.parametrize('mode', ['scatter', 'gather'])
 @pytest.mark.parametrize('world,overlap', [(2, 0), (3, 0), (8, 0), (2, 3), (4, 2), (8, 2)])
-def test_in_process_ranks_match_all_views(world, overlap):
+def test_in_process_ranks_match_all_views(world, overlap, mode):
     nv, grid, channels = 19, (16, 16, 8), 20                # uneven view split, channel slices of unequal size
     n = int(np.prod(grid))
     f, pts, proj = _scene(nv, grid, (0.4, 0.4, 0.4), channels, 92)
@@ -69,7 +70,7 @@ def test_in_process_ranks_match_all_views(world, overlap):
         a = ops.lift_accumulate(f[b:e], pts, proj[b:e], 0)
         acc = a if acc is None else acc + a
     m_ref, c_ref, n_ref = ops.lift_finalize(acc, nv, channels, n, alpha, True)
-    ranks = nd_dist.PeerLift.local_group(world, channels, n, DEV, overlap_sms=overlap)
+    ranks = nd_dist.PeerLift.local_group(world, channels, n, DEV, overlap_sms=overlap, mode=mode)
     streams = [torch.cuda.Stream() for _ in range(world)]
     try:
         torch.cuda.synchronize()
@@ -96,11 +97,41 @@ def test_in_process_ranks_match_all_views(world, overlap):
             peer.close()
 
 
+@pytest.mark.parametrize('world', [2, 8])
+def test_in_process_ranks_without_variance(world):
+    """want_cov=False: the accumulators are [S1 | count], the exchange moves half the bytes and only the mean comes back."""
+    nv, grid, channels = 19, (16, 16, 8), 20
+    n = int(np.prod(grid))
+    f, pts, proj = _scene(nv, grid, (0.4, 0.4, 0.4), channels, 93)
+    mean, _, cnt = lifting.lift_mean_var(f, pts, proj)
+    ranks = nd_dist.PeerLift.local_group(world, channels, n, DEV, want_cov=False)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    try:
+        torch.cuda.synchronize()
+        for epoch in range(2):
+            outs = []
+            for r, (peer, st) in enumerate(zip(ranks, streams)):
+                b, e = nd_dist.view_shard(nv, r, world)
+                with torch.cuda.stream(st):
+                    outs.append(peer(f[b:e], pts, proj[b:e], nv))
+            torch.cuda.synchronize()
+        for peer in ranks:
+            peer.check()
+        for r, (m2, c2, n2) in enumerate(outs):
+            assert c2 is None
+            assert torch.equal(n2, cnt), f'count of rank {r}'
+            assert_close(m2, mean, 1e-4, f'mean of rank {r}')
+            assert torch.equal(m2, outs[0][0])
+    finally:
+        for peer in ranks:
+            peer.close()
+
+
 def test_missing_peer_times_out_instead_of_hanging():
     """A rank whose peer never reaches the exchange step: after the bounded wait the error word is raised on EVERY
     rank, the rows the waiting rank owns are NaN (no stale or partial sums are handed out), the next call fails
     without a synchronisation, and check() fails."""
-    ranks = nd_dist.PeerLift.local_group(2, 4, 64, DEV, timeout_ms=100)
+    ranks = nd_dist.PeerLift.local_group(2, 4, 64, DEV, timeout_ms=100, mode='gather')
     try:
         ranks[0].acc.fill_(1.0)
         ranks[0].mean.fill_(7.0)
