@@ -296,7 +296,7 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------
 # workload: lift
 # ------------------------------------------------------------------------------------------
-def lift_config(n_gpus, scaling, views_total, views_per_gpu, exchange, lanes, want_cov=True):
+def lift_config(n_gpus, scaling, views_total, views_per_gpu, exchange, lanes, want_cov=True, overlap_sms=0):
     if n_gpus == 1:
         part = 'single GPU'
     elif exchange == 'multicast':
@@ -318,7 +318,7 @@ def lift_config(n_gpus, scaling, views_total, views_per_gpu, exchange, lanes, wa
         'geometry': 'the geometry plan (pixel offsets, counts, work distribution; depends on the cameras only) is built '
                     'once per scene geometry and reused by the steps (ops.cached_lift_plan); fresh_geometry times the '
                     'step with the plan rebuilt every call',
-        'partitioning': part, 'scenes_in_flight': lanes if lanes else 1, 'want_cov': want_cov,
+        'partitioning': part, 'scenes_in_flight': lanes if lanes else 1, 'want_cov': want_cov, 'exchange_sms': overlap_sms if lanes else 'all',
     }
 
 
@@ -356,7 +356,7 @@ def bench_lift(args, rank, local_rank, world):
     # N > 1: one peer-mapped segment per scene in flight and one per end-to-end lane
     exchange = args.exchange if n_gpus > 1 else 'none'
     pipeline = n_gpus > 1 and exchange != 'nccl' and not args.no_pipeline
-    overlap_sms = OVERLAP_SMS if pipeline else 0
+    overlap_sms = args.overlap_sms if pipeline else 0
     n_lanes = max(2, args.lanes) if pipeline else 1
     peers = None
     if exchange in ('auto', 'multicast'):
@@ -574,7 +574,7 @@ def bench_lift(args, rank, local_rank, world):
             'metric': 'voxel_view_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': n_gpus,
             'steps': steps, 'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': lift_config(n_gpus, args.scaling, views_total, nv_local, exchange, n_lanes if pipeline else 0, want_cov),
+            'config': lift_config(n_gpus, args.scaling, views_total, nv_local, exchange, n_lanes if pipeline else 0, want_cov, overlap_sms),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': ncu_traffic(), 'peak_source': peak_src,
                          'algorithmic_bytes_per_step': bytes_per_step,
@@ -953,6 +953,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--lanes', type=int, default=2, help='N > 1, pipelined: scenes in flight (streams / peer segments)')
+    ap.add_argument('--overlap-sms', type=int, default=OVERLAP_SMS, help='N > 1, pipelined: SMs left to the exchange kernel')
     ap.add_argument('--no-pipeline', action='store_true',
                     help='N > 1: one scene at a time (default: two scenes in flight on two streams, the exchange of scene i '
                          'on OVERLAP_SMS SMs beside the accumulate of scene i + 1 on the others)')

@@ -150,15 +150,6 @@ int nd_lift_plan_mean_var(const nd_maps *features, const void *plan, size_t plan
 int nd_lift_plan_accumulate(const nd_maps *features, const void *plan, size_t plan_bytes, int64_t n_voxels,
                             uint32_t launch_index, float *s1, float *s2, float *cnt, const nd_lift_options *opt,
                             void *stream);
-/* The view-sharded accumulate with the reduce-scatter fused into its epilogue (no counterpart in the reference; SURVEY.md
- * section 8e): as soon as a CTA has finished the sums of channel c it stores the row into the segment of the rank that owns c
- * (channels split contiguously over the ranks, sizes differing by at most one, first ranks larger).
- *   part_host: HOST array of `world` DEVICE pointers (peer-mapped), entry g = the block inside rank g's segment that
- *     receives THIS rank's partials: [S1: slice x N | S2: slice x N (absent when with_s2 == 0) | count: N] f32,
- *     slice = ceil(channels / world).  Complete (system-wide visible) when the kernel has finished on `stream`. */
-int nd_lift_plan_accumulate_scatter(const nd_maps *features, const void *plan, size_t plan_bytes, int64_t n_voxels,
-                                    uint32_t launch_index, void *const *part_host, int world, int with_s2,
-                                    const nd_lift_options *opt, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * View-sharded form of the same: each rank runs nd_lift_accumulate on
@@ -205,11 +196,6 @@ int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_v
  *       the work, so that the exchange of one scene can run beside the accumulate of the next on the SMs that
  *       nd_lift_options.sm_limit keeps free (the exchange is bound by the links, not by the SMs).
  *     timeout_ms: bound of every wait for a peer (0 = 4000).
- *     scattered: 0 = acc_host[g] is rank g's own accumulator buffer (the kernel loads its channel slice of it over NVLink);
- *       1 = acc_host[g] is the LOCAL block into which rank g has already stored its partial sums of THIS rank's channel
- *       slice (nd_lift_plan_accumulate_scatter: the reduce-scatter half of the exchange is fused into the lift kernel's
- *       epilogue as peer stores) -- [S1: slice x N | S2: slice x N (absent when cov_host is NULL) | count: N] f32 with
- *       slice = ceil(channels / world); the kernel then reads local memory only and its NVLink traffic is the result rows.
  *   Outputs are complete on `stream` when the call's kernels have run.  A peer that does not arrive within the
  *   time-out raises word 2 * ND_MAX_PEERS + 1 (the error word) of EVERY rank's flag block instead of hanging; a rank
  *   that finds its error word set performs no reduce and no peer store, fills the rows it owns with NaN in its own
@@ -226,7 +212,7 @@ int nd_peer_free(void *ptr);
 int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
                            void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
                            int channels, int64_t n_voxels, const float *alpha, int64_t *count, const void *acc_mc,
-                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, int scattered, void *stream);
+                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, void *stream);
 
 
 /* ---------------------------------------------------------------------------------------

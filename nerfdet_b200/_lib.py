@@ -58,8 +58,6 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, POINTER(NdLiftOptions), c_void_p]),
     'nd_lift_plan_accumulate': (c_int, [POINTER(NdMaps), c_void_p, c_size_t, c_int64, ctypes.c_uint32, c_void_p, c_void_p,
                                         c_void_p, POINTER(NdLiftOptions), c_void_p]),
-    'nd_lift_plan_accumulate_scatter': (c_int, [POINTER(NdMaps), c_void_p, c_size_t, c_int64, ctypes.c_uint32, POINTER(c_void_p), c_int,
-                                                c_int, POINTER(NdLiftOptions), c_void_p]),
     'nd_lift_finalize': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
     'nd_peer_alloc': (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
@@ -68,7 +66,7 @@ SIGNATURES = {
     'nd_peer_free': (c_int, [c_void_p]),
     'nd_lift_finalize_peers': (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                        c_int, c_int, ctypes.c_uint32, c_int, c_int, c_int64, c_void_p, c_void_p,
-                                       c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'nd_live_stats': (c_int, [POINTER(NdMaps), POINTER(NdMaps), c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'nd_map_features': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -410,14 +410,10 @@ bool lift_quads_eligible(const nd_maps *f, int64_t n_vox, const nd_lift_options 
 size_t lift_quads_plan_bytes(const nd_maps *f, int64_t n_vox, const nd_lift_options *opt);
 nd_status lift_quads_plan_build(const nd_maps *f, const float *points, const float *proj, int64_t n_vox, const float *depth,
                                 float voxel_z, void *plan, size_t plan_bytes, const nd_lift_options *opt, cudaStream_t st);
-struct QPeers {
-    float *part[ND_MAX_PEERS];
-    int world, with_s2;
-};
 template <typename T, bool kRaw>
 nd_status lift_quads_run(const nd_maps *f, const void *plan, size_t plan_bytes, int64_t n_vox, uint32_t launch_index,
                          int n_views_total, const float *alpha, float *out_a, float *out_b, int64_t *count_i64,
-                         float *count_f32, const nd_lift_options *opt, cudaStream_t st, const QPeers *peers);
+                         float *count_f32, const nd_lift_options *opt, cudaStream_t st);
 
 static size_t scratch_budget(const nd_lift_options *opt) {
     return (opt && opt->scratch_budget_bytes) ? opt->scratch_budget_bytes : ((size_t)64 << 20);
@@ -543,7 +539,7 @@ static nd_status run_lift(const nd_maps *f, const float *points, const float *pr
         nd_status s = lift_quads_plan_build(f, points, proj, n_vox, nullptr, 0.0f, ws, ws_bytes, opt, st);
         if (s != ND_OK) return s;
         return lift_quads_run<T, kRaw>(f, ws, ws_bytes, n_vox, 0u, f->n_views, alpha, out_a, out_b, count_i64, count_f32,
-                                       opt, st, nullptr);
+                                       opt, st);
     }
     ND_REQUIRE(ws != nullptr && ws_bytes >= p.total_bytes, ND_ERR_WORKSPACE,
                "lift: workspace too small (%zu < %zu bytes)", ws_bytes, p.total_bytes);
@@ -704,9 +700,9 @@ int nd_lift_plan_mean_var(const nd_maps *f, const void *plan, size_t plan_bytes,
     cudaStream_t st = (cudaStream_t)stream;
     if (f->dtype == ND_F32)
         return lift_quads_run<float, false>(f, plan, plan_bytes, n_voxels, launch_index, n_views_total, alpha, mean, cov,
-                                            count, nullptr, opt, st, nullptr);
+                                            count, nullptr, opt, st);
     return lift_quads_run<__nv_bfloat16, false>(f, plan, plan_bytes, n_voxels, launch_index, n_views_total, alpha, mean,
-                                                cov, count, nullptr, opt, st, nullptr);
+                                                cov, count, nullptr, opt, st);
 }
 
 int nd_lift_plan_accumulate(const nd_maps *f, const void *plan, size_t plan_bytes, int64_t n_voxels, uint32_t launch_index,
@@ -718,32 +714,9 @@ int nd_lift_plan_accumulate(const nd_maps *f, const void *plan, size_t plan_byte
     cudaStream_t st = (cudaStream_t)stream;
     if (f->dtype == ND_F32)
         return lift_quads_run<float, true>(f, plan, plan_bytes, n_voxels, launch_index, 0, nullptr, s1, s2, nullptr, cnt,
-                                           opt, st, nullptr);
+                                           opt, st);
     return lift_quads_run<__nv_bfloat16, true>(f, plan, plan_bytes, n_voxels, launch_index, 0, nullptr, s1, s2, nullptr,
-                                               cnt, opt, st, nullptr);
-}
-
-int nd_lift_plan_accumulate_scatter(const nd_maps *f, const void *plan, size_t plan_bytes, int64_t n_voxels,
-                                    uint32_t launch_index, void *const *part_host, int world, int with_s2,
-                                    const nd_lift_options *opt, void *stream) {
-    nd_status s = validate_maps(f, "nd_lift_plan_accumulate_scatter");
-    if (s != ND_OK) return s;
-    ND_REQUIRE(plan && part_host, ND_ERR_BAD_ARG, "nd_lift_plan_accumulate_scatter: null pointer");
-    ND_REQUIRE(n_voxels > 0 && world >= 1 && world <= ND_MAX_PEERS, ND_ERR_BAD_SHAPE,
-               "nd_lift_plan_accumulate_scatter: bad shape (world %d)", world);
-    QPeers pe{};
-    pe.world = world;
-    pe.with_s2 = with_s2 ? 1 : 0;
-    for (int g = 0; g < world; ++g) {
-        ND_REQUIRE(part_host[g] != nullptr, ND_ERR_BAD_ARG, "nd_lift_plan_accumulate_scatter: null segment of rank %d", g);
-        pe.part[g] = static_cast<float *>(part_host[g]);
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    if (f->dtype == ND_F32)
-        return lift_quads_run<float, true>(f, plan, plan_bytes, n_voxels, launch_index, 0, nullptr, nullptr, nullptr, nullptr,
-                                           nullptr, opt, st, &pe);
-    return lift_quads_run<__nv_bfloat16, true>(f, plan, plan_bytes, n_voxels, launch_index, 0, nullptr, nullptr, nullptr,
-                                               nullptr, nullptr, opt, st, &pe);
+                                               cnt, opt, st);
 }
 
 int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_views_total, int channels,

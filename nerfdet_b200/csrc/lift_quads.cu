@@ -382,10 +382,6 @@ struct QArgs {
     float *out_a, *out_b;
     int64_t *count_i64;
     float *count_f32;
-    // reduce-scatter over peer memory (raw accumulators only, world > 0): the row of channel c goes straight to the rank that
-    // owns c -- peer[g] = where rank g keeps THIS rank's partials: [S1: slice x N | S2: slice x N (if with_s2) | count: N]
-    float *peer[ND_MAX_PEERS];
-    int world, ch_base, ch_rem, slice, with_s2;
 };
 
 // accumulate one quad (4 voxels per lane) into the registers of slot `slot` (warp-uniform)
@@ -634,17 +630,7 @@ k_lift_quads(const QArgs a) {
             waited = true;
         }
         float *out_a = a.out_a, *out_b = a.out_b;
-        int64_t row = (int64_t)c * a.n_vox;
-        if (kRaw && a.world > 0) {
-            // view-sharded lift, reduce-scatter fused into this epilogue: the finished row of channel c is stored into the
-            // segment of the rank that owns c (a peer-mapped address: the stores ride the NVLink while the other CTAs compute)
-            const int big = a.ch_rem * (a.ch_base + 1);                         // channels owned by the ranks with one extra
-            const int g = c < big ? c / (a.ch_base + 1) : a.ch_rem + (c - big) / max(a.ch_base, 1);
-            const int c_local = c - (g * a.ch_base + min(g, a.ch_rem));
-            out_a = a.peer[g];
-            out_b = a.with_s2 ? a.peer[g] + (int64_t)a.slice * a.n_vox : nullptr;
-            row = (int64_t)c_local * a.n_vox;
-        }
+        const int64_t row = (int64_t)c * a.n_vox;
         const bool vec_ok = (row % 4 == 0) &&
                             ((reinterpret_cast<uintptr_t>(out_a) | reinterpret_cast<uintptr_t>(out_b)) % 16 == 0);
         const float nvt = (float)a.n_views_total;
@@ -704,16 +690,8 @@ k_lift_quads(const QArgs a) {
                 q_store_partial(out_a, out_b, o, a.n_vox - nb, make_float4(oa[0], oa[1], oa[2], oa[3]),
                                 make_float4(ob[0], ob[1], ob[2], ob[3]));
             }
-            if (c == 0) {
-                if (kRaw && a.world > 0) {                                      // every owner needs this rank's counts
-                    for (int g = 0; g < a.world; ++g)
-                        q_store_counts(nullptr, a.peer[g] + (int64_t)(a.with_s2 ? 2 : 1) * a.slice * a.n_vox, nb, a.n_vox - nb, cw);
-                } else {
-                    q_store_counts(a.count_i64, a.count_f32, nb, a.n_vox - nb, cw);
-                }
-            }
+            if (c == 0) q_store_counts(a.count_i64, a.count_f32, nb, a.n_vox - nb, cw);
         }
-        if (kRaw && a.world > 0) __threadfence_system();                       // the peers read these rows after the hand-shake
     }
 }
 
@@ -920,15 +898,10 @@ nd_status lift_quads_plan_build(const nd_maps *f, const float *points, const flo
     return ND_OK;
 }
 
-struct QPeers {            // reduce-scatter destination of the raw accumulators (see QArgs::peer)
-    float *part[ND_MAX_PEERS];
-    int world, with_s2;
-};
-
 template <typename T, bool kRaw>
 nd_status lift_quads_run(const nd_maps *f, const void *plan, size_t plan_bytes, int64_t n_vox, uint32_t launch_index,
                          int n_views_total, const float *alpha, float *out_a, float *out_b, int64_t *count_i64,
-                         float *count_f32, const nd_lift_options *opt, cudaStream_t st, const QPeers *peers) {
+                         float *count_f32, const nd_lift_options *opt, cudaStream_t st) {
     QGeom g;
     ND_REQUIRE(quad_geom(f, n_vox, opt, g), ND_ERR_BAD_ARG, "lift: input not eligible for the plane-resident path");
     ND_REQUIRE(plan != nullptr && plan_bytes >= g.total_bytes, ND_ERR_WORKSPACE, "lift: plan buffer too small (%zu < %zu bytes)",
@@ -956,14 +929,6 @@ nd_status lift_quads_run(const nd_maps *f, const void *plan, size_t plan_bytes, 
     a.pf = opt != nullptr && opt->prefetch_stages != 0 ? (opt->prefetch_stages > 0 ? std::min(opt->prefetch_stages, g.spu) : 0) : 0;
     a.n_views_total = n_views_total > 0 ? n_views_total : g.nv;
     a.alpha = alpha; a.out_a = out_a; a.out_b = out_b; a.count_i64 = count_i64; a.count_f32 = count_f32;
-    if (peers != nullptr && peers->world > 0) {
-        a.world = peers->world;
-        a.ch_base = f->channels / peers->world;
-        a.ch_rem = f->channels % peers->world;
-        a.slice = (f->channels + peers->world - 1) / peers->world;
-        a.with_s2 = peers->with_s2;
-        for (int g = 0; g < peers->world; ++g) a.peer[g] = peers->part[g];
-    }
     void (*kern)(const QArgs) = nullptr;
     switch (g.G) {
         case 1: kern = k_lift_quads<T, kRaw, 1>; break;
@@ -985,8 +950,7 @@ nd_status lift_quads_run(const nd_maps *f, const void *plan, size_t plan_bytes, 
 
 #define ND_INSTANTIATE_QUADS(T, R)                                                                                     \
     template nd_status lift_quads_run<T, R>(const nd_maps *, const void *, size_t, int64_t, uint32_t, int, const float *, \
-                                            float *, float *, int64_t *, float *, const nd_lift_options *, cudaStream_t,  \
-                                            const QPeers *);
+                                            float *, float *, int64_t *, float *, const nd_lift_options *, cudaStream_t);
 ND_INSTANTIATE_QUADS(float, false)
 ND_INSTANTIATE_QUADS(float, true)
 ND_INSTANTIATE_QUADS(__nv_bfloat16, false)

@@ -28,9 +28,7 @@ constexpr int kMaxPeers = ND_MAX_PEERS;
 constexpr int kPeerThreads = 128;
 
 struct PeerArgs {
-    // per source rank g: S1 / S2 rows addressed [c * N + n] with the GLOBAL channel index c, counts [n].  Gathered layout:
-    // rank g's own accumulators (remote loads).  Scattered layout: the LOCAL block rank g stored its partials of this
-    // rank's channel slice into (nd_lift_plan_accumulate_scatter), pointers shifted by the slice start.
+    // rank g's accumulators: S1 / S2 rows [c * N + n], counts [n] (S2 null when no variance is wanted)
     const float *s1[kMaxPeers], *s2[kMaxPeers], *cntp[kMaxPeers];
     float *mean[kMaxPeers];
     float *cov[kMaxPeers];           // all null: no covariance wanted
@@ -328,7 +326,7 @@ int nd_peer_free(void *ptr) {
 int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
                            void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
                            int channels, int64_t n_voxels, const float *alpha, int64_t *count, const void *acc_mc,
-                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, int scattered, void *stream) {
+                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, void *stream) {
     ND_REQUIRE(acc_host && mean_host && flags_host, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: null pointer table");
     ND_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, ND_ERR_BAD_ARG,
                "nd_lift_finalize_peers: world %d / rank %d outside [1, %d]", world, rank, kMaxPeers);
@@ -362,20 +360,11 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     {
         const bool with_s2 = cov_host != nullptr;
         const int64_t cn = (int64_t)channels * n_voxels;
-        const int64_t slice_n = (int64_t)((channels + world - 1) / world) * n_voxels;
-        for (int g = 0; g < world; ++g) {
+        for (int g = 0; g < world; ++g) {                       // [S1: C x N | S2: C x N | count: N], or [S1 | count]
             const float *blk = a.s1[g];
-            if (scattered) {                                    // [S1: slice x N | S2: slice x N | count: N], local
-                a.s1[g] = blk - (int64_t)a.c_begin * n_voxels;
-                a.s2[g] = with_s2 ? blk + slice_n - (int64_t)a.c_begin * n_voxels : nullptr;
-                a.cntp[g] = blk + (with_s2 ? 2 : 1) * slice_n;
-            } else {                                            // [S1: C x N | S2: C x N | count: N], rank g's own
-                a.s2[g] = with_s2 ? blk + cn : nullptr;
-                a.cntp[g] = blk + (with_s2 ? 2 : 1) * cn;
-            }
+            a.s2[g] = with_s2 ? blk + cn : nullptr;
+            a.cntp[g] = blk + (with_s2 ? 2 : 1) * cn;
         }
-        ND_REQUIRE(!scattered || acc_mc == nullptr, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: scattered partials and multicast exclude each other");
-        if (scattered) vec = vec && slice_n % 4 == 0 && ((int64_t)a.c_begin * n_voxels) % 4 == 0;
     }
     const bool mc = acc_mc != nullptr;
     if (mc) {

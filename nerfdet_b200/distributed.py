@@ -104,8 +104,7 @@ class PeerLift:
     """
 
     def __init__(self, channels: int, n_voxels: int, device=None, group=None, want_cov: bool = True,
-                 transport: str = 'ipc', overlap_sms: int = 0, timeout_ms: int = 0, mode: Optional[str] = None,
-                 _local_group=None):
+                 transport: str = 'ipc', overlap_sms: int = 0, timeout_ms: int = 0, _local_group=None):
         """``transport='ipc'``: cudaMalloc segments shared with CUDA IPC handles, per-peer P2P loads / stores.
         ``transport='multicast'``: symmetric-memory segments (``torch.distributed._symmetric_memory``, plumbing only)
         bound to an NVLS multicast object; the kernel then reduces in the NVSwitch (``multimem.ld_reduce``) and
@@ -135,22 +134,7 @@ class PeerLift:
             raise ValueError(f'PeerLift supports up to {_lib.ND_MAX_PEERS} ranks on one box, got {self.world}')
         cn = self.channels * self.n_voxels
         al = lambda b: (b + 255) // 256 * 256
-        # 'scatter' (default over CUDA IPC): the reduce-scatter half of the exchange is fused into the lift kernel -- every
-        # finished channel row is stored straight into the owner's segment (nd_lift_plan_accumulate_scatter), the exchange
-        # kernel then reads LOCAL partials and only the result rows cross the links again.  'gather': every rank keeps
-        # its full accumulators and the exchange kernel loads its channel slice from every peer (also the NVLS multicast form).
-        if mode is None:
-            mode = 'gather' if transport == 'multicast' else 'scatter'
-        if mode not in ('scatter', 'gather') or (mode == 'scatter' and transport == 'multicast'):
-            raise ValueError(f'mode {mode!r} is not available with transport {transport!r}')
-        self.mode = mode
-        k = 2 if self.want_cov else 1
-        self._slice = (self.channels + self.world - 1) // self.world
-        self._block = (k * self._slice + 1) * self.n_voxels                 # floats one rank stores into one owner
-        if mode == 'scatter':
-            self._n_acc = self.world * self._block                          # [world][S1 slice | S2 slice | count]
-        else:
-            self._n_acc = k * cn + self.n_voxels                            # [S1 | S2 | count], or [S1 | count] without cov
+        self._n_acc = ((2 if self.want_cov else 1) * cn + self.n_voxels)    # [S1 | S2 | count], or [S1 | count] without cov
         self._off_acc = al(4 * _lib.ND_PEER_FLAG_WORDS)
         self._off_mean = self._off_acc + al(4 * self._n_acc)
         self._off_cov = self._off_mean + al(4 * cn)
@@ -265,24 +249,18 @@ class PeerLift:
         arr = ctypes.c_void_p * len(bases)
         self._peer_bases = list(bases)
         self._p_flags = arr(*[b for b in bases])
-        if self.mode == 'scatter':
-            # what the finalise kernel reads: the local blocks, one per source rank; where the lift kernel stores: this
-            # rank's block inside every owner's segment
-            self._p_acc = arr(*[bases[self.rank] + self._off_acc + 4 * g * self._block for g in range(len(bases))])
-            self._p_part = arr(*[b + self._off_acc + 4 * self.rank * self._block for b in bases])
-        else:
-            self._p_acc = arr(*[b + self._off_acc for b in bases])
+        self._p_acc = arr(*[b + self._off_acc for b in bases])
         self._p_mean = arr(*[b + self._off_mean for b in bases])
         self._p_cov = arr(*[b + self._off_cov for b in bases])
 
     @classmethod
     def local_group(cls, world: int, channels: int, n_voxels: int, device=None, want_cov: bool = True,
-                    overlap_sms: int = 0, timeout_ms: int = 0, mode: Optional[str] = None):
+                    overlap_sms: int = 0, timeout_ms: int = 0):
         """``world`` ranks inside ONE process on one device (their segments are addressed directly, no IPC): the
         single-GPU test of the multi-rank protocol -- run each rank's call on its own stream.  Small shapes only:
         the waiting CTAs of all ranks must fit the device together."""
         ranks = [cls(channels, n_voxels, device, want_cov=want_cov, overlap_sms=overlap_sms, timeout_ms=timeout_ms,
-                     mode=mode, _local_group=(r, world))
+                     _local_group=(r, world))
                  for r in range(world)]
         bases = [r._base for r in ranks]
         for r in ranks:
@@ -313,7 +291,7 @@ class PeerLift:
             ctypes.c_void_p(self.count.data_ptr()),
             ctypes.c_void_p(mc + self._off_acc) if mc else None, ctypes.c_void_p(mc + self._off_mean) if mc else None,
             ctypes.c_void_p(mc + self._off_cov) if mc and self.want_cov else None,
-            self.overlap_sms, self.timeout_ms, 1 if self.mode == 'scatter' else 0, stream.cuda_stream), 'nd_lift_finalize_peers')
+            self.overlap_sms, self.timeout_ms, stream.cuda_stream), 'nd_lift_finalize_peers')
         with torch.cuda.stream(stream):
             w = 2 * self._lib.ND_MAX_PEERS + 1
             self._err_host.copy_(self.flags[w:w + 1], non_blocking=True)
@@ -332,14 +310,7 @@ class PeerLift:
         sm_limit = 0
         if self.overlap_sms:
             sm_limit = max(torch.cuda.get_device_properties(self.device).multi_processor_count - self.overlap_sms, 1)
-        if self.mode == 'scatter':
-            plan = ops.cached_lift_plan(features_local, points, projection_local, sm_limit=sm_limit)
-            if not plan.eligible:
-                raise RuntimeError('PeerLift(mode="scatter") needs the plane-resident lift kernel (contiguous NCHW planes <= 64 KB); '
-                                   'use mode="gather" for other layouts')
-            plan.accumulate_scatter(features_local, self._p_part, self.world, self.want_cov)
-        else:
-            ops.lift_accumulate_planned(features_local, points, projection_local, self.acc, sm_limit, self.want_cov)
+        ops.lift_accumulate_planned(features_local, points, projection_local, self.acc, sm_limit, self.want_cov)
         mean, cov, count = self.exchange(n_views_total, alpha)
         shape = tuple(points.shape[1:]) if points.dim() == 4 else (self.n_voxels,)
         return (mean.view(self.channels, *shape), cov.view(self.channels, *shape) if cov is not None else None,

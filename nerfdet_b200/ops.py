@@ -198,20 +198,6 @@ class LiftPlan:
                 ctypes.byref(self.opt), self.stream), 'nd_lift_plan_accumulate')
 
 
-def _plan_accumulate_scatter(self, features: Tensor, part_ptrs, world: int, with_s2: bool = True) -> None:
-    """The view-sharded accumulate with the reduce-scatter fused into its epilogue: the sums of every channel are stored
-    into the segment of the rank that owns the channel.  ``part_ptrs``: ctypes array of ``world`` peer-mapped device
-    pointers (``distributed.PeerLift`` keeps them)."""
-    m = _maps(features)
-    with _on(self.device):
-        _lib.check(_lib.load().nd_lift_plan_accumulate_scatter(
-            ctypes.byref(m), _ptr(self.buf), self.bytes, self.n_voxels, self._launch_index(features), part_ptrs, int(world),
-            1 if with_s2 else 0, ctypes.byref(self.opt), self.stream), 'nd_lift_plan_accumulate_scatter')
-
-
-LiftPlan.accumulate_scatter = _plan_accumulate_scatter
-
-
 def _layout_key(features: Tensor):
     return (tuple(features.shape), tuple(features.stride()), features.dtype, features.data_ptr() % 16)
 

@@ -55,9 +55,8 @@ def test_single_rank_equals_fused_lift(nv, grid, channels, overlap):
         peer.close()
 
 
-@pytest.mark.parametrize('mode', ['scatter', 'gather'])
 @pytest.mark.parametrize('world,overlap', [(2, 0), (3, 0), (8, 0), (2, 3), (4, 2), (8, 2)])
-def test_in_process_ranks_match_all_views(world, overlap, mode):
+def test_in_process_ranks_match_all_views(world, overlap):
     nv, grid, channels = 19, (16, 16, 8), 20                # uneven view split, channel slices of unequal size
     n = int(np.prod(grid))
     f, pts, proj = _scene(nv, grid, (0.4, 0.4, 0.4), channels, 92)
@@ -70,7 +69,7 @@ def test_in_process_ranks_match_all_views(world, overlap, mode):
         a = ops.lift_accumulate(f[b:e], pts, proj[b:e], 0)
         acc = a if acc is None else acc + a
     m_ref, c_ref, n_ref = ops.lift_finalize(acc, nv, channels, n, alpha, True)
-    ranks = nd_dist.PeerLift.local_group(world, channels, n, DEV, overlap_sms=overlap, mode=mode)
+    ranks = nd_dist.PeerLift.local_group(world, channels, n, DEV, overlap_sms=overlap)
     streams = [torch.cuda.Stream() for _ in range(world)]
     try:
         torch.cuda.synchronize()
@@ -131,7 +130,7 @@ def test_missing_peer_times_out_instead_of_hanging():
     """A rank whose peer never reaches the exchange step: after the bounded wait the error word is raised on EVERY
     rank, the rows the waiting rank owns are NaN (no stale or partial sums are handed out), the next call fails
     without a synchronisation, and check() fails."""
-    ranks = nd_dist.PeerLift.local_group(2, 4, 64, DEV, timeout_ms=100, mode='gather')
+    ranks = nd_dist.PeerLift.local_group(2, 4, 64, DEV, timeout_ms=100)
     try:
         ranks[0].acc.fill_(1.0)
         ranks[0].mean.fill_(7.0)
