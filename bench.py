@@ -41,7 +41,7 @@ VOXEL_SIZE = (0.16, 0.16, 0.2)
 CHANNELS = 256
 FEAT_HW_PAD = (60, 80)
 FEAT_HW = (59, 80)
-OVERLAP_SMS = 20           # N > 1, pipelined: SMs that carry the exchange kernel while the others accumulate the next scene
+OVERLAP_SMS = 28           # N > 1, pipelined: SMs that carry the exchange kernel while the others accumulate the next scene
 N_INPUT_SETS = 3           # rotated so that no step finds its features in L2
 SWEEP_GRIDS = [((40, 40, 16), (.16, .16, .2)), ((56, 56, 16), (.16, .16, .2)), ((64, 64, 24), (.1, .1, .13)),
                ((80, 80, 32), (.08, .08, .08))]
