@@ -276,6 +276,18 @@ int nd_nerf_mlp_fwd_tc(const nd_mlp_weights *arch, const void *packed, const flo
                        const float *cond, int64_t n_points, int samples_per_ray, float *sigma, float *alpha, float *rgb,
                        void *stream);
 
+/* The same tensor-core kernel at fp32-grade precision ("3 x bf16"): every operand -- inputs, activations, weights -- is
+ * carried as a hi + lo pair of bf16 numbers (16 mantissa bits) and every product as hi*hi + lo*hi + hi*lo with fp32
+ * accumulation in tensor memory; the positional encoding rounds its arguments where the reference does
+ * (nerf_mlp.py:189-196).  Three times the tensor-core work of nd_nerf_mlp_fwd_tc, within BASELINE.json's 1e-4 (fp32)
+ * tolerance: the default precision of the drop-in module.  Own packed layout (hi and lo weight images); same supported
+ * architectures, arguments and outputs as nd_nerf_mlp_fwd_tc. */
+size_t nd_mlp_tc3_packed_bytes(const nd_mlp_weights *w);
+int nd_pack_mlp_weights_tc3(const nd_mlp_weights *w, void *packed, size_t packed_bytes, void *stream);
+int nd_nerf_mlp_fwd_tc3(const nd_mlp_weights *arch, const void *packed, const float *x, const float *features,
+                        const float *cond, int64_t n_points, int samples_per_ray, float *sigma, float *alpha, float *rgb,
+                        void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * R2  render_ray.py:145-189  sample_along_camera_ray: z_vals [R][S] = near + i * (far - near) / (S - 1), optional
  * stratified jitter with caller-supplied uniforms t_rand [R][S] (torch.rand_like drawn by the caller; NULL = det),

@@ -78,6 +78,10 @@ SIGNATURES = {
     'nd_pack_mlp_weights_tc': (c_int, [POINTER(NdMlpWeights), c_void_p, c_size_t, c_void_p]),
     'nd_nerf_mlp_fwd_tc': (c_int, [POINTER(NdMlpWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nd_mlp_tc3_packed_bytes': (c_size_t, [POINTER(NdMlpWeights)]),
+    'nd_pack_mlp_weights_tc3': (c_int, [POINTER(NdMlpWeights), c_void_p, c_size_t, c_void_p]),
+    'nd_nerf_mlp_fwd_tc3': (c_int, [POINTER(NdMlpWeights), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     'nd_sample_rays': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
     'nd_render_gather_stats': (c_int, [c_void_p, c_int64, c_void_p, c_int, POINTER(NdMaps), POINTER(NdMaps),

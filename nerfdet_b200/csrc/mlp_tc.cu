@@ -1,7 +1,10 @@
 // The shared NeRF / geometry MLP on the 5th-generation tensor cores (row M of SURVEY.md section 8a;
-// reference nerf_mlp.py:11-234 as instantiated at nerfdet.py:62-69).  bf16 operands, fp32 accumulation
-// in tensor memory: this is the path BASELINE.json's 1e-2 (bf16) tolerance applies to; the FFMA path
-// in mlp.cu stays the 1e-4 (fp32) one.
+// reference nerf_mlp.py:11-234 as instantiated at nerfdet.py:62-69).  Two precisions of the same kernel:
+//   bf16    bf16 operands, fp32 accumulation in tensor memory: the path BASELINE.json's 1e-2 tolerance applies to;
+//   split   fp32-grade ("3 x bf16"): every operand is carried as hi + lo, two bf16 numbers (16 mantissa bits), and every
+//           product as hi*hi + lo*hi + hi*lo on the tensor cores (fp32 accumulation; the dropped lo*lo term and the
+//           residuals are ~2^-16 relative), the input encoding uses the reference's own argument rounding.  This is the
+//           default, 1e-4 path; the FFMA kernel in mlp.cu remains for architectures this kernel does not take.
 //
 // One persistent CTA per SM walks tiles of 128 points through the whole network:
 //
@@ -47,15 +50,21 @@ constexpr int kTcInChunks = 22;         // 16-byte chunks (8 bf16) a point's IN 
 constexpr int kTcBlockBytes = 16384;    // 128 rows x 128 B: one A block
 constexpr int kTcUnitN = 256;           // output columns per B unit = UMMA N (128: a 256-wide layer is two units per K block)
 constexpr int kTcStageBytes = kTcUnitN * 128;    // rows x 128 B: one B unit
-constexpr int kTcStages = 160 * 1024 / kTcStageBytes;
+constexpr int kTcStages = 160 * 1024 / kTcStageBytes;          // bf16: 5 weight stages beside 3 IN blocks
+constexpr int kTcStagesSplit = 3;                              // split: 3 weight stages beside 6 IN blocks (hi and lo)
 constexpr int kTcMaxUnits = 64, kTcMaxJobs = 12, kTcMaxDepth = 8;
 constexpr int kTcEpiThreads = 256;      // warps 0-7: TMEM lane quarter = warp % 4, column half of a 64-column chunk = warp / 4
 constexpr int kTcThreads = 448;         // + warps 8-11 input encoding, warp 12 weight producer, warp 13 MMA issuer
 constexpr uint32_t kOffIn = 0, kOffB = kOffIn + 3 * kTcBlockBytes, kOffTail = kOffB + kTcStages * kTcStageBytes;   // 212992
+constexpr uint32_t kOffBSplit = kOffIn + 6 * kTcBlockBytes;    // split: IN hi blocks 0-2, IN lo blocks 3-5, then the weight ring
+static_assert(kOffBSplit + kTcStagesSplit * kTcStageBytes <= kOffTail, "split layout must fit below the tail");
 constexpr uint32_t kTailBars = 0, kTailTmem = 256, kTailHead = 512, kTailSigIn = kTailHead + 2 * kTcTile * 16,
                    kTailUnits = kTailSigIn + 4 * kTcTile * 4, kTailPar = kTailUnits + kTcMaxUnits * 16;
 
 enum : uint8_t { kJobRelu = 1, kJobWritesH = 2, kJobSigma = 4, kJobRgb = 8, kJobFreesIn = 16 };
+// unit flags: 1 = first unit of its K block (wait for the A operand), 2 = first K block (overwrite D),
+// split precision: 4 = B holds the hi halves (issue A hi and A lo against it), 8 = B holds the lo halves (A hi only)
+enum : uint8_t { kUnitFirst = 1, kUnitOverwrite = 2, kUnitBHi = 4, kUnitBLo = 8 };
 
 struct TcUnit {                 // kTcUnitN (or 128) output columns x one K block of one job = one B stage
     uint32_t src_off;           // byte offset of the unit in the weight image
@@ -78,6 +87,7 @@ struct TcPackUnit {             // source of one block for the packing kernel
     const float *w;             // reference weight [n][k_ref]
     int n, row0, k_ref, col_base, lo, hi;   // rows row0 .. row0 + n; block column kk in [lo, hi) <- reference column col_base + kk
     uint32_t dst_off;
+    int low_half;               // split precision: 0 = bf16(w), 1 = bf16(w - bf16(w))
 };
 struct TcLayout {
     TcPlan full, density;       // with / without the colour branch
@@ -99,12 +109,10 @@ struct TcArgs {
     int64_t n_points;
     int samples_per_ray, feat_dim, n_tiles;
     float *sigma, *alpha, *rgb;
-    int debug;                  // diagnostics (ND_MLP_TC_DEBUG): 1 = no weight copies, 2 = no MMAs, 4 = no epilogue math,
-                                // 8 = MMA warp ignores the epilogue hand-shakes, 16 = ... and the weight / input barriers (timing only)
 };
 
 // ---- plan / layout (host) -------------------------------------------------------------------------------
-static bool tc_layout(const nd_mlp_weights *w, TcLayout &L, bool report) {
+static bool tc_layout(const nd_mlp_weights *w, TcLayout &L, bool report, bool split = false) {
     const int depth = w->net_depth, feat = w->feature_dim, skip = w->skip_layer;
     const int in_dim = kTcPosDim + feat;
     if (depth < 1 || depth > kTcMaxDepth || w->net_width != kTcWidth || w->cond_width != kTcCondWidth || feat < 0 ||
@@ -135,27 +143,31 @@ static bool tc_layout(const nd_mlp_weights *w, TcLayout &L, bool report) {
         const bool first_kb = j.n_units == 0;
         const int un = j.n < kTcUnitN ? j.n : kTcUnitN;
         for (int nh = 0; nh < j.n / un; ++nh) {
-            if (P.n_units >= kTcMaxUnits) { ++P.n_units; continue; }             // counted, rejected below
-            TcUnit &u = P.units[P.n_units];
-            TcPackUnit &pu = L.pack[P.n_units];
-            ++P.n_units;
-            ++j.n_units;
-            u.src_off = img;
-            u.a_blk = (uint8_t)a_blk;
-            u.k0 = (uint8_t)k0;
-            u.nk = (uint8_t)nk;
-            u.flags = (uint8_t)((nh == 0 ? 1 : 0) | (first_kb ? 2 : 0));
-            u.d_col = (uint16_t)(nh * un);
-            u.n = (uint16_t)un;
-            pu.w = wsrc;
-            pu.n = un;
-            pu.row0 = nh * un;
-            pu.k_ref = k_ref;
-            pu.col_base = col_base;
-            pu.lo = lo;
-            pu.hi = hi;
-            pu.dst_off = img;
-            img += (uint32_t)un * 128u;
+            for (int half = 0; half < (split ? 2 : 1); ++half) {                 // split: the hi weights, then the lo weights
+                if (P.n_units >= kTcMaxUnits) { ++P.n_units; continue; }         // counted, rejected below
+                TcUnit &u = P.units[P.n_units];
+                TcPackUnit &pu = L.pack[P.n_units];
+                ++P.n_units;
+                ++j.n_units;
+                u.src_off = img;
+                u.a_blk = (uint8_t)a_blk;
+                u.k0 = (uint8_t)k0;
+                u.nk = (uint8_t)nk;
+                u.flags = (uint8_t)((nh == 0 && half == 0 ? kUnitFirst : 0) | (first_kb && half == 0 ? kUnitOverwrite : 0) |
+                                    (split ? (half == 0 ? kUnitBHi : kUnitBLo) : 0));
+                u.d_col = (uint16_t)(nh * un);
+                u.n = (uint16_t)un;
+                pu.w = wsrc;
+                pu.n = un;
+                pu.row0 = nh * un;
+                pu.k_ref = k_ref;
+                pu.col_base = col_base;
+                pu.lo = lo;
+                pu.hi = hi;
+                pu.dst_off = img;
+                pu.low_half = half;
+                img += (uint32_t)un * 128u;
+            }
         }
     };
     auto add_h_units = [&](TcJob &j, const float *wsrc, int k_ref) {
@@ -241,7 +253,9 @@ __global__ void k_pack_tc_units(const __grid_constant__ TcPackArgs a, uint8_t *_
     const int r = i >> 6, kk = i & 63;
     float v = 0.0f;
     if (kk >= u.lo && kk < u.hi) v = u.w[(size_t)(u.row0 + r) * u.k_ref + u.col_base + kk];
-    *reinterpret_cast<__nv_bfloat16 *>(img + u.dst_off + sw128_offset(r, kk)) = __float2bfloat16_rn(v);
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    if (u.low_half) h = __float2bfloat16_rn(v - __bfloat162float(h));      // what the hi half leaves of the weight
+    *reinterpret_cast<__nv_bfloat16 *>(img + u.dst_off + sw128_offset(r, kk)) = h;
 }
 
 struct TcParSrc {
@@ -417,17 +431,44 @@ __device__ __forceinline__ void encode_doubling(const float (&x)[3], float *dst)
     }
 }
 
-// kDiag: the diagnostics build honours TcArgs::debug (tools/mlp_bench.py with ND_MLP_TC_DEBUG); the product
-// instantiation carries none of it.
-template <bool kDiag>
+// The reference's own arithmetic (nerf_mlp.py:189-196): sin(fl(x * 2^k)) and sin(fl(fl(x * 2^k) + fl(pi / 2))) with an
+// accurate sinf -- the fp32 rounding of arguments up to ~4000 rad moves the value by up to 1e-4, so the fp32-grade
+// precision must round where the reference rounds.
+template <int kOct>
+__device__ __forceinline__ void encode_exact(const float (&x)[3], float *dst) {
+    const float half_pi = 1.5707963267948966f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dst[i] = x[i];
+#pragma unroll
+    for (int k = 0; k < kOct; ++k) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float sc = __fmul_rn(x[i], (float)(1 << k));
+            dst[3 + k * 3 + i] = sinf(sc);
+            dst[3 + kOct * 3 + k * 3 + i] = sinf(__fadd_rn(sc, half_pi));
+        }
+    }
+}
+
+// hi / lo halves of an fp32 pair as packed bf16x2 words: hi = bf16(v), lo = bf16(v - hi)
+__device__ __forceinline__ void split_bf16(float a0, float a1, uint32_t &hi, uint32_t &lo) {
+    hi = tc::pack_bf16(a0, a1);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    lo = tc::pack_bf16(a0 - h0, a1 - h1);
+}
+
+// kSplit: the fp32-grade "3 x bf16" precision (see the header): A hi / lo halves side by side in tensor memory and in the
+// IN buffer, hi and lo weight units alternating in the weight stream.
+template <bool kSplit>
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
-    const int dbg = kDiag ? a.debug : 0;
+    constexpr int kStages = kSplit ? kTcStagesSplit : kTcStages;
+    constexpr uint32_t kOffBk = kSplit ? kOffBSplit : kOffB;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = tc::smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B operands need 1024-byte alignment
     uint8_t *sm = smem_raw + (base - raw);
-    const uint32_t sIN = base + kOffIn, sB = base + kOffB;
+    const uint32_t sIN = base + kOffIn, sB = base + kOffBk;
     const uint32_t bars = base + kOffTail + kTailBars;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(sm + kOffTail + kTailTmem);
     float *s_head = reinterpret_cast<float *>(sm + kOffTail + kTailHead);          // [2][128][4] (slot t % 2): sigma | rgb partials of column half 1
@@ -436,12 +477,12 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
     // in every job plan (two would race in the density-only plan, where IN is released after the first job).
     float *s_sig_in = reinterpret_cast<float *>(sm + kOffTail + kTailSigIn);
     float *s_par = reinterpret_cast<float *>(sm + kOffTail + kTailPar);
-    const uint32_t b_full = bars, b_empty = bars + 8 * kTcStages, d_full = bars + 8 * 2 * kTcStages,
+    const uint32_t b_full = bars, b_empty = bars + 8 * kStages, d_full = bars + 8 * 2 * kStages,
                    d_empty = d_full + 8 * 2, h_ready = d_full + 8 * 4, in_ready = d_full + 8 * 8, in_free = d_full + 8 * 9;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kTcStages; ++i) { tc::mbar_init(b_full + 8 * i, 1); tc::mbar_init(b_empty + 8 * i, 1); }
+        for (int i = 0; i < kStages; ++i) { tc::mbar_init(b_full + 8 * i, 1); tc::mbar_init(b_empty + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(d_full + 8 * i, 1); tc::mbar_init(d_empty + 8 * i, kTcEpiThreads / 32); }
         for (int i = 0; i < 4; ++i) tc::mbar_init(h_ready + 8 * i, kTcEpiThreads / 32);   // one arrival per warp
         tc::mbar_init(in_ready, 4);
@@ -483,12 +524,9 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                 for (int u = 0; u < P.n_units; ++u) {
                     tc::mbar_wait(b_empty + 8 * stage, ph ^ 1u);
                     const uint32_t bytes = (uint32_t)P.units[u].n * 128u;
-                    if (dbg & 1) { tc::mbar_arrive(b_full + 8 * stage); }
-                    else {
                     tc::mbar_expect_tx(b_full + 8 * stage, bytes);
                     tc::bulk_g2s(sB + stage * kTcStageBytes, a.wimg + P.units[u].src_off, bytes, b_full + 8 * stage);
-                    }
-                    if (++stage == kTcStages) { stage = 0; ph ^= 1u; }
+                    if (++stage == kStages) { stage = 0; ph ^= 1u; }
                 }
             }
         }
@@ -510,7 +548,7 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                     const uint32_t first_unit = P.jobs[j].first_unit, n_units = P.jobs[j].n_units, jflags = P.jobs[j].flags;
                     const uint32_t d = jc & 1u;
                     uint4 ur = s_units[first_unit];
-                    if (!(dbg & 8)) tc::mbar_wait(d_empty + 8 * d, (dpar >> d) & 1u);
+                    tc::mbar_wait(d_empty + 8 * d, (dpar >> d) & 1u);
                     dpar ^= 1u << d;
                     const uint32_t a_region = tmem + (d ^ 1u) * 256u;             // the previous job's region holds this job's A
                     const uint32_t d_region = tmem + d * 256u;
@@ -520,35 +558,48 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                         const uint32_t a_blk = u.z >> 24, uflags = (u.z >> 16) & 0xffu, nk = (u.z >> 8) & 0xffu;
                         const bool from_tmem = a_blk < 4;
                         if (from_tmem) {
-                            if ((uflags & 1u) && !(dbg & 8)) {
+                            if (uflags & kUnitFirst) {
                                 tc::mbar_wait(h_ready + 8 * a_blk, (hpar >> a_blk) & 1u);
                                 hpar ^= 1u << a_blk;
                             }
-                        } else if (!in_ok && !(dbg & 16)) {
+                        } else if (!in_ok) {
                             tc::mbar_wait(in_ready, in_par);
                             in_par ^= 1u;
                             in_ok = true;
                         }
-                        if (!(dbg & 16)) tc::mbar_wait(b_full + 8 * stage, ph);
+                        tc::mbar_wait(b_full + 8 * stage, ph);
                         tc::tc_fence_after();
                         const uint64_t bd = desc_hi | (uint64_t)(bd0 + (uint32_t)stage * (kTcStageBytes >> 4) + (u.z & 0xffu));
                         const uint32_t d_tmem = d_region + u.w;
-                        const uint32_t acc0 = (uflags & 2u) ? 0u : 1u;             // first K block of the job overwrites D
+                        const uint32_t acc0 = (uflags & kUnitOverwrite) ? 0u : 1u;     // first K block of the job overwrites D
                         if (tc::elect_one()) {
-                            if (dbg & 2) {
-                            } else if (from_tmem) {
+                            if (from_tmem) {
                                 // K step s of chunk c: 8 packed columns at column 64 c + 16 s of the previous region
+                                // (split precision: the hi halves; the lo halves sit in the 8 columns behind them)
                                 const uint32_t a_tmem = a_region + u.x;
                                 tc::umma_bf16_ts(d_tmem, a_tmem, bd, u.y, acc0);
                                 if (nk > 1) tc::umma_bf16_ts(d_tmem, a_tmem + 16u, bd + 2u, u.y, 1u);
                                 if (nk > 2) tc::umma_bf16_ts(d_tmem, a_tmem + 32u, bd + 4u, u.y, 1u);
                                 if (nk > 3) tc::umma_bf16_ts(d_tmem, a_tmem + 48u, bd + 6u, u.y, 1u);
+                                if (kSplit && (uflags & kUnitBHi)) {                // A lo x B hi
+                                    tc::umma_bf16_ts(d_tmem, a_tmem + 8u, bd, u.y, 1u);
+                                    if (nk > 1) tc::umma_bf16_ts(d_tmem, a_tmem + 24u, bd + 2u, u.y, 1u);
+                                    if (nk > 2) tc::umma_bf16_ts(d_tmem, a_tmem + 40u, bd + 4u, u.y, 1u);
+                                    if (nk > 3) tc::umma_bf16_ts(d_tmem, a_tmem + 56u, bd + 6u, u.y, 1u);
+                                }
                             } else {
                                 const uint64_t ad = desc_hi | (uint64_t)u.x;           // 32 B per K step = 2 descriptor units
                                 tc::umma_bf16(d_tmem, ad, bd, u.y, acc0);
                                 if (nk > 1) tc::umma_bf16(d_tmem, ad + 2u, bd + 2u, u.y, 1u);
                                 if (nk > 2) tc::umma_bf16(d_tmem, ad + 4u, bd + 4u, u.y, 1u);
                                 if (nk > 3) tc::umma_bf16(d_tmem, ad + 6u, bd + 6u, u.y, 1u);
+                                if (kSplit && (uflags & kUnitBHi)) {                // IN lo (three blocks further on) x B hi
+                                    const uint64_t al = ad + (uint64_t)(3u * (kTcBlockBytes >> 4));
+                                    tc::umma_bf16(d_tmem, al, bd, u.y, 1u);
+                                    if (nk > 1) tc::umma_bf16(d_tmem, al + 2u, bd + 2u, u.y, 1u);
+                                    if (nk > 2) tc::umma_bf16(d_tmem, al + 4u, bd + 4u, u.y, 1u);
+                                    if (nk > 3) tc::umma_bf16(d_tmem, al + 6u, bd + 6u, u.y, 1u);
+                                }
                             }
                             tc::umma_commit(b_empty + 8 * stage);                   // frees the B stage once these MMAs are done
                             if (uu + 1 == n_units) {
@@ -557,7 +608,7 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                             }
                         }
                         __syncwarp();
-                        if (++stage == kTcStages) { stage = 0; ph ^= 1u; }
+                        if (++stage == kStages) { stage = 0; ph ^= 1u; }
                     }
                 }
             }
@@ -571,6 +622,48 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++t) {
             const int64_t gp = (int64_t)tile * kTcTile + r;
             const bool ok = gp < a.n_points;
+            if constexpr (kSplit) {
+                // fp32-grade inputs: the expensive part (60 + 24 accurate sines) is done ahead of the IN buffer's release and
+                // held as fp32; the features are read and everything is split into hi / lo bf16 halves afterwards
+                float enc[kTcPosDim], venc[32];
+                float xyz[3] = {0.f, 0.f, 0.f};
+                if (ok) { xyz[0] = a.x[gp * 3]; xyz[1] = a.x[gp * 3 + 1]; xyz[2] = a.x[gp * 3 + 2]; }
+                encode_exact<kTcPosOct>(xyz, enc);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) venc[i] = 0.0f;
+                if (a.cond != nullptr && ok) {
+                    const int64_t ray = gp / a.samples_per_ray;
+                    const float dir[3] = {a.cond[ray * 3], a.cond[ray * 3 + 1], a.cond[ray * 3 + 2]};
+                    encode_exact<kTcViewOct>(dir, venc);
+                }
+                if (t > 0) tc::mbar_wait(in_free, (uint32_t)(t - 1) & 1u);     // the previous tile's last reader of IN is done
+                const float *fr = a.feat + gp * a.feat_dim;
+                float sig_in = 0.0f;
+#pragma unroll
+                for (int c = 0; c < kTcInChunks; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int idx = c * 8 + e;
+                        if (c >= kTcInPad / 8) v[e] = venc[idx - kTcInPad];
+                        else if (idx < kTcPosDim) v[e] = ok ? enc[idx] : 0.0f;
+                        else v[e] = (ok && idx - kTcPosDim < a.feat_dim) ? __ldg(fr + (idx - kTcPosDim)) : 0.0f;
+                        if (c < kTcInPad / 8) sig_in = fmaf(v[e], ws_in[idx], sig_in);
+                    }
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split_bf16(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+                    const int blk = c >> 3, cc = c & 7;
+                    const uint32_t dst = sIN + blk * kTcBlockBytes + row_addr + (uint32_t)((cc ^ (r & 7)) << 4);
+                    tc::sts_u4(dst, hi[0], hi[1], hi[2], hi[3]);
+                    tc::sts_u4(dst + 3 * kTcBlockBytes, lo[0], lo[1], lo[2], lo[3]);
+                }
+                s_sig_in[(t & 3) * kTcTile + r] = sig_in;
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(in_ready);
+                continue;
+            }
             uint32_t pk[kTcInChunks * 4];
             float sig_in = 0.0f;
             {
@@ -642,14 +735,6 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                 const int n_chunks = job.n >> 6;
                 for (int ch = 0; ch < n_chunks; ++ch) {
                     const int col = ch * 64 + half * 32;
-                    if (dbg & 4) {
-                        if (writes_h) {
-                            tc::tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) tc::mbar_arrive(h_ready + 8 * ch);
-                        }
-                        continue;
-                    }
                     uint32_t v[32];
                     tc::tmem_ld32(tmem + lane_base + d * 256u + (uint32_t)col, v);
                     tc::tmem_ld_wait();
@@ -685,10 +770,22 @@ k_nerf_mlp_tc(const __grid_constant__ TcArgs a) {
                     if (writes_h) {
                         // bf16 pairs back into the columns they came from: K step s at column 16 s of this region
                         uint32_t pkd[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            pkd[i] = relu ? tc::pack_bf16_relu(f[2 * i], f[2 * i + 1]) : tc::pack_bf16(f[2 * i], f[2 * i + 1]);
                         const uint32_t t0 = tmem + lane_base + d * 256u + (uint32_t)col;
+                        if constexpr (kSplit) {
+                            // hi halves where the bf16 precision keeps its operand, lo halves in the 8 columns behind them
+                            uint32_t pkl[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float x0 = relu ? fmaxf(f[2 * i], 0.f) : f[2 * i], x1 = relu ? fmaxf(f[2 * i + 1], 0.f) : f[2 * i + 1];
+                                split_bf16(x0, x1, pkd[i], pkl[i]);
+                            }
+                            tc::tmem_st8(t0 + 8u, pkl);
+                            tc::tmem_st8(t0 + 24u, pkl + 8);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                pkd[i] = relu ? tc::pack_bf16_relu(f[2 * i], f[2 * i + 1]) : tc::pack_bf16(f[2 * i], f[2 * i + 1]);
+                        }
                         tc::tmem_st8(t0, pkd);
                         tc::tmem_st8(t0 + 16u, pkd + 8);
                         tc::tmem_st_wait();
@@ -738,16 +835,16 @@ using namespace nd;
 
 extern "C" {
 
-size_t nd_mlp_tc_packed_bytes(const nd_mlp_weights *w) {
+static size_t tc_packed_bytes(const nd_mlp_weights *w, bool split) {
     TcLayout L;
-    if (w == nullptr || !tc_layout(w, L, false)) return 0;
+    if (w == nullptr || !tc_layout(w, L, false, split)) return 0;
     return L.total_bytes;
 }
 
-int nd_pack_mlp_weights_tc(const nd_mlp_weights *w, void *packed, size_t packed_bytes, void *stream) {
+static int tc_pack(const nd_mlp_weights *w, void *packed, size_t packed_bytes, void *stream, bool split) {
     ND_REQUIRE(w != nullptr && packed != nullptr, ND_ERR_BAD_ARG, "nd_pack_mlp_weights_tc: null pointer");
     TcLayout L;
-    if (!tc_layout(w, L, true)) return ND_ERR_BAD_SHAPE;
+    if (!tc_layout(w, L, true, split)) return ND_ERR_BAD_SHAPE;
     ND_REQUIRE(packed_bytes >= L.total_bytes, ND_ERR_WORKSPACE, "nd_pack_mlp_weights_tc: buffer too small (%zu < %zu)",
                packed_bytes, L.total_bytes);
     ND_REQUIRE((reinterpret_cast<uintptr_t>(packed) % 256) == 0, ND_ERR_BAD_ALIGNMENT,
@@ -790,14 +887,13 @@ int nd_pack_mlp_weights_tc(const nd_mlp_weights *w, void *packed, size_t packed_
     return ND_OK;
 }
 
-int nd_nerf_mlp_fwd_tc(const nd_mlp_weights *arch, const void *packed, const float *x, const float *features,
-                       const float *cond, int64_t n_points, int samples_per_ray, float *sigma, float *alpha, float *rgb,
-                       void *stream) {
+static int tc_forward(const nd_mlp_weights *arch, const void *packed, const float *x, const float *features, const float *cond,
+                      int64_t n_points, int samples_per_ray, float *sigma, float *alpha, float *rgb, void *stream, bool split) {
     ND_REQUIRE(n_points >= 0, ND_ERR_BAD_SHAPE, "nd_nerf_mlp_fwd_tc: negative point count");
     if (n_points == 0) return ND_OK;
     ND_REQUIRE(arch != nullptr && packed != nullptr && x != nullptr, ND_ERR_BAD_ARG, "nd_nerf_mlp_fwd_tc: null pointer");
     TcLayout L;
-    if (!tc_layout(arch, L, true)) return ND_ERR_BAD_SHAPE;
+    if (!tc_layout(arch, L, true, split)) return ND_ERR_BAD_SHAPE;
     ND_REQUIRE(L.feat == 0 || features != nullptr, ND_ERR_BAD_ARG, "nd_nerf_mlp_fwd_tc: features missing");
     ND_REQUIRE(rgb == nullptr || (cond != nullptr && samples_per_ray > 0 && n_points % samples_per_ray == 0),
                ND_ERR_BAD_SHAPE, "nd_nerf_mlp_fwd_tc: rgb needs cond [P / samples_per_ray][3]");
@@ -819,7 +915,7 @@ int nd_nerf_mlp_fwd_tc(const nd_mlp_weights *arch, const void *packed, const flo
     a.sigma = sigma; a.alpha = alpha; a.rgb = want_rgb ? rgb : nullptr;
     const size_t smem = 1024 + kOffTail + kTailPar + (size_t)L.n_par * sizeof(float);
     ND_REQUIRE(smem <= 227 * 1024, ND_ERR_BAD_SHAPE, "nd_nerf_mlp_fwd_tc: %zu bytes of shared memory needed", smem);
-    void (*kern)(const TcArgs) = k_nerf_mlp_tc<false>;
+    void (*kern)(const TcArgs) = split ? k_nerf_mlp_tc<true> : k_nerf_mlp_tc<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         set_error("k_nerf_mlp_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
@@ -831,6 +927,26 @@ int nd_nerf_mlp_fwd_tc(const nd_mlp_weights *arch, const void *packed, const flo
     kern<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(a);
     ND_CUDA_LAUNCH_CHECK("k_nerf_mlp_tc");
     return ND_OK;
+}
+
+size_t nd_mlp_tc_packed_bytes(const nd_mlp_weights *w) { return tc_packed_bytes(w, false); }
+int nd_pack_mlp_weights_tc(const nd_mlp_weights *w, void *packed, size_t packed_bytes, void *stream) {
+    return tc_pack(w, packed, packed_bytes, stream, false);
+}
+int nd_nerf_mlp_fwd_tc(const nd_mlp_weights *arch, const void *packed, const float *x, const float *features,
+                       const float *cond, int64_t n_points, int samples_per_ray, float *sigma, float *alpha, float *rgb,
+                       void *stream) {
+    return tc_forward(arch, packed, x, features, cond, n_points, samples_per_ray, sigma, alpha, rgb, stream, false);
+}
+
+size_t nd_mlp_tc3_packed_bytes(const nd_mlp_weights *w) { return tc_packed_bytes(w, true); }
+int nd_pack_mlp_weights_tc3(const nd_mlp_weights *w, void *packed, size_t packed_bytes, void *stream) {
+    return tc_pack(w, packed, packed_bytes, stream, true);
+}
+int nd_nerf_mlp_fwd_tc3(const nd_mlp_weights *arch, const void *packed, const float *x, const float *features,
+                        const float *cond, int64_t n_points, int samples_per_ray, float *sigma, float *alpha, float *rgb,
+                        void *stream) {
+    return tc_forward(arch, packed, x, features, cond, n_points, samples_per_ray, sigma, alpha, rgb, stream, true);
 }
 
 }  // extern "C"

@@ -4,9 +4,11 @@
 ``VanillaNeRFRadianceField`` keeps the reference constructor, ``forward(x, condition, features)``,
 ``query_density(x, features)`` and -- through an identical sub-module tree -- the reference
 ``state_dict`` keys (``mlp.base.hidden_layers.<i>.weight`` ...), so reference checkpoints load
-unchanged.  The arithmetic runs in ``nd_nerf_mlp_fwd`` (csrc/mlp.cu, fp32 FFMA, 1e-4) or, with
-``precision='bf16'``, in ``nd_nerf_mlp_fwd_tc`` (csrc/mlp_tc.cu: tcgen05 tensor cores, bf16 operands,
-fp32 accumulation in tensor memory, 1e-2); there is no eager fallback.
+unchanged.  The arithmetic runs on the tcgen05 tensor cores (csrc/mlp_tc.cu): ``precision='fp32'`` (default) carries
+every operand as a hi + lo pair of bf16 numbers with fp32 accumulation in tensor memory (``nd_nerf_mlp_fwd_tc3``, 1e-4),
+``precision='bf16'`` uses plain bf16 operands (``nd_nerf_mlp_fwd_tc``, 1e-2); ``precision='fp32_ffma'`` is the FFMA kernel
+(``nd_nerf_mlp_fwd``, csrc/mlp.cu, 1e-4) that also takes the architectures the tensor-core kernel does not.  There is no
+eager fallback.
 Forward only (autograd is row N1 of SURVEY.md section 8f).
 """
 from __future__ import annotations
@@ -76,8 +78,8 @@ class VanillaNeRFRadianceField(nn.Module):
     def __init__(self, net_depth: int = 8, net_width: int = 256, skip_layer: int = 4, feature_dim: int = 0,
                  net_depth_condition: int = 1, net_width_condition: int = 128, *, precision: str = 'fp32') -> None:
         super().__init__()
-        if precision not in ('fp32', 'bf16'):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ('fp32', 'bf16', 'fp32_ffma'):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'fp32_ffma'")
         self.precision = precision                 # may be switched at any time; the packed copy follows
         if net_depth_condition != 1:
             raise NotImplementedError('net_depth_condition != 1 is not used by NeRF-Det and not built')
@@ -86,6 +88,9 @@ class VanillaNeRFRadianceField(nn.Module):
         self.mlp = _NerfMLP(self.posi_encoder.latent_dim, self.view_encoder.latent_dim, feature_dim, net_depth,
                             net_width, skip_layer, net_depth_condition, net_width_condition)
         self.dims = [net_depth, net_width, skip_layer or 0, feature_dim, net_width_condition, 10, 4]
+        # 'fp32' runs on the tensor cores with split operands; architectures that kernel does not take fall to the FFMA one
+        if precision == 'fp32' and not ops.mlp_precision_supported(self.dims, 'fp32'):
+            self.precision = 'fp32_ffma'
         self._packed = None
         self._packed_key = None
 

@@ -587,11 +587,23 @@ def pack_mlp_weights(weights, dims, precision: str = 'fp32') -> Tensor:
 
 
 def _mlp_entry(lib, precision: str):
+    """'fp32': tcgen05 kernel with every operand split into hi + lo bf16 halves (fp32-grade, 1e-4); 'bf16': the same
+    kernel with plain bf16 operands (1e-2); 'fp32_ffma': the FFMA kernel (any architecture)."""
     if precision == 'fp32':
+        return lib.nd_mlp_tc3_packed_bytes, lib.nd_pack_mlp_weights_tc3, lib.nd_nerf_mlp_fwd_tc3
+    if precision == 'fp32_ffma':
         return lib.nd_mlp_packed_bytes, lib.nd_pack_mlp_weights, lib.nd_nerf_mlp_fwd
     if precision == 'bf16':
         return lib.nd_mlp_tc_packed_bytes, lib.nd_pack_mlp_weights_tc, lib.nd_nerf_mlp_fwd_tc
-    raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+    raise ValueError(f"precision must be 'fp32', 'bf16' or 'fp32_ffma', got {precision!r}")
+
+
+def mlp_precision_supported(weights_or_dims, precision: str) -> bool:
+    """Whether the kernel behind ``precision`` takes this architecture (the tensor-core kernel needs net_width 256,
+    net_width_condition 128, 63 + feature_dim <= 144)."""
+    lib = _lib.load()
+    arch = mlp_arch({}, weights_or_dims)
+    return int(_mlp_entry(lib, precision)[0](ctypes.byref(arch))) > 0
 
 
 @torch.library.custom_op(f'{_NS}::nerf_mlp_fwd', mutates_args=())
@@ -600,8 +612,8 @@ def nerf_mlp_fwd(packed: Tensor, dims: List[int], x: Tensor, features: Tensor, c
                  samples_per_ray: int, want_rgb: bool, want_alpha: bool,
                  precision: str = 'fp32') -> Tuple[Tensor, Tensor, Tensor]:
     """sigma [P], rgb [P, 3] (empty unless ``want_rgb``), alpha = 1 - exp(-sigma) [P] (empty unless
-    ``want_alpha``) for P points (reference nerf_mlp.py:217-234).  ``precision``: 'fp32' (FFMA kernel, 1e-4) or
-    'bf16' (tcgen05 kernel, 1e-2); ``packed`` must come from ``pack_mlp_weights`` with the same precision."""
+    ``want_alpha``) for P points (reference nerf_mlp.py:217-234).  ``precision``: 'fp32' (tcgen05 kernel, hi + lo bf16
+    operands, 1e-4), 'bf16' (tcgen05 kernel, 1e-2) or 'fp32_ffma' (FFMA kernel, 1e-4); ``packed`` must come from ``pack_mlp_weights`` with the same precision."""
     _need_cuda(packed, x, features, cond)
     if x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != 3:
         raise ValueError('x must be float32 [P, 3]')

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Times the shared MLP on the GPU: fp32 FFMA kernel vs bf16 tcgen05 kernel, at the
+"""Times the shared MLP on the GPU: the tcgen05 kernel at its two precisions (fp32-grade
+split operands, plain bf16) and the fp32 FFMA kernel, at the
 render shape (2048 rays x 64 samples) and the density-volume shape (40 x 40 x 16 voxels).  CUDA events, 20 launches
 after 5 warm-ups.  Prints one JSON line per (shape, precision)."""
 import json
@@ -18,7 +19,7 @@ FLOP_FULL, FLOP_DENSITY = 734474, 462090
 def main():
     dev = 'cuda'
     torch.manual_seed(0)
-    for prec in ('fp32', 'bf16'):
+    for prec in ('fp32', 'bf16', 'fp32_ffma'):
         field = VanillaNeRFRadianceField(4, 256, 3, 70, 1, 128, precision=prec).to(dev)
         for name, rays, spr, full in (('render 2048x64', 2048, 64, True), ('density 40x40x16', 25600, 1, False)):
             p = rays * spr
