@@ -887,6 +887,20 @@ def bench_render(args, rank, local_rank, world):
         pts, z = render.sample_along_camera_ray(ro, rd, cfg.near_far_range, n_samples, det=True)
         glob = torch.randn(pts.shape[0], n_samples, 70, device=dev)
         mlp_ms, _ = device_timed(lambda i: field(pts, rd, glob), max(5, min(steps, 50)), barrier)
+        # the other precision of the same kernel, as a labelled variant
+        other = 'fp32' if prec == 'bf16' else 'bf16'
+        field2 = VanillaNeRFRadianceField(4, 256, 3, 70, 1, 128, precision=other)
+        field2.load_state_dict({k: v for k, v in state.items() if not k.startswith('mapping.')})
+        field2 = field2.to(dev)
+
+        def step2(i):
+            ro2, rd2 = rays[i % N_INPUT_SETS]
+            return render.render_rays_func(ro2, rd2, None, None, f2d, imgs, cfg.aabb, cfg.near_far_range, n_samples, n_rand, field2,
+                                           sc.img_meta, proj, 'image', 3, False, 0, True)
+        for i in range(3):
+            step2(i)
+        other_ms, _ = device_timed(step2, max(5, min(steps, 50)), barrier)
+        other_mlp_ms, _ = device_timed(lambda i: field2(pts, rd, glob), max(5, min(steps, 50)), barrier)
         # end to end: host ray batch -> selection (host, like the reference) -> device -> render -> rgb / depth -> host
         e2e = None
         if not args.no_e2e and world == 1:
@@ -918,7 +932,7 @@ def bench_render(args, rank, local_rank, world):
                             'ms_per_step': dt * 1e3}
         line = {'metric': 'rays_per_sec', 'value': n_rand / (ms_per_step * 1e-3), 'unit': 'rays/s', 'n_gpus': world, 'steps': steps,
                 'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-                'dtype': 'bf16 operands / f32 accumulate' if prec == 'bf16' else 'f32', 'data': 'synthetic',
+                'dtype': 'bf16 operands / f32 accumulate' if prec == 'bf16' else 'f32-grade (hi + lo bf16 operands / f32 accumulate)', 'data': 'synthetic',
                 'config': {'workload': 'nerfdet_res50_2x_low_res_depth_sp render_rays_func: 2048 rays x 64 samples, 50 source views '
                                        '(R2-R7 + the shared MLP, BASELINE.json configs[2])',
                            'mlp_precision': prec, 'rays_per_step': n_rand, 'samples_per_ray': n_samples,
@@ -927,9 +941,14 @@ def bench_render(args, rank, local_rank, world):
                            'avoided': 'the reference\'s [rays, samples, views, 35] tensor (917 MB) is never built'},
                 'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                              'traffic': None, 'peak_source': peak_src + ' bf16 burst',
-                             'kernel': 'the shared MLP (nd_nerf_mlp_fwd*), 734 474 FLOP per point', 'kernel_ms': mlp_ms,
+                             'kernel': 'the shared MLP on tcgen05 (k_nerf_mlp_tc), 734 474 algorithmic FLOP per point'
+                                       + (' (the fp32-grade precision issues three bf16 products per multiply)' if prec == 'fp32' else ''),
+                             'kernel_ms': mlp_ms,
                              'flops_per_launch': flops},
-                'cpu_baseline': cpu_baseline, 'e2e': e2e, 'gpu_launches': 5 * steps, 'clocks': clocks}
+                'cpu_baseline': cpu_baseline, 'e2e': e2e, 'gpu_launches': 5 * steps, 'clocks': clocks,
+                'variants': {f'mlp_{other}': {'ms_per_step': other_ms, 'value': n_rand / (other_ms * 1e-3), 'mlp_kernel_ms': other_mlp_ms,
+                                              'note': ('fp32-grade: hi + lo bf16 operands, three tensor-core products per multiply (1e-4)'
+                                                       if other == 'fp32' else 'plain bf16 operands (1e-2)')}}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -36,7 +36,7 @@ def _cuda_accumulate(features, points, projection):
 
 def _cuda_finalize(acc, n_views_total, channels, n_voxels, alpha, want_cov):
     from . import ops
-    return ops.lift_finalize(acc, n_views_total, channels, n_voxels, alpha, want_cov)
+    return ops.direct.lift_finalize(acc, n_views_total, channels, n_voxels, alpha, want_cov)
 
 
 def lift_mean_var_view_sharded(features_local: torch.Tensor, points: torch.Tensor,

@@ -75,7 +75,7 @@ def get_points_device(n_voxels, voxel_size, origin, device) -> torch.Tensor:
 def project_voxels(points: torch.Tensor, projection: torch.Tensor, height: int, width: int):
     """x, y (int64) and valid (bool), each [nv, N]: the index arithmetic of
     nerfdet.py:396-403, bit-exact."""
-    return ops.project_voxels(points.reshape(3, -1), projection, int(height), int(width))
+    return ops.direct.project_voxels(points.reshape(3, -1), projection, int(height), int(width))
 
 
 def backproject(features, points, projection, depth, voxel_size):
@@ -88,7 +88,7 @@ def backproject(features, points, projection, depth, voxel_size):
     if depth is not None:
         depth_resized = F.interpolate(depth.unsqueeze(1), size=(h, w), mode='bilinear').squeeze(1)
         voxel_z = float(voxel_size[-1])
-    volume, valid = ops.backproject(features, points.reshape(3, -1), projection, depth_resized, voxel_z)
+    volume, valid = ops.direct.backproject(features, points.reshape(3, -1), projection, depth_resized, voxel_z)
     return volume.view(nv, c, gx, gy, gz), valid.view(nv, 1, gx, gy, gz)
 
 
@@ -114,7 +114,7 @@ def lift_mean_var(features, points, projection, alpha: Optional[torch.Tensor] = 
     if scratch_budget_bytes > 0:
         if depth is not None or out is not None:
             raise NotImplementedError('the depth gate and caller-owned outputs are not available on the staged path')
-        mean, cov, count = ops.lift_mean_var(features, points, projection, al, want_cov, scratch_budget_bytes)
+        mean, cov, count = ops.direct.lift_mean_var(features, points, projection, al, want_cov, scratch_budget_bytes)
     else:
         depth_resized, voxel_z = None, 0.0
         if depth is not None:

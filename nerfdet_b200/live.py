@@ -35,7 +35,7 @@ def map_features_2d(feature_2d: torch.Tensor, mapping) -> torch.Tensor:
         sv, sc, sy, sx = feature_2d.stride()
         if not (sx == 1 and sy == w and (sc * elt) % 16 == 0 and (sv * elt) % 16 == 0 and feature_2d.data_ptr() % 16 == 0):
             feature_2d = feature_2d.contiguous()
-        y = ops.map_features(feature_2d, lin.weight.detach(), lin.bias.detach() if lin.bias is not None else None)
+        y = ops.direct.map_features(feature_2d, lin.weight.detach(), lin.bias.detach() if lin.bias is not None else None)
         return y.permute(0, 3, 1, 2)
     flat = feature_2d.reshape(nv, c, h * w).permute(0, 2, 1).contiguous().float()
     return mapping(flat).view(nv, h, w, -1).permute(0, 3, 1, 2)
@@ -52,7 +52,7 @@ def live_statistics(mapped_2d, rgb_images, points, projection, rgb_projection, m
     (stride 1).  Returns ``global_volume [N, 70]`` (interleaved rows), the feature-level
     count ``[1, X, Y, Z]`` and, on request, ``mean35`` / ``cov35 [35, X, Y, Z]``."""
     gx, gy, gz = points.shape[-3:]
-    glob, mean35, cov35, count = ops.live_stats(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias,
+    glob, mean35, cov35, count = ops.direct.live_stats(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias,
                                                 want_planes)
     out = dict(global_volume=glob, count=count.view(1, gx, gy, gz))
     if want_planes:

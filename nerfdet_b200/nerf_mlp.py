@@ -123,7 +123,7 @@ class VanillaNeRFRadianceField(nn.Module):
         ``return_alpha`` additionally returns 1 - exp(-sigma) (nerfdet.py:258) from the same launch."""
         lead = x.shape[:-1]
         feats = self._features(x, features)
-        sigma, _, alpha = ops.nerf_mlp_fwd(self.packed_weights(), self.dims, x.reshape(-1, 3), feats, None, 1, False,
+        sigma, _, alpha = ops.direct.nerf_mlp_fwd(self.packed_weights(), self.dims, x.reshape(-1, 3), feats, None, 1, False,
                                            return_alpha, self.precision)
         sigma = sigma.view(*lead, 1)
         return (sigma, alpha.view(*lead, 1)) if return_alpha else sigma
@@ -143,7 +143,7 @@ class VanillaNeRFRadianceField(nn.Module):
             if condition.dim() != 2 or condition.shape[0] != lead[0]:
                 raise ValueError(f'condition {tuple(condition.shape)} does not broadcast over x {tuple(x.shape)}')
             cond, spr = condition, p // condition.shape[0]
-        sigma, rgb, _ = ops.nerf_mlp_fwd(self.packed_weights(), self.dims, x.reshape(-1, 3), feats, cond, spr, True, False,
+        sigma, rgb, _ = ops.direct.nerf_mlp_fwd(self.packed_weights(), self.dims, x.reshape(-1, 3), feats, cond, spr, True, False,
                                          self.precision)
         return rgb.view(*lead, 3), sigma.view(*lead, 1)
 

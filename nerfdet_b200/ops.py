@@ -249,7 +249,7 @@ def lift_mean_var_planned(features: Tensor, points: Tensor, projection: Tensor, 
     if depth_resized is not None:
         raise NotImplementedError('the depth gate needs the plane-resident kernel (contiguous NCHW planes <= 64 KB); '
                                   'use backproject() for other layouts')
-    return lift_mean_var(features, points, projection, alpha, want_cov, 0)
+    return lift_mean_var._init_fn(features, points, projection, alpha, want_cov, 0)
 
 
 def lift_accumulate_planned(features: Tensor, points: Tensor, projection: Tensor, acc: Optional[Tensor] = None,
@@ -795,3 +795,19 @@ def volume_sample(volume: Tensor, pts: Tensor, aabb_min: List[float], aabb_max: 
 @volume_sample.register_fake
 def _(volume, pts, aabb_min, aabb_max):
     return pts.new_empty((pts.shape[0], volume.shape[0])), pts.new_empty((pts.shape[0],), dtype=torch.bool)
+
+
+# ------------------------------------------------------------------------------------------
+# The Python functions behind the registered custom ops, for the reference-signature modules (lifting, live, render,
+# nerf_mlp, projection): a call through torch.library's dispatcher costs 50-350 us of host time per op, more than
+# most of these kernels run; the modules call the implementations directly (same validation, same device guard), the
+# registered ops stay for torch.compile / export users.
+# ------------------------------------------------------------------------------------------
+class _Direct:
+    pass
+
+
+direct = _Direct()
+for _name in ('project_voxels', 'backproject', 'lift_mean_var', 'lift_accumulate', 'lift_accumulate_into', 'lift_finalize',
+              'map_features', 'live_stats', 'nerf_mlp_fwd', 'sample_rays', 'render_gather_stats', 'composite', 'volume_sample'):
+    setattr(direct, _name, globals()[_name]._init_fn)

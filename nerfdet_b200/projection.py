@@ -36,7 +36,7 @@ class Projector:
         lead = xyz.shape[:-1]
         if featmaps is None:
             featmaps = train_imgs.new_zeros((train_imgs.shape[0], 0) + tuple(train_imgs.shape[2:]))
-        glob, vmask, pmask, pix, front, vf = ops.render_gather_stats(xyz.reshape(-1, 3), train_cameras, train_imgs,
+        glob, vmask, pmask, pix, front, vf = ops.direct.render_gather_stats(xyz.reshape(-1, 3), train_cameras, train_imgs,
                                                                      featmaps, want_pixels, want_features)
         return lead, glob, vmask, pmask, pix, front, vf
 

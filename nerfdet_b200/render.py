@@ -37,7 +37,7 @@ def sample_along_camera_ray(ray_o, ray_d, depth_range, N_samples, inv_uniform=Fa
     t_rand = None
     if not det:
         t_rand = torch.rand((ray_o.shape[0], N_samples), dtype=torch.float32, device=ray_o.device)   # == rand_like(z_vals)
-    return ops.sample_rays(ray_o, ray_d, float(depth_range[0]), float(depth_range[1]), int(N_samples), t_rand)
+    return ops.direct.sample_rays(ray_o, ray_d, float(depth_range[0]), float(depth_range[1]), int(N_samples), t_rand)
 
 
 def volume_sampling(sample_pts, features, aabb):
@@ -45,16 +45,25 @@ def volume_sampling(sample_pts, features, aabb):
     (render_ray.py:26-46): ``[rays, samples, C]`` and the strict in-box mask."""
     assert features.shape[0] == 1
     r, s = sample_pts.shape[:2]
-    out, inside = ops.volume_sample(features[0], sample_pts.reshape(-1, 3), [float(v) for v in aabb[0]],
+    out, inside = ops.direct.volume_sample(features[0], sample_pts.reshape(-1, 3), [float(v) for v in aabb[0]],
                                     [float(v) for v in aabb[1]])
     return out.view(r, s, -1), inside.view(r, s)
 
 
 def raw2outputs(raw, z_vals, mask, white_bkgd=False):
     """Alpha compositing (render_ray.py:196-247) of ``raw [rays, samples, 4]`` = (rgb, sigma)."""
-    bounds = torch.stack(torch.aminmax(z_vals))          # batch-global clamp bounds, stays on the device
-    rgb, depth, weights, alpha, trans, ray_mask = ops.composite(raw[..., :3].contiguous(), raw[..., 3].contiguous(),
-                                                                z_vals, mask, bounds, bool(white_bkgd))
+    return _composite(raw[..., :3].contiguous(), raw[..., 3].contiguous(), z_vals, mask, white_bkgd)
+
+
+def _composite(rgb_pts, sigma_pts, z_vals, mask, white_bkgd=False, det=False):
+    """``raw2outputs`` on separate colour / density tensors (no cat + slice round trip).  The depth clamp bounds are
+    batch-global (render_ray.py:236) and stay on the device; with deterministic sampling every ray has the same
+    samples, so the first ray's end points are the bounds."""
+    if det and z_vals.shape[0] > 0:
+        bounds = torch.stack([z_vals[0, 0], z_vals[0, -1]])
+    else:
+        bounds = torch.stack(torch.aminmax(z_vals))
+    rgb, depth, weights, alpha, trans, ray_mask = ops.direct.composite(rgb_pts, sigma_pts, z_vals, mask, bounds, bool(white_bkgd))
     return OrderedDict([('rgb', rgb), ('depth', depth), ('weights', weights),
                         ('mask', ray_mask if mask is not None else None), ('alpha', alpha), ('z_vals', z_vals),
                         ('transparency', trans)])
@@ -74,20 +83,20 @@ def render_rays_func(ray_o, ray_d, mean_volume, cov_volume, features_2D, img, aa
     cameras = _compute_projection(img_meta)[0].to(pts.device)
     flat = pts.view(-1, 3)
     if mode == 'image':
-        glob, _, pixel_mask, _, _, _ = ops.render_gather_stats(flat, cameras, img, features_2D, False, False)
+        glob, _, pixel_mask, _, _, _ = ops.direct.render_gather_stats(flat, cameras, img, features_2D, False, False)
         rgb_pts, density_pts = nerf_mlp(pts, ray_d, glob.view(n_rays, n_samples, -1))
         ret['sigma'] = density_pts
     elif mode == 'volume':
         mean_pts, inbound = volume_sampling(pts, mean_volume, aabb)
         cov_pts, inbound = volume_sampling(pts, cov_volume, aabb)
         empty = img.new_zeros((img.shape[0], 0) + tuple(img.shape[2:]))
-        _, _, pixel_mask, _, _, _ = ops.render_gather_stats(flat, cameras, img, empty, False, False)
+        _, _, pixel_mask, _, _, _ = ops.direct.render_gather_stats(flat, cameras, img, empty, False, False)
         rgb_pts, density_pts = nerf_mlp(pts, ray_d, torch.cat([mean_pts, cov_pts], dim=-1))
         density_pts = density_pts * inbound.unsqueeze(dim=-1)
     else:
         raise ValueError(f'unknown mode {mode!r}')
-    raw = torch.cat([rgb_pts, density_pts], dim=-1)
-    ret['outputs_coarse'] = raw2outputs(raw, z_vals, pixel_mask.view(n_rays, n_samples), white_bkgd=white_bkgd)
+    ret['outputs_coarse'] = _composite(rgb_pts, density_pts.reshape(n_rays, n_samples), z_vals,
+                                       pixel_mask.view(n_rays, n_samples), white_bkgd, det=det)
     return ret
 
 
