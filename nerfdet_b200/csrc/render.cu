@@ -8,6 +8,8 @@
 //                          (917 MB at nv = 50) is never materialised
 //   k_composite            render_ray.py:196-247   alpha compositing per ray
 //   k_volume_sample        render_ray.py:26-46     trilinear lookup (dead branch in nerfdet, standalone-callable)
+#include <algorithm>
+
 #include "nd_common.cuh"
 
 namespace nd {
@@ -194,13 +196,29 @@ k_render_gather_stats(const float *__restrict__ pts, int64_t n_pts, const float 
     }
 }
 
-// Channels-last build of the same statistics (the product path): one WARP per ray sample, lane = mapped-feature
-// channel (lanes 0-2 also carry the three image channels).  The projection of the sample into the views runs with
-// lane = view; only views with at least one bilinear corner in bounds (~25 %) are visited afterwards, their
-// sample parameters broadcast with shuffles, and each corner of the feature map is ONE coalesced 128-byte row
-// [pixel][D] instead of D scattered 4-byte loads from D planes.  Same arithmetic (corner order nw, ne, sw, se;
-// views ascending) as the thread-per-sample kernel above, which stays for the materialising compatibility outputs.
-constexpr int kRcWarps = 8, kRcPerWarp = 4;
+// Channels-last build of the same statistics (the product path): one WARP per ray sample.
+//
+//   phase 1, lane = view: project the sample (IEEE divisions: the masks are bit-exact), build the two bilinear
+//            samples (image, feature map) and their four weights, and append the views with at least one corner in
+//            bounds (~35 % of them) to the warp's list in shared memory -- ascending view order, ballot + popc.
+//   phase 2, quarter-warp = view: the four quarters walk the list four entries at a time.  The 8 lanes of a quarter
+//            fetch the 32 mapped channels of a corner as one coalesced 128-byte row [pixel][D] (4 channels per
+//            lane) and one image channel each; corner addresses are clamped into the map, so all eight loads of an
+//            entry are unconditional and in flight together, and a corner outside the map is left out by the
+//            predicate on its FMA (zeros padding of grid_sample, corner order nw, ne, sw, se like ATen).
+//   phase 3: the quarters are combined with shuffles and every lane finishes ONE mapped channel (mean, variance
+//            over ALL views, exp(-var)); three lanes finish the image channels.
+//
+// A warp walks the samples with a grid stride, so the eight warps of a CTA sit on eight consecutive samples of a
+// ray (their corners share L1 lines) and the uneven number of visible views per sample averages out.
+//
+// Measured on B200 at 2048 rays x 64 samples x 50 views (profiles/r02_render_gather.md): 256 us, against 343 us for
+// the round-1 loop (predicated loads issued two at a time, a find-first-set selection per step).  Tried and dropped:
+// a 64-register cap for a fourth CTA per SM (362 us: the eight loads no longer stay in flight together), splitting
+// phase 1 into a cheap candidate pass and one compacted round of sample building (20 % fewer instructions, 267 us:
+// the kernel is bound by the latency of a warp's serial phases, not by issue slots), prefetch.global.L1 of the
+// corner lines from phase 1 (311 us).
+constexpr int kRcWarps = 8, kRcList = 64;
 
 struct ViewSampleG {         // like ViewSample, for arbitrary strides
     int32_t x0, y0;
@@ -225,14 +243,17 @@ __device__ __forceinline__ ViewSampleG make_sample_g(float gx, float gy, int hs,
     return s;
 }
 
-// per (warp, view) sample parameters parked in shared memory by the lane that projected the view and read back by
-// the quarter-warp that gathers the view (broadcast LDS.128)
-struct __align__(16) ViewParams {
-    int32_t offI, offF;      // element offsets of the north-west corners (view base included)
-    uint32_t bits;           // image corners | feature corners << 4 | view mask << 8
-    float fxI, fyI, fxF, fyF;
-    int32_t pad;
+// One listed (sample, view): north-west corners clamped into the maps (so every corner address is loadable),
+// whether the east / south neighbours are one pixel further (else they alias the clamped corner and their
+// predicate is off), and the bilinear weights.  48 bytes = three broadcast LDS.128 per quarter-warp.
+struct __align__(16) ViewEntry {
+    int32_t offI, offF;      // element offsets of the clamped north-west corners (view base included)
+    uint32_t bits;           // image corners | feature corners << 4 | view mask << 8 | dxI, dyI, dxF, dyF << 9
+    float maskf;             // 1.0f when the view sees the sample (in bounds and in front), else 0.0f
+    float wI[4], wF[4];      // nw, ne, sw, se
 };
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 template <typename T> __device__ __forceinline__ float4 load4(const T *p);
 template <> __device__ __forceinline__ float4 load4<float>(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
@@ -242,19 +263,15 @@ template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bf
                        __uint_as_float(r.y & 0xffff0000u));
 }
 
-// One WARP per ray sample.  Projection: lane = view.  Gather: four views per step, one per QUARTER-warp; the 8 lanes
-// of a quarter fetch the 32 mapped channels of a bilinear corner as one coalesced 128-byte row (4 channels per lane),
-// lanes 0-2 of the quarter also fetch the three image channels.  Each lane keeps the masked sum / sum / sum of
-// squares of its channels over the views its quarter visited; the quarters are combined with shuffles at the end.
-template <typename T>
-__global__ void __launch_bounds__(kRcWarps * 32)
+template <typename T, bool kFeat>
+__global__ void __launch_bounds__(kRcWarps * 32, 3)
 k_render_gather_stats_cl(const float *__restrict__ pts, int64_t n_pts, const float *__restrict__ cams, int nv,
                          const float *__restrict__ img, int i_sv, int i_sc, int i_sy, int i_sx, int hi, int wi,
                          const T *__restrict__ feat, int f_sv, int f_sy, int f_sx, int d, int hf, int wf,
                          float *__restrict__ glob, uint8_t *__restrict__ view_mask, uint8_t *__restrict__ pixel_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ViewParams *sV = reinterpret_cast<ViewParams *>(smem_raw) + (threadIdx.x >> 5) * 32;      // [warps][32]
-    float *sP = reinterpret_cast<float *>(smem_raw + sizeof(ViewParams) * 32 * kRcWarps);     // [nv][12] rows 0-2 of K @ E
+    ViewEntry *sL = reinterpret_cast<ViewEntry *>(smem_raw) + (threadIdx.x >> 5) * kRcList;  // [warps][kRcList]
+    float *sP = reinterpret_cast<float *>(smem_raw + sizeof(ViewEntry) * kRcList * kRcWarps); // [nv][12] rows 0-2 of K @ E
     for (int i = threadIdx.x; i < nv * 12; i += blockDim.x) {
         const int v = i / 12, rc = i - v * 12, r = rc >> 2, c = rc & 3;
         const float *K = cams + v * 34 + 2, *E = cams + v * 34 + 18;
@@ -269,21 +286,21 @@ k_render_gather_stats_cl(const float *__restrict__ pts, int64_t n_pts, const flo
     const float h = cams[0], w = cams[1];
     const float wm1 = __fsub_rn(w, 1.0f), hm1 = __fsub_rn(h, 1.0f);
     const int ct = 3 + d;
-    const unsigned full = 0xffffffffu;
+    const unsigned full = 0xffffffffu, below = (1u << lane) - 1u;
     const bool feat_lane = 4 * l8 < d, img_lane = l8 < 3;
-    const float *img_l = img + (img_lane ? l8 * i_sc : 0);
+    const float *img_l = img + (img_lane ? l8 * i_sc : 0);                 // lanes 3-7 of a quarter repeat channel 0
     const T *feat_l = feat + (feat_lane ? 4 * l8 : 0);
-    for (int it = 0; it < kRcPerWarp; ++it) {
-        const int64_t p = ((int64_t)blockIdx.x * kRcWarps + warp) * kRcPerWarp + it;
-        if (p >= n_pts) break;                                             // warp-uniform
+    const int64_t stride = (int64_t)gridDim.x * kRcWarps;
+    for (int64_t p = (int64_t)blockIdx.x * kRcWarps + warp; p < n_pts; p += stride) {
         const float X = __ldg(pts + p * 3), Y = __ldg(pts + p * 3 + 1), Z = __ldg(pts + p * 3 + 2);
-        int cnt = 0;
+        int cnt = 0, n_list = 0;
         float smF[4] = {0.f, 0.f, 0.f, 0.f}, s1F[4] = {0.f, 0.f, 0.f, 0.f}, s2F[4] = {0.f, 0.f, 0.f, 0.f};
         float smI = 0.f, s1I = 0.f, s2I = 0.f;
         for (int v0 = 0; v0 < nv; v0 += 32) {
+            // ---- phase 1: lane = view
             const int v = v0 + lane;
-            ViewParams vp{0, 0, 0u, 0.f, 0.f, 0.f, 0.f, 0};
-            bool m = false;
+            bool m = false, listed = false;
+            ViewEntry e;
             if (v < nv) {
                 const float *P = sP + v * 12;
                 const float q0 = chain4(P, X, Y, Z), q1 = chain4(P + 4, X, Y, Z), q2 = chain4(P + 8, X, Y, Z);
@@ -294,82 +311,88 @@ k_render_gather_stats_cl(const float *__restrict__ pts, int64_t n_pts, const flo
                 const bool front = q2 > 0.0f;
                 const bool inb = (px <= wm1) && (px >= 0.0f) && (py <= hm1) && (py >= 0.0f);
                 m = inb && front;
+                // normalize (projection.py:37-40): 2 * pix / [w - 1, h - 1] - 1
                 const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, px), wm1), 1.0f);
                 const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, py), hm1), 1.0f);
                 const ViewSampleG si = make_sample_g(gx, gy, hi, wi);
                 ViewSampleG sf = make_sample_g(gx, gy, hf, wf);
-                if (d == 0) sf.inb = 0u;
-                vp.offI = v * i_sv + si.y0 * i_sy + si.x0 * i_sx;
-                vp.offF = v * f_sv + sf.y0 * f_sy + sf.x0 * f_sx;
-                vp.bits = si.inb | (sf.inb << 4) | (m ? 0x100u : 0u);
-                vp.fxI = si.fx; vp.fyI = si.fy; vp.fxF = sf.fx; vp.fyF = sf.fy;
+                if (!kFeat) sf.inb = 0u;
+                listed = (si.inb | sf.inb) != 0u;
+                const int xi = clampi(si.x0, 0, wi - 1), yi = clampi(si.y0, 0, hi - 1);
+                const int xf = clampi(sf.x0, 0, wf - 1), yf = clampi(sf.y0, 0, hf - 1);
+                e.offI = v * i_sv + yi * i_sy + xi * i_sx;
+                e.offF = v * f_sv + yf * f_sy + xf * f_sx;
+                e.bits = si.inb | (sf.inb << 4) | (m ? 0x100u : 0u) |
+                         ((si.x0 >= 0 && si.x0 + 1 < wi) ? 0x200u : 0u) | ((si.y0 >= 0 && si.y0 + 1 < hi) ? 0x400u : 0u) |
+                         ((sf.x0 >= 0 && sf.x0 + 1 < wf) ? 0x800u : 0u) | ((sf.y0 >= 0 && sf.y0 + 1 < hf) ? 0x1000u : 0u);
+                e.maskf = m ? 1.0f : 0.0f;
+                e.wI[0] = (1.0f - si.fx) * (1.0f - si.fy); e.wI[1] = si.fx * (1.0f - si.fy);
+                e.wI[2] = (1.0f - si.fx) * si.fy;          e.wI[3] = si.fx * si.fy;
+                e.wF[0] = (1.0f - sf.fx) * (1.0f - sf.fy); e.wF[1] = sf.fx * (1.0f - sf.fy);
+                e.wF[2] = (1.0f - sf.fx) * sf.fy;          e.wF[3] = sf.fx * sf.fy;
                 if (view_mask != nullptr) view_mask[p * nv + v] = m ? 1 : 0;
             }
             cnt += __popc(__ballot_sync(full, m));
-            unsigned act = __ballot_sync(full, (vp.bits & 0xffu) != 0u);
-            if (act == 0u) continue;
-            __syncwarp();                                                  // the previous round's readers are done
-            sV[lane] = vp;
+            const unsigned act = __ballot_sync(full, listed);
+            if (listed) sL[n_list + __popc(act & below)] = e;
+            n_list += __popc(act);
+            if (n_list <= kRcList - 32 && v0 + 32 < nv) continue;          // room for another round of views
             __syncwarp();
-            while (act) {
-                // the next four active views, one per quarter-warp (ascending within a quarter over the steps)
-                int src = -1;
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const int sbit = act ? __ffs(act) - 1 : -1;
-                    if (act) act &= act - 1;
-                    if (qq == quarter) src = sbit;
-                }
-                if (src < 0) continue;
-                const int4 a4 = *reinterpret_cast<const int4 *>(&sV[src]);             // offI, offF, bits, fxI
-                const float4 b4 = *reinterpret_cast<const float4 *>(&sV[src].fyI);     // fyI, fxF, fyF, pad
+            // ---- phase 2: quarter-warp = listed view
+            for (int i = quarter; i < n_list; i += 4) {
+                const int4 a4 = *reinterpret_cast<const int4 *>(&sL[i]);               // offI, offF, bits, maskf
+                const float4 wi4 = *reinterpret_cast<const float4 *>(sL[i].wI);
                 const uint32_t b = (uint32_t)a4.z;
-                const bool mv = (b & 0x100u) != 0;
-                if ((b & 0xfu) && img_lane) {
-                    const float fx = __int_as_float(a4.w), fy = b4.x;
-                    const float *q = img_l + a4.x;
-                    const float v0 = (b & 1u) ? __ldg(q) : 0.0f, v1 = (b & 2u) ? __ldg(q + i_sx) : 0.0f;
-                    const float v2 = (b & 4u) ? __ldg(q + i_sy) : 0.0f, v3 = (b & 8u) ? __ldg(q + i_sy + i_sx) : 0.0f;
+                const float mvf = __int_as_float(a4.w);
+                const float *qi = img_l + a4.x;
+                const int dxi = (b & 0x200u) ? i_sx : 0, dyi = (b & 0x400u) ? i_sy : 0;
+                const float i0 = __ldg(qi), i1 = __ldg(qi + dxi), i2 = __ldg(qi + dyi), i3 = __ldg(qi + dyi + dxi);
+                float4 c0, c1, c2, c3, wf4;
+                if (kFeat) {
+                    const T *qf = feat_l + a4.y;
+                    const int dxf = (b & 0x800u) ? f_sx : 0, dyf = (b & 0x1000u) ? f_sy : 0;
+                    c0 = load4<T>(qf); c1 = load4<T>(qf + dxf); c2 = load4<T>(qf + dyf); c3 = load4<T>(qf + dyf + dxf);
+                    wf4 = *reinterpret_cast<const float4 *>(sL[i].wF);
+                }
+                {
                     float f = 0.0f;
-                    if (b & 1u) f = fmaf(v0, (1.0f - fx) * (1.0f - fy), f);
-                    if (b & 2u) f = fmaf(v1, fx * (1.0f - fy), f);
-                    if (b & 4u) f = fmaf(v2, (1.0f - fx) * fy, f);
-                    if (b & 8u) f = fmaf(v3, fx * fy, f);
-                    smI += mv ? f : 0.0f;
+                    if (b & 1u) f = fmaf(i0, wi4.x, f);
+                    if (b & 2u) f = fmaf(i1, wi4.y, f);
+                    if (b & 4u) f = fmaf(i2, wi4.z, f);
+                    if (b & 8u) f = fmaf(i3, wi4.w, f);
+                    smI = fmaf(f, mvf, smI);                                // sum f * mask, like the reference's product
                     s1I += f;
                     s2I = fmaf(f, f, s2I);
                 }
-                if ((b & 0xf0u) && feat_lane) {
-                    const float fx = b4.y, fy = b4.z;
-                    const T *q = feat_l + a4.y;
-                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 c0 = (b & 0x10u) ? load4<T>(q) : z4, c1 = (b & 0x20u) ? load4<T>(q + f_sx) : z4;
-                    const float4 c2 = (b & 0x40u) ? load4<T>(q + f_sy) : z4, c3 = (b & 0x80u) ? load4<T>(q + f_sy + f_sx) : z4;
-                    const float nw = (1.0f - fx) * (1.0f - fy), ne = fx * (1.0f - fy), sw = (1.0f - fx) * fy, se = fx * fy;
+                if (kFeat) {
                     const float a0[4] = {c0.x, c0.y, c0.z, c0.w}, a1[4] = {c1.x, c1.y, c1.z, c1.w};
                     const float a2[4] = {c2.x, c2.y, c2.z, c2.w}, a3[4] = {c3.x, c3.y, c3.z, c3.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        float f = 0.0f;                                    // corner order nw, ne, sw, se like ATen
-                        if (b & 0x10u) f = fmaf(a0[k], nw, f);
-                        if (b & 0x20u) f = fmaf(a1[k], ne, f);
-                        if (b & 0x40u) f = fmaf(a2[k], sw, f);
-                        if (b & 0x80u) f = fmaf(a3[k], se, f);
-                        smF[k] += mv ? f : 0.0f;
+                        float f = 0.0f;
+                        if (b & 0x10u) f = fmaf(a0[k], wf4.x, f);
+                        if (b & 0x20u) f = fmaf(a1[k], wf4.y, f);
+                        if (b & 0x40u) f = fmaf(a2[k], wf4.z, f);
+                        if (b & 0x80u) f = fmaf(a3[k], wf4.w, f);
+                        smF[k] = fmaf(f, mvf, smF[k]);
                         s1F[k] += f;
                         s2F[k] = fmaf(f, f, s2F[k]);
                     }
                 }
             }
+            n_list = 0;
+            __syncwarp();                                                  // the list is free for the next round
         }
-        // combine the four quarters (lanes l8, l8 + 8, l8 + 16, l8 + 24 hold the same channels)
+        // ---- phase 3: combine the quarters (lanes l8, l8 + 8, l8 + 16, l8 + 24 hold the same channels)
 #pragma unroll
         for (int o = 8; o <= 16; o <<= 1) {
+            if (kFeat) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                smF[k] += __shfl_xor_sync(full, smF[k], o);
-                s1F[k] += __shfl_xor_sync(full, s1F[k], o);
-                s2F[k] += __shfl_xor_sync(full, s2F[k], o);
+                for (int k = 0; k < 4; ++k) {
+                    smF[k] += __shfl_xor_sync(full, smF[k], o);
+                    s1F[k] += __shfl_xor_sync(full, s1F[k], o);
+                    s2F[k] += __shfl_xor_sync(full, s2F[k], o);
+                }
             }
             smI += __shfl_xor_sync(full, smI, o);
             s1I += __shfl_xor_sync(full, s1I, o);
@@ -378,23 +401,20 @@ k_render_gather_stats_cl(const float *__restrict__ pts, int64_t n_pts, const flo
         const float denom = __fadd_rn((float)cnt, 1e-8f);
         float *row = glob + p * (int64_t)(2 * ct);
         if (lane == 0 && pixel_mask != nullptr) pixel_mask[p] = cnt > 1 ? 1 : 0;
-        if (quarter == 0 && img_lane) {
-            const float mean = smI / denom;
-            float ssd = fmaf(-2.0f * mean, s1I, s2I);
+        auto finish = [&](int ch, float sm, float s1, float s2) {
+            const float mean = sm / denom;
+            float ssd = fmaf(-2.0f * mean, s1, s2);                        // sum over ALL views of (f - mean)^2
             ssd = fmaxf(fmaf((float)nv * mean, mean, ssd), 0.0f);
-            row[l8] = mean;
-            row[ct + l8] = expf(-(ssd / denom));
+            row[ch] = mean;
+            row[ct + ch] = expf(-(ssd / denom));
+        };
+        if (kFeat && feat_lane) {                                          // quarter q finishes channel 4 * l8 + q
+            const float sm = quarter == 0 ? smF[0] : quarter == 1 ? smF[1] : quarter == 2 ? smF[2] : smF[3];
+            const float s1 = quarter == 0 ? s1F[0] : quarter == 1 ? s1F[1] : quarter == 2 ? s1F[2] : s1F[3];
+            const float s2 = quarter == 0 ? s2F[0] : quarter == 1 ? s2F[1] : quarter == 2 ? s2F[2] : s2F[3];
+            finish(3 + 4 * l8 + quarter, sm, s1, s2);
         }
-        if (quarter == 1 && feat_lane) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float mean = smF[k] / denom;
-                float ssd = fmaf(-2.0f * mean, s1F[k], s2F[k]);
-                ssd = fmaxf(fmaf((float)nv * mean, mean, ssd), 0.0f);
-                row[3 + 4 * l8 + k] = mean;
-                row[ct + 3 + 4 * l8 + k] = expf(-(ssd / denom));
-            }
-        }
+        if (quarter == 0 && img_lane) finish(l8, smI, s1I, s2I);
     }
 }
 
@@ -543,26 +563,31 @@ int nd_render_gather_stats(const float *pts, int64_t n_points, const float *came
                                      (reinterpret_cast<uintptr_t>(featmaps->data) & 15) == 0)) &&
         pixel_locations == nullptr &&
         in_front == nullptr && view_features == nullptr) {
-        const size_t sm = (size_t)n_views * 12 * sizeof(float) + sizeof(ViewParams) * 32 * kRcWarps;
+        const size_t sm = (size_t)n_views * 12 * sizeof(float) + sizeof(ViewEntry) * kRcList * kRcWarps;
         ND_REQUIRE(sm <= 48 * 1024, ND_ERR_BAD_SHAPE, "nd_render_gather_stats: too many views (%d)", n_views);
         const int64_t span_i = (int64_t)n_views * images->stride_v, span_f = (int64_t)n_views * featmaps->stride_v;
         ND_REQUIRE(span_i < (1ll << 31) && span_f < (1ll << 31) && images->stride_v >= 0 && featmaps->stride_v >= 0,
                    ND_ERR_BAD_SHAPE, "nd_render_gather_stats: source stacks beyond 2^31 elements");
-        const unsigned g = (unsigned)ceil_div(n_points, (int64_t)kRcWarps * kRcPerWarp);
+        // grid-stride over the samples: as many CTAs as stay resident (3 per SM at 80 registers), no more than needed
+        int sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned g = (unsigned)std::min<int64_t>(ceil_div(n_points, (int64_t)kRcWarps), (int64_t)sms * 3);
         cudaStream_t s0 = (cudaStream_t)stream;
-        if (featmaps->dtype == ND_F32)
-            k_render_gather_stats_cl<float><<<g, kRcWarps * 32, sm, s0>>>(
-                pts, n_points, cameras, n_views, (const float *)images->data, (int)images->stride_v, (int)images->stride_c,
-                (int)images->stride_y, (int)images->stride_x, images->height, images->width, (const float *)featmaps->data,
-                (int)featmaps->stride_v, (int)featmaps->stride_y, (int)featmaps->stride_x, featmaps->channels,
-                featmaps->height, featmaps->width, globalfeat, view_mask, pixel_mask);
+#define ND_RC_LAUNCH(T, FEAT)                                                                                          \
+    k_render_gather_stats_cl<T, FEAT><<<g, kRcWarps * 32, sm, s0>>>(                                                   \
+        pts, n_points, cameras, n_views, (const float *)images->data, (int)images->stride_v, (int)images->stride_c,    \
+        (int)images->stride_y, (int)images->stride_x, images->height, images->width, (const T *)featmaps->data,        \
+        (int)featmaps->stride_v, (int)featmaps->stride_y, (int)featmaps->stride_x, featmaps->channels,                 \
+        featmaps->channels ? featmaps->height : 1, featmaps->channels ? featmaps->width : 1, globalfeat, view_mask,    \
+        pixel_mask)
+        if (featmaps->channels == 0)
+            ND_RC_LAUNCH(float, false);
+        else if (featmaps->dtype == ND_F32)
+            ND_RC_LAUNCH(float, true);
         else
-            k_render_gather_stats_cl<__nv_bfloat16><<<g, kRcWarps * 32, sm, s0>>>(
-                pts, n_points, cameras, n_views, (const float *)images->data, (int)images->stride_v, (int)images->stride_c,
-                (int)images->stride_y, (int)images->stride_x, images->height, images->width,
-                (const __nv_bfloat16 *)featmaps->data, (int)featmaps->stride_v, (int)featmaps->stride_y,
-                (int)featmaps->stride_x, featmaps->channels, featmaps->height, featmaps->width, globalfeat, view_mask,
-                pixel_mask);
+            ND_RC_LAUNCH(__nv_bfloat16, true);
+#undef ND_RC_LAUNCH
         ND_CUDA_LAUNCH_CHECK("k_render_gather_stats_cl");
         return ND_OK;
     }

@@ -679,10 +679,12 @@ def _(ray_o, ray_d, near, far, n_samples, t_rand):
 @torch.library.custom_op(f'{_NS}::render_gather_stats', mutates_args=())
 @_guarded
 def render_gather_stats(pts: Tensor, cameras: Tensor, images: Tensor, featmaps: Tensor, want_pixels: bool,
-                        want_view_features: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """R4 + R5 + R6 for P points: ``globalfeat [P, 2*(3+D)]``, ``view_mask bool [P, nv]``,
+                        want_view_features: bool, want_view_mask: bool = True) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """R4 + R5 + R6 for P points: ``globalfeat [P, 2*(3+D)]``, ``view_mask bool [P, nv]`` (empty when not wanted),
     ``pixel_mask bool [P]``, ``pixel_locations [nv, P, 2]``, ``in_front bool [nv, P]`` and
-    ``view_features [P, nv, 3+D]`` (the last three empty unless requested).  Reference projection.py:24-151 + render_ray.py:71-93, 301-303."""
+    ``view_features [P, nv, 3+D]`` (the last three empty unless requested).  ``images`` may be NCHW or channels-last
+    (the gather kernel reads either in place; channels-last keeps the three channels of a pixel in one sector).
+    Reference projection.py:24-151 + render_ray.py:71-93, 301-303."""
     _need_cuda(pts, cameras, images, featmaps)
     if pts.dtype != torch.float32 or pts.dim() != 2 or pts.shape[1] != 3:
         raise ValueError('pts must be float32 [P, 3]')
@@ -691,12 +693,14 @@ def render_gather_stats(pts: Tensor, cameras: Tensor, images: Tensor, featmaps: 
     nv = cameras.shape[0]
     if images.dtype != torch.float32 or images.dim() != 4 or images.shape[0] != nv or images.shape[1] != 3:
         raise ValueError('images must be float32 [n_views, 3, H, W]')
-    images = images.contiguous()
     if want_pixels or want_view_features or featmaps.shape[1] > 32 or featmaps.shape[1] % 4 != 0:
+        images = images.contiguous()
         featmaps = featmaps.contiguous()      # materialising kernel: NCHW planes
     elif featmaps.shape[1] > 0 and (featmaps.stride(1) != 1 or featmaps.stride(3) != featmaps.shape[1]):
         # product kernel: channels-last maps [nv, h, w, D] (what live.map_features_2d hands over; converted otherwise)
         featmaps = featmaps.contiguous(memory_format=torch.channels_last)
+    if not (images.is_contiguous() or images.is_contiguous(memory_format=torch.channels_last)):
+        images = images.contiguous()
     mi, mf = _maps(images), _maps(featmaps)
     if mf.channels == 0:
         mf.data = None
@@ -707,14 +711,14 @@ def render_gather_stats(pts: Tensor, cameras: Tensor, images: Tensor, featmaps: 
     ct = 3 + mf.channels
     dev = pts.device
     glob = torch.empty((p, 2 * ct), dtype=torch.float32, device=dev)
-    view_mask = torch.empty((p, nv), dtype=torch.bool, device=dev)
+    view_mask = torch.empty((p, nv) if want_view_mask else (0,), dtype=torch.bool, device=dev)
     pixel_mask = torch.empty((p,), dtype=torch.bool, device=dev)
     pix = torch.empty((nv, p, 2) if want_pixels else (0,), dtype=torch.float32, device=dev)
     front = torch.empty((nv, p) if want_pixels else (0,), dtype=torch.bool, device=dev)
     vf = torch.empty((p, nv, ct) if want_view_features else (0,), dtype=torch.float32, device=dev)
     lib = _lib.load()
     _lib.check(lib.nd_render_gather_stats(_ptr(pts), p, _ptr(cameras), nv, ctypes.byref(mi), ctypes.byref(mf),
-                                          _ptr(glob), _ptr(view_mask), _ptr(pixel_mask),
+                                          _ptr(glob), _ptr(view_mask) if want_view_mask else None, _ptr(pixel_mask),
                                           _ptr(pix) if want_pixels else None, _ptr(front) if want_pixels else None,
                                           _ptr(vf) if want_view_features else None, _stream()),
                'nd_render_gather_stats')
@@ -722,9 +726,9 @@ def render_gather_stats(pts: Tensor, cameras: Tensor, images: Tensor, featmaps: 
 
 
 @render_gather_stats.register_fake
-def _(pts, cameras, images, featmaps, want_pixels, want_view_features):
+def _(pts, cameras, images, featmaps, want_pixels, want_view_features, want_view_mask=True):
     p, nv, ct = pts.shape[0], cameras.shape[0], 3 + featmaps.shape[1]
-    return (pts.new_empty((p, 2 * ct)), pts.new_empty((p, nv), dtype=torch.bool),
+    return (pts.new_empty((p, 2 * ct)), pts.new_empty((p, nv) if want_view_mask else (0,), dtype=torch.bool),
             pts.new_empty((p,), dtype=torch.bool), pts.new_empty((nv, p, 2) if want_pixels else (0,)),
             pts.new_empty((nv, p) if want_pixels else (0,), dtype=torch.bool),
             pts.new_empty((p, nv, ct) if want_view_features else (0,)))
