@@ -899,7 +899,7 @@ def bench_render(args, rank, local_rank, world):
                                            sc.img_meta, proj, 'image', 3, False, 0, True)
         for i in range(3):
             step2(i)
-        other_ms, _ = device_timed(step2, max(5, min(steps, 50)), barrier)
+        other_ms, _ = device_timed(step2, max(5, min(steps, 300)), barrier)
         other_mlp_ms, _ = device_timed(lambda i: field2(pts, rd, glob), max(5, min(steps, 50)), barrier)
         # end to end: host ray batch -> selection (host, like the reference) -> device -> render -> rgb / depth -> host
         e2e = None

@@ -40,6 +40,26 @@ def _compute_projection(img_meta) -> torch.Tensor:
     return torch.from_numpy(out)
 
 
+_CAMERA_CACHE: "OrderedDict[tuple, torch.Tensor]" = OrderedDict()
+
+
+def _device_cameras(img_meta, device) -> torch.Tensor:
+    """The packed cameras ``[n_views, 34]`` on ``device``.  A pageable host-to-device copy blocks the host until the
+    stream has drained, which serialises every call behind the previous one; the upload goes through pinned memory
+    and is skipped when these exact bytes are already on the device (same scene as one of the last calls)."""
+    cams = _compute_projection(img_meta)[0]
+    key = (cams.numpy().tobytes(), str(device), torch.cuda.current_stream(device).cuda_stream)
+    hit = _CAMERA_CACHE.get(key)
+    if hit is not None:
+        _CAMERA_CACHE.move_to_end(key)
+        return hit
+    dev_cams = cams.pin_memory().to(device, non_blocking=True)
+    _CAMERA_CACHE[key] = dev_cams
+    while len(_CAMERA_CACHE) > 16:
+        _CAMERA_CACHE.popitem(last=False)
+    return dev_cams
+
+
 def sample_along_camera_ray(ray_o, ray_d, depth_range, N_samples, inv_uniform=False, det=False):
     """pts [rays, samples, 3], z_vals [rays, samples] (render_ray.py:145-189)."""
     if inv_uniform:
@@ -90,7 +110,7 @@ def render_rays_func(ray_o, ray_d, mean_volume, cov_volume, features_2D, img, aa
     ret = {'outputs_coarse': None, 'outputs_fine': None, 'gt_rgb': gt_rgb, 'gt_depth': gt_depth}
     pts, z_vals = sample_along_camera_ray(ray_o, ray_d, near_far_range, N_samples, inv_uniform, det)
     n_rays, n_samples = pts.shape[:2]
-    cameras = _compute_projection(img_meta)[0].to(pts.device)
+    cameras = _device_cameras(img_meta, pts.device)
     flat = pts.view(-1, 3)
     if mode == 'image':
         glob, _, pixel_mask, _, _, _ = ops.direct.render_gather_stats(flat, cameras, img, features_2D, False, False, False)

@@ -68,6 +68,29 @@ def main():
         print(f'render_rays_func: {timed(step):.1f} us/step on the device, {host(step):.1f} us host time per call', flush=True)
         print(f'  camera packing on the host: {host(lambda: render._compute_projection(sc.img_meta)):.1f} us; with the upload: '
               f'{host(lambda: render._compute_projection(sc.img_meta)[0].to(dev)):.1f} us', flush=True)
+        # the stages of one call in order, events between them (averaged over 30 calls)
+        names = ['sample_rays', 'camera upload', 'gather', 'mlp', 'bounds', 'composite']
+        acc = np.zeros(len(names))
+        for rep in range(35):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            torch.cuda.synchronize()
+            ev[0].record()
+            pts, z = render.sample_along_camera_ray(ro, rd, cfg.near_far_range, n_samples, det=True)
+            ev[1].record()
+            cams = render._compute_projection(sc.img_meta)[0].to(dev)
+            ev[2].record()
+            glob, _, pm, _, _, _ = ops.direct.render_gather_stats(pts.view(-1, 3), cams, imgs, f2d, False, False, False)
+            ev[3].record()
+            rgb, sig = field(pts, rd, glob.view(n_rand, n_samples, -1))
+            ev[4].record()
+            bounds = torch.stack([z[0, 0], z[0, -1]])
+            ev[5].record()
+            out = ops.direct.composite(rgb, sig.reshape(n_rand, n_samples), z, pm.view(n_rand, n_samples), bounds, False)
+            ev[6].record()
+            torch.cuda.synchronize()
+            if rep >= 5:
+                acc += np.array([ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(len(names))])
+        print('  stages of one call, host not running ahead (us): ' + ', '.join(f'{n} {t / 30:.1f}' for n, t in zip(names, acc)), flush=True)
         pts, z = render.sample_along_camera_ray(ro, rd, cfg.near_far_range, n_samples, det=True)
         cams = render._compute_projection(sc.img_meta)[0].to(dev)
         flat = pts.view(-1, 3)
