@@ -166,6 +166,24 @@ int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_v
                      int channels, int64_t n_voxels, const float *alpha,
                      float *mean, float *cov, int64_t *count, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Backward of nd_lift_mean_var: what torch autograd computes for
+ * nerfdet.py:164-181 with respect to `features` (the reference trains the backbone through this path).
+ *   mean, cov, count   the forward's outputs (cov may be NULL when grad_cov is NULL); the forward must have run
+ *                      WITHOUT alpha (the alpha product of nerfdet.py:259-261 stays an autograd op on the caller's side)
+ *   grad_mean, grad_cov  f32 [C][N] incoming gradients, either may be NULL
+ *   grad_features      [nv][C][height][width] CONTIGUOUS, dtype of `features`; every element is written
+ *   depth_resized, voxel_z, n_views_total   as in the forward (n_views_total 0 = the view count of `features`)
+ * The validity masks come from the same device function as the forward's (bit-identical).  Planes up to 65534 pixels
+ * and 8 planes of fp32 per CTA in shared memory (<= 220 KB: 7040 pixels per plane); ND_ERR_BAD_SHAPE beyond.
+ * workspace: nd_lift_backward_workspace_bytes(), 256-byte aligned.  Three launches.
+ * ------------------------------------------------------------------------------------- */
+size_t nd_lift_backward_workspace_bytes(const nd_maps *features, int64_t n_voxels);
+int nd_lift_backward(const nd_maps *features, const float *points, const float *projection, int64_t n_voxels,
+                     const float *depth_resized, float voxel_z, int n_views_total, const float *mean, const float *cov,
+                     const int64_t *count, const float *grad_mean, const float *grad_cov, void *grad_features,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
 
 /* ---------------------------------------------------------------------------------------
  * Exchange step of the view-sharded lift over NVLink peer memory (no counterpart in the

@@ -60,6 +60,9 @@ SIGNATURES = {
                                         c_void_p, POINTER(NdLiftOptions), c_void_p]),
     'nd_lift_finalize': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
+    'nd_lift_backward_workspace_bytes': (c_size_t, [POINTER(NdMaps), c_int64]),
+    'nd_lift_backward': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int64, c_void_p, ctypes.c_float, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'nd_peer_alloc': (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
     'nd_peer_open': (c_int, [c_void_p, POINTER(c_void_p)]),
     'nd_peer_close': (c_int, [c_void_p]),

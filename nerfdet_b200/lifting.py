@@ -105,15 +105,18 @@ def lift_mean_var(features, points, projection, alpha: Optional[torch.Tensor] = 
     the geometry pass.  The geometry (pixel offsets, counts, work distribution) is planned once per
     (points, projection, depth) tensor identity and reused (``ops.cached_lift_plan``); ``scratch_budget_bytes`` > 0
     forces the generic staged path instead.  ``out`` = caller-owned contiguous ``(mean [C, N] f32, cov [C, N] f32,
-    count [N] int64)`` buffers to write into instead of allocating (the returned tensors are views of them)."""
-    if any(t is not None and t.requires_grad for t in (features, alpha)):
-        raise RuntimeError('lift_mean_var is forward-only: detach() the inputs (the backward of the lift is not built)')
+    count [N] int64)`` buffers to write into instead of allocating (the returned tensors are views of them).
+
+    Differentiable with respect to ``features`` (and ``alpha``) when they require grad: the backward is
+    ``csrc/lift_bwd.cu`` (``_LiftMeanVar``); points / projection / depth get no gradient, as in the reference, where
+    they only enter through integer pixel indices."""
+    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (features, alpha))
     c = features.shape[1]
     gx, gy, gz = points.shape[-3:]
     al = alpha.reshape(-1) if alpha is not None else None
     if scratch_budget_bytes > 0:
-        if depth is not None or out is not None:
-            raise NotImplementedError('the depth gate and caller-owned outputs are not available on the staged path')
+        if depth is not None or out is not None or needs_grad:
+            raise NotImplementedError('the depth gate, caller-owned outputs and autograd are not available on the staged path')
         mean, cov, count = ops.direct.lift_mean_var(features, points, projection, al, want_cov, scratch_budget_bytes)
     else:
         depth_resized, voxel_z = None, 0.0
@@ -123,15 +126,51 @@ def lift_mean_var(features, points, projection, alpha: Optional[torch.Tensor] = 
             key = id(depth)
             ent = _DEPTH_CACHE.get(key)
             if ent is None or ent[0]() is not depth or ent[1] != depth._version or ent[3] != tuple(features.shape[-2:]):
-                resized = F.interpolate(depth.unsqueeze(1), size=tuple(features.shape[-2:]), mode='bilinear').squeeze(1)
+                with torch.no_grad():
+                    resized = F.interpolate(depth.unsqueeze(1), size=tuple(features.shape[-2:]), mode='bilinear').squeeze(1)
                 if len(_DEPTH_CACHE) > 8:
                     _DEPTH_CACHE.clear()
                 ent = (weakref.ref(depth), depth._version, resized, tuple(features.shape[-2:]))
                 _DEPTH_CACHE[key] = ent
             depth_resized, voxel_z = ent[2], float(voxel_size[-1])
-        mean, cov, count = ops.lift_mean_var_planned(features, points, projection, al, want_cov, depth_resized, voxel_z, out)
+        if needs_grad:
+            if out is not None:
+                raise NotImplementedError('caller-owned outputs are forward-only')
+            mean, cov, count = _LiftMeanVar.apply(features, points, projection, want_cov, depth_resized, voxel_z)
+            if al is not None:
+                mean = mean * al.view(1, -1)          # nerfdet.py:259-261 as an autograd op: gradients for both factors
+        else:
+            mean, cov, count = ops.lift_mean_var_planned(features.detach(), points, projection,
+                                                         al.detach() if al is not None else None, want_cov, depth_resized,
+                                                         voxel_z, out)
     return (mean.view(c, gx, gy, gz), cov.view(c, gx, gy, gz) if want_cov else None,
             count.view(1, gx, gy, gz))
+
+
+class _LiftMeanVar(torch.autograd.Function):
+    """Autograd of the fused lift with respect to ``features``: the forward is the
+    plan-based kernel, the backward ``ops.lift_backward`` (``csrc/lift_bwd.cu``) -- the gradient torch autograd
+    produces for nerfdet.py:164-181, scattered through the forward's own validity masks."""
+
+    @staticmethod
+    def forward(ctx, features, points, projection, want_cov, depth_resized, voxel_z):
+        mean, cov, count = ops.lift_mean_var_planned(features.detach(), points, projection, None, want_cov, depth_resized,
+                                                     voxel_z)
+        ctx.save_for_backward(features, points, projection, mean, cov, count)
+        ctx.depth_resized, ctx.voxel_z, ctx.want_cov = depth_resized, voxel_z, want_cov
+        ctx.mark_non_differentiable(count)
+        if not want_cov:
+            ctx.mark_non_differentiable(cov)
+        return mean, cov, count
+
+    @staticmethod
+    def backward(ctx, g_mean, g_cov, _g_count):
+        features, points, projection, mean, cov, count = ctx.saved_tensors
+        if not ctx.want_cov:
+            g_cov = None
+        grad = ops.direct.lift_backward(features.detach(), points, projection, mean, cov if ctx.want_cov else None, count,
+                                        g_mean, g_cov, ctx.depth_resized, ctx.voxel_z, 0)
+        return grad, None, None, None, None, None
 
 
 # resized depth maps, kept per depth tensor so that the geometry plan (keyed on tensor identity) is found again

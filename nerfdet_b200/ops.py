@@ -801,6 +801,57 @@ def _(volume, pts, aabb_min, aabb_max):
     return pts.new_empty((pts.shape[0], volume.shape[0])), pts.new_empty((pts.shape[0],), dtype=torch.bool)
 
 
+@torch.library.custom_op(f'{_NS}::lift_backward', mutates_args=())
+@_guarded
+def lift_backward(features: Tensor, points: Tensor, projection: Tensor, mean: Tensor, cov: Optional[Tensor], count: Tensor,
+                  grad_mean: Optional[Tensor], grad_cov: Optional[Tensor], depth_resized: Optional[Tensor],
+                  voxel_z: float, n_views_total: int) -> Tensor:
+    """Gradient of ``lift_mean_var`` (called without alpha) with respect to ``features`` -- what autograd computes for
+    the reference's nerfdet.py:164-181: a contiguous ``[nv, C, H, W]`` tensor of the features' dtype.  ``mean``,
+    ``cov``, ``count`` are the forward's outputs, ``grad_mean`` / ``grad_cov`` ``[C, N]`` the incoming gradients
+    (either may be None)."""
+    _need_cuda(features, points, projection, mean, cov, count, grad_mean, grad_cov, depth_resized)
+    m = _maps(features)
+    _check_geometry(points, projection, m.n_views)
+    points, _ = _flat_points(points)
+    projection = projection.contiguous()
+    n = points.shape[1]
+    if grad_mean is None and grad_cov is None:
+        return torch.zeros((m.n_views, m.channels, m.height, m.width), dtype=features.dtype, device=features.device)
+    if grad_cov is not None and (cov is None or cov.numel() != m.channels * n):
+        raise ValueError('grad_cov needs the cov the forward returned')
+
+    def f32(t, what, size):
+        if t is None:
+            return None
+        if t.dtype != torch.float32 or t.numel() != size:
+            raise ValueError(f'{what} must be float32 with {size} elements')
+        return t.contiguous()
+    mean, cov = f32(mean, 'mean', m.channels * n), f32(cov, 'cov', m.channels * n) if grad_cov is not None else None
+    grad_mean, grad_cov = f32(grad_mean, 'grad_mean', m.channels * n), f32(grad_cov, 'grad_cov', m.channels * n)
+    if count.dtype != torch.int64 or count.numel() != n:
+        raise ValueError('count must be int64 with one value per voxel')
+    count = count.contiguous()
+    if depth_resized is not None:
+        if depth_resized.dtype != torch.float32 or tuple(depth_resized.shape) != (m.n_views, m.height, m.width):
+            raise ValueError('depth_resized must be float32 [n_views, H, W] at the feature resolution')
+        depth_resized = depth_resized.contiguous()
+    dev = features.device
+    grad = torch.empty((m.n_views, m.channels, m.height, m.width), dtype=features.dtype, device=dev)
+    lib = _lib.load()
+    ws_bytes = lib.nd_lift_backward_workspace_bytes(ctypes.byref(m), n)
+    ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=dev)
+    _lib.check(lib.nd_lift_backward(ctypes.byref(m), _ptr(points), _ptr(projection), n, _ptr(depth_resized), float(voxel_z),
+                                    int(n_views_total), _ptr(mean), _ptr(cov), _ptr(count), _ptr(grad_mean), _ptr(grad_cov),
+                                    _ptr(grad), _ptr(ws), ws_bytes, _stream()), 'nd_lift_backward')
+    return grad
+
+
+@lift_backward.register_fake
+def _(features, points, projection, mean, cov, count, grad_mean, grad_cov, depth_resized, voxel_z, n_views_total):
+    return features.new_empty(tuple(features.shape))
+
+
 # ------------------------------------------------------------------------------------------
 # The Python functions behind the registered custom ops, for the reference-signature modules (lifting, live, render,
 # nerf_mlp, projection): a call through torch.library's dispatcher costs 50-350 us of host time per op, more than
@@ -813,5 +864,6 @@ class _Direct:
 
 direct = _Direct()
 for _name in ('project_voxels', 'backproject', 'lift_mean_var', 'lift_accumulate', 'lift_accumulate_into', 'lift_finalize',
-              'map_features', 'live_stats', 'nerf_mlp_fwd', 'sample_rays', 'render_gather_stats', 'composite', 'volume_sample'):
+              'map_features', 'live_stats', 'nerf_mlp_fwd', 'sample_rays', 'render_gather_stats', 'composite', 'volume_sample',
+              'lift_backward'):
     setattr(direct, _name, globals()[_name]._init_fn)

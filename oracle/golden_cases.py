@@ -45,6 +45,11 @@ CASES = {
     # render_rays_func, deterministic sampling, with intermediates
     'render_det': dict(kind='render_det', seed=7, n_views=6, n_rays=48, N_samples=16, **_TINY),
     'mlp_small': dict(kind='mlp', seed=8, n_rays=32, N_samples=8),
+    # N1: gradients of nerfdet.py:164-181 with respect to the features, from the reference's own autograd
+    'lift_grad_tiny': dict(kind='lift_grad', seed=11, n_views=6, n_voxels=(10, 10, 4),
+                           voxel_size=(0.64, 0.64, 0.8), channels=8, **_TINY),
+    'lift_grad_depth': dict(kind='lift_grad', seed=12, n_views=4, n_voxels=(10, 10, 4),
+                            voxel_size=(0.64, 0.64, 0.8), channels=4, with_depth=True, **_TINY),
     'volume_lookup': dict(kind='volume_lookup', seed=9),
 }
 
@@ -70,6 +75,14 @@ def lift_inputs(case):
         out['depth'] = torch.from_numpy(
             rs.uniform(0.5, 4.0, (cfg.n_views,) + tuple(cfg.pad_shape)).astype(np.float32))
     return out
+
+
+def lift_grad_upstream(case):
+    """Seeded incoming gradients (g_mean, g_cov), each [C, X, Y, Z] float32."""
+    rs = np.random.RandomState(case['seed'] + 500)
+    shape = (case['channels'],) + tuple(case['n_voxels'])
+    return (torch.from_numpy(rs.standard_normal(shape).astype(np.float32)),
+            torch.from_numpy(rs.standard_normal(shape).astype(np.float32)))
 
 
 def extract_inputs(case):

@@ -59,6 +59,37 @@ def gen_lift(case):
     return out
 
 
+def gen_lift_grad(case):
+    """nerfdet.py:164-181 under the reference's own autograd: d(sum(mean * g_mean) + sum(cov * g_cov)) / d features."""
+    ref = ref_loader.load()
+    inp = gc.lift_inputs(case)
+    nd = ref.nerfdet
+    proj = nd.nerfdet._compute_projection(inp['img_meta'], inp['stride'], None)
+    pts = nd.get_points(n_voxels=torch.tensor(inp['n_voxels']), voxel_size=torch.tensor(inp['voxel_size']),
+                        origin=torch.tensor(inp['img_meta']['lidar2img']['origin']))
+    g_mean, g_cov = gc.lift_grad_upstream(case)
+    out = {}
+    for tag, use_cov in (('', True), ('_mean_only', False)):
+        feats = inp['features_sliced'].clone().requires_grad_(True)
+        volume, valid = nd.backproject(feats, pts, proj, inp.get('depth'), inp['voxel_size'])
+        volume_sum = volume.sum(dim=0)                     # nerfdet.py:171-181, verbatim
+        cov_valid = valid.clone().detach()                 # noqa: F841  (kept like the reference)
+        valid = valid.sum(dim=0)
+        volume_mean = volume_sum / (valid + 1e-8)
+        volume_mean[:, valid[0] == 0] = .0
+        volume_cov = torch.sum((volume - volume_mean.unsqueeze(0)) ** 2, dim=0) / (valid + 1e-8)
+        volume_cov[:, valid[0] == 0] = 1e6
+        volume_cov = torch.exp(-volume_cov)
+        loss = (volume_mean * g_mean).sum()
+        if use_cov:
+            loss = loss + (volume_cov * g_cov).sum()
+        loss.backward()
+        out['g_features' + tag] = _np(feats.grad)
+        if use_cov:
+            out['volume_mean'], out['volume_cov'], out['count'] = _np(volume_mean), _np(volume_cov), _np(valid)
+    return out
+
+
 def gen_extract(case):
     ref = ref_loader.load()
     inp = gc.extract_inputs(case)
@@ -142,7 +173,7 @@ def gen_volume_lookup(case):
     return dict(features=_np(feats), inside=_np(masks))
 
 
-GENERATORS = dict(lift=gen_lift, extract=gen_extract, render_det=gen_render_det, mlp=gen_mlp,
+GENERATORS = dict(lift=gen_lift, lift_grad=gen_lift_grad, extract=gen_extract, render_det=gen_render_det, mlp=gen_mlp,
                   volume_lookup=gen_volume_lookup)
 
 
@@ -151,7 +182,10 @@ def main():
         raise SystemExit('reference not available: golden vectors can only be made in the build container')
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    only = sys.argv[1:]                                   # optional case names: regenerate these only
     for name, case in gc.CASES.items():
+        if only and name not in only:
+            continue
         data = GENERATORS[case['kind']](case)
         path = os.path.join(OUT, f'{name}.npz')
         np.savez_compressed(path, **data)

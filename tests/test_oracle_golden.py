@@ -48,6 +48,27 @@ def test_lift_oracle_matches_reference(name):
         assert vd.sum() < valid.sum()
 
 
+@pytest.mark.parametrize('name', [k for k, v in gc.CASES.items() if v['kind'] == 'lift_grad'])
+def test_lift_oracle_autograd_matches_reference_autograd(name):
+    """Row N1: the oracle's lift is differentiable torch code; its gradient with respect to the features equals
+    the one the unmodified reference's autograd produced (fixtures of oracle/make_golden.py:gen_lift_grad)."""
+    case = gc.CASES[name]
+    g = gc.load_golden(name)
+    inp = gc.lift_inputs(case)
+    proj = lo.compute_projection(inp['img_meta'], inp['stride'])
+    pts = lo.get_points(inp['n_voxels'], inp['voxel_size'], inp['img_meta']['lidar2img']['origin'])
+    g_mean, g_cov = gc.lift_grad_upstream(case)
+    for tag, use_cov in (('', True), ('_mean_only', False)):
+        f = inp['features_sliced'].clone().requires_grad_(True)
+        volume, valid = lo.backproject(f, pts, proj, inp.get('depth'), inp['voxel_size'])
+        mean, cov, cnt = lo.mean_var(volume, valid)
+        loss = (mean * g_mean).sum() + ((cov * g_cov).sum() if use_cov else 0.0)
+        loss.backward()
+        assert np.array_equal(cnt.numpy(), g['count'])
+        _close(f.grad, g['g_features' + tag], rtol=1e-4, atol_scale=1e-6, name='g_features' + tag)
+        assert float(f.grad.abs().max()) > 0
+
+
 def test_mlp_oracle_matches_reference():
     g = gc.load_golden('mlp_small')
     inp = gc.mlp_inputs(gc.CASES['mlp_small'])

@@ -117,15 +117,35 @@ def grids():
               f'{mn:.1f}/{med:.1f}/{p90:.1f}; eight plans rotating {us3:.1f} us; each plan: {[round(e) for e in each]}; plan bytes {plans[0].bytes / 1e6:.1f} MB', flush=True)
 
 
+def backward():
+    nv, c, grid = 50, 256, (40, 40, 16)
+    proj, pts = scene(nv, grid, (0.16, 0.16, 0.2), 1000)
+    pd, qd = pts.to(DEV), proj.to(DEV)
+    for dtype in (torch.float32, torch.bfloat16):
+        f = torch.from_numpy(make_features(np.random.RandomState(2000), (nv, c, 60, 80))).to(DEV).to(dtype)[:, :, :59, :80]
+        mean, cov, cnt = ops.lift_mean_var_planned(f, pd, qd, None, True)
+        gm, gc_ = torch.randn_like(mean), torch.randn_like(cov)
+        us = timed(lambda: ops.direct.lift_backward(f, pd, qd, mean, cov, cnt, gm, gc_, None, 0.0, 0), 50)
+        us_m = timed(lambda: ops.direct.lift_backward(f, pd, qd, mean, None, cnt, gm, None, None, 0.0, 0), 50)
+        elt = f.element_size()
+        moved = 2 * nv * c * 59 * 80 * elt + 4 * c * 25600 * 4          # features in + gradient out, mean/cov/g_mean/g_cov in
+        print(f'lift backward {dtype}: {us:.1f} us ({moved / us / 1e3:.0f} GB/s of features + gradient + volumes), '
+              f'mean-only {us_m:.1f} us; forward for comparison '
+              f'{timed(lambda: ops.lift_mean_var_planned(f, pd, qd, None, True), 100):.1f} us', flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--quick', action='store_true')
     ap.add_argument('--steps', type=int, default=300)
     ap.add_argument('--grids', action='store_true', help='time the other voxel grids of the sweep instead')
+    ap.add_argument('--backward', action='store_true', help='time the backward of the lift at the bench shape instead')
     args = ap.parse_args()
     torch.cuda.set_device(0)
     if args.grids:
         return grids()
+    if args.backward:
+        return backward()
     ok = True
     ok &= parity(6, 64, (20, 20, 8), (0.32, 0.32, 0.4), 7)
     ok &= parity(3, 40, (40, 40, 16), (0.16, 0.16, 0.2), 13)
