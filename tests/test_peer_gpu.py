@@ -96,14 +96,14 @@ def test_in_process_ranks_match_all_views(world, overlap):
             peer.close()
 
 
-@pytest.mark.parametrize('world', [2, 8])
-def test_in_process_ranks_without_variance(world):
+@pytest.mark.parametrize('world,overlap', [(2, 0), (8, 0), (2, 3), (8, 2)])
+def test_in_process_ranks_without_variance(world, overlap):
     """want_cov=False: the accumulators are [S1 | count], the exchange moves half the bytes and only the mean comes back."""
     nv, grid, channels = 19, (16, 16, 8), 20
     n = int(np.prod(grid))
     f, pts, proj = _scene(nv, grid, (0.4, 0.4, 0.4), channels, 93)
     mean, _, cnt = lifting.lift_mean_var(f, pts, proj)
-    ranks = nd_dist.PeerLift.local_group(world, channels, n, DEV, want_cov=False)
+    ranks = nd_dist.PeerLift.local_group(world, channels, n, DEV, want_cov=False, overlap_sms=overlap)
     streams = [torch.cuda.Stream() for _ in range(world)]
     try:
         torch.cuda.synchronize()
