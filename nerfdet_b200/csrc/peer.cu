@@ -109,6 +109,10 @@ template <> __device__ __forceinline__ void st_vec<1>(float *p, const float (&r)
 // looping over work items -- the exchange is link-bound, so ~20 SMs carry it while the other SMs run the next scene's
 // accumulate; fat CTAs because the block scheduler spreads small CTAs over all SMs, where none would leave room for a
 // persistent lift CTA).
+// Tried in round 2 and removed: the same narrow grid with the SM's copy engine doing the transport (cp.async.bulk pieces of
+// 4 KB from every rank into a 192 KB shared-memory ring, bulk stores of the finished rows).  Parity-green on two B200s, but a
+// CTA moved only ~6 GB/s over NVLink that way (301 vs 137 us per step at 2 GPUs with 28 CTAs, 489 us with 16): the copy engine
+// keeps far fewer remote requests in flight than 512 threads x 16 vector loads do.
 template <int V, int G, int U, bool MC, int T, bool COV>
 __global__ void __launch_bounds__(T, T > 128 ? 1 : ((G * U <= 4) ? 6 : 4))
 k_lift_finalize_peers(const PeerArgs a) {
@@ -257,241 +261,6 @@ k_lift_finalize_peers(const PeerArgs a) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// The same exchange on a NARROW grid with the copy engine of the SM doing the transport (TMA bulk copies).
-//
-// With ld.global the bytes a CTA keeps in flight are bounded by its registers (512 threads x 16 vectors = 128 KB, and the
-// load / store path of one SM sustained ~34 GB/s at the ~2 us latency of a remote load); a handful of SMs cannot carry the
-// 750 GB/s of the links that way, and every SM the exchange holds is taken from the next scene's accumulate.  Here one
-// thread per CTA issues cp.async.bulk copies of 4 KB row pieces from every rank's segment into a ring in shared memory
-// (up to 192 KB in flight per SM, no registers), eight consumer warps add the pieces in rank order, finalise, and the
-// finished pieces leave as bulk stores from shared memory into every rank's outputs.
-//   stage = the pieces of ONE row (voxel chunk of kBulkChunk, channel c) from all ranks: world x (S1 [+ S2]); the first stage
-//   of a work item carries the ranks' count pieces instead.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int kBulkChunk = 1024;                 // voxels per stage piece (4 KB)
-constexpr int kBulkConsumers = 256;              // 8 consumer warps, 4 voxels per thread
-constexpr int kBulkThreads = kBulkConsumers + 32;
-
-__device__ __forceinline__ uint32_t p_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void p_mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void p_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void p_mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void p_mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void p_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void p_bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void p_fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void p_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kBulkConsumers) : "memory"); }
-
-template <bool COV>
-__global__ void __launch_bounds__(kBulkThreads, 1)
-k_lift_finalize_peers_bulk(const PeerArgs a, const int n_stages) {
-    extern __shared__ __align__(128) unsigned char p_smem[];
-    const int P = kMaxPeers;
-    const int world = a.world;
-    const int per_stage = world * (COV ? 2 : 1);                          // 4 KB pieces per stage
-    // layout: [ring: n_stages x per_stage x 4 KB][out: 2 x (1 + COV) x 4 KB][full / empty barriers]
-    float *ring = reinterpret_cast<float *>(p_smem);
-    float *outb = ring + (size_t)n_stages * per_stage * kBulkChunk;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(outb + 2 * (COV ? 2 : 1) * kBulkChunk);
-    const uint32_t full0 = p_smem_u32(bars), empty0 = p_smem_u32(bars + n_stages);
-    uint32_t *my_flags = a.flags[a.rank];
-    __shared__ int s_bad;
-    if (threadIdx.x == 0) {
-        s_bad = 0;
-        for (int s = 0; s < n_stages; ++s) {
-            p_mbar_init(full0 + 8 * s, 1);
-            p_mbar_init(empty0 + 8 * s, kBulkConsumers / 32);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    // ---- hand-shake: my accumulators are complete; wait for everybody else's (as k_lift_finalize_peers) ----
-    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(a.flags[threadIdx.x] + a.rank, a.epoch);
-    if (threadIdx.x < world && threadIdx.x != a.rank) {
-        if (!spin_until(my_flags + threadIdx.x, a.epoch, a.timeout_ns)) {
-            s_bad = 1;
-            raise_error_everywhere(a.flags, world);
-        }
-    }
-    if (threadIdx.x == 0 && ld_acquire_sys(my_flags + 2 * P + 1) != 0u) s_bad = 1;
-    __syncthreads();
-    const bool bad = s_bad != 0;
-    const int64_t cn = (int64_t)a.channels * a.n_vox;
-    (void)cn;
-    if (bad) {
-        // no reduce, no peer traffic: the rows this CTA owns become NaN in the LOCAL outputs
-        for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-            const int tile = item % a.n_tiles, sub = item / a.n_tiles;
-            const int c0 = a.c_begin + sub * a.ch_per_cta, c1 = min(a.c_end, c0 + a.ch_per_cta);
-            for (int c = c0; c < c1; ++c)
-                for (int64_t n = (int64_t)tile * kBulkChunk + threadIdx.x; n < min((int64_t)(tile + 1) * kBulkChunk, a.n_vox);
-                     n += blockDim.x) {
-                    a.mean[a.rank][(int64_t)c * a.n_vox + n] = __int_as_float(0x7fc00000);
-                    if constexpr (COV) a.cov[a.rank][(int64_t)c * a.n_vox + n] = __int_as_float(0x7fc00000);
-                }
-        }
-    } else if (threadIdx.x >= kBulkConsumers) {
-        // ---- producer: one thread walks the stages of this CTA's work items and issues the bulk loads ----
-        if (threadIdx.x == kBulkConsumers) {
-            p_fence_async();                                               // the peers' rows were written through the generic proxy
-            uint32_t it = 0;
-            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-                const int tile = item % a.n_tiles, sub = item / a.n_tiles;
-                const int64_t n0 = (int64_t)tile * kBulkChunk;
-                const uint32_t bytes = (uint32_t)(min((int64_t)kBulkChunk, a.n_vox - n0) * sizeof(float));
-                const int c0 = a.c_begin + sub * a.ch_per_cta, c1 = min(a.c_end, c0 + a.ch_per_cta);
-                for (int c = c0 - 1; c < c1; ++c, ++it) {                  // c0 - 1: the count stage of the item
-                    const uint32_t s = it % (uint32_t)n_stages, ph = (it / (uint32_t)n_stages) & 1u;
-                    p_mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                    float *dst = ring + (size_t)s * per_stage * kBulkChunk;
-                    const uint32_t bar = full0 + 8 * s;
-                    if (c < c0) {
-                        p_mbar_expect_tx(bar, bytes * (uint32_t)world);
-                        for (int g = 0; g < world; ++g) p_bulk_g2s(p_smem_u32(dst + (size_t)g * kBulkChunk), a.cntp[g] + n0, bytes, bar);
-                    } else {
-                        p_mbar_expect_tx(bar, bytes * (uint32_t)per_stage);
-                        const int64_t o = (int64_t)c * a.n_vox + n0;
-                        for (int g = 0; g < world; ++g) {
-                            p_bulk_g2s(p_smem_u32(dst + (size_t)g * kBulkChunk), a.s1[g] + o, bytes, bar);
-                            if constexpr (COV) p_bulk_g2s(p_smem_u32(dst + (size_t)(world + g) * kBulkChunk), a.s2[g] + o, bytes, bar);
-                        }
-                    }
-                }
-            }
-        }
-    } else {
-        // ---- consumers: 4 voxels per thread ----
-        const int t4 = threadIdx.x * 4;
-        uint32_t it = 0, ost = 0;
-        for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-            const int tile = item % a.n_tiles, sub = item / a.n_tiles;
-            const int64_t n0 = (int64_t)tile * kBulkChunk;
-            const int len = (int)min((int64_t)kBulkChunk, a.n_vox - n0);
-            const uint32_t bytes = (uint32_t)len * sizeof(float);
-            const bool live = t4 < len;
-            const int c0 = a.c_begin + sub * a.ch_per_cta, c1 = min(a.c_end, c0 + a.ch_per_cta);
-            float cnt[4] = {0.f, 0.f, 0.f, 0.f}, al[4] = {1.f, 1.f, 1.f, 1.f}, inv[4];
-            {   // count stage
-                const uint32_t s = it % (uint32_t)n_stages, ph = (it / (uint32_t)n_stages) & 1u;
-                p_mbar_wait(full0 + 8 * s, ph);
-                const float *src = ring + (size_t)s * per_stage * kBulkChunk;
-                if (live) {
-                    for (int g = 0; g < world; ++g) {
-                        const float4 v = *reinterpret_cast<const float4 *>(src + (size_t)g * kBulkChunk + t4);
-                        cnt[0] += v.x; cnt[1] += v.y; cnt[2] += v.z; cnt[3] += v.w;
-                    }
-                }
-                __syncwarp();
-                if ((threadIdx.x & 31) == 0) p_mbar_arrive(empty0 + 8 * s);
-                ++it;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) inv[j] = (float)a.n_views_total - cnt[j];
-                if (live) {
-                    if (a.alpha != nullptr) {
-                        const float4 v = __ldg(reinterpret_cast<const float4 *>(a.alpha + n0 + t4));
-                        al[0] = v.x; al[1] = v.y; al[2] = v.z; al[3] = v.w;
-                    }
-                    if (sub == 0 && a.count != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) a.count[n0 + t4 + j] = (int64_t)cnt[j];
-                    }
-                }
-            }
-            for (int c = c0; c < c1; ++c, ++it, ++ost) {
-                const uint32_t s = it % (uint32_t)n_stages, ph = (it / (uint32_t)n_stages) & 1u;
-                float *ob = outb + (size_t)(ost & 1u) * (COV ? 2 : 1) * kBulkChunk;
-                // the bulk stores that last read this output buffer (two stages ago) are done reading it
-                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                p_mbar_wait(full0 + 8 * s, ph);
-                p_consumer_sync();
-                const float *src = ring + (size_t)s * per_stage * kBulkChunk;
-                if (live) {
-                    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-                    for (int g = 0; g < world; ++g) {                      // rank order
-                        const float4 v = *reinterpret_cast<const float4 *>(src + (size_t)g * kBulkChunk + t4);
-                        s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
-                        if constexpr (COV) {
-                            const float4 w = *reinterpret_cast<const float4 *>(src + (size_t)(world + g) * kBulkChunk + t4);
-                            s2[0] += w.x; s2[1] += w.y; s2[2] += w.z; s2[3] += w.w;
-                        }
-                    }
-                    float m[4], cv[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        m[j] = 0.f;
-                        cv[j] = 0.f;
-                        if (cnt[j] > 0.f) {                                // same formula as k_lift_finalize (lift.cu)
-                            const float mm = s1[j] / cnt[j];
-                            if constexpr (COV) {
-                                float ssd = fmaxf(fmaf(-mm, s1[j], s2[j]), 0.0f);
-                                ssd = fmaf(inv[j] * mm, mm, ssd);
-                                cv[j] = expf(-(ssd / cnt[j]));
-                            }
-                            m[j] = mm * al[j];
-                        }
-                    }
-                    *reinterpret_cast<float4 *>(ob + t4) = make_float4(m[0], m[1], m[2], m[3]);
-                    if constexpr (COV) *reinterpret_cast<float4 *>(ob + kBulkChunk + t4) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-                }
-                __syncwarp();
-                if ((threadIdx.x & 31) == 0) p_mbar_arrive(empty0 + 8 * s);
-                p_fence_async();                                           // my piece of the output buffer, for the copy engine
-                p_consumer_sync();
-                if (threadIdx.x == 0) {
-                    const int64_t o = (int64_t)c * a.n_vox + n0;
-                    for (int g = 0; g < world; ++g) {
-                        p_bulk_s2g(a.mean[g] + o, p_smem_u32(ob), bytes);
-                        if constexpr (COV) p_bulk_s2g(a.cov[g] + o, p_smem_u32(ob + kBulkChunk), bytes);
-                    }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-            }
-        }
-        if (threadIdx.x == 0) {
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every row has arrived in the peers' outputs
-            p_fence_async();
-        }
-    }
-    // ---- completion: the last CTA tells every peer that this rank is done with their segments ----
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t total = gridDim.x;
-        const uint32_t prev = atomicAdd(my_flags + 2 * P, 1u);
-        if (prev == total - 1) {
-            my_flags[2 * P] = 0u;
-            __threadfence_system();
-            for (int g = 0; g < world; ++g) st_release_sys(a.flags[g] + P + a.rank, a.epoch);
-        }
-    }
-}
-
 __global__ void k_peer_wait_done(const PeerArgs a) {
     uint32_t *my_flags = a.flags[a.rank];
     if (threadIdx.x < a.world) {
@@ -614,40 +383,6 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
     }
     const int v = vec ? 4 : 1;
     const int slice = a.c_end - a.c_begin;
-    if (max_ctas > 0 && vec && !mc && slice > 0) {
-        // narrow grid: the bulk-copy kernel (one CTA per SM, the copy engine keeps up to 192 KB in flight)
-        const bool with_s2 = cov_host != nullptr;
-        const int per_stage = world * (with_s2 ? 2 : 1);
-        const size_t piece = (size_t)kBulkChunk * sizeof(float);
-        int n_stages = (int)((192 * 1024) / (per_stage * piece));
-        n_stages = n_stages > 12 ? 12 : n_stages < 2 ? 2 : n_stages;
-        const size_t smem = (size_t)n_stages * per_stage * piece + 2 * (with_s2 ? 2 : 1) * piece + (size_t)2 * n_stages * 8;
-        const int64_t tiles = ceil_div(n_voxels, (int64_t)kBulkChunk);
-        int64_t subs = ceil_div((int64_t)max_ctas * 6, tiles);            // ~6 work items per CTA so that the CTAs finish together
-        if (subs > slice) subs = slice;
-        if (subs < 1) subs = 1;
-        a.ch_per_cta = (int)ceil_div(slice, subs);
-        a.n_tiles = (int)tiles;
-        a.n_items = (int)(tiles * ceil_div(slice, a.ch_per_cta));
-        const dim3 grid((unsigned)(max_ctas < a.n_items ? max_ctas : a.n_items));
-        cudaStream_t st = (cudaStream_t)stream;
-        cudaError_t e;
-        if (with_s2) {
-            e = cudaFuncSetAttribute(k_lift_finalize_peers_bulk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) k_lift_finalize_peers_bulk<true><<<grid, kBulkThreads, smem, st>>>(a, n_stages);
-        } else {
-            e = cudaFuncSetAttribute(k_lift_finalize_peers_bulk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e == cudaSuccess) k_lift_finalize_peers_bulk<false><<<grid, kBulkThreads, smem, st>>>(a, n_stages);
-        }
-        if (e != cudaSuccess) {
-            set_error("nd_lift_finalize_peers: %s", cudaGetErrorString(e));
-            return ND_ERR_CUDA;
-        }
-        ND_CUDA_LAUNCH_CHECK("k_lift_finalize_peers_bulk");
-        k_peer_wait_done<<<1, 32, 0, st>>>(a);
-        ND_CUDA_LAUNCH_CHECK("k_peer_wait_done");
-        return ND_OK;
-    }
     const int gb = (mc || world <= 1) ? 1 : world <= 2 ? 2 : world <= 4 ? 4 : 8;   // compile-time bound of the instantiation
     const bool narrow = max_ctas > 0 && vec;
     // narrow: 512 threads x 16 vector loads in flight per thread = 128 KB per SM (a remote load takes ~2 us; with 4 loads per
