@@ -174,9 +174,10 @@ int nd_lift_finalize(const float *s1, const float *s2, const float *cnt, int n_v
  *   grad_mean, grad_cov  f32 [C][N] incoming gradients, either may be NULL
  *   grad_features      [nv][C][height][width] CONTIGUOUS, dtype of `features`; every element is written
  *   depth_resized, voxel_z, n_views_total   as in the forward (n_views_total 0 = the view count of `features`)
- * The validity masks come from the same device function as the forward's (bit-identical).  Planes up to 65534 pixels
- * and 8 planes of fp32 per CTA in shared memory (<= 220 KB: 7040 pixels per plane); ND_ERR_BAD_SHAPE beyond.
- * workspace: nd_lift_backward_workspace_bytes(), 256-byte aligned.  Three launches.
+ * The validity masks come from the same device function as the forward's (bit-identical).  The sums are gathers over a
+ * CSR of the voxels of every pixel, added in ascending voxel order: the gradient is deterministic.  Planes up to 20480
+ * pixels (ND_ERR_BAD_SHAPE beyond), any lattice size (parts of 25 600 voxels, one gather launch per part).
+ * workspace: nd_lift_backward_workspace_bytes(), 256-byte aligned.  2 + parts launches.
  * ------------------------------------------------------------------------------------- */
 size_t nd_lift_backward_workspace_bytes(const nd_maps *features, int64_t n_voxels);
 int nd_lift_backward(const nd_maps *features, const float *points, const float *projection, int64_t n_voxels,

@@ -13,17 +13,22 @@
 //
 //   k_bwd_index    pixel offset (uint16, 0xffff = invalid) of every voxel-view: project_nearest() + the depth gate, the
 //                  same device function the forward kernels use, so the masks are bit-identical to the forward's
-//   k_bwd_coef     a, b [C][N] from mean, cov, count and the incoming gradients
-//   k_bwd_scatter  one CTA per (view, group of 4 channels): the A and B planes of the group live in shared memory
-//                  (8 x 18.9 KB at 59 x 80), the CTA walks the voxels of the view with red.shared.add.f32 and writes the
-//                  finished planes with coalesced stores.  A CTA owns its planes: no global atomics, no memset of the
-//                  241.7 MB gradient.
+// The sums are GATHERS, the mirror image of the forward kernel -- there the planes sit in shared memory and the voxels gather
+// from them, here the coefficient row of a channel sits in shared memory and the pixels gather from it.
+//   k_bwd_csr      per (view, part of <= 25 600 voxels): the voxels of every pixel as a CSR (counting sort in shared memory,
+//                  every pixel's short list sorted by voxel index, so the sums have ONE order: the gradient is deterministic)
+//   k_bwd_gather   one CTA per (channel, range of views): a, b of the part's voxels computed from mean / cov / count and the
+//                  incoming gradients straight into shared memory (float2 x 25 600 = 205 KB); then, per view, one thread per
+//                  pixel reads its 8-byte record {count, first three voxels}, adds the coefficients of its voxels, forms
+//                  A + x * B and stores it (coalesced).  No atomics, no memset of the 241.7 MB gradient; parts beyond the
+//                  first add to what the previous launch wrote.
+// The first version scattered with red.shared.add.f32 into planes in shared memory: a compare-and-swap loop on sm_100a
+// (ATOMS.CAST.SPIN; 0.73 T atomics/s on the whole GPU against 2.1 T/s for native int32 adds, tools/microbench8.cu), 1.32 ms
+// at the bench shape.
 #include "nd_common.cuh"
 
 namespace nd {
 
-constexpr int kBwdGroup = 4;            // channels per scatter CTA
-constexpr int kBwdThreads = 512;
 
 __global__ void k_bwd_index(const float *__restrict__ points, const float *__restrict__ proj, int64_t n_vox, int height,
                             int width, const float *__restrict__ depth, float voxel_z, uint16_t *__restrict__ idx) {
@@ -47,85 +52,178 @@ __global__ void k_bwd_index(const float *__restrict__ points, const float *__res
     idx[(int64_t)v * n_vox + n] = ok ? (uint16_t)off : (uint16_t)0xffffu;
 }
 
-__global__ void k_bwd_coef(const float *__restrict__ mean, const float *__restrict__ cov, const int64_t *__restrict__ count,
-                           const float *__restrict__ g_mean, const float *__restrict__ g_cov, int channels, int64_t n_vox,
-                           int n_views_total, float *__restrict__ a, float *__restrict__ b) {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = blockIdx.y;
-    if (n >= n_vox) return;
-    const int64_t i = (int64_t)c * n_vox + n;
-    const int64_t cnt = count[n];
-    float ca = 0.0f, cb = 0.0f;
-    if (cnt > 0) {
-        const float denom = __fadd_rn((float)cnt, 1e-8f);
-        const float m = mean[i];
-        const float gm = g_mean != nullptr ? g_mean[i] : 0.0f;
-        const float gv = (g_cov != nullptr && cov != nullptr) ? -cov[i] * g_cov[i] : 0.0f;
-        cb = 2.0f * gv / denom;
-        const float gm_total = gm - 2.0f * gv * m * (denom - (float)n_views_total) / denom;
-        ca = gm_total / denom - cb * m;
-    }
-    a[i] = ca;
-    b[i] = cb;
-}
-
 template <typename T> __device__ __forceinline__ T from_f32_t(float v);
 template <> __device__ __forceinline__ float from_f32_t<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32_t<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-__device__ __forceinline__ void red_shared_add(float *p, float v) {
-    asm volatile("red.shared.add.f32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v) : "memory");
+// ---------------------------------------------------------------------------------------------------------------------
+// gather form
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kBwdPartMax = 25600;      // voxels whose (a, b) fit shared memory as float2
+constexpr int kBwdCsrPixels = 20480;    // planes the CSR builder takes (start + cursor words and the part's list in shared memory)
+constexpr int kBwdCsrThreads = 1024;
+
+// the coefficients of one (channel, voxel); count == 0: no gradient (the forward wrote constants there)
+__device__ __forceinline__ float2 bwd_coef(float m, float cv, int64_t cnt, float gm, float gc, int n_views_total) {
+    if (cnt <= 0) return make_float2(0.0f, 0.0f);
+    const float denom = __fadd_rn((float)cnt, 1e-8f);
+    const float gv = -cv * gc;
+    const float cb = 2.0f * gv / denom;
+    const float gm_total = gm - 2.0f * gv * m * (denom - (float)n_views_total) / denom;
+    return make_float2(gm_total / denom - cb * m, cb);
 }
 
-// grid (ceil(C / kBwdGroup), nv).  Shared memory: A[kBwdGroup][plane], B[kBwdGroup][plane] fp32.
-template <typename T>
-__global__ void __launch_bounds__(kBwdThreads)
-k_bwd_scatter(const T *__restrict__ feat, int64_t sv, int64_t sc, int64_t sy, int64_t sx, int channels, int height, int width,
-              const uint16_t *__restrict__ idx, const float *__restrict__ a, const float *__restrict__ b, int64_t n_vox,
-              T *__restrict__ g_feat) {
-    extern __shared__ __align__(16) float s_planes[];
-    const int v = blockIdx.y, c0 = blockIdx.x * kBwdGroup;
-    const int plane = height * width;
-    const int nc = min(kBwdGroup, channels - c0);
-    float *sA = s_planes, *sB = s_planes + (size_t)kBwdGroup * plane;
-    for (int i = threadIdx.x; i < 2 * kBwdGroup * plane; i += blockDim.x) s_planes[i] = 0.0f;
+// grid (parts, nv).  rec: uint2 [nv][parts][plane]; start: uint16 [nv][parts][plane + 1]; list: uint16 [nv][parts][part_len] (voxel index inside the part)
+__global__ void __launch_bounds__(kBwdCsrThreads)
+k_bwd_csr(const uint16_t *__restrict__ idx, int64_t n_vox, int part_len, int plane, uint16_t *__restrict__ start,
+          uint16_t *__restrict__ list, uint2 *__restrict__ rec) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint32_t *s_start = reinterpret_cast<uint32_t *>(s_raw);               // [plane + 1]
+    uint32_t *s_cur = s_start + plane + 1;                                 // [plane]
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_cur + plane);        // [part_len]
+    __shared__ uint32_t s_warp[32];
+    const int part = blockIdx.x, v = blockIdx.y, parts = gridDim.x;
+    const int64_t n0 = (int64_t)part * part_len;
+    const int len = (int)min((int64_t)part_len, n_vox - n0);
+    const uint16_t *row = idx + (int64_t)v * n_vox + n0;
+    for (int i = threadIdx.x; i <= plane; i += blockDim.x) s_start[i] = 0u;
     __syncthreads();
-    const uint16_t *row = idx + (int64_t)v * n_vox;
-    const float *a0 = a + (int64_t)c0 * n_vox, *b0 = b + (int64_t)c0 * n_vox;
-    // two consecutive voxels per thread and pass (one 32-bit load of the offsets); a warp covers 64 voxels of a z-run pair,
-    // which a view sees or misses as a whole most of the time, so the coefficient loads of unseen runs are skipped
-    const bool pairs = (n_vox & 1) == 0 && (reinterpret_cast<uintptr_t>(row) & 3) == 0;
-    if (pairs) {
-        for (int64_t n = 2 * (int64_t)threadIdx.x; n < n_vox; n += 2 * (int64_t)blockDim.x) {
-            const uint32_t two = __ldg(reinterpret_cast<const uint32_t *>(row + n));
-            const uint32_t o0 = two & 0xffffu, o1 = two >> 16;
-            if ((o0 & o1) == 0xffffu) continue;
+    for (int n = threadIdx.x; n < len; n += blockDim.x) {
+        const uint32_t o = row[n];
+        if (o != 0xffffu) atomicAdd(&s_start[o], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the pixel counts: a run of consecutive pixels per thread, then a block scan of the run sums
+    const int per = (plane + blockDim.x - 1) / blockDim.x;
+    const int p0 = min(threadIdx.x * per, plane), p1 = min(p0 + per, plane);
+    uint32_t sum = 0;
+    for (int p = p0; p < p1; ++p) sum += s_start[p];
+    uint32_t inc = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-            for (int k = 0; k < kBwdGroup; ++k) {
-                if (k < nc) {
-                    const float2 ca = __ldg(reinterpret_cast<const float2 *>(a0 + (int64_t)k * n_vox + n));
-                    const float2 cb = __ldg(reinterpret_cast<const float2 *>(b0 + (int64_t)k * n_vox + n));
-                    if (o0 != 0xffffu) { red_shared_add(sA + k * plane + o0, ca.x); red_shared_add(sB + k * plane + o0, cb.x); }
-                    if (o1 != 0xffffu) { red_shared_add(sA + k * plane + o1, ca.y); red_shared_add(sB + k * plane + o1, cb.y); }
-                }
-            }
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
         }
-    } else {
-        for (int64_t n = threadIdx.x; n < n_vox; n += blockDim.x) {
-            const uint32_t o = row[n];
-            if (o == 0xffffu) continue;
-            for (int k = 0; k < nc; ++k) {
-                red_shared_add(sA + k * plane + o, a0[(int64_t)k * n_vox + n]);
-                red_shared_add(sB + k * plane + o, b0[(int64_t)k * n_vox + n]);
-            }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    uint32_t run = inc - sum + (warp > 0 ? s_warp[warp - 1] : 0u);        // exclusive prefix of this thread's run
+    for (int p = p0; p < p1; ++p) {
+        const uint32_t c = s_start[p];
+        s_start[p] = run;
+        s_cur[p] = run;
+        run += c;
+    }
+    if (threadIdx.x == 0) s_start[plane] = s_warp[31];
+    __syncthreads();
+    for (int n = threadIdx.x; n < len; n += blockDim.x) {
+        const uint32_t o = row[n];
+        if (o != 0xffffu) s_list[atomicAdd(&s_cur[o], 1u)] = (uint16_t)n;
+    }
+    __syncthreads();
+    // one order per pixel: ascending voxel index (the lists are short: 1.8 voxels per touched pixel at the bench shape)
+    for (int p = threadIdx.x; p < plane; p += blockDim.x) {
+        const int a = (int)s_start[p], b = (int)s_start[p + 1];
+        for (int i = a + 1; i < b; ++i) {
+            const uint16_t key = s_list[i];
+            int j = i - 1;
+            while (j >= a && s_list[j] > key) { s_list[j + 1] = s_list[j]; --j; }
+            s_list[j + 1] = key;
         }
     }
     __syncthreads();
-    // g = A + x * B, written in the layout of a contiguous [nv][C][height][width] gradient
-    for (int i = threadIdx.x; i < nc * plane; i += blockDim.x) {
-        const int k = i / plane, p = i - k * plane, y = p / width, x = p - y * width;
-        const float f = to_f32<T>(feat[v * sv + (int64_t)(c0 + k) * sc + (int64_t)y * sy + (int64_t)x * sx]);
-        g_feat[((int64_t)v * channels + c0 + k) * plane + p] = from_f32_t<T>(fmaf(f, sB[k * plane + p], sA[k * plane + p]));
+    uint16_t *g_start = start + ((int64_t)v * parts + part) * (plane + 1);
+    uint16_t *g_list = list + ((int64_t)v * parts + part) * part_len;
+    uint2 *g_rec = rec + ((int64_t)v * parts + part) * plane;
+    for (int i = threadIdx.x; i <= plane; i += blockDim.x) g_start[i] = (uint16_t)s_start[i];
+    const int total = (int)s_start[plane];
+    for (int i = threadIdx.x; i < total; i += blockDim.x) g_list[i] = s_list[i];
+    // what the gather kernel reads per pixel: one 8-byte record {count, first three voxels}; the 5 % of the pixels with more
+    // than three voxels continue in the list at start[p] + 3
+    for (int p = threadIdx.x; p < plane; p += blockDim.x) {
+        const int a = (int)s_start[p], cnt = (int)s_start[p + 1] - a;
+        const uint32_t e0 = cnt > 0 ? s_list[a] : 0u, e1 = cnt > 1 ? s_list[a + 1] : 0u, e2 = cnt > 2 ? s_list[a + 2] : 0u;
+        g_rec[p] = make_uint2((uint32_t)cnt | (e0 << 16), e1 | (e2 << 16));
+    }
+}
+
+// grid (view ranges, C), one launch per part.  Shared memory: float2 [part_len] coefficients.  A thread owns kBwdPpt pixel
+// positions (the same in every view: their offsets inside a feature plane are computed once) and per view reads ONE 8-byte
+// record per pixel -- count and the first three voxels -- with coalesced loads.
+constexpr int kBwdPpt = 5;
+constexpr int kBwdGatherThreads = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(kBwdGatherThreads, 1)
+k_bwd_gather(const T *__restrict__ feat, int64_t sv, int64_t sc, int64_t sy, int64_t sx, int n_views, int channels, int height,
+             int width, const float *__restrict__ mean, const float *__restrict__ cov, const int64_t *__restrict__ count,
+             const float *__restrict__ g_mean, const float *__restrict__ g_cov, int64_t n_vox, int n_views_total, int part,
+             int parts, int part_len, const uint2 *__restrict__ rec, const uint16_t *__restrict__ start,
+             const uint16_t *__restrict__ list, T *__restrict__ g_feat) {
+    extern __shared__ __align__(16) float2 s_coef[];
+    const int c = blockIdx.y;
+    const int plane = height * width;
+    const int64_t n0 = (int64_t)part * part_len;
+    const int len = (int)min((int64_t)part_len, n_vox - n0);
+    const int v_per = (n_views + gridDim.x - 1) / gridDim.x;
+    const int v0 = blockIdx.x * v_per, v1 = min(n_views, v0 + v_per);
+    const int64_t row = (int64_t)c * n_vox + n0;
+    for (int n = threadIdx.x; n < len; n += blockDim.x)
+        s_coef[n] = bwd_coef(mean[row + n], g_cov != nullptr ? cov[row + n] : 0.0f, count[n0 + n],
+                             g_mean != nullptr ? g_mean[row + n] : 0.0f, g_cov != nullptr ? g_cov[row + n] : 0.0f, n_views_total);
+    __syncthreads();
+    for (int pb = 0; pb < plane; pb += kBwdPpt * kBwdGatherThreads) {
+        int64_t foff[kBwdPpt];
+#pragma unroll
+        for (int j = 0; j < kBwdPpt; ++j) {
+            const int p = min(pb + j * kBwdGatherThreads + (int)threadIdx.x, plane - 1);
+            const int y = p / width, x = p - y * width;
+            foff[j] = (int64_t)y * sy + (int64_t)x * sx;
+        }
+        for (int v = v0; v < v1; ++v) {
+            const int64_t vp = (int64_t)v * parts + part;
+            const uint2 *rc = rec + vp * plane;
+            const T *fv = feat + v * sv + (int64_t)c * sc;
+            T *gv = g_feat + ((int64_t)v * channels + c) * plane;
+            uint2 r[kBwdPpt];
+            float x[kBwdPpt], prev[kBwdPpt];
+#pragma unroll
+            for (int j = 0; j < kBwdPpt; ++j) {                            // all loads of the view up front
+                const int p = pb + j * kBwdGatherThreads + threadIdx.x;
+                r[j] = p < plane ? __ldg(rc + p) : make_uint2(0u, 0u);
+                x[j] = (r[j].x & 0xffffu) ? to_f32<T>(fv[foff[j]]) : 0.0f;
+                prev[j] = (part > 0 && p < plane) ? to_f32<T>(gv[p]) : 0.0f;   // what the previous part's launch left
+            }
+#pragma unroll
+            for (int j = 0; j < kBwdPpt; ++j) {
+                const int p = pb + j * kBwdGatherThreads + threadIdx.x;
+                if (p >= plane) continue;
+                const int cnt = (int)(r[j].x & 0xffffu);
+                float A = 0.0f, B = 0.0f;                                  // ascending voxel index: one order, deterministic
+                if (cnt > 0) { const float2 ab = s_coef[r[j].x >> 16]; A += ab.x; B += ab.y; }
+                if (cnt > 1) { const float2 ab = s_coef[r[j].y & 0xffffu]; A += ab.x; B += ab.y; }
+                if (cnt > 2) { const float2 ab = s_coef[r[j].y >> 16]; A += ab.x; B += ab.y; }
+                if (cnt > 3) {
+                    const uint16_t *ls = list + vp * part_len + start[vp * (plane + 1) + p];
+                    for (int k = 3; k < cnt; ++k) {
+                        const float2 ab = s_coef[__ldg(ls + k)];
+                        A += ab.x;
+                        B += ab.y;
+                    }
+                }
+                gv[p] = from_f32_t<T>(prev[j] + (cnt > 0 ? fmaf(x[j], B, A) : 0.0f));
+            }
+        }
     }
 }
 
@@ -135,11 +233,18 @@ using namespace nd;
 
 extern "C" {
 
+static int bwd_parts(int64_t n_voxels, int64_t) { return (int)ceil_div(n_voxels, (int64_t)kBwdPartMax); }
+static int bwd_part_len(int64_t n_voxels, int64_t plane) { return (int)ceil_div(n_voxels, (int64_t)bwd_parts(n_voxels, plane)); }
+
 size_t nd_lift_backward_workspace_bytes(const nd_maps *features, int64_t n_voxels) {
     if (features == nullptr || n_voxels <= 0) return 0;
     const size_t idx = ((size_t)features->n_views * n_voxels * sizeof(uint16_t) + 255) & ~(size_t)255;
-    const size_t coef = ((size_t)features->channels * n_voxels * sizeof(float) + 255) & ~(size_t)255;
-    return idx + 2 * coef;
+    const size_t plane = (size_t)features->height * features->width;
+    const size_t parts = (size_t)bwd_parts(n_voxels, (int64_t)plane);
+    const size_t st = ((size_t)features->n_views * parts * (plane + 1) * sizeof(uint16_t) + 255) & ~(size_t)255;
+    const size_t rc = ((size_t)features->n_views * parts * plane * sizeof(uint2) + 255) & ~(size_t)255;
+    const size_t ls = ((size_t)features->n_views * parts * (size_t)bwd_part_len(n_voxels, (int64_t)plane) * sizeof(uint16_t) + 255) & ~(size_t)255;
+    return idx + st + ls + rc;
 }
 
 int nd_lift_backward(const nd_maps *features, const float *points, const float *projection, int64_t n_voxels,
@@ -154,10 +259,8 @@ int nd_lift_backward(const nd_maps *features, const float *points, const float *
     ND_REQUIRE(nv > 0 && ch > 0 && h > 0 && w > 0 && n_voxels > 0 && nv <= 65535, ND_ERR_BAD_SHAPE, "nd_lift_backward: bad shape");
     ND_REQUIRE(features->dtype == ND_F32 || features->dtype == ND_BF16, ND_ERR_BAD_ARG, "nd_lift_backward: dtype");
     const int64_t plane = (int64_t)h * w;
-    ND_REQUIRE(plane < 0xffff, ND_ERR_BAD_SHAPE, "nd_lift_backward: planes of %lld pixels (limit 65534)", (long long)plane);
-    const size_t smem = (size_t)2 * kBwdGroup * plane * sizeof(float);
-    ND_REQUIRE(smem <= 220 * 1024, ND_ERR_BAD_SHAPE, "nd_lift_backward: planes of %lld pixels do not fit shared memory",
-               (long long)plane);
+    ND_REQUIRE(plane <= kBwdCsrPixels, ND_ERR_BAD_SHAPE, "nd_lift_backward: planes of %lld pixels (limit %d)", (long long)plane,
+               kBwdCsrPixels);
     ND_REQUIRE(workspace_bytes >= nd_lift_backward_workspace_bytes(features, n_voxels) &&
                    (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
                ND_ERR_WORKSPACE, "nd_lift_backward: workspace too small or not 256-byte aligned");
@@ -166,36 +269,51 @@ int nd_lift_backward(const nd_maps *features, const float *points, const float *
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     uint16_t *idx = reinterpret_cast<uint16_t *>(ws);
     const size_t idx_bytes = ((size_t)nv * n_voxels * sizeof(uint16_t) + 255) & ~(size_t)255;
-    const size_t coef_bytes = ((size_t)ch * n_voxels * sizeof(float) + 255) & ~(size_t)255;
-    float *a = reinterpret_cast<float *>(ws + idx_bytes), *b = reinterpret_cast<float *>(ws + idx_bytes + coef_bytes);
     k_bwd_index<<<dim3((unsigned)ceil_div(n_voxels, 256), nv), 256, 0, st>>>(points, projection, n_voxels, h, w, depth_resized,
                                                                              voxel_z, idx);
     ND_CUDA_LAUNCH_CHECK("k_bwd_index");
-    k_bwd_coef<<<dim3((unsigned)ceil_div(n_voxels, 256), ch), 256, 0, st>>>(mean, cov, count, grad_mean, grad_cov, ch, n_voxels,
-                                                                            n_views_total, a, b);
-    ND_CUDA_LAUNCH_CHECK("k_bwd_coef");
-    const dim3 grid((unsigned)ceil_div(ch, kBwdGroup), nv);
-    cudaError_t e;
-    if (features->dtype == ND_F32) {
-        auto kern = k_bwd_scatter<float>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        const int parts = bwd_parts(n_voxels, plane), part_len = bwd_part_len(n_voxels, plane);
+        const size_t st_bytes = ((size_t)nv * parts * (size_t)(plane + 1) * sizeof(uint16_t) + 255) & ~(size_t)255;
+        const size_t ls_bytes = ((size_t)nv * parts * (size_t)part_len * sizeof(uint16_t) + 255) & ~(size_t)255;
+        uint16_t *start = reinterpret_cast<uint16_t *>(ws + idx_bytes), *list = reinterpret_cast<uint16_t *>(ws + idx_bytes + st_bytes);
+        uint2 *rec = reinterpret_cast<uint2 *>(ws + idx_bytes + st_bytes + ls_bytes);
+        const size_t csr_smem = (size_t)(2 * plane + 1) * sizeof(uint32_t) + (size_t)part_len * sizeof(uint16_t);
+        cudaError_t e = cudaFuncSetAttribute(k_bwd_csr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csr_smem);
         if (e == cudaSuccess)
-            kern<<<grid, kBwdThreads, smem, st>>>((const float *)features->data, features->stride_v, features->stride_c,
-                                                  features->stride_y, features->stride_x, ch, h, w, idx, a, b, n_voxels,
-                                                  (float *)grad_features);
-    } else {
-        auto kern = k_bwd_scatter<__nv_bfloat16>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            kern<<<grid, kBwdThreads, smem, st>>>((const __nv_bfloat16 *)features->data, features->stride_v, features->stride_c,
-                                                  features->stride_y, features->stride_x, ch, h, w, idx, a, b, n_voxels,
-                                                  (__nv_bfloat16 *)grad_features);
+            k_bwd_csr<<<dim3(parts, nv), kBwdCsrThreads, csr_smem, st>>>(idx, n_voxels, part_len, (int)plane, start, list, rec);
+        const size_t g_smem = (size_t)part_len * sizeof(float2);
+        // enough CTAs for ~3 rounds on the SMs (one CTA per SM: the coefficient row takes the shared memory)
+        int sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int vsplit = (int)ceil_div((int64_t)3 * sms, (int64_t)ch);
+        vsplit = vsplit < 1 ? 1 : vsplit > nv ? nv : vsplit;
+        for (int part = 0; part < parts && e == cudaSuccess; ++part) {
+            if (features->dtype == ND_F32) {
+                auto kern = k_bwd_gather<float>;
+                e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem);
+                if (e == cudaSuccess)
+                    kern<<<dim3(vsplit, ch), kBwdGatherThreads, g_smem, st>>>((const float *)features->data, features->stride_v, features->stride_c,
+                                                                features->stride_y, features->stride_x, nv, ch, h, w, mean, cov, count,
+                                                                grad_mean, grad_cov, n_voxels, n_views_total, part, parts, part_len,
+                                                                rec, start, list, (float *)grad_features);
+            } else {
+                auto kern = k_bwd_gather<__nv_bfloat16>;
+                e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_smem);
+                if (e == cudaSuccess)
+                    kern<<<dim3(vsplit, ch), kBwdGatherThreads, g_smem, st>>>((const __nv_bfloat16 *)features->data, features->stride_v,
+                                                                features->stride_c, features->stride_y, features->stride_x, nv, ch, h, w,
+                                                                mean, cov, count, grad_mean, grad_cov, n_voxels, n_views_total, part,
+                                                                parts, part_len, rec, start, list, (__nv_bfloat16 *)grad_features);
+            }
+        }
+        if (e != cudaSuccess) {
+            set_error("nd_lift_backward: %s", cudaGetErrorString(e));
+            return ND_ERR_CUDA;
+        }
+        ND_CUDA_LAUNCH_CHECK("k_bwd_gather");
     }
-    if (e != cudaSuccess) {
-        set_error("nd_lift_backward: %s", cudaGetErrorString(e));
-        return ND_ERR_CUDA;
-    }
-    ND_CUDA_LAUNCH_CHECK("k_bwd_scatter");
     return ND_OK;
 }
 
