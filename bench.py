@@ -488,10 +488,12 @@ def bench_lift(args, rank, local_rank, world):
     if n_gpus == 1:
         extras['step_times_us'] = per_step_times(lambda i: step(dev_sets[i % N_INPUT_SETS]), min(max(steps, 20), 200))
         f_views = [d[:, :, :FEAT_HW[0], :FEAT_HW[1]] for d in dev_sets]
-        fresh_ms, _ = device_timed(lambda i: ops.lift_mean_var(f_views[i % N_INPUT_SETS], pts_d, proj_d, None, True, 0),
+        for i in range(3):                                  # (the first call of an entry point pays its one-off costs)
+            ops.direct.lift_mean_var(f_views[i], pts_d, proj_d, None, True, 0)
+        fresh_ms, _ = device_timed(lambda i: ops.direct.lift_mean_var(f_views[i % N_INPUT_SETS], pts_d, proj_d, None, True, 0),
                                    min(steps, 200), barrier)
         extras['fresh_geometry'] = {'ms_per_step': fresh_ms, 'value': views_total * n_vox / (fresh_ms * 1e-3),
-                                    'note': 'the one-shot op nd_lift_mean_var: geometry plan (2 kernels) + lift, every step'}
+                                    'note': 'the one-shot entry nd_lift_mean_var: geometry plan (3 kernels) + lift, every step'}
         bf_sets = [d.to(torch.bfloat16) for d in dev_sets]
         bf_views = [d[:, :, :FEAT_HW[0], :FEAT_HW[1]] for d in bf_sets]
         for i in range(3):
