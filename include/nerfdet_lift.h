@@ -353,6 +353,45 @@ int nd_volume_sample_trilinear(const float *volume, int channels, int d0, int d1
                                int64_t n_points, const float *aabb_min_host, const float *aabb_max_host, float *out,
                                uint8_t *inside, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Row N3: the producers of the render branch's inputs on the GPU.
+ *
+ * nd_generate_rays   datasets/pipelines/multi_view.py:124-132 + data_augment_utils.py:410-424 (get_dtu_raydir) +
+ *   formating.py:70-75.  intrinsic3x3_host: the NeRF intrinsics (rows 0-1 already divided by ori_h / img_h), row-major,
+ *   HOST memory; rot f64 [nt][3][3] (camrotc2w) and lightpos f32 [nt][3] on the device.  Pixel grid
+ *   [margin, width - margin) x [margin, height - margin), rows = y.  ray_d, ray_o f32 [nt][(H-2m)*(W-2m)][3].
+ * nd_denorm_images   multi_view.py:107-110 (mmcv.imdenormalize(img, mean, std, to_bgr).astype(uint8) / 255.0) +
+ *   formating.py:87-91.  img f32 [n][3][H][W] = the normalised network input; mean3_host / std3_host f64 HOST;
+ *   out f32 [n][3][H][W] in [0, 1], channels swapped when to_bgr.
+ * ------------------------------------------------------------------------------------- */
+int nd_generate_rays(const float *intrinsic3x3_host, const double *rot, const float *lightpos, int n_target_views, int height,
+                     int width, int margin, float *ray_d, float *ray_o, void *stream);
+int nd_denorm_images(const float *img, const double *mean3_host, const double *std3_host, int to_bgr, int64_t n_images,
+                     int height, int width, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Row N4: the metrics of the render_testing evaluator, batched over the rendered views
+ * (mmdet3d/models/model_utils/save_rendered_img.py:10-78; SSIM = skimage.metrics.structural_similarity of the pinned
+ * scikit-image 0.18.1 as the reference ends up calling it: per channel, 7 x 7 uniform window, sample covariance,
+ * K1 = 0.01, K2 = 0.03, float64, map cropped by 3 pixels; data_range = 2 for float images there).
+ *   pred f32 [nv][H][W][3]; target f32 or f64 [nv][H][W][3]; psnr_ssim f64 [nv][2] = {PSNR, SSIM} per view.
+ *   nd_depth_sqerr: out f64 [n_pixels] = mean over the views of (depth - gt_depth)^2 (the reference's "rsme" map).
+ * ------------------------------------------------------------------------------------- */
+size_t nd_image_metrics_workspace_bytes(int n_views, int height, int width);
+int nd_image_metrics(const float *pred, const void *target, int target_is_f64, int n_views, int height, int width,
+                     double data_range, double *psnr_ssim, void *workspace, size_t workspace_bytes, void *stream);
+int nd_depth_sqerr(const float *depth, const void *gt_depth, int gt_is_f64, int n_views, int64_t n_pixels, double *out,
+                   void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Row N2: hand-over to FastIndoorImVoxelNeck (necks/imvoxelnet.py:8-67, nerfdet.py:262-267).
+ *   volume f32 [C][N] (alpha * mean as the lift writes it) -> out [N][C] in out_dtype (ND_F32 / ND_BF16): the
+ *   channels-last-3D layout of a [1, C, X, Y, Z] tensor, which cuDNN's Conv3d takes without a conversion pass;
+ *   valid f32 [N] or NULL = (float)count, the `valids.float()` the head up-samples (nerfdet.py:287, imvoxel_head_v2.py:93).
+ * ------------------------------------------------------------------------------------- */
+int nd_volume_to_neck(const float *volume, const int64_t *count, int channels, int64_t n_voxels, int out_dtype, void *out,
+                      float *valid, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

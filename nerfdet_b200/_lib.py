@@ -63,6 +63,13 @@ SIGNATURES = {
     'nd_lift_backward_workspace_bytes': (c_size_t, [POINTER(NdMaps), c_int64]),
     'nd_lift_backward': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int64, c_void_p, ctypes.c_float, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'nd_generate_rays': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'nd_denorm_images': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    'nd_image_metrics_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'nd_image_metrics': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_double, c_void_p, c_void_p, c_size_t,
+                                 c_void_p]),
+    'nd_depth_sqerr': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),
+    'nd_volume_to_neck': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     'nd_peer_alloc': (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
     'nd_peer_open': (c_int, [c_void_p, POINTER(c_void_p)]),
     'nd_peer_close': (c_int, [c_void_p]),

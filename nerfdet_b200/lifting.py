@@ -173,5 +173,18 @@ class _LiftMeanVar(torch.autograd.Function):
         return grad, None, None, None, None, None
 
 
+def volume_for_neck(volume: torch.Tensor, valid: torch.Tensor, dtype: torch.dtype = torch.bfloat16):
+    """Row N2: the lifted ``volume [C, X, Y, Z]`` (``alpha * mean``, nerfdet.py:259-261) and the view
+    counts ``valid [1, X, Y, Z]`` as ``FastIndoorImVoxelNeck`` and the head consume them (nerfdet.py:262-267, 287):
+    ``x [1, C, X, Y, Z]`` in ``dtype`` with channels-last-3D strides -- the layout cuDNN's first Conv3d wants, written
+    by one transposing kernel instead of ``stack`` + cast + ``contiguous(memory_format=channels_last_3d)`` -- and
+    ``valids [1, 1, X, Y, Z]`` float32 (= ``valids.float()``)."""
+    if dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError('dtype must be torch.bfloat16 or torch.float32')
+    c, gx, gy, gz = volume.shape
+    out, vf = ops.direct.volume_to_neck(volume.reshape(c, -1), valid.reshape(-1), dtype == torch.bfloat16)
+    return out.view(1, gx, gy, gz, c).permute(0, 4, 1, 2, 3), vf.view(1, 1, gx, gy, gz)
+
+
 # resized depth maps, kept per depth tensor so that the geometry plan (keyed on tensor identity) is found again
 _DEPTH_CACHE = {}

@@ -852,6 +852,139 @@ def _(features, points, projection, mean, cov, count, grad_mean, grad_cov, depth
     return features.new_empty(tuple(features.shape))
 
 
+@torch.library.custom_op(f'{_NS}::generate_rays', mutates_args=())
+@_guarded
+def generate_rays(intrinsic: Tensor, rot: Tensor, lightpos: Tensor, height: int, width: int, margin: int) -> Tuple[Tensor, Tensor]:
+    """Row N3: ``ray_d``, ``ray_o`` float32 ``[nt, (H - 2m) * (W - 2m), 3]`` of the target views' pixel grids (reference
+    multi_view.py:124-132 + data_augment_utils.py:410-424 + formating.py:70-75).  ``intrinsic``: host float32 ``[3, 3]`` (or
+    larger; the top-left block is read) NeRF intrinsics; ``rot`` float64 ``[nt, 3, 3]`` and ``lightpos`` float32 ``[nt, 3]``
+    on the device."""
+    _need_cuda(rot, lightpos)
+    if intrinsic.is_cuda or intrinsic.dim() != 2 or intrinsic.shape[0] < 3 or intrinsic.shape[1] < 3:
+        raise ValueError('intrinsic must be a host tensor [>=3, >=3]')
+    if rot.dtype != torch.float64 or rot.dim() != 3 or tuple(rot.shape[1:]) != (3, 3):
+        raise ValueError('rot must be float64 [nt, 3, 3]')
+    nt = rot.shape[0]
+    if lightpos.dtype != torch.float32 or tuple(lightpos.shape) != (nt, 3):
+        raise ValueError('lightpos must be float32 [nt, 3]')
+    k = intrinsic[:3, :3].to(torch.float32).contiguous()
+    rot, lightpos = rot.contiguous(), lightpos.contiguous()
+    npix = (height - 2 * margin) * (width - 2 * margin)
+    ray_d = torch.empty((nt, max(npix, 0), 3), dtype=torch.float32, device=rot.device)
+    ray_o = torch.empty_like(ray_d)
+    lib = _lib.load()
+    _lib.check(lib.nd_generate_rays(ctypes.c_void_p(k.data_ptr()), _ptr(rot), _ptr(lightpos), nt, int(height), int(width),
+                                    int(margin), _ptr(ray_d), _ptr(ray_o), _stream()), 'nd_generate_rays')
+    return ray_d, ray_o
+
+
+@generate_rays.register_fake
+def _(intrinsic, rot, lightpos, height, width, margin):
+    nt, npix = rot.shape[0], (height - 2 * margin) * (width - 2 * margin)
+    return rot.new_empty((nt, npix, 3), dtype=torch.float32), rot.new_empty((nt, npix, 3), dtype=torch.float32)
+
+
+@torch.library.custom_op(f'{_NS}::denorm_images', mutates_args=())
+@_guarded
+def denorm_images(img: Tensor, mean: List[float], std: List[float], to_bgr: bool) -> Tensor:
+    """Row N3: ``mmcv.imdenormalize(img, mean, std, to_bgr).astype(uint8) / 255`` (reference multi_view.py:107-110) of the
+    normalised network input ``img [n, 3, H, W]`` float32 on the device: float32 ``[n, 3, H, W]`` in [0, 1]."""
+    _need_cuda(img)
+    if img.dtype != torch.float32 or img.dim() != 4 or img.shape[1] != 3:
+        raise ValueError('img must be float32 [n, 3, H, W]')
+    if len(mean) != 3 or len(std) != 3:
+        raise ValueError('mean and std must have three entries')
+    img = img.contiguous()
+    out = torch.empty_like(img)
+    m = (ctypes.c_double * 3)(*[float(v) for v in mean])
+    sd = (ctypes.c_double * 3)(*[float(v) for v in std])
+    lib = _lib.load()
+    _lib.check(lib.nd_denorm_images(_ptr(img), m, sd, int(bool(to_bgr)), img.shape[0], img.shape[2], img.shape[3], _ptr(out),
+                                    _stream()), 'nd_denorm_images')
+    return out
+
+
+@denorm_images.register_fake
+def _(img, mean, std, to_bgr):
+    return torch.empty_like(img)
+
+
+@torch.library.custom_op(f'{_NS}::image_metrics', mutates_args=())
+@_guarded
+def image_metrics(pred: Tensor, target: Tensor, data_range: float) -> Tensor:
+    """Row N4: float64 ``[nv, 2]`` = {PSNR, SSIM} of ``pred`` float32 against ``target`` float32 / float64, both
+    ``[nv, H, W, 3]`` (reference save_rendered_img.py:13-38 with scikit-image 0.18.1's structural_similarity)."""
+    _need_cuda(pred, target)
+    if pred.dtype != torch.float32 or pred.dim() != 4 or pred.shape[-1] != 3 or tuple(pred.shape) != tuple(target.shape):
+        raise ValueError('pred must be float32 [nv, H, W, 3] and target of the same shape')
+    if target.dtype not in (torch.float32, torch.float64):
+        raise TypeError('target must be float32 or float64')
+    pred, target = pred.contiguous(), target.contiguous()
+    nv, h, w = pred.shape[:3]
+    out = torch.empty((nv, 2), dtype=torch.float64, device=pred.device)
+    lib = _lib.load()
+    ws_bytes = lib.nd_image_metrics_workspace_bytes(nv, h, w)
+    ws = torch.empty((max(ws_bytes, 16),), dtype=torch.uint8, device=pred.device)
+    _lib.check(lib.nd_image_metrics(_ptr(pred), _ptr(target), int(target.dtype == torch.float64), nv, h, w, float(data_range),
+                                    _ptr(out), _ptr(ws), ws_bytes, _stream()), 'nd_image_metrics')
+    return out
+
+
+@image_metrics.register_fake
+def _(pred, target, data_range):
+    return pred.new_empty((pred.shape[0], 2), dtype=torch.float64)
+
+
+@torch.library.custom_op(f'{_NS}::depth_sqerr', mutates_args=())
+@_guarded
+def depth_sqerr(depth: Tensor, gt_depth: Tensor) -> Tensor:
+    """Row N4: mean over the views of ``(depth - gt_depth) ** 2`` per pixel, float64, shape of one view
+    (the "rsme" the reference accumulates at save_rendered_img.py:51, 78)."""
+    _need_cuda(depth, gt_depth)
+    if depth.dtype != torch.float32 or tuple(depth.shape) != tuple(gt_depth.shape) or depth.dim() < 2:
+        raise ValueError('depth must be float32 [nv, ...] and gt_depth of the same shape')
+    if gt_depth.dtype not in (torch.float32, torch.float64):
+        raise TypeError('gt_depth must be float32 or float64')
+    depth, gt_depth = depth.contiguous(), gt_depth.contiguous()
+    nv = depth.shape[0]
+    out = torch.empty(tuple(depth.shape[1:]), dtype=torch.float64, device=depth.device)
+    lib = _lib.load()
+    _lib.check(lib.nd_depth_sqerr(_ptr(depth), _ptr(gt_depth), int(gt_depth.dtype == torch.float64), nv, out.numel(), _ptr(out),
+                                  _stream()), 'nd_depth_sqerr')
+    return out
+
+
+@depth_sqerr.register_fake
+def _(depth, gt_depth):
+    return depth.new_empty(tuple(depth.shape[1:]), dtype=torch.float64)
+
+
+@torch.library.custom_op(f'{_NS}::volume_to_neck', mutates_args=())
+@_guarded
+def volume_to_neck(volume: Tensor, count: Tensor, bf16: bool) -> Tuple[Tensor, Tensor]:
+    """Row N2: ``volume`` float32 ``[C, N]`` -> ``[N, C]`` (bf16 or float32: the channels-last-3D storage of the neck's
+    input) and ``valids`` float32 ``[N]`` = the view counts as floats (reference nerfdet.py:262-267, 287)."""
+    _need_cuda(volume, count)
+    if volume.dtype != torch.float32 or volume.dim() != 2:
+        raise ValueError('volume must be float32 [C, N]')
+    c, n = volume.shape
+    if count.dtype != torch.int64 or count.numel() != n:
+        raise ValueError('count must be int64 with one value per voxel')
+    volume, count = volume.contiguous(), count.contiguous()
+    out = torch.empty((n, c), dtype=torch.bfloat16 if bf16 else torch.float32, device=volume.device)
+    valid = torch.empty((n,), dtype=torch.float32, device=volume.device)
+    lib = _lib.load()
+    _lib.check(lib.nd_volume_to_neck(_ptr(volume), _ptr(count), c, n, ND_BF16 if bf16 else ND_F32, _ptr(out), _ptr(valid),
+                                     _stream()), 'nd_volume_to_neck')
+    return out, valid
+
+
+@volume_to_neck.register_fake
+def _(volume, count, bf16):
+    c, n = volume.shape
+    return (volume.new_empty((n, c), dtype=torch.bfloat16 if bf16 else torch.float32), volume.new_empty((n,)))
+
+
 # ------------------------------------------------------------------------------------------
 # The Python functions behind the registered custom ops, for the reference-signature modules (lifting, live, render,
 # nerf_mlp, projection): a call through torch.library's dispatcher costs 50-350 us of host time per op, more than
@@ -865,5 +998,5 @@ class _Direct:
 direct = _Direct()
 for _name in ('project_voxels', 'backproject', 'lift_mean_var', 'lift_accumulate', 'lift_accumulate_into', 'lift_finalize',
               'map_features', 'live_stats', 'nerf_mlp_fwd', 'sample_rays', 'render_gather_stats', 'composite', 'volume_sample',
-              'lift_backward'):
+              'lift_backward', 'generate_rays', 'denorm_images', 'image_metrics', 'depth_sqerr', 'volume_to_neck'):
     setattr(direct, _name, globals()[_name]._init_fn)

@@ -180,6 +180,7 @@ def make_rays(cfg: SceneConfig, rs: np.random.RandomState, img_meta: Dict) -> Di
         gt_rgb=torch.from_numpy(gt_rgb),
         gt_depth=torch.from_numpy(gt_depth),
         nerf_sizes=torch.from_numpy(nerf_sizes),
+        camrotc2w=torch.from_numpy(np.stack([c[:3, :3] for c in tcams]).astype(np.float64)),   # the target cameras themselves
     )
 
 

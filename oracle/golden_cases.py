@@ -51,6 +51,9 @@ CASES = {
     'lift_grad_depth': dict(kind='lift_grad', seed=12, n_views=4, n_voxels=(10, 10, 4),
                             voxel_size=(0.64, 0.64, 0.8), channels=4, with_depth=True, **_TINY),
     'volume_lookup': dict(kind='volume_lookup', seed=9),
+    # N3: ray directions of two target cameras (reference get_dtu_raydir) and de-normalised images (cv2 arithmetic)
+    'rays_small': dict(kind='rays', seed=13, n_target_views=2, height=48, width=64, margin=10, n_images=3,
+                       ori_shape=(968, 1296), img_shape=(47, 64)),
 }
 
 
@@ -83,6 +86,24 @@ def lift_grad_upstream(case):
     shape = (case['channels'],) + tuple(case['n_voxels'])
     return (torch.from_numpy(rs.standard_normal(shape).astype(np.float32)),
             torch.from_numpy(rs.standard_normal(shape).astype(np.float32)))
+
+
+IMG_NORM = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375])
+
+
+def rays_inputs(case):
+    """Seeded cameras (float64 rotations like the dataset's camrotc2w) and normalised images (HWC float32)."""
+    rs = np.random.RandomState(case['seed'])
+    nt = case['n_target_views']
+    q, _ = np.linalg.qr(rs.standard_normal((nt, 3, 3)))
+    k = np.array([[1170.19, 0., 647.75, 0.], [0., 1170.19, 483.75, 0.], [0., 0., 1., 0.], [0., 0., 0., 1.]], dtype=np.float32)
+    img_meta = dict(lidar2img=dict(intrinsic=k), ori_shape=case['ori_shape'] + (3,), img_shape=case['img_shape'] + (3,))
+    pixels = rs.randint(0, 256, (case['n_images'], case['height'], case['width'], 3)).astype(np.float32)
+    mean, std = np.array(IMG_NORM['mean'], dtype=np.float32), np.array(IMG_NORM['std'], dtype=np.float32)
+    img = ((pixels - mean) / std).astype(np.float32)            # what Normalize hands on (RGB, HWC)
+    img[:, -1] = 0.0                                            # a padded row, as Pad leaves it
+    return dict(img_meta=img_meta, camrotc2w=q.astype(np.float64), lightpos=rs.standard_normal((nt, 3)).astype(np.float32),
+                img_hwc=img, height=case['height'], width=case['width'], margin=case['margin'])
 
 
 def extract_inputs(case):

@@ -90,6 +90,35 @@ def gen_lift_grad(case):
     return out
 
 
+def gen_rays(case):
+    """N3: the reference's own get_dtu_raydir (taken out of the unmodified data_augment_utils.py, whose module imports mmcv)
+    on the pipeline's pixel grid, and OpenCV's imdenormalize arithmetic (what mmcv.imdenormalize calls)."""
+    import ast
+    import cv2
+    src_path = os.path.join(ref_loader.REFERENCE_ROOT, 'mmdet3d/datasets/pipelines/data_augment_utils.py')
+    tree = ast.parse(open(src_path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'get_dtu_raydir'][0]
+    ns = {'np': np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), src_path, 'exec'), ns)
+    inp = gc.rays_inputs(case)
+    k = inp['img_meta']['lidar2img']['intrinsic'].copy()                  # multi_view.py:117-118
+    ratio = inp['img_meta']['ori_shape'][0] / inp['img_meta']['img_shape'][0]
+    k[:2] = k[:2] / ratio
+    h, w, m = inp['height'], inp['width'], inp['margin']
+    px, py = np.meshgrid(np.arange(m, w - m).astype(np.float32), np.arange(m, h - m).astype(np.float32))  # :124-127
+    pixelcoords = np.stack((px, py), axis=-1).astype(np.float32)
+    dirs = [np.reshape(ns['get_dtu_raydir'](pixelcoords, k, r).astype(np.float32), (-1, 3)) for r in inp['camrotc2w']]
+    mean = np.array(gc.IMG_NORM['mean']).reshape(1, -1).astype(np.float64)   # multi_view.py:28-29 + mmcv.imdenormalize
+    std = np.array(gc.IMG_NORM['std']).reshape(1, -1).astype(np.float64)
+    den = []
+    for img in inp['img_hwc']:
+        t = cv2.multiply(img, std)
+        cv2.add(t, mean, t)
+        cv2.cvtColor(t, cv2.COLOR_RGB2BGR, t)
+        den.append((t.astype(np.uint8) / 255.0).transpose(2, 0, 1))        # multi_view.py:107-110, formating.py:88
+    return dict(raydirs=np.stack(dirs), denorm=np.stack(den).astype(np.float32))
+
+
 def gen_extract(case):
     ref = ref_loader.load()
     inp = gc.extract_inputs(case)
@@ -173,7 +202,7 @@ def gen_volume_lookup(case):
     return dict(features=_np(feats), inside=_np(masks))
 
 
-GENERATORS = dict(lift=gen_lift, lift_grad=gen_lift_grad, extract=gen_extract, render_det=gen_render_det, mlp=gen_mlp,
+GENERATORS = dict(lift=gen_lift, lift_grad=gen_lift_grad, rays=gen_rays, extract=gen_extract, render_det=gen_render_det, mlp=gen_mlp,
                   volume_lookup=gen_volume_lookup)
 
 

@@ -69,6 +69,24 @@ def test_lift_oracle_autograd_matches_reference_autograd(name):
         assert float(f.grad.abs().max()) > 0
 
 
+def test_rays_oracle_matches_reference_and_opencv():
+    """Row N3: ray directions against the reference's own get_dtu_raydir, de-normalised images against OpenCV's
+    arithmetic (what mmcv.imdenormalize calls) -- both bit for bit."""
+    from oracle import rays_oracle as rys
+    case = gc.CASES['rays_small']
+    g = gc.load_golden('rays_small')
+    inp = gc.rays_inputs(case)
+    k = inp['img_meta']['lidar2img']['intrinsic'].copy()
+    k[:2] = k[:2] / (inp['img_meta']['ori_shape'][0] / inp['img_meta']['img_shape'][0])
+    for t, rot in enumerate(inp['camrotc2w']):
+        d = rys.raydirs(k, rot, inp['height'], inp['width'], inp['margin'])
+        assert np.array_equal(d, g['raydirs'][t])
+    for i, img in enumerate(inp['img_hwc']):
+        den = rys.denorm(img, gc.IMG_NORM['mean'], gc.IMG_NORM['std'], True).transpose(2, 0, 1).astype(np.float32)
+        assert np.array_equal(den, g['denorm'][i])
+    assert 0.0 <= g['denorm'].min() and g['denorm'].max() <= 1.0 and g['denorm'].std() > 0.1
+
+
 def test_mlp_oracle_matches_reference():
     g = gc.load_golden('mlp_small')
     inp = gc.mlp_inputs(gc.CASES['mlp_small'])
