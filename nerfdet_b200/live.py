@@ -35,7 +35,11 @@ def map_features_2d(feature_2d: torch.Tensor, mapping) -> torch.Tensor:
         sv, sc, sy, sx = feature_2d.stride()
         if not (sx == 1 and sy == w and (sc * elt) % 16 == 0 and (sv * elt) % 16 == 0 and feature_2d.data_ptr() % 16 == 0):
             feature_2d = feature_2d.contiguous()
-        y = ops.direct.map_features(feature_2d, lin.weight.detach(), lin.bias.detach() if lin.bias is not None else None)
+        if torch.is_grad_enabled() and (feature_2d.requires_grad or lin.weight.requires_grad):
+            # training: through the registered op, whose autograd formula is two cuBLAS GEMMs
+            y = ops.map_features(feature_2d, lin.weight, lin.bias)
+        else:
+            y = ops.direct.map_features(feature_2d, lin.weight.detach(), lin.bias.detach() if lin.bias is not None else None)
         return y.permute(0, 3, 1, 2)
     flat = feature_2d.reshape(nv, c, h * w).permute(0, 2, 1).contiguous().float()
     return mapping(flat).view(nv, h, w, -1).permute(0, 3, 1, 2)

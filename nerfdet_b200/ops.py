@@ -986,6 +986,52 @@ def _(volume, count, bf16):
 
 
 # ------------------------------------------------------------------------------------------
+# Autograd of the registered ops.  lift_mean_var: nd_lift_backward; map_features: the two
+# plain GEMMs of a Linear's backward go to cuBLAS through torch (library GEMMs, not a hot kernel of this path).
+# ------------------------------------------------------------------------------------------
+def _lift_setup_context(ctx, inputs, output):
+    features, points, projection, alpha, want_cov, _budget = inputs
+    mean, cov, count = output
+    ctx.has_alpha, ctx.want_cov = alpha is not None, bool(want_cov)
+    ctx.save_for_backward(features, points, projection, mean, cov, count)
+
+
+def _lift_backward(ctx, g_mean, g_cov, _g_count):
+    if ctx.has_alpha:
+        raise RuntimeError('the registered lift_mean_var op is differentiable without alpha only; '
+                           'lifting.lift_mean_var applies alpha as an autograd op')
+    features, points, projection, mean, cov, count = ctx.saved_tensors
+    grad = lift_backward._init_fn(features, points, projection, mean, cov if ctx.want_cov else None, count, g_mean,
+                                  g_cov if ctx.want_cov else None, None, 0.0, 0)
+    return grad, None, None, None, None, None
+
+
+lift_mean_var.register_autograd(_lift_backward, setup_context=_lift_setup_context)
+
+
+def _map_setup_context(ctx, inputs, output):
+    features, weight, bias = inputs
+    ctx.has_bias = bias is not None
+    ctx.save_for_backward(features, weight)
+
+
+def _map_backward(ctx, g_out):
+    features, weight = ctx.saved_tensors                     # g_out: [nv, h, w, out] channels-last, features: [nv, C, h, w]
+    g2 = g_out.reshape(-1, g_out.shape[-1]).float()
+    g_feat = g_w = g_b = None
+    if ctx.needs_input_grad[0]:
+        g_feat = (g2 @ weight).view(*g_out.shape[:3], -1).permute(0, 3, 1, 2).to(features.dtype)
+    if ctx.needs_input_grad[1]:
+        g_w = torch.einsum('vhwo,vchw->oc', g_out.float(), features.float())
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+        g_b = g2.sum(dim=0)
+    return g_feat, g_w, g_b
+
+
+map_features.register_autograd(_map_backward, setup_context=_map_setup_context)
+
+
+# ------------------------------------------------------------------------------------------
 # The Python functions behind the registered custom ops, for the reference-signature modules (lifting, live, render,
 # nerf_mlp, projection): a call through torch.library's dispatcher costs 50-350 us of host time per op, more than
 # most of these kernels run; the modules call the implementations directly (same validation, same device guard), the
