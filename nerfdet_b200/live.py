@@ -66,14 +66,19 @@ def live_statistics(mapped_2d, rgb_images, points, projection, rgb_projection, m
 
 
 def lift_scene(feature: torch.Tensor, img_meta: Dict, n_voxels, voxel_size, mapping=None, nerf_mlp=None,
-               denorm_images: Optional[torch.Tensor] = None, stride: int = 4, want_cov: bool = False) -> Dict:
+               denorm_images: Optional[torch.Tensor] = None, stride: int = 4, want_cov: bool = False,
+               depth: Optional[torch.Tensor] = None) -> Dict:
     """One scene of ``extract_feat``'s loop body (nerfdet.py:152-261) without ``render_rays``.
 
     ``feature [nv, C, Hf, Wf]`` is the un-sliced FPN output of the scene's views.  With ``mapping``,
     ``nerf_mlp`` and ``denorm_images [nv, 3, Hp, Wp]`` given, the returned ``volume`` is
     ``alpha * volume_mean`` (the density-weighted volume ``neck_3d`` receives); without them it is the plain
     ``volume_mean``.  Keys: volume [C,X,Y,Z], valid [1,X,Y,Z] int64, and, when available, volume_cov,
-    feature_2d [nv,32,h,w], global_volume [N,70], alpha [N]."""
+    feature_2d [nv,32,h,w], global_volume [N,70], alpha [N].
+
+    ``depth [nv, Hp, Wp]`` (the ``*_depth`` configs) gates the 256-channel lift like ``backproject`` does
+    (nerfdet.py:164, 405-411).  The live 35-channel statistics have no depth gate yet: asking for both raises instead of
+    silently using un-gated views for the density."""
     dev = feature.device
     projection = lifting.compute_projection(img_meta, stride).to(dev)
     points = lifting.get_points_device(n_voxels, voxel_size, img_meta['lidar2img']['origin'], dev)
@@ -83,6 +88,9 @@ def lift_scene(feature: torch.Tensor, img_meta: Dict, n_voxels, voxel_size, mapp
     out = {}
     alpha = None
     if mapping is not None and nerf_mlp is not None and denorm_images is not None:
+        if depth is not None:
+            raise NotImplementedError('depth-gated live statistics (nerf_density with a depth prior) are not built; '
+                                      'lift without mapping / nerf_mlp, or use lifting.backproject')
         feature_2d = map_features_2d(sliced, mapping)
         rgb_projection = lifting.compute_projection(img_meta, 1).to(dev)
         rgb = denorm_images[:, :, :img_meta['img_shape'][0], :img_meta['img_shape'][1]]
@@ -91,7 +99,8 @@ def lift_scene(feature: torch.Tensor, img_meta: Dict, n_voxels, voxel_size, mapp
         _, alpha = nerf_mlp.query_density(pts, live['global_volume'], return_alpha=True)
         out.update(feature_2d=feature_2d, global_volume=live['global_volume'], alpha=alpha.view(-1),
                    rgb_projection=rgb_projection)
-    mean, cov, valid = lifting.lift_mean_var(sliced, points, projection, alpha=alpha, want_cov=want_cov)
+    mean, cov, valid = lifting.lift_mean_var(sliced, points, projection, alpha=alpha, want_cov=want_cov, depth=depth,
+                                             voxel_size=voxel_size if depth is not None else None)
     out.update(volume=mean, valid=valid, points=points, projection=projection)
     if want_cov:
         out['volume_cov'] = cov

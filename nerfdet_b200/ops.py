@@ -571,7 +571,7 @@ def pack_mlp_weights(weights, dims, precision: str = 'fp32') -> Tensor:
     """One-time re-layout of the reference weights for the kernel at hand: ``nd_pack_mlp_weights`` (fp32 FFMA path,
     k-major transposition) or ``nd_pack_mlp_weights_tc`` (bf16 tcgen05 path, swizzled UMMA operand images)."""
     tensors = [t for t in weights.values() if t is not None]
-    _need_cuda(*tensors)
+    dev = _need_cuda(*tensors)
     for t in tensors:
         if t.dtype != torch.float32 or not t.is_contiguous():
             raise TypeError('MLP weights must be contiguous float32 tensors')
@@ -582,7 +582,8 @@ def pack_mlp_weights(weights, dims, precision: str = 'fp32') -> Tensor:
     if nbytes == 0:
         raise RuntimeError(f'unsupported MLP architecture {tuple(dims)} for precision {precision!r}')
     packed = torch.empty((nbytes,), dtype=torch.uint8, device=tensors[0].device)
-    _lib.check(pack_fn(ctypes.byref(arch), _ptr(packed), nbytes, _stream()), 'nd_pack_mlp_weights')
+    with _on(dev):                                           # grids and the stream are per device
+        _lib.check(pack_fn(ctypes.byref(arch), _ptr(packed), nbytes, _stream()), 'nd_pack_mlp_weights')
     return packed
 
 
