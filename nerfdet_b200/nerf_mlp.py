@@ -9,16 +9,65 @@ every operand as a hi + lo pair of bf16 numbers with fp32 accumulation in tensor
 ``precision='bf16'`` uses plain bf16 operands (``nd_nerf_mlp_fwd_tc``, 1e-2); ``precision='fp32_ffma'`` is the FFMA kernel
 (``nd_nerf_mlp_fwd``, csrc/mlp.cu, 1e-4) that also takes the architectures the tensor-core kernel does not.  There is no
 eager fallback.
-Forward only (autograd is row N1 of SURVEY.md section 8f).
+
+Autograd (row N1 of SURVEY.md section 8f): the forward is always the CUDA kernel; when an input or a parameter requires
+grad, the backward re-evaluates the network's fp32 formula with torch ops under autograd (``_torch_math``: its GEMMs go
+to cuBLAS -- library GEMMs, not a kernel of this repository; dgrad / wgrad on tcgen05 are not built) and returns the
+gradients of that formula, so the module trains as a drop-in.
 """
 from __future__ import annotations
 
+import math
 from typing import Optional, Tuple
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
+
+
+def _encode(x: torch.Tensor, n_octaves: int) -> torch.Tensor:
+    """``SinusoidalEncoder`` (nerf_mlp.py:181-197): [x, sin(2^k x), sin(2^k x + pi / 2)], k outer, xyz inner."""
+    scales = torch.tensor([2 ** k for k in range(n_octaves)], device=x.device, dtype=x.dtype)
+    scaled = (x[..., None, :] * scales[:, None]).reshape(*x.shape[:-1], n_octaves * x.shape[-1])
+    return torch.cat([x, torch.sin(torch.cat([scaled, scaled + 0.5 * math.pi], dim=-1))], dim=-1)
+
+
+class _FieldFn(torch.autograd.Function):
+    """Forward: the CUDA kernel.  Backward: torch autograd through ``field._torch_math`` on the saved inputs."""
+
+    @staticmethod
+    def forward(ctx, field, want_rgb, spr, x, cond, feats, *params):
+        sigma, rgb, _ = ops.direct.nerf_mlp_fwd(field.packed_weights(), field.dims, x, feats, cond, spr, want_rgb, False,
+                                                field.precision)
+        ctx.field, ctx.want_rgb, ctx.spr, ctx.has_cond = field, want_rgb, spr, cond is not None
+        ctx.save_for_backward(x, cond if cond is not None else x.new_empty(0), feats)
+        if not want_rgb:
+            rgb = x.new_empty((0, 3))
+            ctx.mark_non_differentiable(rgb)
+        return sigma, rgb
+
+    @staticmethod
+    def backward(ctx, g_sigma, g_rgb):
+        field = ctx.field
+        x, cond, feats = ctx.saved_tensors
+        params = list(field._weights().values())
+        need = ctx.needs_input_grad[3:]
+        with torch.enable_grad():
+            leaves = [x.detach().requires_grad_(need[0]),
+                      cond.detach().requires_grad_(bool(need[1])) if ctx.has_cond else None,
+                      feats.detach().requires_grad_(need[2])]
+            sigma, rgb = field._torch_math(leaves[0], leaves[1], leaves[2], ctx.spr, ctx.want_rgb)
+            outs, gouts = [sigma], [g_sigma.reshape(sigma.shape)]
+            if ctx.want_rgb:
+                outs.append(rgb)
+                gouts.append(g_rgb.reshape(rgb.shape))
+            cands = leaves + params
+            wanted = [t for t, n in zip(cands, need) if n and t is not None]
+            grads = iter(torch.autograd.grad(outs, wanted, gouts, allow_unused=True)) if wanted else iter(())
+        result = [next(grads) if (n and t is not None) else None for t, n in zip(cands, need)]
+        return (None, None, None) + tuple(result)
 
 
 class _Linears(nn.Module):
@@ -117,12 +166,41 @@ class VanillaNeRFRadianceField(nn.Module):
             self._packed_key = key
         return self._packed
 
+    # ---- the fp32 formula in torch ops (backward only) -----------------------------------------
+    def _torch_math(self, x, cond, feats, spr: int, want_rgb: bool):
+        """(relu(sigma) [P, 1], sigmoid(rgb) [P, 3] or None) exactly as nerf_mlp.py:80-161, 224-234 chains them."""
+        m, skip = self.mlp, self.dims[2]
+        inp = torch.cat([_encode(x, 10), feats], dim=-1) if feats.shape[-1] else _encode(x, 10)
+        h = inp
+        for i, lin in enumerate(m.base.hidden_layers):
+            h = torch.relu(F.linear(h, lin.weight, lin.bias))
+            if skip and i % skip == 0 and i > 0:
+                h = torch.cat([h, inp], dim=-1)
+        sigma = torch.relu(F.linear(h, m.sigma_layer.output_layer.weight, m.sigma_layer.output_layer.bias))
+        if not want_rgb:
+            return sigma, None
+        bott = F.linear(h, m.bottleneck_layer.output_layer.weight, m.bottleneck_layer.output_layer.bias)
+        enc = _encode(cond, 4)
+        if spr > 1:
+            enc = enc.repeat_interleave(spr, dim=0)
+        lin = m.rgb_layer.hidden_layers[0]
+        t = torch.relu(F.linear(torch.cat([bott, enc], dim=-1), lin.weight, lin.bias))
+        return sigma, torch.sigmoid(F.linear(t, m.rgb_layer.output_layer.weight, m.rgb_layer.output_layer.bias))
+
+    def _needs_grad(self, *tensors) -> bool:
+        return torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in tensors)
+                                            or any(p.requires_grad for p in self._weights().values()))
+
     # ---- reference interface ---------------------------------------------------------------
     def query_density(self, x, features=None, return_alpha: bool = False):
         """relu(sigma) for points ``x [..., 3]`` with ``features [..., feature_dim]`` (nerf_mlp.py:224-227).
         ``return_alpha`` additionally returns 1 - exp(-sigma) (nerfdet.py:258) from the same launch."""
         lead = x.shape[:-1]
         feats = self._features(x, features)
+        if self._needs_grad(x, feats):
+            sigma, _ = _FieldFn.apply(self, False, 1, x.reshape(-1, 3), None, feats, *self._weights().values())
+            sigma = sigma.view(*lead, 1)
+            return (sigma, 1 - torch.exp(-sigma)) if return_alpha else sigma
         sigma, _, alpha = ops.direct.nerf_mlp_fwd(self.packed_weights(), self.dims, x.reshape(-1, 3), feats, None, 1, False,
                                            return_alpha, self.precision)
         sigma = sigma.view(*lead, 1)
@@ -143,6 +221,9 @@ class VanillaNeRFRadianceField(nn.Module):
             if condition.dim() != 2 or condition.shape[0] != lead[0]:
                 raise ValueError(f'condition {tuple(condition.shape)} does not broadcast over x {tuple(x.shape)}')
             cond, spr = condition, p // condition.shape[0]
+        if self._needs_grad(x, cond, feats):
+            sigma, rgb = _FieldFn.apply(self, True, spr, x.reshape(-1, 3), cond, feats, *self._weights().values())
+            return rgb.view(*lead, 3), sigma.view(*lead, 1)
         sigma, rgb, _ = ops.direct.nerf_mlp_fwd(self.packed_weights(), self.dims, x.reshape(-1, 3), feats, cond, spr, True, False,
                                          self.precision)
         return rgb.view(*lead, 3), sigma.view(*lead, 1)

@@ -123,8 +123,8 @@ def test_tc_render_vs_reference():
                                   inp['N_samples'], ray_o.shape[0], field, inp['img_meta'], Projector(), 'image', 3,
                                   False, 0, True)
     oc = ret['outputs_coarse']
-    assert np.array_equal(oc['mask'].cpu().numpy(), g['mask'])
-    assert np.array_equal(oc['z_vals'].cpu().numpy(), g['z_vals'])
+    assert np.array_equal(oc['mask'].detach().cpu().numpy(), g['mask'])
+    assert np.array_equal(oc['z_vals'].detach().cpu().numpy(), g['z_vals'])
     for k in ('rgb', 'depth', 'weights', 'alpha', 'transparency'):
         assert_norm_close(oc[k], g[k], 1e-2, k)
     assert_norm_close(ret['sigma'], g['sigma'], 1e-2, 'sigma')
@@ -146,7 +146,7 @@ def test_tc_mlp_per_element_tolerance_report():
     rgb, sigma = field(x.to(DEV), d.to(DEV), f.to(DEV))
     out = {}
     for name, a, b in (('rgb', rgb, r_ref), ('sigma', sigma, s_ref)):
-        a, b = a.cpu().double().numpy(), b.double().numpy()
+        a, b = a.detach().cpu().double().numpy(), b.double().numpy()
         tol = 1e-2 * np.abs(b) + 1e-5 * np.abs(b).max()
         bad = np.abs(a - b) > tol
         out[name] = (float(bad.mean()), float(np.abs(a - b).max() / np.abs(b).max()))

@@ -165,7 +165,8 @@ def main():
     views = [s[:, :, :59, :80] for s in sets]
     n_vox = int(np.prod(grid))
     bytes_step = nv * c * 59 * 80 * 4 + 2 * c * n_vox * 4 + n_vox * 8 + nv * 48
-    variants = [dict(), dict(prefetch_stages=6), dict(stages=4), dict(views_per_stage=1)]
+    variants = [dict(), dict(stages=2), dict(stages=3), dict(stages=4), dict(stages=5), dict(stages=6), dict(views_per_stage=1),
+                dict(views_per_stage=1, stages=6), dict(prefetch_stages=6)]
     if args.quick:
         variants = variants[:1]
     for kw in variants:
