@@ -321,7 +321,7 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------
 # workload: lift
 # ------------------------------------------------------------------------------------------
-def lift_config(n_gpus, scaling, views_total, views_per_gpu, exchange, lanes, want_cov=True, overlap_sms=0):
+def lift_config(n_gpus, scaling, views_total, views_per_gpu, exchange, lanes, want_cov=True, overlap_sms=0, owner='every rank'):
     if n_gpus == 1:
         part = 'single GPU'
     elif exchange == 'multicast':
@@ -344,6 +344,7 @@ def lift_config(n_gpus, scaling, views_total, views_per_gpu, exchange, lanes, wa
                     'once per scene geometry and reused by the steps (ops.cached_lift_plan); fresh_geometry times the '
                     'step with the plan rebuilt every call',
         'partitioning': part, 'scenes_in_flight': lanes if lanes else 1, 'want_cov': want_cov, 'exchange_sms': overlap_sms if lanes else 'all',
+        'result_owner': owner,
     }
 
 
@@ -413,12 +414,16 @@ def bench_lift(args, rank, local_rank, world):
             peers, exchange, pipeline, n_lanes = None, 'nccl', False, 1
     use_peer = peers is not None
 
-    def step(feats, lane=0):
+    owner_rotate = bool(getattr(args, 'owner', 'all') == 'rotate') and n_gpus > 1
+
+    def step(feats, lane=0, scene=-1):
         f = feats[:, :, :FEAT_HW[0], :FEAT_HW[1]]
         if n_gpus == 1:
             return lifting.lift_mean_var(f, pts_d, proj_d, want_cov=want_cov)
         if use_peer:
-            return peers[lane](f, pts_d, proj_d, views_total)
+            # --owner rotate: scene i belongs to rank i % N (a data-parallel detector runs neck and heads of a scene on one
+            # GPU); only the owner receives the finished volumes
+            return peers[lane](f, pts_d, proj_d, views_total, owner=scene % n_gpus if owner_rotate and scene >= 0 else -1)
         return nd_dist.lift_mean_var_view_sharded(f, pts_d, proj_d, n_views_total=views_total, want_cov=want_cov)
 
     def barrier():
@@ -437,14 +442,14 @@ def bench_lift(args, rank, local_rank, world):
         out = None
         if not pipeline:
             for i in range(count):
-                out = step(dev_sets[i % N_INPUT_SETS])
+                out = step(dev_sets[i % N_INPUT_SETS], 0, i)
             return out
         cur = torch.cuda.current_stream()
         for st in dev_lanes:
             st.wait_stream(cur)
         for i in range(count):
             with torch.cuda.stream(dev_lanes[i % n_lanes]):
-                out = step(dev_sets[i % N_INPUT_SETS], i % n_lanes)
+                out = step(dev_sets[i % N_INPUT_SETS], i % n_lanes, i)
         for st in dev_lanes:
             cur.wait_stream(st)
         return out
@@ -641,7 +646,8 @@ def bench_lift(args, rank, local_rank, world):
             'metric': 'voxel_view_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': n_gpus,
             'steps': steps, 'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': lift_config(n_gpus, args.scaling, views_total, nv_local, exchange, n_lanes if pipeline else 0, want_cov, overlap_sms),
+            'config': lift_config(n_gpus, args.scaling, views_total, nv_local, exchange, n_lanes if pipeline else 0, want_cov, overlap_sms,
+                                  'the rank the scene belongs to (scene i -> rank i % N)' if owner_rotate and use_peer else 'every rank'),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': ncu_traffic(), 'peak_source': peak_src,
                          'algorithmic_bytes_per_step': bytes_per_step,
@@ -1036,6 +1042,9 @@ def main():
     ap.add_argument('--no-cov', action='store_true',
                     help='lift: mean and count only (the live path never reads the 256-channel volume_cov, SURVEY.md section 0.5); '
                          'a labelled variant of the workload: half the bytes are written, and half cross the links at N > 1')
+    ap.add_argument('--owner', default='all', choices=['all', 'rotate'],
+                    help='N > 1: which ranks receive the finished volumes of a scene: all of them (all-gather), or the rank the '
+                         'scene belongs to, rotating with the scene index (a data-parallel detector; halves the exchange bytes)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--lanes', type=int, default=2, help='N > 1, pipelined: scenes in flight (streams / peer segments)')

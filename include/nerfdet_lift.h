@@ -215,6 +215,10 @@ int nd_lift_backward(const nd_maps *features, const float *points, const float *
  *       the work, so that the exchange of one scene can run beside the accumulate of the next on the SMs that
  *       nd_lift_options.sm_limit keeps free (the exchange is bound by the links, not by the SMs).
  *     timeout_ms: bound of every wait for a peer (0 = 4000).
+ *     owner_rank: -1 = every rank receives the finished rows (all-gather); r >= 0 = only rank r does (the rank whose
+ *       scene this is: a data-parallel detector runs neck and heads of a scene on one GPU) -- the other ranks' outputs
+ *       are not written, and a GPU's links carry (G-1)/G x 52.5 MB of partial sums plus, averaged over rotating owners,
+ *       1/G of the rows instead of all of them.  All ranks must pass the same value.
  *   Outputs are complete on `stream` when the call's kernels have run.  A peer that does not arrive within the
  *   time-out raises word 2 * ND_MAX_PEERS + 1 (the error word) of EVERY rank's flag block instead of hanging; a rank
  *   that finds its error word set performs no reduce and no peer store, fills the rows it owns with NaN in its own
@@ -231,7 +235,7 @@ int nd_peer_free(void *ptr);
 int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
                            void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
                            int channels, int64_t n_voxels, const float *alpha, int64_t *count, const void *acc_mc,
-                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, void *stream);
+                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, int owner_rank, void *stream);
 
 
 /* ---------------------------------------------------------------------------------------

@@ -76,7 +76,7 @@ SIGNATURES = {
     'nd_peer_free': (c_int, [c_void_p]),
     'nd_lift_finalize_peers': (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                        c_int, c_int, ctypes.c_uint32, c_int, c_int, c_int64, c_void_p, c_void_p,
-                                       c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'nd_live_stats': (c_int, [POINTER(NdMaps), POINTER(NdMaps), c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'nd_map_features': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -34,6 +34,7 @@ struct PeerArgs {
     float *cov[kMaxPeers];           // all null: no covariance wanted
     uint32_t *flags[kMaxPeers];      // [0, P): ready, [P, 2P): done, [2P]: CTA counter, [2P + 1]: error
     int world, rank;
+    int owner;                       // >= 0: only this rank receives the finished rows (its scene); -1: every rank
     uint32_t epoch;
     unsigned long long timeout_ns;   // bound of every wait for a peer
     int n_views_total, channels, c_begin, c_end, ch_per_cta, n_tiles, n_items;
@@ -237,7 +238,7 @@ k_lift_finalize_peers(const PeerArgs a) {
                 } else {
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
-                        if (g < a.world) {
+                        if (g < a.world && (a.owner < 0 || g == a.owner)) {
                             st_vec<V>(a.mean[g] + o, m);
                             if constexpr (COV) st_vec<V>(a.cov[g] + o, cv);
                         }
@@ -330,7 +331,7 @@ int nd_peer_free(void *ptr) {
 int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, void *const *cov_host,
                            void *const *flags_host, int world, int rank, uint32_t epoch, int n_views_total,
                            int channels, int64_t n_voxels, const float *alpha, int64_t *count, const void *acc_mc,
-                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, void *stream) {
+                           void *mean_mc, void *cov_mc, int max_ctas, int timeout_ms, int owner_rank, void *stream) {
     ND_REQUIRE(acc_host && mean_host && flags_host, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: null pointer table");
     ND_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, ND_ERR_BAD_ARG,
                "nd_lift_finalize_peers: world %d / rank %d outside [1, %d]", world, rank, kMaxPeers);
@@ -348,8 +349,12 @@ int nd_lift_finalize_peers(const void *const *acc_host, void *const *mean_host, 
         vec = vec && reinterpret_cast<uintptr_t>(a.s1[g]) % 16 == 0 && reinterpret_cast<uintptr_t>(a.mean[g]) % 16 == 0 &&
               reinterpret_cast<uintptr_t>(a.cov[g]) % 16 == 0 && ((int64_t)channels * n_voxels) % 4 == 0;
     }
+    ND_REQUIRE(owner_rank >= -1 && owner_rank < world, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: owner rank %d outside [-1, %d)",
+               owner_rank, world);
+    ND_REQUIRE(owner_rank < 0 || acc_mc == nullptr, ND_ERR_BAD_ARG, "nd_lift_finalize_peers: the multicast transport stores to every rank");
     a.world = world;
     a.rank = rank;
+    a.owner = owner_rank;
     a.epoch = epoch;
     a.timeout_ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 4000) * 1000000ull;
     a.n_views_total = n_views_total;

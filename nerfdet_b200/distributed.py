@@ -268,8 +268,9 @@ class PeerLift:
         return ranks
 
     # -- the op ---------------------------------------------------------------------------------
-    def exchange(self, n_views_total: int, alpha: Optional[torch.Tensor] = None):
-        """Reduce + finalise the accumulators already in ``self.acc`` (epoch advances by one)."""
+    def exchange(self, n_views_total: int, alpha: Optional[torch.Tensor] = None, owner: int = -1):
+        """Reduce + finalise the accumulators already in ``self.acc`` (epoch advances by one).  ``owner`` >= 0: only that
+        rank receives the result (returns ``(None, None, count)`` elsewhere); every rank must pass the same value."""
         from . import ops
         ctypes = self._ct
         if alpha is not None:
@@ -291,7 +292,7 @@ class PeerLift:
             ctypes.c_void_p(self.count.data_ptr()),
             ctypes.c_void_p(mc + self._off_acc) if mc else None, ctypes.c_void_p(mc + self._off_mean) if mc else None,
             ctypes.c_void_p(mc + self._off_cov) if mc and self.want_cov else None,
-            self.overlap_sms, self.timeout_ms, stream.cuda_stream), 'nd_lift_finalize_peers')
+            self.overlap_sms, self.timeout_ms, int(owner), stream.cuda_stream), 'nd_lift_finalize_peers')
         with torch.cuda.stream(stream):
             w = 2 * self._lib.ND_MAX_PEERS + 1
             self._err_host.copy_(self.flags[w:w + 1], non_blocking=True)
@@ -299,11 +300,16 @@ class PeerLift:
             ev = torch.cuda.Event()
             ev.record(stream)
             _last_exchange[self.device.index] = ev
+        if owner >= 0 and owner != self.rank:
+            return None, None, self.count
         return self.mean, (self.cov if self.want_cov else None), self.count
 
     def __call__(self, features_local: torch.Tensor, points: torch.Tensor, projection_local: torch.Tensor,
-                 n_views_total: int, alpha: Optional[torch.Tensor] = None):
-        """Same results on every rank as ``lifting.lift_mean_var`` over all views (see class docstring for lifetime)."""
+                 n_views_total: int, alpha: Optional[torch.Tensor] = None, owner: int = -1):
+        """Same results on every rank as ``lifting.lift_mean_var`` over all views (see class docstring for lifetime).
+        ``owner`` >= 0 (same value on every rank): the scene belongs to that rank -- a data-parallel detector runs the neck
+        and heads of a scene on one GPU -- and only it receives mean / cov (``None`` elsewhere); the result rows then cross
+        the links once instead of G - 1 times."""
         from . import ops
         if features_local.shape[1] != self.channels or points[0].numel() != self.n_voxels:
             raise ValueError('PeerLift was built for another shape')
@@ -311,7 +317,9 @@ class PeerLift:
         if self.overlap_sms:
             sm_limit = max(torch.cuda.get_device_properties(self.device).multi_processor_count - self.overlap_sms, 1)
         ops.lift_accumulate_planned(features_local, points, projection_local, self.acc, sm_limit, self.want_cov)
-        mean, cov, count = self.exchange(n_views_total, alpha)
+        mean, cov, count = self.exchange(n_views_total, alpha, owner)
+        if mean is None:
+            return None, None, None
         shape = tuple(points.shape[1:]) if points.dim() == 4 else (self.n_voxels,)
         return (mean.view(self.channels, *shape), cov.view(self.channels, *shape) if cov is not None else None,
                 count.view(1, *shape))

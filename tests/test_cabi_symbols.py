@@ -64,12 +64,14 @@ def test_peer_entry_points_validate_arguments_without_a_gpu():
     from nerfdet_b200 import _lib
     lib = _lib.load()
     null = ctypes.POINTER(ctypes.c_void_p)()
-    args = (1, 0, 1, 4, 2, 8, None, None, None, None, None, 0, 0, None)
+    args = (1, 0, 1, 4, 2, 8, None, None, None, None, None, 0, 0, -1, None)
     assert lib.nd_lift_finalize_peers(null, null, null, null, *args) == 1                 # ND_ERR_BAD_ARG: no tables
     assert b'null' in lib.nd_last_error_string()
     one = (ctypes.c_void_p * 1)(ctypes.c_void_p(256))
-    assert lib.nd_lift_finalize_peers(one, one, None, one, 9, 0, 1, 4, 2, 8, None, None, None, None, None, 0, 0, None) == 1
+    assert lib.nd_lift_finalize_peers(one, one, None, one, 9, 0, 1, 4, 2, 8, None, None, None, None, None, 0, 0, -1, None) == 1
     assert b'world' in lib.nd_last_error_string()                                         # more ranks than ND_MAX_PEERS
-    assert lib.nd_lift_finalize_peers(one, one, None, one, 1, 0, 0, 4, 2, 8, None, None, None, None, None, 0, 0, None) == 1
+    assert lib.nd_lift_finalize_peers(one, one, None, one, 1, 0, 0, 4, 2, 8, None, None, None, None, None, 0, 0, -1, None) == 1
     assert b'epoch' in lib.nd_last_error_string()                                         # epoch 0 = initial flag state
+    assert lib.nd_lift_finalize_peers(one, one, None, one, 1, 0, 1, 4, 2, 8, None, None, None, None, None, 0, 0, 3, None) == 1
+    assert b'owner' in lib.nd_last_error_string()                                         # owner outside the world
     assert lib.nd_peer_close(None) == 0 and lib.nd_peer_free(None) == 0

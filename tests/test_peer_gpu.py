@@ -96,6 +96,46 @@ def test_in_process_ranks_match_all_views(world, overlap):
             peer.close()
 
 
+@pytest.mark.parametrize('world,overlap', [(2, 0), (4, 2), (8, 0)])
+def test_owner_rank_receives_the_scene(world, overlap):
+    """owner >= 0: only that rank's outputs are written (bit-identical to the all-gather form), the owner rotates with the scene."""
+    nv, grid, channels = 19, (16, 16, 8), 20
+    n = int(np.prod(grid))
+    f, pts, proj = _scene(nv, grid, (0.4, 0.4, 0.4), channels, 95)
+    ranks = nd_dist.PeerLift.local_group(world, channels, n, DEV, overlap_sms=overlap)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    try:
+        def run(owner):
+            outs = []
+            for r, (peer, st) in enumerate(zip(ranks, streams)):
+                b, e = nd_dist.view_shard(nv, r, world)
+                with torch.cuda.stream(st):
+                    outs.append(peer(f[b:e], pts, proj[b:e], nv, owner=owner))
+            torch.cuda.synchronize()
+            return outs
+        full = [(m.clone(), c.clone(), k.clone()) for m, c, k in run(-1)]
+        for peer in ranks:
+            peer.mean.fill_(-7.0)
+            peer.cov.fill_(-7.0)
+        for scene in range(world + 1):
+            owner = scene % world
+            outs = run(owner)
+            for r, o in enumerate(outs):
+                if r == owner:
+                    assert torch.equal(o[0], full[r][0]) and torch.equal(o[1], full[r][1]) and torch.equal(o[2], full[r][2])
+                else:
+                    assert o[0] is None and o[1] is None
+            if scene == 0:                                   # nobody but the owner was written to
+                for r, peer in enumerate(ranks):
+                    if r != owner:
+                        assert float(peer.mean.max()) == -7.0 and float(peer.cov.min()) == -7.0
+        for peer in ranks:
+            peer.check()
+    finally:
+        for peer in ranks:
+            peer.close()
+
+
 @pytest.mark.parametrize('world,overlap', [(2, 0), (8, 0), (2, 3), (8, 2)])
 def test_in_process_ranks_without_variance(world, overlap):
     """want_cov=False: the accumulators are [S1 | count], the exchange moves half the bytes and only the mean comes back."""
