@@ -336,6 +336,19 @@ int nd_render_gather_stats(const float *pts, int64_t n_points, const float *came
                            uint8_t *pixel_mask, float *pixel_locations, uint8_t *in_front, float *view_features, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Backward of nd_render_gather_stats with respect to the mapped feature maps (what autograd
+ * computes for projection.py:91-151 + render_ray.py:71-93).
+ *   featmaps        f32 channels-last [nv][h][w][D] contiguous (D <= 32, D % 4 == 0): the forward's input
+ *   globalfeat      f32 [P][2 * (3 + D)]: the forward's output;  grad_globalfeat: the incoming gradient, same shape
+ *   grad_featmaps   f32 [nv][h][w][D], ZEROED by the caller: the gradient is accumulated with vector reductions
+ *   image_height / image_width: the size of the image stack the forward sampled (only its masks enter here)
+ * The images and the sample positions get no gradient.
+ * ------------------------------------------------------------------------------------- */
+int nd_render_gather_stats_bwd(const float *pts, int64_t n_points, const float *cameras, int n_views, int image_height,
+                               int image_width, const nd_maps *featmaps, const float *globalfeat, const float *grad_globalfeat,
+                               float *grad_featmaps, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * R7  render_ray.py:196-247  raw2outputs: alpha = 1 - exp(-sigma) (no interval term), T = cumprod(1 - alpha + 1e-10)
  * shifted, weights = alpha * T, rgb = sum w rgb, depth = sum w z / (sum w + 1e-8) clamped to z_bounds = {min, max} of
  * the whole batch's z_vals (render_ray.py:236; 2 floats in DEVICE memory so that no host sync is needed),

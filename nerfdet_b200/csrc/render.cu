@@ -418,6 +418,150 @@ k_render_gather_stats_cl(const float *__restrict__ pts, int64_t n_pts, const flo
     }
 }
 
+// Backward of the same statistics with respect to the mapped feature maps (row N1; autograd of projection.py:91-151 +
+// render_ray.py:71-93 for `featmaps`).  Per sample and channel, with denom = count + 1e-8, mean and e = exp(-var) from the
+// forward's output row and g_mean, g_e the incoming gradients:  g_var = -e * g_e and every listed view receives
+//   g_f = m_v * (g_mean / denom - 2 g_var (S1 - nv * mean) / denom^2) + 2 g_var (f_v - mean) / denom
+// (m_v = the view mask, S1 = the sum of f over ALL views), which the bilinear weights spread over the four corners
+// (zeros padding: corners outside the map take nothing).  Same phases as the forward kernel: list the visible views, walk
+// the list once for S1, once more to recompute f_v and scatter -- 16-byte vector reductions (red.global.add.v4.f32) into
+// the channels-last gradient.  The images get no gradient (they are input data).
+__device__ __forceinline__ void red_add_f4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kRcWarps * 32, 3)
+k_render_gather_stats_bwd(const float *__restrict__ pts, int64_t n_pts, const float *__restrict__ cams, int nv, int list_cap,
+                          int hi, int wi, const float *__restrict__ feat, int f_sv, int f_sy, int f_sx, int d, int hf, int wf,
+                          const float *__restrict__ glob, const float *__restrict__ g_glob, float *__restrict__ g_feat) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ViewEntry *sL = reinterpret_cast<ViewEntry *>(smem_raw) + (size_t)(threadIdx.x >> 5) * list_cap;  // [warps][list_cap >= nv]
+    float *sP = reinterpret_cast<float *>(smem_raw + sizeof(ViewEntry) * (size_t)list_cap * kRcWarps);
+    for (int i = threadIdx.x; i < nv * 12; i += blockDim.x) {
+        const int v = i / 12, rc = i - v * 12, r = rc >> 2, c = rc & 3;
+        const float *K = cams + v * 34 + 2, *E = cams + v * 34 + 18;
+        float t = __fmul_rn(K[r * 4 + 0], E[0 * 4 + c]);                   // see k_render_gather_stats
+        t = __fadd_rn(t, __fmul_rn(K[r * 4 + 1], E[1 * 4 + c]));
+        t = __fadd_rn(t, __fmul_rn(K[r * 4 + 2], E[2 * 4 + c]));
+        t = __fadd_rn(t, __fmul_rn(K[r * 4 + 3], E[3 * 4 + c]));
+        sP[i] = t;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, quarter = lane >> 3, l8 = lane & 7;
+    const float h = cams[0], w = cams[1];
+    const float wm1 = __fsub_rn(w, 1.0f), hm1 = __fsub_rn(h, 1.0f);
+    const int ct = 3 + d;
+    const unsigned full = 0xffffffffu, below = (1u << lane) - 1u;
+    const bool feat_lane = 4 * l8 < d;
+    const int c_off = feat_lane ? 4 * l8 : 0;
+    const int64_t stride = (int64_t)gridDim.x * kRcWarps;
+    for (int64_t p = (int64_t)blockIdx.x * kRcWarps + warp; p < n_pts; p += stride) {
+        const float X = __ldg(pts + p * 3), Y = __ldg(pts + p * 3 + 1), Z = __ldg(pts + p * 3 + 2);
+        int cnt = 0, n_list = 0;
+        for (int v0 = 0; v0 < nv; v0 += 32) {                              // phase 1: the forward's, feature map only
+            const int v = v0 + lane;
+            bool m = false, listed = false;
+            ViewEntry e;
+            if (v < nv) {
+                const float *P = sP + v * 12;
+                const float q0 = chain4(P, X, Y, Z), q1 = chain4(P + 4, X, Y, Z), q2 = chain4(P + 8, X, Y, Z);
+                const float zc = fmaxf(q2, 1e-8f);
+                float px = __fdiv_rn(q0, zc), py = __fdiv_rn(q1, zc);
+                px = fminf(fmaxf(px, -1e6f), 1e6f);
+                py = fminf(fmaxf(py, -1e6f), 1e6f);
+                const bool front = q2 > 0.0f;
+                const bool inb = (px <= wm1) && (px >= 0.0f) && (py <= hm1) && (py >= 0.0f);
+                m = inb && front;
+                const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, px), wm1), 1.0f);
+                const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, py), hm1), 1.0f);
+                const ViewSampleG sf = make_sample_g(gx, gy, hf, wf);
+                listed = sf.inb != 0u;
+                const int xf = clampi(sf.x0, 0, wf - 1), yf = clampi(sf.y0, 0, hf - 1);
+                e.offI = 0;
+                e.offF = v * f_sv + yf * f_sy + xf * f_sx;
+                e.bits = (sf.inb << 4) | ((sf.x0 >= 0 && sf.x0 + 1 < wf) ? 0x800u : 0u) | ((sf.y0 >= 0 && sf.y0 + 1 < hf) ? 0x1000u : 0u);
+                e.maskf = m ? 1.0f : 0.0f;
+                e.wI[0] = e.wI[1] = e.wI[2] = e.wI[3] = 0.0f;
+                e.wF[0] = (1.0f - sf.fx) * (1.0f - sf.fy); e.wF[1] = sf.fx * (1.0f - sf.fy);
+                e.wF[2] = (1.0f - sf.fx) * sf.fy;          e.wF[3] = sf.fx * sf.fy;
+            }
+            cnt += __popc(__ballot_sync(full, m));
+            const unsigned act = __ballot_sync(full, listed);
+            if (listed) sL[n_list + __popc(act & below)] = e;
+            n_list += __popc(act);
+        }
+        __syncwarp();
+        // the bilinear value of a listed view for this lane's four channels
+        auto value = [&](int i, float (&f)[4], uint32_t &b, float4 &w4, const float *&q, int &dxf, int &dyf, float &mvf) {
+            const int4 a4 = *reinterpret_cast<const int4 *>(&sL[i]);
+            w4 = *reinterpret_cast<const float4 *>(sL[i].wF);
+            b = (uint32_t)a4.z;
+            mvf = __int_as_float(a4.w);
+            q = feat + c_off + a4.y;
+            dxf = (b & 0x800u) ? f_sx : 0;
+            dyf = (b & 0x1000u) ? f_sy : 0;
+            const float4 c0 = load4<float>(q), c1 = load4<float>(q + dxf), c2 = load4<float>(q + dyf), c3 = load4<float>(q + dyf + dxf);
+            const float a0[4] = {c0.x, c0.y, c0.z, c0.w}, a1[4] = {c1.x, c1.y, c1.z, c1.w};
+            const float a2[4] = {c2.x, c2.y, c2.z, c2.w}, a3[4] = {c3.x, c3.y, c3.z, c3.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float t = 0.0f;
+                if (b & 0x10u) t = fmaf(a0[k], w4.x, t);
+                if (b & 0x20u) t = fmaf(a1[k], w4.y, t);
+                if (b & 0x40u) t = fmaf(a2[k], w4.z, t);
+                if (b & 0x80u) t = fmaf(a3[k], w4.w, t);
+                f[k] = t;
+            }
+        };
+        float s1[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = quarter; i < n_list; i += 4) {                        // pass A: sum over all views
+            float f[4], mvf;
+            uint32_t b;
+            float4 w4;
+            const float *q;
+            int dxf, dyf;
+            value(i, f, b, w4, q, dxf, dyf, mvf);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s1[k] += f[k];
+        }
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s1[k] += __shfl_xor_sync(full, s1[k], o);
+        const float denom = __fadd_rn((float)cnt, 1e-8f);
+        const float *row = glob + p * (int64_t)(2 * ct), *grow = g_glob + p * (int64_t)(2 * ct);
+        float cm[4], cb[4], mean[4];                                       // g_f = m_v * cm + cb * (f - mean)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ch = 3 + c_off + k;
+            mean[k] = feat_lane ? row[ch] : 0.0f;
+            const float gvar = feat_lane ? -row[ct + ch] * grow[ct + ch] : 0.0f;
+            const float gm = feat_lane ? grow[ch] : 0.0f;
+            cb[k] = 2.0f * gvar / denom;
+            cm[k] = gm / denom - cb[k] * (s1[k] - (float)nv * mean[k]) / denom;
+        }
+        if (feat_lane) {
+            for (int i = quarter; i < n_list; i += 4) {                    // pass B: recompute, scatter
+                float f[4], mvf;
+                uint32_t b;
+                float4 w4;
+                const float *q;
+                int dxf, dyf;
+                value(i, f, b, w4, q, dxf, dyf, mvf);
+                float g[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) g[k] = fmaf(mvf, cm[k], cb[k] * (f[k] - mean[k]));
+                float *gq = g_feat + (q - feat);
+                if (b & 0x10u) red_add_f4(gq, g[0] * w4.x, g[1] * w4.x, g[2] * w4.x, g[3] * w4.x);
+                if (b & 0x20u) red_add_f4(gq + dxf, g[0] * w4.y, g[1] * w4.y, g[2] * w4.y, g[3] * w4.y);
+                if (b & 0x40u) red_add_f4(gq + dyf, g[0] * w4.z, g[1] * w4.z, g[2] * w4.z, g[3] * w4.z);
+                if (b & 0x80u) red_add_f4(gq + dyf + dxf, g[0] * w4.w, g[1] * w4.w, g[2] * w4.w, g[3] * w4.w);
+            }
+        }
+        __syncwarp();                                                      // the list is free for the next sample
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // R7
 // -------------------------------------------------------------------------------------------------
@@ -623,6 +767,41 @@ int nd_render_gather_stats(const float *pts, int64_t n_points, const float *came
         return ND_ERR_CUDA;
     }
     ND_CUDA_LAUNCH_CHECK("k_render_gather_stats");
+    return ND_OK;
+}
+
+int nd_render_gather_stats_bwd(const float *pts, int64_t n_points, const float *cameras, int n_views, int image_height,
+                               int image_width, const nd_maps *featmaps, const float *globalfeat, const float *grad_globalfeat,
+                               float *grad_featmaps, void *stream) {
+    ND_REQUIRE(pts && cameras && featmaps && featmaps->data && globalfeat && grad_globalfeat && grad_featmaps, ND_ERR_BAD_ARG,
+               "nd_render_gather_stats_bwd: null pointer");
+    ND_REQUIRE(n_views > 0 && featmaps->n_views == n_views && n_points >= 0 && image_height > 0 && image_width > 0,
+               ND_ERR_BAD_SHAPE, "nd_render_gather_stats_bwd: bad shape");
+    ND_REQUIRE(featmaps->dtype == ND_F32 && featmaps->stride_c == 1 && featmaps->channels > 0 && featmaps->channels <= 32 &&
+                   featmaps->channels % 4 == 0 && featmaps->stride_x == featmaps->channels &&
+                   featmaps->stride_y == (int64_t)featmaps->width * featmaps->channels &&
+                   featmaps->stride_v == (int64_t)featmaps->height * featmaps->width * featmaps->channels &&
+                   (reinterpret_cast<uintptr_t>(featmaps->data) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad_featmaps) & 15) == 0,
+               ND_ERR_BAD_SHAPE, "nd_render_gather_stats_bwd: contiguous channels-last f32 maps [nv][h][w][D], D <= 32, D %% 4 == 0");
+    if (n_points == 0) return ND_OK;
+    const int list_cap = (n_views + 31) & ~31;
+    const size_t sm = (size_t)n_views * 12 * sizeof(float) + sizeof(ViewEntry) * (size_t)list_cap * kRcWarps;
+    ND_REQUIRE(sm <= 200 * 1024, ND_ERR_BAD_SHAPE, "nd_render_gather_stats_bwd: too many views (%d)", n_views);
+    ND_REQUIRE((int64_t)n_views * featmaps->stride_v < (1ll << 31), ND_ERR_BAD_SHAPE, "nd_render_gather_stats_bwd: maps beyond 2^31 elements");
+    cudaError_t e = cudaFuncSetAttribute(k_render_gather_stats_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) {
+        set_error("nd_render_gather_stats_bwd: %s", cudaGetErrorString(e));
+        return ND_ERR_CUDA;
+    }
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned g = (unsigned)std::min<int64_t>(ceil_div(n_points, (int64_t)kRcWarps), (int64_t)sms * 3);
+    k_render_gather_stats_bwd<<<g, kRcWarps * 32, sm, (cudaStream_t)stream>>>(
+        pts, n_points, cameras, n_views, list_cap, image_height, image_width, (const float *)featmaps->data, (int)featmaps->stride_v,
+        (int)featmaps->stride_y, (int)featmaps->stride_x, featmaps->channels, featmaps->height, featmaps->width, globalfeat,
+        grad_globalfeat, grad_featmaps);
+    ND_CUDA_LAUNCH_CHECK("k_render_gather_stats_bwd");
     return ND_OK;
 }
 

@@ -986,6 +986,38 @@ def _(volume, count, bf16):
     return (volume.new_empty((n, c), dtype=torch.bfloat16 if bf16 else torch.float32), volume.new_empty((n,)))
 
 
+@torch.library.custom_op(f'{_NS}::render_gather_stats_bwd', mutates_args=())
+@_guarded
+def render_gather_stats_bwd(pts: Tensor, cameras: Tensor, image_height: int, image_width: int, featmaps: Tensor,
+                            globalfeat: Tensor, grad_globalfeat: Tensor) -> Tensor:
+    """Row N1: gradient of ``render_gather_stats``' ``globalfeat`` with respect to ``featmaps`` (``[nv, D, h, w]``,
+    float32): a ``[nv, D, h, w]`` tensor with channels-last strides.  Reference: autograd of projection.py:91-151 +
+    render_ray.py:71-93."""
+    _need_cuda(pts, cameras, featmaps, globalfeat, grad_globalfeat)
+    if featmaps.dtype != torch.float32 or featmaps.dim() != 4:
+        raise ValueError('featmaps must be float32 [nv, D, h, w]')
+    fm = featmaps.contiguous(memory_format=torch.channels_last)
+    m = _maps(fm)
+    p = pts.shape[0]
+    ct = 3 + m.channels
+    if tuple(globalfeat.shape) != (p, 2 * ct) or tuple(grad_globalfeat.shape) != (p, 2 * ct):
+        raise ValueError(f'globalfeat and its gradient must be [{p}, {2 * ct}]')
+    pts, cameras = pts.contiguous(), cameras.contiguous()
+    globalfeat, grad_globalfeat = globalfeat.contiguous().float(), grad_globalfeat.contiguous().float()
+    grad = torch.zeros((m.n_views, m.height, m.width, m.channels), dtype=torch.float32, device=pts.device)
+    lib = _lib.load()
+    _lib.check(lib.nd_render_gather_stats_bwd(_ptr(pts), p, _ptr(cameras), m.n_views, int(image_height), int(image_width),
+                                              ctypes.byref(m), _ptr(globalfeat), _ptr(grad_globalfeat), _ptr(grad), _stream()),
+               'nd_render_gather_stats_bwd')
+    return grad.permute(0, 3, 1, 2)
+
+
+@render_gather_stats_bwd.register_fake
+def _(pts, cameras, image_height, image_width, featmaps, globalfeat, grad_globalfeat):
+    nv, d, h, w = featmaps.shape
+    return featmaps.new_empty((nv, h, w, d)).permute(0, 3, 1, 2)
+
+
 # ------------------------------------------------------------------------------------------
 # Autograd of the registered ops (SURVEY.md section 8f, row N1).  lift_mean_var: nd_lift_backward; map_features: the two
 # plain GEMMs of a Linear's backward go to cuBLAS through torch (library GEMMs, not a hot kernel of this path).
@@ -1045,5 +1077,5 @@ class _Direct:
 direct = _Direct()
 for _name in ('project_voxels', 'backproject', 'lift_mean_var', 'lift_accumulate', 'lift_accumulate_into', 'lift_finalize',
               'map_features', 'live_stats', 'nerf_mlp_fwd', 'sample_rays', 'render_gather_stats', 'composite', 'volume_sample',
-              'lift_backward', 'generate_rays', 'denorm_images', 'image_metrics', 'depth_sqerr', 'volume_to_neck'):
+              'lift_backward', 'generate_rays', 'denorm_images', 'image_metrics', 'depth_sqerr', 'volume_to_neck', 'render_gather_stats_bwd'):
     setattr(direct, _name, globals()[_name]._init_fn)

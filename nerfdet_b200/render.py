@@ -93,10 +93,66 @@ def _composite(rgb_pts, sigma_pts, z_vals, mask, white_bkgd=False, det=False):
         bounds = torch.stack([z_vals[0, 0], z_vals[0, -1]])
     else:
         bounds = torch.stack(torch.aminmax(z_vals))
-    rgb, depth, weights, alpha, trans, ray_mask = ops.direct.composite(rgb_pts, sigma_pts, z_vals, mask, bounds, bool(white_bkgd))
+    if torch.is_grad_enabled() and (rgb_pts.requires_grad or sigma_pts.requires_grad):
+        rgb, depth, weights, alpha, trans, ray_mask = _CompositeFn.apply(rgb_pts.contiguous(), sigma_pts.contiguous(), z_vals, mask,
+                                                                         bounds, bool(white_bkgd))
+    else:
+        rgb, depth, weights, alpha, trans, ray_mask = ops.direct.composite(rgb_pts, sigma_pts, z_vals, mask, bounds, bool(white_bkgd))
     return OrderedDict([('rgb', rgb), ('depth', depth), ('weights', weights),
                         ('mask', ray_mask if mask is not None else None), ('alpha', alpha), ('z_vals', z_vals),
                         ('transparency', trans)])
+
+
+class _GatherStatsFn(torch.autograd.Function):
+    """``render_gather_stats`` with a gradient for the mapped feature maps (row N1, ``nd_render_gather_stats_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, flat, cameras, img, features_2D):
+        glob, _, pixel_mask, _, _, _ = ops.direct.render_gather_stats(flat, cameras, img, features_2D.detach(), False, False, False)
+        ctx.save_for_backward(flat, cameras, features_2D, glob)
+        ctx.img_hw = tuple(img.shape[-2:])
+        ctx.mark_non_differentiable(pixel_mask)
+        return glob, pixel_mask
+
+    @staticmethod
+    def backward(ctx, g_glob, _g_mask):
+        flat, cameras, features_2D, glob = ctx.saved_tensors
+        grad = ops.direct.render_gather_stats_bwd(flat, cameras, ctx.img_hw[0], ctx.img_hw[1], features_2D.detach(), glob, g_glob)
+        return None, None, None, grad
+
+
+class _CompositeFn(torch.autograd.Function):
+    """``nd_composite`` forward; the backward differentiates the same formula (render_ray.py:196-247) written in torch ops
+    on the saved inputs -- a few element-wise kernels on ``[rays, samples]`` tensors."""
+
+    @staticmethod
+    def forward(ctx, rgb_pts, sigma_pts, z_vals, mask, bounds, white_bkgd):
+        out = ops.direct.composite(rgb_pts, sigma_pts, z_vals, mask, bounds, white_bkgd)
+        ctx.save_for_backward(rgb_pts, sigma_pts, z_vals, bounds)
+        ctx.white_bkgd = white_bkgd
+        ctx.mark_non_differentiable(out[5])
+        return out
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_weights, g_alpha, g_trans, _g_mask):
+        rgb_pts, sigma_pts, z_vals, bounds = ctx.saved_tensors
+        with torch.enable_grad():
+            rgb = rgb_pts.detach().requires_grad_(True)
+            sigma = sigma_pts.detach().requires_grad_(True)
+            alpha = 1. - torch.exp(-sigma)
+            trans = torch.cumprod(1. - alpha + 1e-10, dim=-1)[:, :-1]
+            trans = torch.cat((torch.ones_like(trans[:, 0:1]), trans), dim=-1)
+            weights = alpha * trans
+            rgb_map = torch.sum(weights.unsqueeze(2) * rgb, dim=1)
+            if ctx.white_bkgd:
+                rgb_map = rgb_map + (1. - torch.sum(weights, dim=-1, keepdim=True))
+            depth = torch.sum(weights * z_vals, dim=-1) / (torch.sum(weights, dim=-1) + 1e-8)
+            depth = torch.maximum(torch.minimum(depth, bounds[1]), bounds[0])
+            outs = [rgb_map, depth, weights, alpha, trans]
+            gouts = [g_rgb, g_depth, g_weights, g_alpha, g_trans]
+            pairs = [(o, g) for o, g in zip(outs, gouts) if g is not None]
+            g_in = torch.autograd.grad([o for o, _ in pairs], [rgb, sigma], [g for _, g in pairs], allow_unused=True)
+        return g_in[0], g_in[1], None, None, None, None
 
 
 def render_rays_func(ray_o, ray_d, mean_volume, cov_volume, features_2D, img, aabb, near_far_range, N_samples,
@@ -113,7 +169,10 @@ def render_rays_func(ray_o, ray_d, mean_volume, cov_volume, features_2D, img, aa
     cameras = _device_cameras(img_meta, pts.device)
     flat = pts.view(-1, 3)
     if mode == 'image':
-        glob, _, pixel_mask, _, _, _ = ops.direct.render_gather_stats(flat, cameras, img, features_2D, False, False, False)
+        if torch.is_grad_enabled() and features_2D.requires_grad:
+            glob, pixel_mask = _GatherStatsFn.apply(flat, cameras, img, features_2D)
+        else:
+            glob, _, pixel_mask, _, _, _ = ops.direct.render_gather_stats(flat, cameras, img, features_2D, False, False, False)
         rgb_pts, density_pts = nerf_mlp(pts, ray_d, glob.view(n_rays, n_samples, -1))
         ret['sigma'] = density_pts
     elif mode == 'volume':
