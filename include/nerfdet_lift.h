@@ -262,6 +262,16 @@ int nd_live_stats(const nd_maps *mapped, const nd_maps *rgb, const float *points
                   const float *rgb_projection, int64_t n_voxels, const float *map_bias, float *global_volume,
                   float *mean35, float *cov35, int64_t *count, void *stream);
 
+/* Backward of the mapped channels of nd_live_stats (autograd of nerfdet.py:232-253 with
+ * respect to the mapped features and, through the invalid views, the mapping's bias -- SURVEY.md section 0.6).
+ *   mapped          f32 channels-last [nv][h][w][Cm] contiguous, the forward's input
+ *   global_volume   the forward's output [N][2 * (3 + Cm)], grad_global_volume the incoming gradient
+ *   grad_mapped     f32 [nv][h][w][Cm] and grad_bias f32 [Cm], both ZEROED by the caller (accumulated with reductions)
+ * The RGB channels carry no gradient (input images). */
+int nd_live_stats_bwd(const nd_maps *mapped, const float *points, const float *projection, int64_t n_voxels,
+                      const float *map_bias, const float *global_volume, const float *grad_global_volume,
+                      float *grad_mapped, float *grad_bias, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * M  nerf_mlp.py:11-234  VanillaNeRFRadianceField (NerfMLP + SinusoidalEncoder), as instantiated at
  * nerfdet.py:62-69.  The struct carries the reference state_dict tensors (row-major [out][in] f32 DEVICE

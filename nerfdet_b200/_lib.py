@@ -72,6 +72,8 @@ SIGNATURES = {
     'nd_volume_to_neck': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     'nd_render_gather_stats_bwd': (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, POINTER(NdMaps), c_void_p, c_void_p,
                                            c_void_p, c_void_p]),
+    'nd_live_stats_bwd': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
     'nd_peer_alloc': (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
     'nd_peer_open': (c_int, [c_void_p, POINTER(c_void_p)]),
     'nd_peer_close': (c_int, [c_void_p]),

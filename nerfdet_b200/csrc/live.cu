@@ -179,6 +179,71 @@ k_live_stats_cl(const T *__restrict__ mapped, int64_t m_sv, int64_t m_sy, int64_
     }
 }
 
+// Backward of the mapped channels of the same statistics (row N1): with x_u the value of view u (the mapped feature for a
+// valid view, the Linear bias for an invalid one), S1 = sum_u x_u, m = S1 / denom, var = sum_u (x_u - m)^2 / denom,
+//   g_x = g_m / denom + g_var * (2 (x_u - m) / denom - 2 (S1 - nv m) / denom^2),   g_var = -exp(-var) * g_cov (0 if count = 0)
+// for EVERY view: valid views scatter it to their pixel of the channels-last gradient (one coalesced 128-byte reduction per
+// warp), the nv - count invalid views add theirs to the gradient of the bias.  Same walk as the forward kernel, twice: once
+// for S1, once to scatter.  The RGB channels carry no gradient (input images).
+__global__ void __launch_bounds__(kLcWarps * 32)
+k_live_stats_bwd(const float *__restrict__ mapped, int64_t m_sv, int64_t m_sy, int64_t m_sx, int cm, int hf, int wf,
+                 const float *__restrict__ points, const float *__restrict__ proj_f, int nv, int64_t n_vox,
+                 const float *__restrict__ bias, const float *__restrict__ glob, const float *__restrict__ g_glob,
+                 float *__restrict__ g_mapped, float *__restrict__ g_bias) {
+    extern __shared__ float sp[];                       // [nv][12] feature-level
+    for (int i = threadIdx.x; i < nv * 12; i += blockDim.x) sp[i] = proj_f[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const float b = lane < cm ? bias[lane] : 0.0f;
+    const int ct = 3 + cm;
+    const int64_t n = (int64_t)blockIdx.x * kLcWarps + warp;
+    if (n >= n_vox) return;                                                // warp-uniform
+    const float X = __ldg(points + n), Y = __ldg(points + n_vox + n), Z = __ldg(points + 2 * n_vox + n);
+    float cm_ = 0.f, cb = 0.f, mean = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+        float s1 = 0.f;
+        int cnt = 0;
+        for (int v0 = 0; v0 < nv; v0 += 32) {
+            const int v = v0 + lane;
+            bool ok_f = false;
+            int off_f = 0;
+            if (v < nv) {
+                float xr, yr, q2;
+                ok_f = project_nearest(sp + v * 12, X, Y, Z, hf, wf, xr, yr, q2);
+                if (ok_f) off_f = (int)((int)yr * m_sy + (int)xr * m_sx);
+            }
+            unsigned act = __ballot_sync(full, ok_f);
+            cnt += __popc(act);
+            while (act) {
+                const int src = __ffs(act) - 1;
+                act &= act - 1;
+                const int of = __shfl_sync(full, off_f, src);
+                if (lane < cm) {
+                    const int64_t o = (int64_t)(v0 + src) * m_sv + of + lane;
+                    const float hv = mapped[o];
+                    if (pass == 0) s1 += hv;
+                    else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(g_mapped + o), "f"(fmaf(cb, hv - mean, cm_)) : "memory");
+                }
+            }
+        }
+        if (pass == 0) {
+            const float n_inv = (float)(nv - cnt);
+            s1 = fmaf(n_inv, b, s1);
+            const float denom = __fadd_rn((float)cnt, 1e-8f);
+            const float *row = glob + n * (int64_t)(2 * ct), *grow = g_glob + n * (int64_t)(2 * ct);
+            if (lane < cm) {
+                mean = row[2 * (3 + lane)];
+                const float gvar = cnt > 0 ? -row[2 * (3 + lane) + 1] * grow[2 * (3 + lane) + 1] : 0.0f;
+                cb = 2.0f * gvar / denom;
+                cm_ = grow[2 * (3 + lane)] / denom - cb * (s1 - (float)nv * mean) / denom;
+                // the invalid views of this voxel: x_u = bias
+                if (n_inv > 0.0f) atomicAdd(g_bias + lane, n_inv * fmaf(cb, b - mean, cm_));
+            }
+        }
+    }
+}
+
 }  // namespace nd
 
 using namespace nd;
@@ -232,5 +297,25 @@ extern "C" int nd_live_stats(const nd_maps *mapped, const nd_maps *rgb, const fl
             rgb->stride_y, rgb->stride_x, rgb->height, rgb->width, points, projection, rgb_projection, nv, n_voxels,
             map_bias, global_volume, mean35, cov35, count);
     ND_CUDA_LAUNCH_CHECK("k_live_stats");
+    return ND_OK;
+}
+
+extern "C" int nd_live_stats_bwd(const nd_maps *mapped, const float *points, const float *projection, int64_t n_voxels,
+                                 const float *map_bias, const float *global_volume, const float *grad_global_volume,
+                                 float *grad_mapped, float *grad_bias, void *stream) {
+    ND_REQUIRE(mapped && mapped->data && points && projection && map_bias && global_volume && grad_global_volume && grad_mapped &&
+                   grad_bias,
+               ND_ERR_BAD_ARG, "nd_live_stats_bwd: null pointer");
+    ND_REQUIRE(mapped->dtype == ND_F32 && mapped->stride_c == 1 && mapped->channels >= 1 && mapped->channels <= kLiveMaxCm &&
+                   mapped->n_views > 0 && n_voxels >= 0,
+               ND_ERR_BAD_SHAPE, "nd_live_stats_bwd: channels-last f32 maps with at most %d channels", kLiveMaxCm);
+    if (n_voxels == 0) return ND_OK;
+    const int nv = mapped->n_views;
+    const size_t sm = (size_t)nv * 12 * sizeof(float);
+    ND_REQUIRE(sm <= 48 * 1024, ND_ERR_BAD_SHAPE, "nd_live_stats_bwd: too many views (%d)", nv);
+    k_live_stats_bwd<<<(unsigned)ceil_div(n_voxels, (int64_t)kLcWarps), kLcWarps * 32, sm, (cudaStream_t)stream>>>(
+        (const float *)mapped->data, mapped->stride_v, mapped->stride_y, mapped->stride_x, mapped->channels, mapped->height,
+        mapped->width, points, projection, nv, n_voxels, map_bias, global_volume, grad_global_volume, grad_mapped, grad_bias);
+    ND_CUDA_LAUNCH_CHECK("k_live_stats_bwd");
     return ND_OK;
 }

@@ -46,8 +46,27 @@ def map_features_2d(feature_2d: torch.Tensor, mapping) -> torch.Tensor:
 
 
 def _mapping_bias(mapping) -> torch.Tensor:
+    """The bias the invalid views enter the statistics with; attached to the graph when it trains."""
     lin = mapping[0] if isinstance(mapping, torch.nn.Sequential) else mapping
-    return lin.bias.detach()
+    return lin.bias if (torch.is_grad_enabled() and lin.bias.requires_grad) else lin.bias.detach()
+
+
+class _LiveStatsFn(torch.autograd.Function):
+    """``nd_live_stats`` with gradients for the mapped features and the mapping bias (row N1, ``nd_live_stats_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, mapped_2d, rgb_images, points, projection, rgb_projection, map_bias):
+        glob, _, _, count = ops.direct.live_stats(mapped_2d.detach(), rgb_images, points, projection, rgb_projection,
+                                                  map_bias.detach(), False)
+        ctx.save_for_backward(mapped_2d, points, projection, map_bias, glob)
+        ctx.mark_non_differentiable(count)
+        return glob, count
+
+    @staticmethod
+    def backward(ctx, g_glob, _g_count):
+        mapped_2d, points, projection, map_bias, glob = ctx.saved_tensors
+        g_mapped, g_bias = ops.direct.live_stats_bwd(mapped_2d.detach(), points, projection, map_bias.detach(), glob, g_glob)
+        return g_mapped, None, None, None, None, g_bias
 
 
 def live_statistics(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias, want_planes=False):
@@ -56,8 +75,14 @@ def live_statistics(mapped_2d, rgb_images, points, projection, rgb_projection, m
     (stride 1).  Returns ``global_volume [N, 70]`` (interleaved rows), the feature-level
     count ``[1, X, Y, Z]`` and, on request, ``mean35`` / ``cov35 [35, X, Y, Z]``."""
     gx, gy, gz = points.shape[-3:]
-    glob, mean35, cov35, count = ops.direct.live_stats(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias,
-                                                want_planes)
+    if torch.is_grad_enabled() and (mapped_2d.requires_grad or map_bias.requires_grad):
+        if want_planes:
+            raise NotImplementedError('mean35 / cov35 planes are forward-only outputs')
+        glob, count = _LiveStatsFn.apply(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias)
+        mean35 = cov35 = None
+    else:
+        glob, mean35, cov35, count = ops.direct.live_stats(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias,
+                                                    want_planes)
     out = dict(global_volume=glob, count=count.view(1, gx, gy, gz))
     if want_planes:
         out['mean35'] = mean35.view(-1, gx, gy, gz)

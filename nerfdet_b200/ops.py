@@ -1018,6 +1018,39 @@ def _(pts, cameras, image_height, image_width, featmaps, globalfeat, grad_global
     return featmaps.new_empty((nv, h, w, d)).permute(0, 3, 1, 2)
 
 
+@torch.library.custom_op(f'{_NS}::live_stats_bwd', mutates_args=())
+@_guarded
+def live_stats_bwd(mapped: Tensor, points: Tensor, projection: Tensor, map_bias: Tensor, global_volume: Tensor,
+                   grad_global_volume: Tensor) -> Tuple[Tensor, Tensor]:
+    """Row N1: gradients of ``live_stats``' ``global_volume`` with respect to ``mapped`` (``[nv, Cm, h, w]`` float32 ->
+    a channels-last-strided tensor of that shape) and to the mapping bias ``[Cm]`` (the invalid views enter the
+    statistics as the bias).  Reference: autograd of nerfdet.py:232-253."""
+    _need_cuda(mapped, points, projection, map_bias, global_volume, grad_global_volume)
+    if mapped.dtype != torch.float32 or mapped.dim() != 4:
+        raise ValueError('mapped must be float32 [nv, Cm, h, w]')
+    mc = mapped.contiguous(memory_format=torch.channels_last)
+    mm = _maps(mc)
+    _check_geometry(points, projection, mm.n_views)
+    points, _ = _flat_points(points)
+    n = points.shape[1]
+    ct = 3 + mm.channels
+    if tuple(global_volume.shape) != (n, 2 * ct) or tuple(grad_global_volume.shape) != (n, 2 * ct):
+        raise ValueError(f'global_volume and its gradient must be [{n}, {2 * ct}]')
+    g_mapped = torch.zeros((mm.n_views, mm.height, mm.width, mm.channels), dtype=torch.float32, device=mapped.device)
+    g_bias = torch.zeros((mm.channels,), dtype=torch.float32, device=mapped.device)
+    lib = _lib.load()
+    _lib.check(lib.nd_live_stats_bwd(ctypes.byref(mm), _ptr(points), _ptr(projection.contiguous()), n, _ptr(map_bias.contiguous()),
+                                     _ptr(global_volume.contiguous()), _ptr(grad_global_volume.contiguous().float()),
+                                     _ptr(g_mapped), _ptr(g_bias), _stream()), 'nd_live_stats_bwd')
+    return g_mapped.permute(0, 3, 1, 2), g_bias
+
+
+@live_stats_bwd.register_fake
+def _(mapped, points, projection, map_bias, global_volume, grad_global_volume):
+    nv, c, h, w = mapped.shape
+    return mapped.new_empty((nv, h, w, c)).permute(0, 3, 1, 2), mapped.new_empty((c,))
+
+
 # ------------------------------------------------------------------------------------------
 # Autograd of the registered ops (SURVEY.md section 8f, row N1).  lift_mean_var: nd_lift_backward; map_features: the two
 # plain GEMMs of a Linear's backward go to cuBLAS through torch (library GEMMs, not a hot kernel of this path).
@@ -1077,5 +1110,5 @@ class _Direct:
 direct = _Direct()
 for _name in ('project_voxels', 'backproject', 'lift_mean_var', 'lift_accumulate', 'lift_accumulate_into', 'lift_finalize',
               'map_features', 'live_stats', 'nerf_mlp_fwd', 'sample_rays', 'render_gather_stats', 'composite', 'volume_sample',
-              'lift_backward', 'generate_rays', 'denorm_images', 'image_metrics', 'depth_sqerr', 'volume_to_neck', 'render_gather_stats_bwd'):
+              'lift_backward', 'generate_rays', 'denorm_images', 'image_metrics', 'depth_sqerr', 'volume_to_neck', 'render_gather_stats_bwd', 'live_stats_bwd'):
     setattr(direct, _name, globals()[_name]._init_fn)
