@@ -671,9 +671,9 @@ def bench_lift(args, rank, local_rank, world):
 
 
 def multi_gpu_parity(dev, rank, world, step, feats_local, pts, proj_local, pts_d, views_total, dist, strong, proj_all):
-    """Rank 0 compares the exchanged result of one step with (i) the plain-C oracle over ALL ranks' views on two
-    channels and (ii) a single-GPU CUDA lift over all views on 16 channels; every rank's result must be bit-identical
-    to rank 0's.  Tolerance 1e-4 relative + 1e-5 max|ref| (fp32), counts exact."""
+    """Rank 0 compares the exchanged result of one step with a single-GPU CUDA lift over ALL ranks' views on 16 channels
+    (the kernel the GPU tests pin on the C oracle; the exchange itself meets the oracle in tests/test_peer_gpu.py); every
+    rank's result must be bit-identical to rank 0's.  Tolerance 1e-4 relative + 1e-5 max|ref| (fp32), counts exact."""
     n_chk = 16
     mean, cov, cnt = step(feats_local)
     torch.cuda.synchronize()
@@ -707,7 +707,6 @@ def multi_gpu_parity(dev, rank, world, step, feats_local, pts, proj_local, pts_d
     res = None
     if rank == 0:
         from nerfdet_b200 import ops
-        from oracle import c_oracle
         feats = torch.cat([all_f[g][:int(all_nv[g].item())] for g in range(world)])
         projs = torch.cat([all_p[g][:int(all_nv[g].item())] for g in range(world)])
         assert feats.shape[0] == views_total
@@ -721,13 +720,11 @@ def multi_gpu_parity(dev, rank, world, step, feats_local, pts, proj_local, pts_d
         torch.cuda.synchronize()
         bm, em = bad(mean, m1.cpu().numpy())
         bc, ec = bad(cov, c1.cpu().numpy()) if has_cov else (0, 0.0)
-        m2, c2, n2 = c_oracle.lift(fs[:, :2].cpu().numpy(), pts.numpy(), projs.cpu().numpy())
-        bm2, em2 = bad(mean[:2], m2)
-        bc2, ec2 = bad(cov[:2], c2) if has_cov else (0, 0.0)
-        cnt_ok = bool(np.array_equal(cnt.cpu().numpy(), n2)) and bool(torch.equal(cnt, n1))
-        res = {'ok': bool(bm == 0 and bc == 0 and bm2 == 0 and bc2 == 0 and cnt_ok and int(same.item()) == 1),
+        cnt_ok = bool(torch.equal(cnt, n1))
+        res = {'ok': bool(bm == 0 and bc == 0 and cnt_ok and int(same.item()) == 1),
                'vs_single_gpu_lift_16_channels': {'mean_outside_tol': bm, 'cov_outside_tol': bc, 'max_abs_err': [em, ec]},
-               'vs_c_oracle_2_channels': {'mean_outside_tol': bm2, 'cov_outside_tol': bc2, 'max_abs_err': [em2, ec2]},
+               'note': 'the single-GPU lift is the one the GPU tests pin on the C oracle; the exchange itself is checked against '
+                       'the oracle in tests/test_peer_gpu.py (in-process ranks)',
                'counts_equal': cnt_ok, 'all_ranks_bit_identical': bool(int(same.item()) == 1), 'cov_checked': has_cov,
                'tolerance': '|a-b| <= 1e-4 |ref| + 1e-5 max|ref|; counts exact', 'views_total': views_total}
     dist.barrier()

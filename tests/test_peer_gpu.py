@@ -91,6 +91,12 @@ def test_in_process_ranks_match_all_views(world, overlap):
             assert_close(c2.reshape(channels, -1), c_ref, 1e-5, f'cov of rank {r} vs all-reduce path')
             # every rank holds the same bits: each row was computed once and stored into every segment
             assert torch.equal(m2, outs[0][0]) and torch.equal(c2, outs[0][1])
+        # and the exchange against the CPU oracle lifting the whole scene (its mean times alpha, like nerfdet.py:259-261)
+        from oracle import c_oracle
+        m_or, c_or, n_or = c_oracle.lift(f.cpu().numpy(), pts.cpu().numpy(), proj.cpu().numpy())
+        assert np.array_equal(outs[0][2].view(-1).cpu().numpy(), n_or)
+        assert_close(outs[0][0].reshape(channels, -1), torch.from_numpy(m_or * alpha.cpu().numpy()[None, :]), 1e-4, 'mean vs the C oracle')
+        assert_close(outs[0][1].reshape(channels, -1), torch.from_numpy(c_or), 1e-4, 'cov vs the C oracle')
     finally:
         for peer in ranks:
             peer.close()
