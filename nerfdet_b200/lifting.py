@@ -28,14 +28,35 @@ def compute_projection(img_meta, stride: int, angles=None) -> torch.Tensor:
     intrinsic = torch.tensor(img_meta['lidar2img']['intrinsic'][:3, :3])
     ratio = img_meta['ori_shape'][0] / (img_meta['img_shape'][0] / stride)
     intrinsic[:2] /= ratio
-    # one host copy of all extrinsics, then the reference's own per-view 3x3 @ 3x4 product (the very same mm on the very
-    # same values: the projection matrices, and with them the pixel indices, stay bit-identical to the reference's)
+    # one host copy of all extrinsics, then the reference's product K' @ E_v[:3] for every view.  The reference calls torch.mm
+    # once per view (0.7 ms of host time at 50 views); ONE mm over the views' columns side by side runs the same fp32
+    # multiply-add chain per output element and gives the same bits -- which is checked against the per-view loop on the first
+    # call of the process (and on any call where the check has not passed, the loop is what is returned): the projection
+    # matrices, and with them the pixel indices, stay bit-identical to the reference's.
     import numpy as np
     extr = torch.from_numpy(np.ascontiguousarray(np.stack([np.asarray(e) for e in img_meta['lidar2img']['extrinsic']])))
-    out = torch.empty((extr.shape[0], 3, 4), dtype=intrinsic.dtype)
-    for i in range(extr.shape[0]):
-        torch.mm(intrinsic, extr[i, :3], out=out[i])
-    return out
+    nv = extr.shape[0]
+    if extr.dtype != intrinsic.dtype:
+        extr = extr.to(intrinsic.dtype)
+
+    def per_view():
+        out = torch.empty((nv, 3, 4), dtype=intrinsic.dtype)
+        for i in range(nv):
+            torch.mm(intrinsic, extr[i, :3], out=out[i])
+        return out
+
+    global _ONE_MM_CHECKED
+    if nv == 0 or _ONE_MM_CHECKED is False:
+        return per_view()
+    fast = torch.mm(intrinsic, extr[:, :3].permute(1, 0, 2).reshape(3, nv * 4)).view(3, nv, 4).permute(1, 0, 2).contiguous()
+    if _ONE_MM_CHECKED is None:
+        slow = per_view()
+        _ONE_MM_CHECKED = bool(torch.equal(fast, slow))
+        return slow
+    return fast
+
+
+_ONE_MM_CHECKED = None      # None: not compared yet; True: one mm == per-view mm on this machine; False: keep the loop
 
 
 @torch.no_grad()
