@@ -105,7 +105,7 @@ def lift_scene(feature: torch.Tensor, img_meta: Dict, n_voxels, voxel_size, mapp
     (nerfdet.py:164, 405-411).  The live 35-channel statistics have no depth gate yet: asking for both raises instead of
     silently using un-gated views for the density."""
     dev = feature.device
-    projection = lifting.compute_projection(img_meta, stride).to(dev)
+    projection = lifting.to_device(lifting.compute_projection(img_meta, stride), dev)
     points = lifting.get_points_device(n_voxels, voxel_size, img_meta['lidar2img']['origin'], dev)
     height = img_meta['img_shape'][0] // stride
     width = img_meta['img_shape'][1] // stride
@@ -117,7 +117,7 @@ def lift_scene(feature: torch.Tensor, img_meta: Dict, n_voxels, voxel_size, mapp
             raise NotImplementedError('depth-gated live statistics (nerf_density with a depth prior) are not built; '
                                       'lift without mapping / nerf_mlp, or use lifting.backproject')
         feature_2d = map_features_2d(sliced, mapping)
-        rgb_projection = lifting.compute_projection(img_meta, 1).to(dev)
+        rgb_projection = lifting.to_device(lifting.compute_projection(img_meta, 1), dev)
         rgb = denorm_images[:, :, :img_meta['img_shape'][0], :img_meta['img_shape'][1]]
         live = live_statistics(feature_2d, rgb, points, projection, rgb_projection, _mapping_bias(mapping))
         pts = points.view(3, -1).permute(1, 0).contiguous()

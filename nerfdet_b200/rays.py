@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .lifting import to_device
 
 
 def nerf_intrinsics(img_meta) -> torch.Tensor:
@@ -27,8 +28,8 @@ def generate_ray_batch(img_meta, camrotc2w, lightpos, height: int, width: int, m
     """``ray_o`` / ``ray_d`` ``[1, nt, n_pix, 3]`` float32 and ``nerf_sizes [1, nt, 3]`` as the collated batch holds them
     (multi_view.py:124-132, 149; formating.py:55-75), for ``nt`` target cameras given by their camera-to-world rotations
     ``camrotc2w [nt, 3, 3]`` and centres ``lightpos [nt, 3]`` (numpy or torch, any float dtype)."""
-    rot = torch.as_tensor(np.asarray(camrotc2w), dtype=torch.float64).to(device)
-    pos = torch.as_tensor(np.asarray(lightpos), dtype=torch.float32).to(device)
+    rot = to_device(torch.as_tensor(np.asarray(camrotc2w), dtype=torch.float64), device)
+    pos = to_device(torch.as_tensor(np.asarray(lightpos), dtype=torch.float32), device)
     ray_d, ray_o = ops.direct.generate_rays(nerf_intrinsics(img_meta), rot, pos, int(height), int(width), int(margin))
     nt = rot.shape[0]
     sizes = torch.tensor([[height - 2 * margin, width - 2 * margin, 3]] * nt).unsqueeze(0)
