@@ -125,3 +125,24 @@ def test_reciprocal_quotient_is_correctly_rounded():
         r = (a.astype(np.float64) - q0.astype(np.float64) * float(n)).astype(np.float32)
         q = (q0.astype(np.float64) + r.astype(np.float64) * float(rc)).astype(np.float32)
         assert np.array_equal(q, (a / cf).astype(np.float32)), n
+
+
+def test_ssim_restatement_against_the_definition():
+    """oracle/metrics_oracle.ssim (scipy uniform filter, the way scikit-image 0.18.1 evaluates it) against the definition
+    written out per pixel: 7 x 7 window means, sample covariance, the map cropped by 3 pixels, mean over channels."""
+    from oracle import metrics_oracle as mt
+    rs = np.random.RandomState(4)
+    a = rs.uniform(0, 1, (15, 17, 3)).astype(np.float32)
+    b = np.clip(a + 0.1 * rs.standard_normal(a.shape), 0, 1)
+    c1, c2, vals = (0.01 * 2.0) ** 2, (0.03 * 2.0) ** 2, []
+    for ch in range(3):
+        x, y = a[..., ch].astype(np.float64), b[..., ch].astype(np.float64)
+        for i in range(3, 15 - 3):
+            for j in range(3, 17 - 3):
+                wx, wy = x[i - 3:i + 4, j - 3:j + 4], y[i - 3:i + 4, j - 3:j + 4]
+                ux, uy = wx.mean(), wy.mean()
+                vx, vy = wx.var(ddof=1), wy.var(ddof=1)
+                vxy = ((wx - ux) * (wy - uy)).sum() / 48.0
+                vals.append((2 * ux * uy + c1) * (2 * vxy + c2) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2)))
+    assert abs(mt.ssim(a, b) - float(np.mean(vals))) < 1e-12
+    assert abs(mt.ssim(a, a.astype(np.float64)) - 1.0) < 1e-12
