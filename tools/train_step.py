@@ -94,6 +94,11 @@ def main():
         r_us = timed(call)
     print(f'render_rays_func (2048 rays x 64 samples x 50 views, fp32-grade MLP): forward {r_us:.0f} us, forward + backward '
           f'{timed(render_fb):.0f} us', flush=True)
+    field.precision = 'bf16'
+    with torch.no_grad():
+        r_us = timed(call)
+    print(f'render_rays_func, bf16 MLP (backward GEMMs in bf16 too): forward {r_us:.0f} us, forward + backward '
+          f'{timed(render_fb):.0f} us', flush=True)
 
 
 if __name__ == '__main__':
