@@ -97,7 +97,7 @@ def main():
     field.precision = 'bf16'
     with torch.no_grad():
         r_us = timed(call)
-    print(f'render_rays_func, bf16 MLP (backward GEMMs in bf16 too): forward {r_us:.0f} us, forward + backward '
+    print(f'render_rays_func, bf16 MLP forward (its backward re-evaluates the fp32 formula): forward {r_us:.0f} us, forward + backward '
           f'{timed(render_fb):.0f} us', flush=True)
 
 
