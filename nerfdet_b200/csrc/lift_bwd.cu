@@ -9,7 +9,8 @@
 // (the second term of a: d var / d mean = -2 (S1 - nv * mean) / denom with S1 = mean * denom).  Every voxel that lands
 // on pixel p of view v reads the SAME x = features[v][c][p], so the scatter back into the feature map is
 //   g_features[v][c][p] = A[p] + features[v][c][p] * B[p],    A[p] = sum_{n -> p} a_n,   B[p] = sum_{n -> p} b_n,
-// i.e. two scatter-adds of per-voxel coefficients -- the exact transpose of the forward gather -- and no gather at all.
+// i.e. two sums of per-voxel coefficients over the voxels of a pixel -- the exact transpose of the forward gather -- and no
+// feature gather at all.
 //
 //   k_bwd_index    pixel offset (uint16, 0xffff = invalid) of every voxel-view: project_nearest() + the depth gate, the
 //                  same device function the forward kernels use, so the masks are bit-identical to the forward's
@@ -28,7 +29,6 @@
 #include "nd_common.cuh"
 
 namespace nd {
-
 
 __global__ void k_bwd_index(const float *__restrict__ points, const float *__restrict__ proj, int64_t n_vox, int height,
                             int width, const float *__restrict__ depth, float voxel_z, uint16_t *__restrict__ idx) {
@@ -233,17 +233,17 @@ using namespace nd;
 
 extern "C" {
 
-static int bwd_parts(int64_t n_voxels, int64_t) { return (int)ceil_div(n_voxels, (int64_t)kBwdPartMax); }
-static int bwd_part_len(int64_t n_voxels, int64_t plane) { return (int)ceil_div(n_voxels, (int64_t)bwd_parts(n_voxels, plane)); }
+static int bwd_parts(int64_t n_voxels) { return (int)ceil_div(n_voxels, (int64_t)kBwdPartMax); }
+static int bwd_part_len(int64_t n_voxels) { return (int)ceil_div(n_voxels, (int64_t)bwd_parts(n_voxels)); }
 
 size_t nd_lift_backward_workspace_bytes(const nd_maps *features, int64_t n_voxels) {
     if (features == nullptr || n_voxels <= 0) return 0;
     const size_t idx = ((size_t)features->n_views * n_voxels * sizeof(uint16_t) + 255) & ~(size_t)255;
     const size_t plane = (size_t)features->height * features->width;
-    const size_t parts = (size_t)bwd_parts(n_voxels, (int64_t)plane);
+    const size_t parts = (size_t)bwd_parts(n_voxels);
     const size_t st = ((size_t)features->n_views * parts * (plane + 1) * sizeof(uint16_t) + 255) & ~(size_t)255;
     const size_t rc = ((size_t)features->n_views * parts * plane * sizeof(uint2) + 255) & ~(size_t)255;
-    const size_t ls = ((size_t)features->n_views * parts * (size_t)bwd_part_len(n_voxels, (int64_t)plane) * sizeof(uint16_t) + 255) & ~(size_t)255;
+    const size_t ls = ((size_t)features->n_views * parts * (size_t)bwd_part_len(n_voxels) * sizeof(uint16_t) + 255) & ~(size_t)255;
     return idx + st + ls + rc;
 }
 
@@ -273,7 +273,7 @@ int nd_lift_backward(const nd_maps *features, const float *points, const float *
                                                                              voxel_z, idx);
     ND_CUDA_LAUNCH_CHECK("k_bwd_index");
     {
-        const int parts = bwd_parts(n_voxels, plane), part_len = bwd_part_len(n_voxels, plane);
+        const int parts = bwd_parts(n_voxels), part_len = bwd_part_len(n_voxels);
         const size_t st_bytes = ((size_t)nv * parts * (size_t)(plane + 1) * sizeof(uint16_t) + 255) & ~(size_t)255;
         const size_t ls_bytes = ((size_t)nv * parts * (size_t)part_len * sizeof(uint16_t) + 255) & ~(size_t)255;
         uint16_t *start = reinterpret_cast<uint16_t *>(ws + idx_bytes), *list = reinterpret_cast<uint16_t *>(ws + idx_bytes + st_bytes);
