@@ -234,8 +234,12 @@ def render_rays(ray_batch, mean_volume, cov_volume, features_2D, img, aabb, near
         gt_depth = gt_depth.view(-1, 1) if len(gt_depth) != 0 else None
         assert view_num * H * W == ray_o.shape[0]
         rgbs, depths = [], []
-        for i in range(0, ray_o.shape[0], N_rand):
-            ret = render_rays_func(ray_o[i:i + N_rand], ray_d[i:i + N_rand], mean_volume, cov_volume, features_2D, img,
+        # the reference walks the image in chunks of N_rand rays (render_ray.py:480-500); with deterministic sampling every ray
+        # is independent of its batch (same z_vals, hence the same depth clamp bounds), so larger chunks give the same pixels
+        # with 32x fewer launch sequences at N_rand = 2048
+        chunk = max(int(N_rand), 1 << 16)
+        for i in range(0, ray_o.shape[0], chunk):
+            ret = render_rays_func(ray_o[i:i + chunk], ray_d[i:i + chunk], mean_volume, cov_volume, features_2D, img,
                                    aabb, near_far_range, N_samples, N_rand, gt_rgb=gt_rgb, gt_depth=gt_depth,
                                    **common(True))
             rgbs.append(ret['outputs_coarse']['rgb'])
