@@ -101,5 +101,21 @@ def main():
           f'{timed(render_fb):.0f} us', flush=True)
 
 
+    # row N4: one full target image (220 x 300 rays x 64 samples) through render_rays(render_testing=True) + the metrics
+    from nerfdet_b200 import evaluate
+    rbt = {k: (v[:, :1] if torch.is_tensor(v) and v.dim() >= 3 else v) for k, v in rb.items() if k != 'camrotc2w'}
+    rbt['nerf_sizes'] = rb['nerf_sizes'][:, :1]
+    with torch.no_grad():
+        def full():
+            return render.render_rays(rbt, None, None, f2d.detach(), imgs, cfg.aabb, cfg.near_far_range, 64, 2048, field, sc.img_meta,
+                                      pj, 'image', is_train=False, render_testing=True)
+        us = timed(full, 5, 2)
+        out = full()
+        m_us = timed(lambda: evaluate.image_metrics(out['outputs_coarse']['rgb'], out['gt_rgb'].to(DEV)), 20, 3)
+    n_rays = out['outputs_coarse']['rgb'].shape[1] * out['outputs_coarse']['rgb'].shape[2]
+    print(f'render_testing, one {out["outputs_coarse"]["rgb"].shape[1]} x {out["outputs_coarse"]["rgb"].shape[2]} image ({n_rays} rays x 64 '
+          f'samples, bf16 MLP): {us / 1e3:.2f} ms = {n_rays / us:.2f} M rays/s; PSNR + SSIM of the image: {m_us:.0f} us', flush=True)
+
+
 if __name__ == '__main__':
     main()
