@@ -76,6 +76,9 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
+    for f in os.listdir(OBJ_DIR):                            # objects of sources that no longer exist
+        if f.endswith('.o') and os.path.join(OBJ_DIR, f) not in objs:
+            os.remove(os.path.join(OBJ_DIR, f))
     cmd = [nvcc, '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
