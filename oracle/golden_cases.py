@@ -45,6 +45,8 @@ CASES = {
     # render_rays_func, deterministic sampling, with intermediates
     'render_det': dict(kind='render_det', seed=7, n_views=6, n_rays=48, N_samples=16, **_TINY),
     'mlp_small': dict(kind='mlp', seed=8, n_rays=32, N_samples=8),
+    # N1: gradients of render_rays_func (rgb, depth) w.r.t. the mapped features and the field's weights, reference autograd
+    'render_grad': dict(kind='render_grad', seed=7, n_views=6, n_rays=48, N_samples=16, **_TINY),
     # N1: gradients of nerfdet.py:164-181 with respect to the features, from the reference's own autograd
     'lift_grad_tiny': dict(kind='lift_grad', seed=11, n_views=6, n_voxels=(10, 10, 4),
                            voxel_size=(0.64, 0.64, 0.8), channels=8, **_TINY),
@@ -104,6 +106,18 @@ def rays_inputs(case):
     img[:, -1] = 0.0                                            # a padded row, as Pad leaves it
     return dict(img_meta=img_meta, camrotc2w=q.astype(np.float64), lightpos=rs.standard_normal((nt, 3)).astype(np.float32),
                 img_hwc=img, height=case['height'], width=case['width'], margin=case['margin'])
+
+
+RENDER_GRAD_KEYS = ('mlp.base.hidden_layers.0.weight', 'mlp.base.hidden_layers.3.bias', 'mlp.sigma_layer.output_layer.weight',
+                    'mlp.bottleneck_layer.output_layer.bias', 'mlp.rgb_layer.hidden_layers.0.weight',
+                    'mlp.rgb_layer.output_layer.weight', 'mlp.rgb_layer.output_layer.bias')
+
+
+def render_grad_upstream(case):
+    """Seeded incoming gradients for the rendered colour [rays, 3] and depth [rays]."""
+    rs = np.random.RandomState(case['seed'] + 700)
+    return (torch.from_numpy(rs.standard_normal((case['n_rays'], 3)).astype(np.float32)),
+            torch.from_numpy(rs.standard_normal((case['n_rays'],)).astype(np.float32)))
 
 
 def extract_inputs(case):

@@ -180,6 +180,30 @@ def gen_render_det(case):
                 pixel_locations=_np(pix), in_front=_np(front))
 
 
+def gen_render_grad(case):
+    """N1: the reference's render_rays_func under its own autograd -- d(sum(rgb * g_rgb) + sum(depth * g_depth)) with
+    respect to the mapped feature maps and the field's weights (a selection of them is stored)."""
+    ref = ref_loader.load()
+    inp = gc.render_inputs(case)
+    field = ref.nerf_mlp.VanillaNeRFRadianceField(
+        net_depth=4, net_width=256, skip_layer=3, feature_dim=70,
+        net_depth_condition=1, net_width_condition=128)
+    field.load_state_dict({k: v for k, v in inp['state'].items() if not k.startswith('mapping.')})
+    feat = inp['featmaps'].clone().requires_grad_(True)
+    ret = ref.render_ray.render_rays_func(
+        inp['ray_o'], inp['ray_d'], None, None, feat, inp['images'],
+        inp['aabb'], inp['near_far_range'], inp['N_samples'], inp['ray_o'].shape[0],
+        field, inp['img_meta'], ref.projection.Projector(), 'image', 3, False, 0, True)
+    g_rgb, g_depth = gc.render_grad_upstream(case)
+    oc = ret['outputs_coarse']
+    ((oc['rgb'] * g_rgb).sum() + (oc['depth'] * g_depth).sum()).backward()
+    out = {'g_featmaps': _np(feat.grad), 'rgb': _np(oc['rgb']), 'depth': _np(oc['depth'])}
+    params = dict(field.named_parameters())
+    for k in gc.RENDER_GRAD_KEYS:
+        out['g_' + k] = _np(params[k].grad)
+    return out
+
+
 def gen_mlp(case):
     ref = ref_loader.load()
     inp = gc.mlp_inputs(case)
@@ -202,7 +226,7 @@ def gen_volume_lookup(case):
     return dict(features=_np(feats), inside=_np(masks))
 
 
-GENERATORS = dict(lift=gen_lift, lift_grad=gen_lift_grad, rays=gen_rays, extract=gen_extract, render_det=gen_render_det, mlp=gen_mlp,
+GENERATORS = dict(lift=gen_lift, lift_grad=gen_lift_grad, rays=gen_rays, render_grad=gen_render_grad, extract=gen_extract, render_det=gen_render_det, mlp=gen_mlp,
                   volume_lookup=gen_volume_lookup)
 
 

@@ -87,6 +87,26 @@ def test_rays_oracle_matches_reference_and_opencv():
     assert 0.0 <= g['denorm'].min() and g['denorm'].max() <= 1.0 and g['denorm'].std() > 0.1
 
 
+def test_render_oracle_autograd_matches_reference_autograd():
+    """Row N1, render branch: torch autograd through the oracle (grid_sample, masked statistics, MLP, compositing) gives
+    the gradients the unmodified reference's render_rays_func gave (fixture of oracle/make_golden.py:gen_render_grad)."""
+    case = gc.CASES['render_grad']
+    g = gc.load_golden('render_grad')
+    inp = gc.render_inputs(case)
+    so = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in inp['state'].items()}
+    fo = inp['featmaps'].clone().requires_grad_(True)
+    out = ro.render_image_mode(inp['ray_o'], inp['ray_d'], fo, inp['images'], inp['near_far_range'], case['N_samples'],
+                               mo.FieldOracle(so), inp['img_meta'], det=True)['outputs_coarse']
+    _close(out['rgb'].detach(), g['rgb'], name='rgb')
+    _close(out['depth'].detach(), g['depth'], name='depth')
+    g_rgb, g_depth = gc.render_grad_upstream(case)
+    ((out['rgb'] * g_rgb).sum() + (out['depth'] * g_depth).sum()).backward()
+    _close(fo.grad, g['g_featmaps'], rtol=1e-3, atol_scale=1e-5, name='g_featmaps')
+    for k in gc.RENDER_GRAD_KEYS:
+        _close(so[k].grad, g['g_' + k], rtol=1e-3, atol_scale=1e-5, name=k)
+    assert float(np.abs(g['g_featmaps']).max()) > 0
+
+
 def test_mlp_oracle_matches_reference():
     g = gc.load_golden('mlp_small')
     inp = gc.mlp_inputs(gc.CASES['mlp_small'])
