@@ -146,3 +146,41 @@ def test_ssim_restatement_against_the_definition():
                 vals.append((2 * ux * uy + c1) * (2 * vxy + c2) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2)))
     assert abs(mt.ssim(a, b) - float(np.mean(vals))) < 1e-12
     assert abs(mt.ssim(a, a.astype(np.float64)) - 1.0) < 1e-12
+
+
+def _run_bench(argv, env_extra=None, timeout=300):
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    return subprocess.run([sys.executable, os.path.join(root, 'bench.py')] + argv, cwd=root, env=env, timeout=timeout,
+                          capture_output=True, text=True)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` needs no GPU: ONE JSON line on rank 0 with the arm's own cpu_baseline and an e2e that
+    repeats the line's value with zero copy bytes; the other ranks of a torchrun launch exit 0 without work."""
+    import json
+    r = _run_bench(['--impl', 'reference', '--gpus', '1', '--steps', '1', '--warmup', '0'])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'voxel_view_samples_per_sec' and d['unit'] == 'samples/s'
+    assert d['higher_is_better'] is True and d['n_gpus'] == 1 and d['steps'] == 1 and d['gpu_launches'] == 0
+    assert d['value'] > 0 and abs(d['value'] - 50 * 25600 / (d['ms_per_step'] * 1e-3)) <= 1e-6 * d['value']
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_baseline']['value'] == d['value'] and d['cpu_baseline']['sample']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert d['config']['views'] == 50 and d['config']['n_voxels'] == [40, 40, 16]
+    r1 = _run_bench(['--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'],
+                    {'RANK': '1', 'LOCAL_RANK': '1', 'WORLD_SIZE': '2'}, timeout=120)
+    assert r1.returncode == 0 and r1.stdout.strip() == ''
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='CPU-only box check')
+def test_bench_product_arm_fails_loudly_without_a_gpu():
+    r = _run_bench(['--steps', '1', '--warmup', '0'], timeout=120)
+    assert r.returncode != 0 and 'no CPU fallback' in (r.stderr + r.stdout)
