@@ -43,6 +43,7 @@ FEAT_HW_PAD = (60, 80)
 FEAT_HW = (59, 80)
 OVERLAP_SMS = 28           # N > 1, pipelined: SMs that carry the exchange kernel while the others accumulate the next scene
 N_INPUT_SETS = 3           # rotated so that no step finds its features in L2
+HEAD_START_CYCLES = 400_000  # torch.cuda._sleep ahead of the timed region of the lift: ~200 us at 1965 MHz
 SWEEP_GRIDS = [((40, 40, 16), (.16, .16, .2)), ((56, 56, 16), (.16, .16, .2)), ((64, 64, 24), (.1, .1, .13)),
                ((80, 80, 32), (.08, .08, .08))]
 REF_COPY = os.path.join(ROOT, 'baseline', '_ref')     # the four reference files, copied by __graft_entry__.build()
@@ -463,6 +464,10 @@ def bench_lift(args, rank, local_rank, world):
     run_steps(warmup)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # a ~200 us delay kernel ahead of the first event: the host enqueues the first steps while it spins, so the region
+    # between the events is K steps of DEVICE time and not the host latency of the first launch on an idle GPU (30-45 us
+    # of a 1.8 ms region at K = 20 -- and more on a slower or busier host; tools/prewarm_probe.py)
+    torch.cuda._sleep(HEAD_START_CYCLES)
     ev0.record()
     out = run_steps(steps)
     ev1.record()
@@ -659,7 +664,9 @@ def bench_lift(args, rank, local_rank, world):
                          'algorithmic_bytes_per_step': bytes_per_step,
                          'kernel': 'k_lift_quads (the only kernel of a step with a cached geometry plan)',
                          'note': 'per GPU; CUDA events around the K steps on the launching stream; consecutive steps overlap '
-                                 '(programmatic dependent launch), step_times_us has the event-separated single-step time'},
+                                 '(programmatic dependent launch), step_times_us has the event-separated single-step time; a '
+                                 '~200 us delay kernel runs ahead of the first event so that the region holds device time only '
+                                 '(not the host latency of the first launch after the synchronize)'},
             'cpu_baseline': cpu_baseline, 'gpu_eager_baseline': gpu_eager, 'e2e': e2e,
             'gpu_launches': launches * steps, 'clocks': clocks,
         }
