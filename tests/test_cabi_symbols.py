@@ -75,3 +75,23 @@ def test_peer_entry_points_validate_arguments_without_a_gpu():
     assert lib.nd_lift_finalize_peers(one, one, None, one, 1, 0, 1, 4, 2, 8, None, None, None, None, None, 0, 0, 3, None) == 1
     assert b'owner' in lib.nd_last_error_string()                                         # owner outside the world
     assert lib.nd_peer_close(None) == 0 and lib.nd_peer_free(None) == 0
+
+
+@pytest.mark.parametrize('compiler,flags', [('gcc', ['-std=c99', '-x', 'c']), ('g++', ['-std=c++17', '-x', 'c++'])])
+def test_header_is_plain_c_and_cxx(tmp_path, compiler, flags):
+    """The boundary is a C ABI: include/nerfdet_lift.h compiles on its own as C99 and as C++ (no torch, no CUDA headers),
+    and the ctypes mirrors of its structs have the sizes the C compiler gives them."""
+    import shutil
+    import subprocess
+    if shutil.which(compiler) is None:
+        pytest.skip(f'{compiler} not installed')
+    from nerfdet_b200 import _lib
+    src = tmp_path / 'abi.c'
+    src.write_text('#include <stdio.h>\n#include "nerfdet_lift.h"\n'
+                   'int main(void) { printf("%zu %zu %zu\\n", sizeof(nd_maps), sizeof(nd_lift_options), sizeof(nd_mlp_weights)); return 0; }\n')
+    exe = tmp_path / 'abi'
+    r = subprocess.run([compiler, '-Wall', '-Wextra', '-pedantic', '-Werror', f'-I{os.path.join(ROOT, "include")}'] + flags +
+                       [str(src), '-o', str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(_lib.NdMaps), ctypes.sizeof(_lib.NdLiftOptions), ctypes.sizeof(_lib.NdMlpWeights)]
