@@ -262,6 +262,18 @@ int nd_live_stats(const nd_maps *mapped, const nd_maps *rgb, const float *points
                   const float *rgb_projection, int64_t n_voxels, const float *map_bias, float *global_volume,
                   float *mean35, float *cov35, int64_t *count, void *stream);
 
+/* The same statistics with the depth gate of backproject (row B4, nerfdet.py:405-411) on BOTH gathers, as
+ * extract_feat(depth=...) applies it (nerfdet.py:164-169 for the features that `mapping` then sees, :204-210 for the RGB
+ * volume): a voxel-view that projects into the map is kept only if |z - depth[v][y][x]| < voxel_z.
+ *   depth_mapped  f32 [nv][h][w]  the depth maps resized to the MAPPED feature resolution (F.interpolate bilinear, done
+ *                 by the caller like the reference does), depth_rgb f32 [nv][H][W] resized to the rgb maps' resolution;
+ *                 both NULL = no gate (nd_live_stats).  A gated-out view counts as invalid: bias for the mapped
+ *                 channels, 0 for RGB, not counted. */
+int nd_live_stats_gated(const nd_maps *mapped, const nd_maps *rgb, const float *points, const float *projection,
+                        const float *rgb_projection, int64_t n_voxels, const float *map_bias, const float *depth_mapped,
+                        const float *depth_rgb, float voxel_z, float *global_volume, float *mean35, float *cov35,
+                        int64_t *count, void *stream);
+
 /* Backward of the mapped channels of nd_live_stats (autograd of nerfdet.py:232-253 with
  * respect to the mapped features and, through the invalid views, the mapping's bias -- SURVEY.md section 0.6).
  *   mapped          f32 channels-last [nv][h][w][Cm] contiguous, the forward's input
@@ -271,6 +283,11 @@ int nd_live_stats(const nd_maps *mapped, const nd_maps *rgb, const float *points
 int nd_live_stats_bwd(const nd_maps *mapped, const float *points, const float *projection, int64_t n_voxels,
                       const float *map_bias, const float *global_volume, const float *grad_global_volume,
                       float *grad_mapped, float *grad_bias, void *stream);
+
+/* Backward of nd_live_stats_gated: the same validity (depth gate on the mapped gather included) as its forward. */
+int nd_live_stats_bwd_gated(const nd_maps *mapped, const float *points, const float *projection, int64_t n_voxels,
+                            const float *map_bias, const float *depth_mapped, float voxel_z, const float *global_volume,
+                            const float *grad_global_volume, float *grad_mapped, float *grad_bias, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * M  nerf_mlp.py:11-234  VanillaNeRFRadianceField (NerfMLP + SinusoidalEncoder), as instantiated at

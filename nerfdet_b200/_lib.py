@@ -83,6 +83,10 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'nd_live_stats': (c_int, [POINTER(NdMaps), POINTER(NdMaps), c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nd_live_stats_gated': (c_int, [POINTER(NdMaps), POINTER(NdMaps), c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                    c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nd_live_stats_bwd_gated': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     'nd_map_features': (c_int, [POINTER(NdMaps), c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'nd_mlp_packed_bytes': (c_size_t, [POINTER(NdMlpWeights)]),
     'nd_pack_mlp_weights': (c_int, [POINTER(NdMlpWeights), c_void_p, c_size_t, c_void_p]),

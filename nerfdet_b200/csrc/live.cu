@@ -18,12 +18,22 @@ namespace nd {
 
 constexpr int kLiveMaxCm = 32;
 
+// B4 (nerfdet.py:405-411) for a voxel-view that passed project_nearest: |z - depth[v][y][x]| < voxel_z with the depth map
+// already resized to this level's resolution; no depth map = no gate.  Same arithmetic as k_backproject / k_q_index.
+__device__ __forceinline__ bool depth_keeps(const float *__restrict__ depth, int v, int height, int width, float xr, float yr,
+                                            float z, float voxel_z) {
+    if (depth == nullptr) return true;
+    const float d = __ldg(depth + ((int64_t)v * height + (int)yr) * width + (int)xr);
+    return (z > __fsub_rn(d, voxel_z)) && (z < __fadd_rn(d, voxel_z));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128)
 k_live_stats(const T *__restrict__ mapped, int64_t m_sv, int64_t m_sc, int64_t m_sy, int64_t m_sx, int cm, int hf, int wf,
              const float *__restrict__ rgb, int64_t r_sv, int64_t r_sc, int64_t r_sy, int64_t r_sx, int hr, int wr,
              const float *__restrict__ points, const float *__restrict__ proj_f, const float *__restrict__ proj_r, int nv,
-             int64_t n_vox, const float *__restrict__ bias, float *__restrict__ glob, float *__restrict__ mean_out,
+             int64_t n_vox, const float *__restrict__ bias, const float *__restrict__ depth_f,
+             const float *__restrict__ depth_r, float voxel_z, float *__restrict__ glob, float *__restrict__ mean_out,
              float *__restrict__ cov_out, int64_t *__restrict__ count_out) {
     extern __shared__ float sp[];                       // [nv][12] feature-level, [nv][12] rgb-level, [cm] bias
     float *spr = sp + nv * 12;
@@ -44,10 +54,12 @@ k_live_stats(const T *__restrict__ mapped, int64_t m_sv, int64_t m_sc, int64_t m
     int cnt = 0;
     for (int v = 0; v < nv; ++v) {
         float xr, yr, q2;
-        const bool ok_f = project_nearest(sp + v * 12, X, Y, Z, hf, wf, xr, yr, q2);
+        const bool ok_f = project_nearest(sp + v * 12, X, Y, Z, hf, wf, xr, yr, q2) &&
+                          depth_keeps(depth_f, v, hf, wf, xr, yr, q2, voxel_z);
         const int64_t off_f = (int64_t)v * m_sv + (int64_t)(int)yr * m_sy + (int64_t)(int)xr * m_sx;
         float xr2, yr2, q22;
-        const bool ok_r = project_nearest(spr + v * 12, X, Y, Z, hr, wr, xr2, yr2, q22);
+        const bool ok_r = project_nearest(spr + v * 12, X, Y, Z, hr, wr, xr2, yr2, q22) &&
+                          depth_keeps(depth_r, v, hr, wr, xr2, yr2, q22, voxel_z);
         const int64_t off_r = (int64_t)v * r_sv + (int64_t)(int)yr2 * r_sy + (int64_t)(int)xr2 * r_sx;
         cnt += ok_f ? 1 : 0;
 #pragma unroll
@@ -100,7 +112,8 @@ __global__ void __launch_bounds__(kLcWarps * 32)
 k_live_stats_cl(const T *__restrict__ mapped, int64_t m_sv, int64_t m_sy, int64_t m_sx, int cm, int hf, int wf,
                 const float *__restrict__ rgb, int64_t r_sv, int64_t r_sc, int64_t r_sy, int64_t r_sx, int hr, int wr,
                 const float *__restrict__ points, const float *__restrict__ proj_f, const float *__restrict__ proj_r, int nv,
-                int64_t n_vox, const float *__restrict__ bias, float *__restrict__ glob, float *__restrict__ mean_out,
+                int64_t n_vox, const float *__restrict__ bias, const float *__restrict__ depth_f,
+                const float *__restrict__ depth_r, float voxel_z, float *__restrict__ glob, float *__restrict__ mean_out,
                 float *__restrict__ cov_out, int64_t *__restrict__ count_out) {
     extern __shared__ float sp[];                       // [nv][12] feature-level, [nv][12] rgb-level
     float *spr = sp + nv * 12;
@@ -125,9 +138,11 @@ k_live_stats_cl(const T *__restrict__ mapped, int64_t m_sv, int64_t m_sy, int64_
             int off_f = 0, off_r = 0;
             if (v < nv) {
                 float xr, yr, q2;
-                ok_f = project_nearest(sp + v * 12, X, Y, Z, hf, wf, xr, yr, q2);
+                ok_f = project_nearest(sp + v * 12, X, Y, Z, hf, wf, xr, yr, q2) &&
+                       depth_keeps(depth_f, v, hf, wf, xr, yr, q2, voxel_z);
                 if (ok_f) off_f = (int)((int)yr * m_sy + (int)xr * m_sx);
-                ok_r = project_nearest(spr + v * 12, X, Y, Z, hr, wr, xr, yr, q2);
+                ok_r = project_nearest(spr + v * 12, X, Y, Z, hr, wr, xr, yr, q2) &&
+                       depth_keeps(depth_r, v, hr, wr, xr, yr, q2, voxel_z);
                 if (ok_r) off_r = (int)((int)yr * r_sy + (int)xr * r_sx);
             }
             const unsigned bf = __ballot_sync(full, ok_f), br = __ballot_sync(full, ok_r);
@@ -188,7 +203,8 @@ k_live_stats_cl(const T *__restrict__ mapped, int64_t m_sv, int64_t m_sy, int64_
 __global__ void __launch_bounds__(kLcWarps * 32)
 k_live_stats_bwd(const float *__restrict__ mapped, int64_t m_sv, int64_t m_sy, int64_t m_sx, int cm, int hf, int wf,
                  const float *__restrict__ points, const float *__restrict__ proj_f, int nv, int64_t n_vox,
-                 const float *__restrict__ bias, const float *__restrict__ glob, const float *__restrict__ g_glob,
+                 const float *__restrict__ bias, const float *__restrict__ depth_f, float voxel_z,
+                 const float *__restrict__ glob, const float *__restrict__ g_glob,
                  float *__restrict__ g_mapped, float *__restrict__ g_bias) {
     extern __shared__ float sp[];                       // [nv][12] feature-level
     for (int i = threadIdx.x; i < nv * 12; i += blockDim.x) sp[i] = proj_f[i];
@@ -210,7 +226,8 @@ k_live_stats_bwd(const float *__restrict__ mapped, int64_t m_sv, int64_t m_sy, i
             int off_f = 0;
             if (v < nv) {
                 float xr, yr, q2;
-                ok_f = project_nearest(sp + v * 12, X, Y, Z, hf, wf, xr, yr, q2);
+                ok_f = project_nearest(sp + v * 12, X, Y, Z, hf, wf, xr, yr, q2) &&
+                       depth_keeps(depth_f, v, hf, wf, xr, yr, q2, voxel_z);
                 if (ok_f) off_f = (int)((int)yr * m_sy + (int)xr * m_sx);
             }
             unsigned act = __ballot_sync(full, ok_f);
@@ -248,9 +265,12 @@ k_live_stats_bwd(const float *__restrict__ mapped, int64_t m_sv, int64_t m_sy, i
 
 using namespace nd;
 
-extern "C" int nd_live_stats(const nd_maps *mapped, const nd_maps *rgb, const float *points, const float *projection,
-                             const float *rgb_projection, int64_t n_voxels, const float *map_bias, float *global_volume,
-                             float *mean35, float *cov35, int64_t *count, void *stream) {
+extern "C" int nd_live_stats_gated(const nd_maps *mapped, const nd_maps *rgb, const float *points, const float *projection,
+                                   const float *rgb_projection, int64_t n_voxels, const float *map_bias,
+                                   const float *depth_mapped, const float *depth_rgb, float voxel_z, float *global_volume,
+                                   float *mean35, float *cov35, int64_t *count, void *stream) {
+    ND_REQUIRE((depth_mapped == nullptr) == (depth_rgb == nullptr), ND_ERR_BAD_ARG,
+               "nd_live_stats_gated: the depth gate needs the depth map at both resolutions (or neither)");
     ND_REQUIRE(mapped && rgb && mapped->data && rgb->data && points && projection && rgb_projection && map_bias &&
                    global_volume,
                ND_ERR_BAD_ARG, "nd_live_stats: null pointer");
@@ -273,13 +293,13 @@ extern "C" int nd_live_stats(const nd_maps *mapped, const nd_maps *rgb, const fl
                 (const float *)mapped->data, mapped->stride_v, mapped->stride_y, mapped->stride_x, mapped->channels,
                 mapped->height, mapped->width, (const float *)rgb->data, rgb->stride_v, rgb->stride_c, rgb->stride_y,
                 rgb->stride_x, rgb->height, rgb->width, points, projection, rgb_projection, nv, n_voxels, map_bias,
-                global_volume, mean35, cov35, count);
+                depth_mapped, depth_rgb, voxel_z, global_volume, mean35, cov35, count);
         else
             k_live_stats_cl<__nv_bfloat16><<<g, kLcWarps * 32, sm, st>>>(
                 (const __nv_bfloat16 *)mapped->data, mapped->stride_v, mapped->stride_y, mapped->stride_x, mapped->channels,
                 mapped->height, mapped->width, (const float *)rgb->data, rgb->stride_v, rgb->stride_c, rgb->stride_y,
                 rgb->stride_x, rgb->height, rgb->width, points, projection, rgb_projection, nv, n_voxels, map_bias,
-                global_volume, mean35, cov35, count);
+                depth_mapped, depth_rgb, voxel_z, global_volume, mean35, cov35, count);
         ND_CUDA_LAUNCH_CHECK("k_live_stats_cl");
         return ND_OK;
     }
@@ -289,20 +309,28 @@ extern "C" int nd_live_stats(const nd_maps *mapped, const nd_maps *rgb, const fl
             (const float *)mapped->data, mapped->stride_v, mapped->stride_c, mapped->stride_y, mapped->stride_x,
             mapped->channels, mapped->height, mapped->width, (const float *)rgb->data, rgb->stride_v, rgb->stride_c,
             rgb->stride_y, rgb->stride_x, rgb->height, rgb->width, points, projection, rgb_projection, nv, n_voxels,
-            map_bias, global_volume, mean35, cov35, count);
+            map_bias, depth_mapped, depth_rgb, voxel_z, global_volume, mean35, cov35, count);
     else
         k_live_stats<__nv_bfloat16><<<grid, 128, smem, st>>>(
             (const __nv_bfloat16 *)mapped->data, mapped->stride_v, mapped->stride_c, mapped->stride_y, mapped->stride_x,
             mapped->channels, mapped->height, mapped->width, (const float *)rgb->data, rgb->stride_v, rgb->stride_c,
             rgb->stride_y, rgb->stride_x, rgb->height, rgb->width, points, projection, rgb_projection, nv, n_voxels,
-            map_bias, global_volume, mean35, cov35, count);
+            map_bias, depth_mapped, depth_rgb, voxel_z, global_volume, mean35, cov35, count);
     ND_CUDA_LAUNCH_CHECK("k_live_stats");
     return ND_OK;
 }
 
-extern "C" int nd_live_stats_bwd(const nd_maps *mapped, const float *points, const float *projection, int64_t n_voxels,
-                                 const float *map_bias, const float *global_volume, const float *grad_global_volume,
-                                 float *grad_mapped, float *grad_bias, void *stream) {
+extern "C" int nd_live_stats(const nd_maps *mapped, const nd_maps *rgb, const float *points, const float *projection,
+                             const float *rgb_projection, int64_t n_voxels, const float *map_bias, float *global_volume,
+                             float *mean35, float *cov35, int64_t *count, void *stream) {
+    return nd_live_stats_gated(mapped, rgb, points, projection, rgb_projection, n_voxels, map_bias, nullptr, nullptr, 0.0f,
+                               global_volume, mean35, cov35, count, stream);
+}
+
+extern "C" int nd_live_stats_bwd_gated(const nd_maps *mapped, const float *points, const float *projection, int64_t n_voxels,
+                                       const float *map_bias, const float *depth_mapped, float voxel_z,
+                                       const float *global_volume, const float *grad_global_volume, float *grad_mapped,
+                                       float *grad_bias, void *stream) {
     ND_REQUIRE(mapped && mapped->data && points && projection && map_bias && global_volume && grad_global_volume && grad_mapped &&
                    grad_bias,
                ND_ERR_BAD_ARG, "nd_live_stats_bwd: null pointer");
@@ -315,7 +343,15 @@ extern "C" int nd_live_stats_bwd(const nd_maps *mapped, const float *points, con
     ND_REQUIRE(sm <= 48 * 1024, ND_ERR_BAD_SHAPE, "nd_live_stats_bwd: too many views (%d)", nv);
     k_live_stats_bwd<<<(unsigned)ceil_div(n_voxels, (int64_t)kLcWarps), kLcWarps * 32, sm, (cudaStream_t)stream>>>(
         (const float *)mapped->data, mapped->stride_v, mapped->stride_y, mapped->stride_x, mapped->channels, mapped->height,
-        mapped->width, points, projection, nv, n_voxels, map_bias, global_volume, grad_global_volume, grad_mapped, grad_bias);
+        mapped->width, points, projection, nv, n_voxels, map_bias, depth_mapped, voxel_z, global_volume, grad_global_volume,
+        grad_mapped, grad_bias);
     ND_CUDA_LAUNCH_CHECK("k_live_stats_bwd");
     return ND_OK;
+}
+
+extern "C" int nd_live_stats_bwd(const nd_maps *mapped, const float *points, const float *projection, int64_t n_voxels,
+                                 const float *map_bias, const float *global_volume, const float *grad_global_volume,
+                                 float *grad_mapped, float *grad_bias, void *stream) {
+    return nd_live_stats_bwd_gated(mapped, points, projection, n_voxels, map_bias, nullptr, 0.0f, global_volume,
+                                   grad_global_volume, grad_mapped, grad_bias, stream);
 }

@@ -55,34 +55,52 @@ class _LiveStatsFn(torch.autograd.Function):
     """``nd_live_stats`` with gradients for the mapped features and the mapping bias (row N1, ``nd_live_stats_bwd``)."""
 
     @staticmethod
-    def forward(ctx, mapped_2d, rgb_images, points, projection, rgb_projection, map_bias):
+    def forward(ctx, mapped_2d, rgb_images, points, projection, rgb_projection, map_bias, depth_mapped, depth_rgb, voxel_z):
         glob, _, _, count = ops.direct.live_stats(mapped_2d.detach(), rgb_images, points, projection, rgb_projection,
-                                                  map_bias.detach(), False)
+                                                  map_bias.detach(), False, depth_mapped, depth_rgb, voxel_z)
         ctx.save_for_backward(mapped_2d, points, projection, map_bias, glob)
+        ctx.depth_mapped, ctx.voxel_z = depth_mapped, voxel_z
         ctx.mark_non_differentiable(count)
         return glob, count
 
     @staticmethod
     def backward(ctx, g_glob, _g_count):
         mapped_2d, points, projection, map_bias, glob = ctx.saved_tensors
-        g_mapped, g_bias = ops.direct.live_stats_bwd(mapped_2d.detach(), points, projection, map_bias.detach(), glob, g_glob)
-        return g_mapped, None, None, None, None, g_bias
+        g_mapped, g_bias = ops.direct.live_stats_bwd(mapped_2d.detach(), points, projection, map_bias.detach(), glob, g_glob,
+                                                     ctx.depth_mapped, ctx.voxel_z)
+        return g_mapped, None, None, None, None, g_bias, None, None, None
 
 
-def live_statistics(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias, want_planes=False):
+def live_statistics(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias, want_planes=False,
+                    depth: Optional[torch.Tensor] = None, voxel_size=None):
     """B8 + B9.  ``mapped_2d [nv, 32, h, w]`` (B7 output), ``rgb_images [nv, 3, H, W]`` = the
     ``denorm_images[:, :, :img_h, :img_w]`` slice, projections at feature level (stride 4) and image level
     (stride 1).  Returns ``global_volume [N, 70]`` (interleaved rows), the feature-level
-    count ``[1, X, Y, Z]`` and, on request, ``mean35`` / ``cov35 [35, X, Y, Z]``."""
+    count ``[1, X, Y, Z]`` and, on request, ``mean35`` / ``cov35 [35, X, Y, Z]``.
+
+    ``depth [nv, Hp, Wp]`` with ``voxel_size`` gates both gathers like ``backproject`` (nerfdet.py:405-411) does when
+    ``extract_feat`` is called with a depth prior: resized bilinearly to each map's resolution (``F.interpolate``, like
+    the reference), a voxel-view is kept only if ``|z - depth[y, x]| < voxel_size[-1]``."""
     gx, gy, gz = points.shape[-3:]
+    depth_mapped = depth_rgb = None
+    voxel_z = 0.0
+    if depth is not None:
+        if voxel_size is None:
+            raise ValueError('depth needs voxel_size (the gate is |z - depth| < voxel_size[-1])')
+        with torch.no_grad():
+            d = depth.float().unsqueeze(1)
+            depth_mapped = F.interpolate(d, size=tuple(mapped_2d.shape[-2:]), mode='bilinear').squeeze(1)
+            depth_rgb = F.interpolate(d, size=tuple(rgb_images.shape[-2:]), mode='bilinear').squeeze(1)
+        voxel_z = float(voxel_size[-1])
     if torch.is_grad_enabled() and (mapped_2d.requires_grad or map_bias.requires_grad):
         if want_planes:
             raise NotImplementedError('mean35 / cov35 planes are forward-only outputs')
-        glob, count = _LiveStatsFn.apply(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias)
+        glob, count = _LiveStatsFn.apply(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias,
+                                         depth_mapped, depth_rgb, voxel_z)
         mean35 = cov35 = None
     else:
         glob, mean35, cov35, count = ops.direct.live_stats(mapped_2d, rgb_images, points, projection, rgb_projection, map_bias,
-                                                    want_planes)
+                                                           want_planes, depth_mapped, depth_rgb, voxel_z)
     out = dict(global_volume=glob, count=count.view(1, gx, gy, gz))
     if want_planes:
         out['mean35'] = mean35.view(-1, gx, gy, gz)
@@ -101,9 +119,9 @@ def lift_scene(feature: torch.Tensor, img_meta: Dict, n_voxels, voxel_size, mapp
     ``volume_mean``.  Keys: volume [C,X,Y,Z], valid [1,X,Y,Z] int64, and, when available, volume_cov,
     feature_2d [nv,32,h,w], global_volume [N,70], alpha [N].
 
-    ``depth [nv, Hp, Wp]`` (the ``*_depth`` configs) gates the 256-channel lift like ``backproject`` does
-    (nerfdet.py:164, 405-411).  The live 35-channel statistics have no depth gate yet: asking for both raises instead of
-    silently using un-gated views for the density."""
+    ``depth [nv, Hp, Wp]`` (``extract_feat(depth=...)``) gates every gather of the scene like ``backproject`` does
+    (nerfdet.py:164-169, 204-210, 405-411): the 256-channel lift in its geometry plan, the live 35-channel statistics
+    (mapped features and RGB) in ``nd_live_stats_gated``."""
     dev = feature.device
     projection = lifting.to_device(lifting.compute_projection(img_meta, stride), dev)
     points = lifting.get_points_device(n_voxels, voxel_size, img_meta['lidar2img']['origin'], dev)
@@ -113,13 +131,11 @@ def lift_scene(feature: torch.Tensor, img_meta: Dict, n_voxels, voxel_size, mapp
     out = {}
     alpha = None
     if mapping is not None and nerf_mlp is not None and denorm_images is not None:
-        if depth is not None:
-            raise NotImplementedError('depth-gated live statistics (nerf_density with a depth prior) are not built; '
-                                      'lift without mapping / nerf_mlp, or use lifting.backproject')
         feature_2d = map_features_2d(sliced, mapping)
         rgb_projection = lifting.to_device(lifting.compute_projection(img_meta, 1), dev)
         rgb = denorm_images[:, :, :img_meta['img_shape'][0], :img_meta['img_shape'][1]]
-        live = live_statistics(feature_2d, rgb, points, projection, rgb_projection, _mapping_bias(mapping))
+        live = live_statistics(feature_2d, rgb, points, projection, rgb_projection, _mapping_bias(mapping), depth=depth,
+                               voxel_size=voxel_size if depth is not None else None)
         pts = points.view(3, -1).permute(1, 0).contiguous()
         _, alpha = nerf_mlp.query_density(pts, live['global_volume'], return_alpha=True)
         out.update(feature_2d=feature_2d, global_volume=live['global_volume'], alpha=alpha.view(-1),

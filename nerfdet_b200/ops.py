@@ -508,13 +508,22 @@ def _(features, weight, bias):
 @torch.library.custom_op(f'{_NS}::live_stats', mutates_args=())
 @_guarded
 def live_stats(mapped: Tensor, rgb: Tensor, points: Tensor, projection: Tensor, rgb_projection: Tensor,
-               map_bias: Tensor, want_planes: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+               map_bias: Tensor, want_planes: bool, depth_mapped: Optional[Tensor] = None,
+               depth_rgb: Optional[Tensor] = None, voxel_z: float = 0.0) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """B8 + B9 (reference nerfdet.py:200-210, 232-253).  Returns ``global_volume [N, 2*(3+Cm)]``
     (channel-interleaved rows), ``mean35`` / ``cov35 [3+Cm, N]`` (empty unless ``want_planes``) and the
-    feature-level view count ``int64 [N]``."""
-    _need_cuda(mapped, rgb, points, projection, rgb_projection, map_bias)
+    feature-level view count ``int64 [N]``.  ``depth_mapped [nv, h, w]`` / ``depth_rgb [nv, H, W]`` (the depth maps
+    resized to the two resolutions) with ``voxel_z`` apply backproject's depth gate (nerfdet.py:405-411) to both gathers."""
+    _need_cuda(mapped, rgb, points, projection, rgb_projection, map_bias, depth_mapped, depth_rgb)
     mm = _maps(mapped)
     mr = _maps(rgb)
+    if (depth_mapped is None) != (depth_rgb is None):
+        raise ValueError('the depth gate needs the depth maps at both resolutions (depth_mapped and depth_rgb)')
+    if depth_mapped is not None:
+        for d, m, what in ((depth_mapped, mm, 'depth_mapped'), (depth_rgb, mr, 'depth_rgb')):
+            if d.dtype != torch.float32 or tuple(d.shape) != (m.n_views, m.height, m.width):
+                raise ValueError(f'{what} must be float32 [{m.n_views}, {m.height}, {m.width}], got {tuple(d.shape)}')
+        depth_mapped, depth_rgb = depth_mapped.contiguous(), depth_rgb.contiguous()
     if rgb.dtype != torch.float32 or mr.channels != 3:
         raise ValueError('rgb must be float32 [n_views, 3, h, w]')
     _check_geometry(points, projection, mm.n_views)
@@ -534,15 +543,15 @@ def live_stats(mapped: Tensor, rgb: Tensor, points: Tensor, projection: Tensor, 
     rgb_projection = rgb_projection.contiguous()
     map_bias = map_bias.contiguous()
     lib = _lib.load()
-    _lib.check(lib.nd_live_stats(ctypes.byref(mm), ctypes.byref(mr), _ptr(points), _ptr(projection),
-                                 _ptr(rgb_projection), n, _ptr(map_bias), _ptr(glob),
-                                 _ptr(mean35) if want_planes else None, _ptr(cov35) if want_planes else None,
-                                 _ptr(count), _stream()), 'nd_live_stats')
+    _lib.check(lib.nd_live_stats_gated(ctypes.byref(mm), ctypes.byref(mr), _ptr(points), _ptr(projection),
+                                       _ptr(rgb_projection), n, _ptr(map_bias), _ptr(depth_mapped), _ptr(depth_rgb),
+                                       float(voxel_z), _ptr(glob), _ptr(mean35) if want_planes else None,
+                                       _ptr(cov35) if want_planes else None, _ptr(count), _stream()), 'nd_live_stats')
     return glob, mean35, cov35, count
 
 
 @live_stats.register_fake
-def _(mapped, rgb, points, projection, rgb_projection, map_bias, want_planes):
+def _(mapped, rgb, points, projection, rgb_projection, map_bias, want_planes, depth_mapped=None, depth_rgb=None, voxel_z=0.0):
     n = points[0].numel()
     ct = 3 + mapped.shape[1]
     f = lambda *s: mapped.new_empty(s, dtype=torch.float32)
@@ -1021,11 +1030,12 @@ def _(pts, cameras, image_height, image_width, featmaps, globalfeat, grad_global
 @torch.library.custom_op(f'{_NS}::live_stats_bwd', mutates_args=())
 @_guarded
 def live_stats_bwd(mapped: Tensor, points: Tensor, projection: Tensor, map_bias: Tensor, global_volume: Tensor,
-                   grad_global_volume: Tensor) -> Tuple[Tensor, Tensor]:
+                   grad_global_volume: Tensor, depth_mapped: Optional[Tensor] = None, voxel_z: float = 0.0) -> Tuple[Tensor, Tensor]:
     """Row N1: gradients of ``live_stats``' ``global_volume`` with respect to ``mapped`` (``[nv, Cm, h, w]`` float32 ->
     a channels-last-strided tensor of that shape) and to the mapping bias ``[Cm]`` (the invalid views enter the
-    statistics as the bias).  Reference: autograd of nerfdet.py:232-253."""
-    _need_cuda(mapped, points, projection, map_bias, global_volume, grad_global_volume)
+    statistics as the bias).  ``depth_mapped`` / ``voxel_z``: the forward's depth gate.  Reference: autograd of
+    nerfdet.py:232-253."""
+    _need_cuda(mapped, points, projection, map_bias, global_volume, grad_global_volume, depth_mapped)
     if mapped.dtype != torch.float32 or mapped.dim() != 4:
         raise ValueError('mapped must be float32 [nv, Cm, h, w]')
     mc = mapped.contiguous(memory_format=torch.channels_last)
@@ -1039,14 +1049,19 @@ def live_stats_bwd(mapped: Tensor, points: Tensor, projection: Tensor, map_bias:
     g_mapped = torch.zeros((mm.n_views, mm.height, mm.width, mm.channels), dtype=torch.float32, device=mapped.device)
     g_bias = torch.zeros((mm.channels,), dtype=torch.float32, device=mapped.device)
     lib = _lib.load()
-    _lib.check(lib.nd_live_stats_bwd(ctypes.byref(mm), _ptr(points), _ptr(projection.contiguous()), n, _ptr(map_bias.contiguous()),
-                                     _ptr(global_volume.contiguous()), _ptr(grad_global_volume.contiguous().float()),
-                                     _ptr(g_mapped), _ptr(g_bias), _stream()), 'nd_live_stats_bwd')
+    if depth_mapped is not None:
+        if depth_mapped.dtype != torch.float32 or tuple(depth_mapped.shape) != (mm.n_views, mm.height, mm.width):
+            raise ValueError(f'depth_mapped must be float32 [{mm.n_views}, {mm.height}, {mm.width}]')
+        depth_mapped = depth_mapped.contiguous()
+    _lib.check(lib.nd_live_stats_bwd_gated(ctypes.byref(mm), _ptr(points), _ptr(projection.contiguous()), n,
+                                           _ptr(map_bias.contiguous()), _ptr(depth_mapped), float(voxel_z),
+                                           _ptr(global_volume.contiguous()), _ptr(grad_global_volume.contiguous().float()),
+                                           _ptr(g_mapped), _ptr(g_bias), _stream()), 'nd_live_stats_bwd')
     return g_mapped.permute(0, 3, 1, 2), g_bias
 
 
 @live_stats_bwd.register_fake
-def _(mapped, points, projection, map_bias, global_volume, grad_global_volume):
+def _(mapped, points, projection, map_bias, global_volume, grad_global_volume, depth_mapped=None, voxel_z=0.0):
     nv, c, h, w = mapped.shape
     return mapped.new_empty((nv, h, w, c)).permute(0, 3, 1, 2), mapped.new_empty((c,))
 

@@ -42,6 +42,11 @@ CASES = {
     'extract_small': dict(kind='extract', seed=6, torch_seed=1234, n_views=5, n_voxels=(8, 8, 4),
                           voxel_size=(0.8, 0.8, 0.8), channels=256, n_target_views=2,
                           N_samples=8, N_rand=64, **_TINY),
+    # the voxel side of extract_feat with a depth prior: backproject's gate on the 256-channel volume AND on the RGB volume
+    # (nerfdet.py:164-169, 204-210), i.e. depth-gated live statistics and density
+    'extract_depth': dict(kind='extract_depth', seed=16, torch_seed=4321, n_views=6, n_voxels=(10, 10, 4),
+                          voxel_size=(0.64, 0.64, 0.8), channels=256, n_target_views=1,
+                          N_samples=8, N_rand=64, **_TINY),
     # render_rays_func, deterministic sampling, with intermediates
     'render_det': dict(kind='render_det', seed=7, n_views=6, n_rays=48, N_samples=16, **_TINY),
     'mlp_small': dict(kind='mlp', seed=8, n_rays=32, N_samples=8),
@@ -128,6 +133,14 @@ def extract_inputs(case):
                 near_far_range=list(cfg.near_far_range), N_samples=case['N_samples'],
                 N_rand=case['N_rand'], ray_batch=sc.ray_batch,
                 state=make_mlp_state(case['seed'] + 100))
+
+
+def extract_depth_inputs(case):
+    """extract_inputs plus a seeded depth prior ``[nv, Hp, Wp]`` that keeps roughly a third of the voxel-views."""
+    inp = extract_inputs(case)
+    rs = np.random.RandomState(case['seed'] + 1000)
+    inp['depth'] = torch.from_numpy(rs.uniform(0.5, 4.0, (case['n_views'],) + tuple(inp['pad_shape'])).astype(np.float32))
+    return inp
 
 
 def render_inputs(case):

@@ -164,13 +164,14 @@ def density_volume(points, global_volume, volume_mean, count, field):
 
 
 def extract_lift(features_sliced, img_meta, n_voxels, voxel_size, denorm_images=None,
-                 w_map=None, b_map=None, field=None, stride: int = 4):
+                 w_map=None, b_map=None, field=None, stride: int = 4, depth=None):
     """The whole voxel side of ``extract_feat`` for one scene (nerfdet.py:152-261,
     minus ``render_rays``).  Returns a dict of every intermediate the parity tests
-    compare."""
+    compare.  ``depth [nv, Hp, Wp]``: the depth prior ``extract_feat`` hands to both
+    ``backproject`` calls (nerfdet.py:164-169, 204-210)."""
     proj = compute_projection(img_meta, stride)
     pts = get_points(n_voxels, voxel_size, img_meta['lidar2img']['origin'])
-    volume, valid = backproject(features_sliced, pts, proj)
+    volume, valid = backproject(features_sliced, pts, proj, depth, voxel_size)
     mean, cov, count = mean_var(volume, valid)
     out = dict(projection=proj, points=pts, volume_mean=mean, volume_cov=cov, count=count)
     if denorm_images is None:
@@ -178,7 +179,7 @@ def extract_lift(features_sliced, img_meta, n_voxels, voxel_size, denorm_images=
     h, w = img_meta['img_shape'][:2]
     imgs = denorm_images.reshape([-1] + list(denorm_images.shape)[2:])
     rgb_proj = compute_projection(img_meta, 1)
-    rgb_volume, _ = backproject(imgs[:, :, :h, :w], pts, rgb_proj)
+    rgb_volume, _ = backproject(imgs[:, :, :h, :w], pts, rgb_proj, depth, voxel_size)
     glob, mean35, cov35 = live_stats(volume, valid, rgb_volume, w_map, b_map)
     out.update(rgb_projection=rgb_proj, global_volume=glob, mean35=mean35, cov35=cov35,
                feature_2d=map_features_2d(features_sliced, w_map, b_map))

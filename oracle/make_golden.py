@@ -150,6 +150,34 @@ def gen_extract(case):
                 t_rand=_np(t_rand))
 
 
+def gen_extract_depth(case):
+    """The unmodified reference's extract_feat called WITH a depth prior (nerfdet.py:133-139): both backproject calls are
+    gated.  Saves what it returns for the voxel side (x, valids) and the rows it hands to query_density (recorded by
+    wrapping the bound method of this one instance -- instrumentation, the reference code is untouched)."""
+    ref = ref_loader.load()
+    inp = gc.extract_depth_inputs(case)
+    det = ref_loader.build_reference_detector(
+        inp['features'], inp['n_voxels'], inp['voxel_size'], inp['aabb'], inp['near_far_range'],
+        inp['N_samples'], inp['N_rand'])
+    sd = inp['state']
+    det.nerf_mlp.load_state_dict({k: v for k, v in sd.items() if not k.startswith('mapping.')})
+    det.mapping.load_state_dict({'0.weight': sd['mapping.0.weight'], '0.bias': sd['mapping.0.bias']})
+    det.eval()
+    seen = {}
+    query = det.nerf_mlp.query_density
+
+    def recording_query(points, features):
+        seen['global_volume'] = features.detach().clone()
+        return query(points, features)
+    det.nerf_mlp.query_density = recording_query
+    ref.render_ray.rng = np.random.RandomState(234)
+    torch.manual_seed(case['torch_seed'])
+    img = torch.zeros((1, inp['features'].shape[0], 3) + tuple(inp['pad_shape']))
+    with torch.no_grad():
+        x, valids, _, _, _ = det.extract_feat(img, [inp['img_meta']], 'train', inp['depth'].unsqueeze(0), inp['ray_batch'])
+    return dict(x=_np(x[0]), valids=_np(valids[0]), global_volume=_np(seen['global_volume']))
+
+
 def gen_render_det(case):
     ref = ref_loader.load()
     inp = gc.render_inputs(case)
@@ -226,7 +254,7 @@ def gen_volume_lookup(case):
     return dict(features=_np(feats), inside=_np(masks))
 
 
-GENERATORS = dict(lift=gen_lift, lift_grad=gen_lift_grad, rays=gen_rays, render_grad=gen_render_grad, extract=gen_extract, render_det=gen_render_det, mlp=gen_mlp,
+GENERATORS = dict(lift=gen_lift, lift_grad=gen_lift_grad, rays=gen_rays, render_grad=gen_render_grad, extract=gen_extract, extract_depth=gen_extract_depth, render_det=gen_render_det, mlp=gen_mlp,
                   volume_lookup=gen_volume_lookup)
 
 

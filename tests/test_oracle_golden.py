@@ -191,6 +191,28 @@ def test_extract_feat_oracle_matches_reference():
     _close(gt_depth, g['gt_depth'], name='gt_depth')
 
 
+def test_extract_feat_oracle_with_depth_prior_matches_reference():
+    """extract_feat(depth=...): backproject's gate (row B4) on the 256-channel volume and on the RGB volume, hence on the
+    live statistics and the density.  The fixture holds what the unmodified reference returned (x, valids) and the rows it
+    handed to query_density."""
+    case = gc.CASES['extract_depth']
+    g = gc.load_golden('extract_depth')
+    inp = gc.extract_depth_inputs(case)
+    sd = inp['state']
+    meta = inp['img_meta']
+    h, w = meta['img_shape'][0] // 4, meta['img_shape'][1] // 4
+    args = (inp['features'][:, :, :h, :w], meta, inp['n_voxels'], inp['voxel_size'], inp['ray_batch']['denorm_images'],
+            sd['mapping.0.weight'], sd['mapping.0.bias'], mo.FieldOracle(sd))
+    res = lo.extract_lift(*args, depth=inp['depth'])
+    assert np.array_equal(res['count'].numpy(), g['valids'])
+    obs = g['valids'].reshape(-1) > 0
+    assert obs.any() and (~obs).any()
+    _close(res['global_volume'][torch.from_numpy(obs)], g['global_volume'][obs], rtol=1e-4, atol_scale=1e-5, name='global_volume')
+    _close(res['x_scene'], g['x'], rtol=1e-4, atol_scale=1e-5, name='x_scene')
+    ungated = lo.extract_lift(*args)                      # the gate must matter in this fixture
+    assert int(ungated['count'].sum()) > 2 * int(g['valids'].sum())
+
+
 def test_bf16_mlp_oracle_within_bf16_tolerance_of_reference():
     """oracle/mlp_oracle.py:FieldOracleBf16 (the operand roundings of the tensor-core kernel) stays within
     BASELINE.json's bf16 tolerance (1e-2, normalised by the tensor's max) of the reference fixture."""
