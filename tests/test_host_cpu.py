@@ -184,3 +184,26 @@ def test_bench_reference_arm_prints_the_contract_line():
 def test_bench_product_arm_fails_loudly_without_a_gpu():
     r = _run_bench(['--steps', '1', '--warmup', '0'], timeout=120)
     assert r.returncode != 0 and 'no CPU fallback' in (r.stderr + r.stdout)
+
+
+def test_bench_algorithmic_bytes_and_clock_parsing():
+    """The roofline numerator is SURVEY.md section 8d's formula (294.3 MB per scene at configs[1], 535.9 MB at 100 views,
+    662.7 MB at 80x80x32) and the clock sampler keeps only samples taken under load."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_under_test', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.algorithmic_bytes(50, 256, 59, 80, 25600) == 50 * 256 * 59 * 80 * 4 + 2 * 256 * 25600 * 4 + 25600 * 8 + 50 * 48
+    assert round(bench.algorithmic_bytes(50, 256, 59, 80, 25600) / 1e6, 1) == 294.3
+    assert abs(bench.algorithmic_bytes(100, 256, 59, 80, 25600) / 1e6 - 535.9) < 0.1      # SURVEY truncates 535.97
+    assert abs(bench.algorithmic_bytes(50, 256, 59, 80, 204800) / 1e6 - 662.7) < 0.1
+    s = bench.ClockSampler(0)
+    s.proc = type('P', (), {'terminate': lambda self: None, 'wait': lambda self, timeout=None: 0, 'kill': lambda self: None})()
+    s.lines = ['345, 1965, 0, Not Active, Not Active, Not Active, Not Active',
+               '1965, 1965, 100, Not Active, Not Active, Not Active, Not Active',
+               '1785, 1965, 100, Not Active, Not Active, Not Active, Active', 'garbage']
+    c = s.stop()
+    assert c['sm_mhz'] == 1875.0 and c['sm_max_mhz'] == 1965.0 and c['reasons'] == ['sw_power_cap']
+    assert c['samples'] == 4 and c['samples_under_load'] == 2
