@@ -95,3 +95,25 @@ def test_header_is_plain_c_and_cxx(tmp_path, compiler, flags):
     assert r.returncode == 0, r.stderr
     sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [ctypes.sizeof(_lib.NdMaps), ctypes.sizeof(_lib.NdLiftOptions), ctypes.sizeof(_lib.NdMlpWeights)]
+
+
+def test_cxx_host_example_compiles_and_links_against_the_library(tmp_path):
+    """examples/host_plan_lift.cpp -- a C++ host on the raw ABI (plan once per scene, one launch per lift) -- builds against
+    the header and links against the in-tree library; without a GPU it must fail with a CUDA error message, not crash."""
+    import shutil
+    import subprocess
+    cuda = '/usr/local/cuda'
+    if shutil.which('g++') is None or not os.path.isfile(os.path.join(cuda, 'include', 'cuda_runtime.h')):
+        pytest.skip('g++ or the CUDA runtime headers are not installed')
+    from nerfdet_b200 import _lib
+    libdir = os.path.dirname(_lib.library_path())
+    exe = tmp_path / 'host_plan_lift'
+    r = subprocess.run(['g++', '-std=c++17', '-Wall', '-Wextra', '-Werror', f'-I{os.path.join(ROOT, "include")}',
+                        f'-I{cuda}/include', os.path.join(ROOT, 'examples', 'host_plan_lift.cpp'), f'-L{libdir}',
+                        '-lnerfdet_lift', f'-L{cuda}/lib64', '-lcudart', f'-Wl,-rpath,{libdir}', f'-Wl,-rpath,{cuda}/lib64',
+                        '-o', str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+        assert run.returncode == 1 and 'cudaMalloc' in run.stderr and 'ABI version' in run.stdout
